@@ -1,0 +1,55 @@
+// Instantiates every kernel of the hot path for one (DIM, MECH, Model, G) combination.
+#pragma once
+#include "forward.cuh"
+#include "kernel_table.h"
+
+namespace c8 {
+
+template <class C>
+__global__ void k_init_xi(double* xi, long long xi_ld, int n_elems) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_elems) return;
+  double v[C::NXI];
+  C::Model::init(v);
+#pragma unroll
+  for (int q = 0; q < C::NXI; ++q) xi[size_t(q) * xi_ld + e] = v[q];
+}
+
+template <class C>
+struct Launch {
+  static void forward_jacobian(const FwdArgs& a, cudaStream_t s) {
+    if (a.mesh.n_elems == 0) return;
+    const long long threads = (long long)a.mesh.n_elems * C::G;
+    const int block = 128;
+    k_forward_jacobian<C><<<(unsigned)((threads + block - 1) / block), block, 0, s>>>(a);
+  }
+  static void global_residual(const FwdArgs& a, cudaStream_t s) {
+    if (a.mesh.n_elems == 0) return;
+    const int block = 128;
+    k_global_residual<C><<<(a.mesh.n_elems + block - 1) / block, block, 0, s>>>(a);
+  }
+  static void init_xi(double* xi, long long xi_ld, int n_elems, cudaStream_t s) {
+    if (n_elems == 0) return;
+    k_init_xi<C><<<(n_elems + 255) / 256, 256, 0, s>>>(xi, xi_ld, n_elems);
+  }
+  static KernelTable table() {
+    KernelTable t;
+    t.dim = C::D; t.mech = C::M; t.local_type = C::Model::TYPE;
+    t.nn = C::NN; t.nb = C::NB; t.nx = C::NX; t.nxi = C::NXI; t.npar = C::NPAR; t.group = C::G;
+    t.finite = C::Model::FINITE;
+    t.forward_jacobian = &forward_jacobian;
+    t.global_residual = &global_residual;
+    t.init_xi = &init_xi;
+    return t;
+  }
+};
+
+}  // namespace c8
+
+#define C8_DEFINE_COMBO(NAME, DIM, MECH, MODEL, G)                                   \
+  namespace c8 {                                                                     \
+  const KernelTable* table_##NAME() {                                                \
+    static const KernelTable t = Launch<Cfg<DIM, MECH, MODEL<DIM>, G>>::table();     \
+    return &t;                                                                       \
+  }                                                                                  \
+  }

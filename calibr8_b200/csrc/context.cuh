@@ -1,0 +1,69 @@
+// The C-ABI context: resident mesh, BSR pattern, element->block offsets, model
+// parameters, scratch.  Replaces what Disc / LinearAlg / State hold for this
+// path in the reference (src/disc.hpp:72-483, src/linear_alg.hpp:6-84).
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "kernel_table.h"
+
+struct c8_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+
+  // mesh
+  int dim = 0, nn = 0, n_elems = 0, n_nodes = 0, n_es = 1;
+  std::vector<int> h_conn;
+  std::vector<double> h_coords;  // [n_nodes][dim]
+  std::vector<int> h_rowptr, h_colind;  // node graph (BSR pattern)
+  int nnzb = 0;
+  int* d_conn = nullptr;
+  double* d_coords = nullptr;
+  int* d_elem_es = nullptr;
+  int* d_rowptr = nullptr;
+  int* d_colind = nullptr;
+  int* d_eoff = nullptr;
+  long long xi_ld = 0;
+
+  // model
+  const c8::KernelTable* kt = nullptr;
+  int global_type = -1, local_type = -1;
+  c8::ModelArgs model{};
+  double* d_params = nullptr;
+
+  // scratch / resident system
+  int* d_nfailed = nullptr;
+  double* d_A = nullptr;       // resident BSR values [nnzb*nb*nb]
+  double* d_b = nullptr;       // [n_nodes*nb]
+  double* d_x = nullptr, *d_xp = nullptr;
+  double* d_xi = nullptr, *d_xip = nullptr;
+  double* d_stage = nullptr;   // staging for host<->device layout conversion
+  size_t stage_bytes = 0;
+  double* h_pinned = nullptr;
+  size_t pinned_bytes = 0;
+
+  c8::MeshArgs mesh_args() const {
+    c8::MeshArgs m;
+    m.n_elems = n_elems; m.n_nodes = n_nodes; m.conn = d_conn; m.coords = d_coords;
+    m.elem_es = d_elem_es; m.eoff = d_eoff;
+    return m;
+  }
+};
+
+namespace c8 {
+int fail(c8_ctx* ctx, int code, const std::string& msg);
+bool cuda_ok(c8_ctx* ctx, cudaError_t e, const char* what);
+double* stage(c8_ctx* ctx, size_t bytes);
+double* pinned(c8_ctx* ctx, size_t bytes);
+}  // namespace c8
+
+#define C8_CUDA(ctx, call)                                        \
+  do {                                                            \
+    if (!c8::cuda_ok((ctx), (call), #call)) return C8_ERR_CUDA;   \
+  } while (0)
+#define C8_REQUIRE(ctx, cond, msg)                                \
+  do {                                                            \
+    if (!(cond)) return c8::fail((ctx), C8_ERR_USAGE, (msg));     \
+  } while (0)

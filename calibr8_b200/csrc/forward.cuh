@@ -1,0 +1,379 @@
+// K1 / K2: the forward element loop of the reference,
+//   eval_forward_jacobian   src/evaluations.cpp:12-154
+//   eval_global_residual    src/evaluations.cpp:156-259
+// One thread GROUP of G threads per element (= per coupled quadrature point;
+// linear simplices carry one).  The AD seeding choreography of the reference
+// (Appendix B of SURVEY.md) becomes three register-resident passes:
+//   P1  local Newton, xi seeded, width NXI split over the group   -> dC/dxi
+//   P2  C re-evaluated with the element dofs seeded, width NX     -> dC/dx
+//       dxi/dx = -(dC/dxi)^-1 dC/dx   (group Gauss-Jordan, groupsolve.cuh)
+//   P3  global residual with x seeded and xi carrying dxi/dx      -> R_e, dR/dx
+// followed by the pressure-mass ip set and ONE scatter per element (the
+// reference scatters the full block once per integration point, 5x per tet).
+#pragma once
+#include "args.h"
+#include "groupsolve.cuh"
+#include "mechanics.cuh"
+
+namespace c8 {
+
+template <int DIM, int MECH, class Model_, int G_>
+struct Cfg {
+  using Model = Model_;
+  using MT = MechTraits<DIM, MECH>;
+  static constexpr int D = DIM, M = MECH, G = G_;
+  static constexpr int NN = MT::NN, NB = MT::NB, NX = MT::NX;
+  static constexpr int NXI = Model::NXI, NPAR = Model::NPAR;
+  static constexpr int LX = (NX + G - 1) / G;
+  static constexpr int LXI = (NXI + G - 1) / G;
+  static_assert(32 % G == 0, "group must divide the warp");
+  // position of element dof (n, eq) in the reference's residual-major order
+  static C8_DI int ref_dof(int n, int eq) { return eq < DIM ? n * DIM + eq : NN * DIM + n; }
+};
+
+template <class C>
+struct Elem {
+  int nodes[C::NN];
+  Geom<C::D> g;
+  double xn[C::NN][C::NB];
+  double xpn[C::NN][C::NB];
+  double par[C::NPAR];
+  double xip[C::NXI];
+};
+
+template <class C>
+C8_DI void load_elem(const MeshArgs& m, const ModelArgs& md, const double* __restrict__ x,
+                     const double* __restrict__ x_prev, const double* __restrict__ xi_prev,
+                     long long xi_ld, int e, Elem<C>& E) {
+#pragma unroll
+  for (int n = 0; n < C::NN; ++n) E.nodes[n] = __ldg(&m.conn[size_t(e) * C::NN + n]);
+  load_geom<C::D>(m.coords, E.nodes, E.g);
+#pragma unroll
+  for (int n = 0; n < C::NN; ++n)
+#pragma unroll
+    for (int q = 0; q < C::NB; ++q) {
+      E.xn[n][q] = __ldg(&x[size_t(E.nodes[n]) * C::NB + q]);
+      E.xpn[n][q] = x_prev ? __ldg(&x_prev[size_t(E.nodes[n]) * C::NB + q]) : 0.0;
+    }
+  const int es = m.elem_es ? __ldg(&m.elem_es[e]) : 0;
+#pragma unroll
+  for (int q = 0; q < C::NPAR; ++q) E.par[q] = __ldg(&md.params[es * md.npar + q]);
+#pragma unroll
+  for (int q = 0; q < C::NXI; ++q) E.xip[q] = __ldg(&xi_prev[size_t(q) * xi_ld + e]);
+}
+
+// The local Newton of LocalResidual::solve_nonlinear (e.g. src/small_J2.cpp:121-173).
+// xi: in = values gathered from the current xi field, out = converged state.
+// Cd: the last residual evaluation with xi seeded (value + this thread's dC/dxi columns).
+// Returns the branch (0/1) or -1 when not converged within max_iters.
+template <class C>
+C8_DI int local_newton(const Kin<C::D, double, double>& k0, const Elem<C>& E, const ModelArgs& md,
+                       double (&xi)[C::NXI], Dual<C::LXI> (&Cd)[C::NXI], unsigned mask, int t) {
+  using Model = typename C::Model;
+  constexpr int NXI = C::NXI, LXI = C::LXI;
+  if constexpr (!Model::HAS_NEWTON) {
+    Model::guess(k0, E.xip, xi);
+#pragma unroll
+    for (int q = 0; q < NXI; ++q) Cd[q] = make_dual<LXI>(0.0);
+    return 0;
+  } else {
+    Model::guess(k0, E.xip, xi);
+    int path = 0, iter = 1;
+    double R_norm_0 = 1.0;
+    bool converged = false;
+    while (iter <= md.max_iters && !converged) {
+      Dual<LXI> xs[NXI];
+#pragma unroll
+      for (int q = 0; q < NXI; ++q) xs[q] = seeded<LXI>(xi[q], q, t * LXI);
+      path = Model::residual(k0, xs, E.xip, E.par, md.abs_tol, Cd);
+      double nrm = 0.0;
+#pragma unroll
+      for (int q = 0; q < NXI; ++q) nrm += Cd[q].v * Cd[q].v;
+      const double R_norm = sqrt(nrm);
+      if (iter == 1) R_norm_0 = R_norm;
+      const double R_norm_rel = R_norm / R_norm_0;
+      if ((R_norm_rel < md.rel_tol) || (R_norm < md.abs_tol)) { converged = true; break; }
+      double Jc[NXI][LXI], rhs[NXI], dummy[NXI][1];
+#pragma unroll
+      for (int q = 0; q < NXI; ++q) {
+        rhs[q] = -Cd[q].v;
+#pragma unroll
+        for (int s = 0; s < LXI; ++s) Jc[q][s] = Cd[q].d[s];
+      }
+      group_gauss_jordan<NXI, LXI, 0, C::G>(Jc, dummy, rhs, mask);
+#pragma unroll
+      for (int q = 0; q < NXI; ++q) xi[q] += rhs[q];
+      ++iter;
+    }
+    if (iter > md.max_iters && !converged) return -1;
+    return path;
+  }
+}
+
+// dxi/dx = -(dC/dxi)^-1 dC/dx for the columns this thread owns (Bc in: dC/dx, out: dxi/dx)
+template <class C, int LB>
+C8_DI void local_sensitivity(const Dual<C::LXI> (&Cd)[C::NXI], double (&Bc)[C::NXI][LB],
+                             unsigned mask) {
+  if constexpr (!C::Model::HAS_NEWTON) {
+    // Elastic: C == 0 identically, the reference's LU of a zero matrix returns 0
+#pragma unroll
+    for (int q = 0; q < C::NXI; ++q)
+#pragma unroll
+      for (int s = 0; s < LB; ++s) Bc[q][s] = 0.0;
+  } else {
+    double Jc[C::NXI][C::LXI], dummy[C::NXI];
+#pragma unroll
+    for (int q = 0; q < C::NXI; ++q) {
+      dummy[q] = 0.0;
+#pragma unroll
+      for (int s = 0; s < C::LXI; ++s) Jc[q][s] = Cd[q].d[s];
+#pragma unroll
+      for (int s = 0; s < LB; ++s) Bc[q][s] = -Bc[q][s];
+    }
+    group_gauss_jordan<C::NXI, C::LXI, LB, C::G>(Jc, Bc, dummy, mask);
+  }
+}
+
+// Seeded kinematics at the coupled point: grad u (Dual), p, grad p  (x seeded)
+template <class C>
+struct SeededX {
+  static constexpr int L = C::LX;
+  XLanes<C::D, C::NB, L> xl;
+  Mat<Dual<L>, C::D> gu;
+  Dual<L> p;
+  Dual<L> gp[C::D];
+  C8_DI void init(const Elem<C>& E, const Mat<double, C::D>& gu0, int t) {
+    xl.init(t * L, E.g);
+    gu = grad_u_seeded<C::D, C::NB, L>(gu0, xl);
+    if constexpr (C::M == MECH_MIXED) {
+      const double Nc = 1.0 / C::NN;
+      double pv = 0.0;
+#pragma unroll
+      for (int n = 0; n < C::NN; ++n) pv += E.xn[n][C::D] * Nc;
+      p.v = pv;
+#pragma unroll
+      for (int s = 0; s < L; ++s) p.d[s] = (xl.eq[s] == C::D) ? Nc : 0.0;
+#pragma unroll
+      for (int j = 0; j < C::D; ++j) {
+        double gv = 0.0;
+#pragma unroll
+        for (int n = 0; n < C::NN; ++n) gv += E.xn[n][C::D] * E.g.gN[n][j];
+        gp[j].v = gv;
+#pragma unroll
+        for (int s = 0; s < L; ++s) gp[j].d[s] = (xl.eq[s] == C::D) ? xl.gsel[s][j] : 0.0;
+      }
+    } else {
+      p = make_dual<L>(0.0);
+    }
+  }
+};
+
+// Scatter one element row (value + this thread's derivative lanes).
+template <class C>
+struct Scatter {
+  const FwdArgs& a;
+  const Elem<C>& E;
+  const XLanes<C::D, C::NB, C::LX>& xl;
+  int e, t;
+  C8_DI void row(int n, int eq, const Dual<C::LX>& r) const {
+    constexpr int NB = C::NB, NN = C::NN, NX = C::NX;
+    const int row_dof = n * NB + eq;
+    if (a.b && (row_dof % C::G) == t) atomicAdd(&a.b[size_t(E.nodes[n]) * NB + eq], r.v);
+    if (a.elem_R && (row_dof % C::G) == t) a.elem_R[size_t(e) * NX + C::ref_dof(n, eq)] = r.v;
+#pragma unroll
+    for (int s = 0; s < C::LX; ++s) {
+      if (xl.nsel[s] == 0.0) continue;
+      const int nc = xl.node[s], qc = xl.eq[s];
+      if (a.vals) {
+        if (!a.transpose) {
+          const int blk = __ldg(&a.mesh.eoff[size_t(e) * NN * NN + n * NN + nc]);
+          atomicAdd(&a.vals[size_t(blk) * NB * NB + eq * NB + qc], r.d[s]);
+        } else {
+          const int blk = __ldg(&a.mesh.eoff[size_t(e) * NN * NN + nc * NN + n]);
+          atomicAdd(&a.vals[size_t(blk) * NB * NB + qc * NB + eq], r.d[s]);
+        }
+      }
+      if (a.elem_J)
+        a.elem_J[(size_t(e) * NX + C::ref_dof(n, eq)) * NX + C::ref_dof(nc, qc)] = r.d[s];
+    }
+  }
+};
+
+template <class C>
+__global__ void __launch_bounds__(128) k_forward_jacobian(const FwdArgs a) {
+  using Model = typename C::Model;
+  constexpr int D = C::D, NN = C::NN, NB = C::NB, NXI = C::NXI, LX = C::LX, G = C::G;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = gid / G, t = gid % G;
+  if (e >= a.mesh.n_elems) return;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane / G * G));
+
+  Elem<C> E;
+  load_elem<C>(a.mesh, a.model, a.x, a.x_prev, a.xi_prev, a.xi_ld, e, E);
+  double xi[NXI];
+#pragma unroll
+  for (int q = 0; q < NXI; ++q) xi[q] = a.xi[size_t(q) * a.xi_ld + e];
+
+  Kin<D, double, double> k0;
+  k0.gu = grad_u_val<D, NB>(E.xn, E.g);
+  k0.gup = grad_u_val<D, NB>(E.xpn, E.g);
+
+  // ---- P1: local Newton ---------------------------------------------------
+  Dual<C::LXI> Cd[NXI];
+  const int path = local_newton<C>(k0, E, a.model, xi, Cd, mask, t);
+  if (path < 0) {
+    if (t == 0) atomicAdd(a.n_failed, 1);
+    if (a.path && t == 0) a.path[e] = -1;
+    return;  // the reference aborts the assembly (src/evaluations.cpp:95-97)
+  }
+#pragma unroll
+  for (int q = 0; q < NXI; ++q)
+    if (q % G == t) a.xi[size_t(q) * a.xi_ld + e] = xi[q];
+  if (a.path && t == 0) a.path[e] = (signed char)path;
+
+  // ---- P2: dC/dx, then dxi/dx ---------------------------------------------
+  SeededX<C> sx;
+  sx.init(E, k0.gu, t);
+  Kin<D, Dual<LX>, double> k2;
+  k2.gu = sx.gu;
+  k2.gup = k0.gup;
+  Dual<LX> xid[NXI];
+  {
+    Dual<LX> C2[NXI];
+    Model::residual(k2, xi, E.xip, E.par, a.model.abs_tol, C2);
+    double Bc[NXI][LX];
+#pragma unroll
+    for (int q = 0; q < NXI; ++q)
+#pragma unroll
+      for (int s = 0; s < LX; ++s) Bc[q][s] = C2[q].d[s];
+    local_sensitivity<C, LX>(Cd, Bc, mask);
+#pragma unroll
+    for (int q = 0; q < NXI; ++q) {
+      xid[q].v = xi[q];
+#pragma unroll
+      for (int s = 0; s < LX; ++s) xid[q].d[s] = Bc[q][s];
+    }
+  }
+
+  // ---- P3: element residual and total Jacobian, scattered row by row ------
+  const double wdv = quad1_weight<D>() * E.g.dv;
+  const Scatter<C> sc{a, E, sx.xl, e, t};
+  {
+    const Mat<Dual<LX>, D> P = first_pk<D, C::M, Model>(k2, sx.p, xid, E.par, a.model.thickness);
+#pragma unroll
+    for (int n = 0; n < NN; ++n)
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        Dual<LX> r = P(i, 0) * (E.g.gN[n][0] * wdv);
+#pragma unroll
+        for (int j = 1; j < D; ++j) r += P(i, j) * (E.g.gN[n][j] * wdv);
+        sc.row(n, i, r);
+      }
+  }
+  if constexpr (C::M == MECH_MIXED) {
+    Dual<LX> Rp[NN];
+    {
+      Dual<LX> hp, sv[D];
+      pressure_terms<D, Model>(k2, sx.gp, xid, E.par, E.g.h, a.model.stab_mult, hp, sv);
+      const double Nc = 1.0 / NN;
+#pragma unroll
+      for (int n = 0; n < NN; ++n) {
+        Dual<LX> r = hp * (Nc * wdv);
+#pragma unroll
+        for (int i = 0; i < D; ++i) r += sv[i] * (E.g.gN[n][i] * wdv);
+        Rp[n] = -r;
+      }
+    }
+    // pressure-mass ip set (quadrature order 2), src/mechanics.cpp:206-215
+    const double ipk = 1.0 / Model::pscale(E.par);
+#pragma unroll
+    for (int q = 0; q < Quad2<D>::NPT; ++q) {
+      double N[NN];
+      Quad2<D>::basis(q, N);
+      Dual<LX> pq;
+      pq.v = 0.0;
+#pragma unroll
+      for (int n = 0; n < NN; ++n) pq.v += E.xn[n][D] * N[n];
+#pragma unroll
+      for (int s = 0; s < LX; ++s) {
+        double Ns = 0.0;
+#pragma unroll
+        for (int n = 0; n < NN; ++n) Ns = pick(sx.xl.node[s] == n, N[n], Ns);
+        pq.d[s] = (sx.xl.eq[s] == D) ? Ns : 0.0;
+      }
+      const double wq = Quad2<D>::weight() * E.g.dv;
+      const Dual<LX> pk = pq * ipk;
+#pragma unroll
+      for (int n = 0; n < NN; ++n) Rp[n] -= pk * (N[n] * wq);
+    }
+#pragma unroll
+    for (int n = 0; n < NN; ++n) sc.row(n, D, Rp[n]);
+  }
+}
+
+// K2: residual only (eval_global_residual): no Newton, xi given, T = double
+template <class C>
+__global__ void __launch_bounds__(128) k_global_residual(const FwdArgs a) {
+  using Model = typename C::Model;
+  constexpr int D = C::D, NN = C::NN, NB = C::NB, NXI = C::NXI;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.mesh.n_elems) return;
+  Elem<C> E;
+  load_elem<C>(a.mesh, a.model, a.x, a.x_prev, a.xi_prev, a.xi_ld, e, E);
+  double xi[NXI];
+#pragma unroll
+  for (int q = 0; q < NXI; ++q) xi[q] = a.xi[size_t(q) * a.xi_ld + e];
+  Kin<D, double, double> k0;
+  k0.gu = grad_u_val<D, NB>(E.xn, E.g);
+  k0.gup = grad_u_val<D, NB>(E.xpn, E.g);
+  const double wdv = quad1_weight<D>() * E.g.dv;
+  double p = 0.0, gp[D];
+  if constexpr (C::M == MECH_MIXED) {
+#pragma unroll
+    for (int n = 0; n < NN; ++n) p += E.xn[n][D] * (1.0 / NN);
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      gp[j] = 0.0;
+#pragma unroll
+      for (int n = 0; n < NN; ++n) gp[j] += E.xn[n][D] * E.g.gN[n][j];
+    }
+  }
+  const Mat<double, D> P = first_pk<D, C::M, Model>(k0, p, xi, E.par, a.model.thickness);
+#pragma unroll
+  for (int n = 0; n < NN; ++n)
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      double r = 0.0;
+#pragma unroll
+      for (int j = 0; j < D; ++j) r += P(i, j) * (E.g.gN[n][j] * wdv);
+      atomicAdd(&a.b[size_t(E.nodes[n]) * NB + i], r);
+    }
+  if constexpr (C::M == MECH_MIXED) {
+    double hp, sv[D], Rp[NN];
+    pressure_terms<D, Model>(k0, gp, xi, E.par, E.g.h, a.model.stab_mult, hp, sv);
+#pragma unroll
+    for (int n = 0; n < NN; ++n) {
+      double r = hp * ((1.0 / NN) * wdv);
+#pragma unroll
+      for (int i = 0; i < D; ++i) r += sv[i] * (E.g.gN[n][i] * wdv);
+      Rp[n] = -r;
+    }
+    const double ipk = 1.0 / Model::pscale(E.par);
+#pragma unroll
+    for (int q = 0; q < Quad2<D>::NPT; ++q) {
+      double N[NN];
+      Quad2<D>::basis(q, N);
+      double pq = 0.0;
+#pragma unroll
+      for (int n = 0; n < NN; ++n) pq += E.xn[n][D] * N[n];
+      const double wq = Quad2<D>::weight() * E.g.dv;
+#pragma unroll
+      for (int n = 0; n < NN; ++n) Rp[n] -= pq * ipk * (N[n] * wq);
+    }
+#pragma unroll
+    for (int n = 0; n < NN; ++n) atomicAdd(&a.b[size_t(E.nodes[n]) * NB + D], Rp[n]);
+  }
+}
+
+}  // namespace c8

@@ -1,0 +1,677 @@
+// Constitutive models (LocalResidual<T> of the reference) as device-side static
+// templates.  Every function is generic in the scalar type of each input group
+//   TK  current kinematics (grad u)      TKP previous-step kinematics (grad u_prev)
+//   TX  local state xi                   TXP previous local state xi_prev
+//   TP  material parameters
+// so that each AD pass only carries derivative lanes where it is seeded.
+//
+// Reference semantics restated (file:line of the reference):
+//   Elastic               src/elastic.cpp:76-139
+//   SmallJ2               src/small_J2.cpp:121-297
+//   SmallHill             src/small_hill.cpp:137-324, src/yield_functions.hpp:34-99
+//   SmallHillPlaneStress  src/small_hill_plane_stress.cpp:135-327
+//   SmallHillPlaneStrain  src/small_hill_plane_strain.cpp:135-331
+//   HyperJ2               src/hyper_J2.cpp:136-360
+//   HyperJ2PlaneStress    src/hyper_J2_plane_stress.cpp:140-411
+//   HyperJ2PlaneStrain    src/hyper_J2_plane_strain.cpp:129-372
+// Packed xi order = the reference's residual order (sym tensor first, then scalars).
+#pragma once
+#include "tensor.cuh"
+
+namespace c8 {
+
+enum LocalType {
+  L_ELASTIC = 0, L_SMALL_J2 = 1, L_SMALL_HILL = 2, L_SMALL_HILL_PLANE_STRESS = 3,
+  L_HYPER_J2 = 4, L_HYPER_J2_PLANE_STRESS = 5, L_SMALL_HILL_PLANE_STRAIN = 6,
+  L_HYPER_J2_PLANE_STRAIN = 7
+};
+enum { PATH_ELASTIC = 0, PATH_PLASTIC = 1 };
+
+template <int DIM, class TK, class TKP>
+struct Kin {
+  Mat<TK, DIM> gu;    // grad u at the point
+  Mat<TKP, DIM> gup;  // grad u_prev at the point
+};
+
+template <class A, class B, class C, class D, class E>
+using prom5_t = prom_t<prom4_t<A, B, C, D>, E>;
+
+C8_DI bool is_plastic(double f, double abs_tol) { return (f > abs_tol) || (fabs(f) < abs_tol); }
+
+// material_params.hpp:12-30
+template <class T> C8_DI T mu_of(const T& E, const T& nu) { return E / (2.0 * (1.0 + nu)); }
+template <class T> C8_DI T kappa_of(const T& E, const T& nu) { return E / (3.0 * (1.0 - 2.0 * nu)); }
+template <class T> C8_DI T lambda_of(const T& E, const T& nu) {
+  return E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
+}
+
+template <class TK, int DIM> C8_DI Mat<TK, DIM> sym_grad(const Mat<TK, DIM>& gu) {
+  Mat<TK, DIM> e;
+#pragma unroll
+  for (int i = 0; i < DIM; ++i)
+#pragma unroll
+    for (int j = 0; j < DIM; ++j) e.a[i][j] = 0.5 * (gu.a[i][j] + gu.a[j][i]);
+  return e;
+}
+// eps - tr(eps)/3 I   (note: /3 also when DIM == 2, src/small_J2.cpp:275)
+template <class TK, int DIM> C8_DI Mat<TK, DIM> dev3(const Mat<TK, DIM>& eps) {
+  const TK th = trace(eps) / 3.0;
+  Mat<TK, DIM> r = eps;
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) r.a[i][i] = eps.a[i][i] - th;
+  return r;
+}
+
+// ---- Hill-48, src/yield_functions.hpp:34-99 ---------------------------------
+template <class T> struct Hill { T F, G, H, L, M, N; };
+template <class T>
+C8_DI Hill<T> hill_params(const T& R00, const T& R11, const T& R22, const T& R01, const T& R02,
+                          const T& R12) {
+  Hill<T> h;
+  const T i00 = inv_sqr(R00), i11 = inv_sqr(R11), i22 = inv_sqr(R22);
+  h.F = 0.5 * (i11 + i22 - i00);
+  h.G = 0.5 * (i22 + i00 - i11);
+  h.H = 0.5 * (i00 + i11 - i22);
+  h.L = 1.5 * inv_sqr(R12);
+  h.M = 1.5 * inv_sqr(R02);
+  h.N = 1.5 * inv_sqr(R01);
+  return h;
+}
+template <class TS, class TP>
+C8_DI prom_t<TS, TP> hill_value(const Mat<TS, 3>& t, const Hill<TP>& h) {
+  return dsqrt(h.F * sqr(t(1, 1) - t(2, 2)) + h.G * sqr(t(2, 2) - t(0, 0)) +
+               h.H * sqr(t(0, 0) - t(1, 1)) +
+               2.0 * (h.L * sqr(t(1, 2)) + h.M * sqr(t(0, 2)) + h.N * sqr(t(0, 1))));
+}
+template <class TS, class TP, class TH>
+C8_DI Mat<prom3_t<TS, TP, TH>, 3> hill_normal(const Mat<TS, 3>& t, const Hill<TP>& h, const TH& hv) {
+  using R = prom3_t<TS, TP, TH>;
+  Mat<R, 3> n;
+  const R ih = 1.0 / hv;
+  n(0, 0) = ((h.G + h.H) * t(0, 0) - h.H * t(1, 1) - h.G * t(2, 2)) * ih;
+  n(1, 1) = ((h.F + h.H) * t(1, 1) - h.H * t(0, 0) - h.F * t(2, 2)) * ih;
+  n(2, 2) = ((h.G + h.F) * t(2, 2) - h.G * t(0, 0) - h.F * t(1, 1)) * ih;
+  n(0, 1) = (h.N * t(0, 1)) * ih;
+  n(0, 2) = (h.M * t(0, 2)) * ih;
+  n(1, 2) = (h.L * t(1, 2)) * ih;
+  n(1, 0) = n(0, 1); n(2, 0) = n(0, 2); n(2, 1) = n(1, 2);
+  return n;
+}
+template <class T> C8_DI Mat<T, 3> embed3(const Mat<T, 2>& a) {
+  Mat<T, 3> r = mat_zero<T, 3>();
+  r(0, 0) = a(0, 0); r(0, 1) = a(0, 1); r(1, 0) = a(1, 0); r(1, 1) = a(1, 1);
+  return r;
+}
+template <class T> C8_DI Mat<T, 3> embed3(const Mat<T, 3>& a) { return a; }
+template <class T> C8_DI Mat<T, 2> extract2(const Mat<T, 3>& a) {
+  Mat<T, 2> r;
+  r(0, 0) = a(0, 0); r(0, 1) = a(0, 1); r(1, 0) = a(1, 0); r(1, 1) = a(1, 1);
+  return r;
+}
+
+// small-strain deviatoric stress 2 mu (dev3(eps) - pstrain), shared by several models
+template <int DIM, class TK, class TX, class TP>
+C8_DI Mat<prom3_t<TK, TX, TP>, DIM> small_dev_stress(const Mat<TK, DIM>& gu, const TX* xi,
+                                                     const TP& E, const TP& nu) {
+  const TP mu = mu_of(E, nu);
+  const Mat<TK, DIM> de = dev3(sym_grad(gu));
+  const Mat<TX, DIM> ps = unpack_sym<TX, DIM>(xi);
+  return scale(2.0 * mu, de - ps);
+}
+
+// =============================================================================
+template <int DIM>
+struct Elastic {
+  static constexpr int NXI = 1, NPAR = 4, TYPE = L_ELASTIC;
+  static constexpr bool FINITE = false, HAS_NEWTON = false, PLANE_STRESS = false;
+  static constexpr int Z_STRETCH = -1;
+  static C8_DI void init(double* xi) { xi[0] = 0.0; }
+  template <class K> static C8_DI void guess(const K&, const double*, double* xi) { xi[0] = 0.0; }
+  template <class TK, class TKP, class TX, class TXP, class TP>
+  static C8_DI int residual(const Kin<DIM, TK, TKP>&, const TX*, const TXP*, const TP*, double,
+                            prom5_t<TK, TKP, TX, TXP, TP>* C) {
+    C[0] = conv<prom5_t<TK, TKP, TX, TXP, TP>>(0.0);  // evaluate() leaves R untouched (== 0)
+    return 0;
+  }
+  template <class TK, class TKP, class TX, class TP>
+  static C8_DI Mat<prom3_t<TK, TX, TP>, DIM> dev_cauchy(const Kin<DIM, TK, TKP>& k, const TX*,
+                                                        const TP* par) {
+    using R = prom3_t<TK, TX, TP>;
+    const TP mu = mu_of(par[0], par[1]);
+    return mat_conv<R>(scale(2.0 * mu, dev3(sym_grad(k.gu))));
+  }
+  template <class TK, class TKP, class TX, class TP>
+  static C8_DI prom3_t<TK, TX, TP> hydro(const Kin<DIM, TK, TKP>& k, const TX*, const TP* par) {
+    const TP kappa = kappa_of(par[0], par[1]);
+    return conv<prom3_t<TK, TX, TP>>(kappa * trace(sym_grad(k.gu)) -
+                                     par[2] * par[3] * par[0] / (1.0 - 2.0 * par[1]));
+  }
+  template <class TP> static C8_DI TP pscale(const TP* par) { return kappa_of(par[0], par[1]); }
+};
+
+// =============================================================================
+template <int DIM>
+struct SmallJ2 {
+  static constexpr int NS = SymIdx<DIM>::n;
+  static constexpr int NXI = NS + 1, NPAR = 6, TYPE = L_SMALL_J2;
+  static constexpr bool FINITE = false, HAS_NEWTON = true, PLANE_STRESS = false;
+  static constexpr int Z_STRETCH = -1;
+  static C8_DI void init(double* xi) {
+#pragma unroll
+    for (int i = 0; i < NXI; ++i) xi[i] = 0.0;
+  }
+  template <class K> static C8_DI void guess(const K&, const double* xip, double* xi) {
+#pragma unroll
+    for (int i = 0; i < NXI; ++i) xi[i] = xip[i];
+  }
+  template <class TK, class TKP, class TX, class TXP, class TP>
+  static C8_DI int residual(const Kin<DIM, TK, TKP>& k, const TX* xi, const TXP* xip,
+                            const TP* par, double abs_tol, prom5_t<TK, TKP, TX, TXP, TP>* C) {
+    using R = prom5_t<TK, TKP, TX, TXP, TP>;
+    const double sqrt_23 = 0.81649658092772603, sqrt_32 = 1.2247448713915890;
+    const TP mu = mu_of(par[0], par[1]);
+    const auto s = small_dev_stress<DIM>(k.gu, xi, par[0], par[1]);
+    const auto s_mag = norm(s);
+    const auto sigma_yield = par[3] + par[2] * xi[NS];
+    const auto f = (s_mag - sqrt_23 * sigma_yield) / val(mu);
+    if (is_plastic(val(f), abs_tol)) {
+      const auto dgam = sqrt_32 * (xi[NS] - xip[NS]);
+      const auto g = dgam / s_mag;
+#pragma unroll
+      for (int i = 0; i < DIM; ++i)
+#pragma unroll
+        for (int j = i; j < DIM; ++j) {
+          const int q = SymIdx<DIM>::idx(i, j);
+          C[q] = conv<R>(xi[q] - xip[q] - g * s.a[i][j]);
+        }
+      C[NS] = conv<R>(f);
+      return PATH_PLASTIC;
+    }
+#pragma unroll
+    for (int q = 0; q < NXI; ++q) C[q] = conv<R>(xi[q] - xip[q]);
+    return PATH_ELASTIC;
+  }
+  template <class TK, class TKP, class TX, class TP>
+  static C8_DI Mat<prom3_t<TK, TX, TP>, DIM> dev_cauchy(const Kin<DIM, TK, TKP>& k, const TX* xi,
+                                                        const TP* par) {
+    return mat_conv<prom3_t<TK, TX, TP>>(small_dev_stress<DIM>(k.gu, xi, par[0], par[1]));
+  }
+  template <class TK, class TKP, class TX, class TP>
+  static C8_DI prom3_t<TK, TX, TP> hydro(const Kin<DIM, TK, TKP>& k, const TX*, const TP* par) {
+    const TP kappa = kappa_of(par[0], par[1]);
+    return conv<prom3_t<TK, TX, TP>>(kappa * trace(sym_grad(k.gu)) -
+                                     par[4] * par[5] * par[0] / (1.0 - 2.0 * par[1]));
+  }
+  template <class TP> static C8_DI TP pscale(const TP* par) { return kappa_of(par[0], par[1]); }
+};
+
+// =============================================================================
+// SmallHill (3-D only: the Hill function reads the zz components)
+template <int DIM>
+struct SmallHill {
+  static_assert(DIM == 3, "small_hill is a 3-D model");
+  static constexpr int NS = 6, NXI = 7, NPAR = 11, TYPE = L_SMALL_HILL;
+  static constexpr bool FINITE = false, HAS_NEWTON = true, PLANE_STRESS = false;
+  static constexpr int Z_STRETCH = -1;
+  static C8_DI void init(double* xi) {
+#pragma unroll
+    for (int i = 0; i < NXI; ++i) xi[i] = 0.0;
+  }
+  template <class K> static C8_DI void guess(const K&, const double* xip, double* xi) {
+#pragma unroll
+    for (int i = 0; i < NXI; ++i) xi[i] = xip[i];
+  }
+  template <class TK, class TKP, class TX, class TXP, class TP>
+  static C8_DI int residual(const Kin<3, TK, TKP>& k, const TX* xi, const TXP* xip, const TP* par,
+                            double abs_tol, prom5_t<TK, TKP, TX, TXP, TP>* C) {
+    using R = prom5_t<TK, TKP, TX, TXP, TP>;
+    const TP mu = mu_of(par[0], par[1]);
+    const Hill<TP> hp = hill_params(par[3], par[4], par[5], par[6], par[7], par[8]);
+    const auto s = small_dev_stress<3>(k.gu, xi, par[0], par[1]);
+    const auto hill = hill_value(s, hp);
+    const auto sigma_yield = par[2] + par[9] * (1.0 - dexp(-par[10] * xi[NS]));
+    const auto f = (hill - sigma_yield) / val(mu);
+    if (is_plastic(val(f), abs_tol)) {
+      const auto n = hill_normal(s, hp, hill);
+      const auto dgam = xi[NS] - xip[NS];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = i; j < 3; ++j) {
+          const int q = SymIdx<3>::idx(i, j);
+          C[q] = conv<R>(xi[q] - xip[q] - dgam * n.a[i][j]);
+        }
+      C[5] = conv<R>(xi[0] + xi[3] + xi[5]);  // R_pstrain(2,2) := tr(pstrain), src/small_hill.cpp:241
+      C[NS] = conv<R>(f);
+      return PATH_PLASTIC;
+    }
+#pragma unroll
+    for (int q = 0; q < NXI; ++q) C[q] = conv<R>(xi[q] - xip[q]);
+    return PATH_ELASTIC;
+  }
+  template <class TK, class TKP, class TX, class TP>
+  static C8_DI Mat<prom3_t<TK, TX, TP>, 3> dev_cauchy(const Kin<3, TK, TKP>& k, const TX* xi,
+                                                      const TP* par) {
+    return mat_conv<prom3_t<TK, TX, TP>>(small_dev_stress<3>(k.gu, xi, par[0], par[1]));
+  }
+  template <class TK, class TKP, class TX, class TP>
+  static C8_DI prom3_t<TK, TX, TP> hydro(const Kin<3, TK, TKP>& k, const TX*, const TP* par) {
+    const TP kappa = kappa_of(par[0], par[1]);
+    return conv<prom3_t<TK, TX, TP>>(kappa * trace(sym_grad(k.gu)));
+  }
+  template <class TP> static C8_DI TP pscale(const TP* par) { return kappa_of(par[0], par[1]); }
+};
+
+// =============================================================================
+template <int DIM>
+struct SmallHillPlaneStress {
+  static_assert(DIM == 2, "plane stress is 2-D");
+  static constexpr int NS = 3, NXI = 4, NPAR = 9, TYPE = L_SMALL_HILL_PLANE_STRESS;
+  static constexpr bool FINITE = false, HAS_NEWTON = true, PLANE_STRESS = true;
+  static constexpr int Z_STRETCH = -1;
+  static C8_DI void init(double* xi) {
+#pragma unroll
+    for (int i = 0; i < NXI; ++i) xi[i] = 0.0;
+  }
+  template <class K> static C8_DI void guess(const K&, const double* xip, double* xi) {
+#pragma unroll
+    for (int i = 0; i < NXI; ++i) xi[i] = xip[i];
+  }
+  // full in-plane Cauchy stress with eps_zz eliminated, src/small_hill_plane_stress.cpp:278-327
+  template <class TK, class TKP, class TX, class TP>
+  static C8_DI Mat<prom3_t<TK, TX, TP>, 2> cauchy(const Kin<2, TK, TKP>& k, const TX* xi,
+                                                  const TP* par) {
+    using R = prom3_t<TK, TX, TP>;
+    const TP mu = mu_of(par[0], par[1]);
+    const TP lambda = lambda_of(par[0], par[1]);
+    const Mat<TK, 2> eps = sym_grad(k.gu);
+    const Mat<TX, 2> ps = unpack_sym<TX, 2>(xi);
+    const R eps_zz = -(lambda * trace(eps) + 2.0 * mu * trace(ps)) / (lambda + 2.0 * mu);
+    const R eps_kk = trace(eps) + eps_zz;
+    Mat<R, 2> sig = mat_conv<R>(scale(2.0 * mu, eps - ps));
+    const R l = lambda * eps_kk;
+    sig(0, 0) += l; sig(1, 1) += l;
+    return sig;
+  }
+  template <class TK, class TKP, class TX, class TXP, class TP>
+  static C8_DI int residual(const Kin<2, TK, TKP>& k, const TX* xi, const TXP* xip, const TP* par,
+                            double abs_tol, prom5_t<TK, TKP, TX, TXP, TP>* C) {
+    using R = prom5_t<TK, TKP, TX, TXP, TP>;
+    const TP mu = mu_of(par[0], par[1]);
+    const TP one = conv<TP>(1.0);
+    const Hill<TP> hp = hill_params(par[5], par[6], par[7], par[8], one, one);
+    const auto sig3 = embed3(cauchy(k, xi, par));
+    const auto hill = hill_value(sig3, hp);
+    const auto sigma_yield = par[2] + par[3] * (1.0 - dexp(-par[4] * xi[NS]));
+    const auto f = (hill - sigma_yield) / val(mu);
+    if (is_plastic(val(f), abs_tol)) {
+      const auto n = hill_normal(sig3, hp, hill);
+      const auto dgam = xi[NS] - xip[NS];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = i; j < 2; ++j) {
+          const int q = SymIdx<2>::idx(i, j);
+          C[q] = conv<R>(xi[q] - xip[q] - dgam * n.a[i][j]);
+        }
+      C[NS] = conv<R>(f);
+      return PATH_PLASTIC;
+    }
+#pragma unroll
+    for (int q = 0; q < NXI; ++q) C[q] = conv<R>(xi[q] - xip[q]);
+    return PATH_ELASTIC;
+  }
+  template <class TP> static C8_DI TP pscale(const TP*) { return conv<TP>(0.0); }
+};
+
+// =============================================================================
+template <int DIM>
+struct SmallHillPlaneStrain {
+  static_assert(DIM == 2, "plane strain is 2-D");
+  static constexpr int NS = 3, NXI = 4, NPAR = 9, TYPE = L_SMALL_HILL_PLANE_STRAIN;
+  static constexpr bool FINITE = false, HAS_NEWTON = true, PLANE_STRESS = false;
+  static constexpr int Z_STRETCH = -1;
+  static C8_DI void init(double* xi) {
+#pragma unroll
+    for (int i = 0; i < NXI; ++i) xi[i] = 0.0;
+  }
+  template <class K> static C8_DI void guess(const K&, const double* xip, double* xi) {
+#pragma unroll
+    for (int i = 0; i < NXI; ++i) xi[i] = xip[i];
+  }
+  template <class TK, class TKP, class TX, class TXP, class TP>
+  static C8_DI int residual(const Kin<2, TK, TKP>& k, const TX* xi, const TXP* xip, const TP* par,
+                            double abs_tol, prom5_t<TK, TKP, TX, TXP, TP>* C) {
+    using R = prom5_t<TK, TKP, TX, TXP, TP>;
+    const TP mu = mu_of(par[0], par[1]);
+    const TP one = conv<TP>(1.0);
+    const Hill<TP> hp = hill_params(par[5], par[6], par[7], par[8], one, one);
+    const auto s2 = small_dev_stress<2>(k.gu, xi, par[0], par[1]);
+    const Mat<TK, 2> eps = sym_grad(k.gu);
+    auto s3 = embed3(s2);
+    s3(2, 2) = 2.0 * mu * (-trace(eps) / 3.0 + (xi[0] + xi[2]));
+    const auto hill = hill_value(s3, hp);
+    const auto sigma_yield = par[2] + par[3] * (1.0 - dexp(-par[4] * xi[NS]));
+    const auto f = (hill - sigma_yield) / val(mu);
+    if (is_plastic(val(f), abs_tol)) {
+      const auto n = hill_normal(s3, hp, hill);
+      const auto dgam = xi[NS] - xip[NS];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = i; j < 2; ++j) {
+          const int q = SymIdx<2>::idx(i, j);
+          C[q] = conv<R>(xi[q] - xip[q] - dgam * n.a[i][j]);
+        }
+      C[NS] = conv<R>(f);
+      return PATH_PLASTIC;
+    }
+#pragma unroll
+    for (int q = 0; q < NXI; ++q) C[q] = conv<R>(xi[q] - xip[q]);
+    return PATH_ELASTIC;
+  }
+  template <class TK, class TKP, class TX, class TP>
+  static C8_DI Mat<prom3_t<TK, TX, TP>, 2> dev_cauchy(const Kin<2, TK, TKP>& k, const TX* xi,
+                                                      const TP* par) {
+    return mat_conv<prom3_t<TK, TX, TP>>(small_dev_stress<2>(k.gu, xi, par[0], par[1]));
+  }
+  template <class TK, class TKP, class TX, class TP>
+  static C8_DI prom3_t<TK, TX, TP> hydro(const Kin<2, TK, TKP>& k, const TX*, const TP* par) {
+    const TP kappa = kappa_of(par[0], par[1]);
+    return conv<prom3_t<TK, TX, TP>>(kappa * trace(sym_grad(k.gu)));
+  }
+  template <class TP> static C8_DI TP pscale(const TP* par) { return kappa_of(par[0], par[1]); }
+};
+
+// =============================================================================
+// be_bar_trial = rF_bar (zeta_old + Ie_old I) rF_bar^T, src/hyper_J2.cpp:136-154
+template <int DIM, class TK, class TKP, class TXP>
+C8_DI Mat<prom3_t<TK, TKP, TXP>, DIM> be_bar_trial(const Kin<DIM, TK, TKP>& k,
+                                                   const Mat<TXP, DIM>& zeta_old,
+                                                   const TXP& Ie_old,
+                                                   prom_t<TK, TKP>* det_rF_13_out = nullptr) {
+  const Mat<TK, DIM> F = add_diag(k.gu, 1.0);
+  const Mat<TKP, DIM> Fp = add_diag(k.gup, 1.0);
+  const auto rF = F * inverse(Fp);
+  const auto d13 = dcbrt(det(rF));
+  if (det_rF_13_out) *det_rF_13_out = d13;
+  const auto rFb = scale(1.0 / d13, rF);
+  const Mat<TXP, DIM> core = add_diag(zeta_old, Ie_old);
+  return rFb * core * transpose(rFb);
+}
+
+template <class TX, class TP>
+C8_DI prom_t<TX, TP> hyper_yield(const TX& alpha, const TP& Y, const TP& S, const TP& D,
+                                       const TP& A, const TP& n, const TP& K) {
+  // sigma_y = Y + S (1 - exp(-D alpha)) + A (alpha + 1e-12)^n + K alpha, src/hyper_J2.cpp:260-262
+  return conv<prom_t<TX, TP>>(Y + S * (1.0 - dexp(-D * alpha)) +
+                                    A * dpow(alpha + 1e-12, n) + K * alpha);
+}
+
+template <int DIM>
+struct HyperJ2 {
+  static constexpr int NS = SymIdx<DIM>::n;
+  static constexpr int NXI = NS + 2, NPAR = 8, TYPE = L_HYPER_J2;
+  static constexpr bool FINITE = true, HAS_NEWTON = true, PLANE_STRESS = false;
+  static constexpr int Z_STRETCH = -1;
+  static C8_DI void init(double* xi) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) xi[i] = 0.0;
+    xi[NS] = 1.0; xi[NS + 1] = 0.0;
+  }
+  // trial-state initial guess, src/hyper_J2.cpp:167-179
+  template <class K> static C8_DI void guess(const K& k, const double* xip, double* xi) {
+    const Mat<double, DIM> zo = unpack_sym<double, DIM>(xip);
+    const Mat<double, DIM> bt = be_bar_trial<DIM>(k, zo, xip[NS]);
+    const Mat<double, DIM> z = dev(bt);
+    pack_sym<double, DIM>(z, xi);
+    xi[NS] = trace(bt) / 3.0;
+    xi[NS + 1] = xip[NS + 1];
+  }
+  template <class TK, class TKP, class TX, class TXP, class TP>
+  static C8_DI int residual(const Kin<DIM, TK, TKP>& k, const TX* xi, const TXP* xip,
+                            const TP* par, double abs_tol, prom5_t<TK, TKP, TX, TXP, TP>* C) {
+    using R = prom5_t<TK, TKP, TX, TXP, TP>;
+    const double sqrt_23 = 0.81649658092772603, sqrt_32 = 1.2247448713915890;
+    const TP mu = mu_of(par[0], par[1]);
+    const Mat<TXP, DIM> zo = unpack_sym<TXP, DIM>(xip);
+    const auto bt = be_bar_trial<DIM>(k, zo, xip[NS]);
+    const auto dbt = dev(bt);
+    const Mat<TX, DIM> zeta = unpack_sym<TX, DIM>(xi);
+    const TX Ie = xi[NS], alpha = xi[NS + 1];
+    const auto s = scale(mu, zeta);
+    const auto s_mag = norm(s);
+    const auto sy = hyper_yield<TX, TP>(alpha, par[2], par[3], par[4], par[5], par[6], par[7]);
+    const auto f = (s_mag - sqrt_23 * sy) / val(mu);
+    if (is_plastic(val(f), abs_tol)) {
+      const auto dgam = sqrt_32 * (alpha - xip[NS + 1]);
+      const auto g = (2.0 * dgam * Ie) / s_mag;
+#pragma unroll
+      for (int i = 0; i < DIM; ++i)
+#pragma unroll
+        for (int j = i; j < DIM; ++j) {
+          const int q = SymIdx<DIM>::idx(i, j);
+          C[q] = conv<R>(zeta.a[i][j] - dbt.a[i][j] + g * s.a[i][j]);
+        }
+      C[NS] = conv<R>(det(add_diag(zeta, Ie)) - 1.0);
+      C[NS + 1] = conv<R>(f);
+      return PATH_PLASTIC;
+    }
+#pragma unroll
+    for (int i = 0; i < DIM; ++i)
+#pragma unroll
+      for (int j = i; j < DIM; ++j) {
+        const int q = SymIdx<DIM>::idx(i, j);
+        C[q] = conv<R>(zeta.a[i][j] - dbt.a[i][j]);
+      }
+    C[NS] = conv<R>(Ie - trace(bt) / 3.0);
+    C[NS + 1] = conv<R>(alpha - xip[NS + 1]);
+    return PATH_ELASTIC;
+  }
+  template <class TK, class TKP, class TX, class TP>
+  static C8_DI Mat<prom3_t<TK, TX, TP>, DIM> dev_cauchy(const Kin<DIM, TK, TKP>& k, const TX* xi,
+                                                        const TP* par) {
+    const TP mu = mu_of(par[0], par[1]);
+    const TK J = det(add_diag(k.gu, 1.0));
+    const Mat<TX, DIM> zeta = unpack_sym<TX, DIM>(xi);
+    return mat_conv<prom3_t<TK, TX, TP>>(scale(mu / J, zeta));
+  }
+  template <class TK, class TKP, class TX, class TP>
+  static C8_DI prom3_t<TK, TX, TP> hydro(const Kin<DIM, TK, TKP>& k, const TX*, const TP* par) {
+    const TP kappa = kappa_of(par[0], par[1]);
+    const TK J = det(add_diag(k.gu, 1.0));
+    return conv<prom3_t<TK, TX, TP>>(kappa / 2.0 * (J - 1.0 / J));
+  }
+  template <class TP> static C8_DI TP pscale(const TP* par) { return kappa_of(par[0], par[1]); }
+};
+
+// =============================================================================
+template <int DIM>
+struct HyperJ2PlaneStrain {
+  static_assert(DIM == 2, "plane strain is 2-D");
+  static constexpr int NS = 3, NXI = 5, NPAR = 6, TYPE = L_HYPER_J2_PLANE_STRAIN;
+  static constexpr bool FINITE = true, HAS_NEWTON = true, PLANE_STRESS = false;
+  static constexpr int Z_STRETCH = -1;
+  static C8_DI void init(double* xi) {
+    xi[0] = xi[1] = xi[2] = 0.0; xi[3] = 1.0; xi[4] = 0.0;
+  }
+  // 3-D be_bar with zz = (-tr zeta_old + Ie_old)/cbrt(det rF)^2, src/hyper_J2_plane_strain.cpp:129-151
+  template <class TK, class TKP, class TXP>
+  static C8_DI void trial(const Kin<2, TK, TKP>& k, const TXP* xip,
+                          Mat<prom3_t<TK, TKP, TXP>, 2>& zeta_trial, prom3_t<TK, TKP, TXP>& Ie_trial) {
+    const Mat<TXP, 2> zo = unpack_sym<TXP, 2>(xip);
+    prom_t<TK, TKP> d13;
+    const auto b2 = be_bar_trial<2>(k, zo, xip[3], &d13);
+    const auto bzz = (-(xip[0] + xip[2]) + xip[3]) / (d13 * d13);
+    Ie_trial = (b2(0, 0) + b2(1, 1) + bzz) / 3.0;
+    zeta_trial = b2;
+    zeta_trial(0, 0) -= Ie_trial; zeta_trial(1, 1) -= Ie_trial;
+  }
+  template <class K> static C8_DI void guess(const K& k, const double* xip, double* xi) {
+    Mat<double, 2> zt; double Iet;
+    trial(k, xip, zt, Iet);
+    pack_sym<double, 2>(zt, xi);
+    xi[3] = Iet; xi[4] = xip[4];
+  }
+  template <class TK, class TKP, class TX, class TXP, class TP>
+  static C8_DI int residual(const Kin<2, TK, TKP>& k, const TX* xi, const TXP* xip, const TP* par,
+                            double abs_tol, prom5_t<TK, TKP, TX, TXP, TP>* C) {
+    using R = prom5_t<TK, TKP, TX, TXP, TP>;
+    const double sqrt_23 = 0.81649658092772603, sqrt_32 = 1.2247448713915890;
+    const TP mu = mu_of(par[0], par[1]);
+    Mat<prom3_t<TK, TKP, TXP>, 2> zt; prom3_t<TK, TKP, TXP> Iet;
+    trial(k, xip, zt, Iet);
+    const Mat<TX, 2> zeta = unpack_sym<TX, 2>(xi);
+    const TX Ie = xi[3], alpha = xi[4];
+    Mat<TX, 3> z3 = embed3(zeta);
+    z3(2, 2) = -(xi[0] + xi[2]);
+    const auto s_mag = norm(scale(mu, z3));
+    // sigma_y = Y + K alpha + (Y_inf - Y)(1 - exp(-delta alpha)), :269-270 ; params E,nu,K,Y,Y_inf,delta
+    const auto sy = par[3] + par[2] * alpha + (par[4] - par[3]) * (1.0 - dexp(-par[5] * alpha));
+    const auto f = (s_mag - sqrt_23 * sy) / val(mu);
+    if (is_plastic(val(f), abs_tol)) {
+      const auto dgam = sqrt_32 * (alpha - xip[4]);
+      const auto g = (2.0 * dgam * Ie) * mu / s_mag;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = i; j < 2; ++j) {
+          const int q = SymIdx<2>::idx(i, j);
+          C[q] = conv<R>(zeta.a[i][j] - zt.a[i][j] + g * zeta.a[i][j]);
+        }
+      C[3] = conv<R>(det(add_diag(z3, Ie)) - 1.0);
+      C[4] = conv<R>(f);
+      return PATH_PLASTIC;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = i; j < 2; ++j) {
+        const int q = SymIdx<2>::idx(i, j);
+        C[q] = conv<R>(zeta.a[i][j] - zt.a[i][j]);
+      }
+    C[3] = conv<R>(Ie - Iet);
+    C[4] = conv<R>(alpha - xip[4]);
+    return PATH_ELASTIC;
+  }
+  template <class TK, class TKP, class TX, class TP>
+  static C8_DI Mat<prom3_t<TK, TX, TP>, 2> dev_cauchy(const Kin<2, TK, TKP>& k, const TX* xi,
+                                                      const TP* par) {
+    const TP mu = mu_of(par[0], par[1]);
+    const TK J = det(add_diag(k.gu, 1.0));
+    return mat_conv<prom3_t<TK, TX, TP>>(scale(mu / J, unpack_sym<TX, 2>(xi)));
+  }
+  template <class TK, class TKP, class TX, class TP>
+  static C8_DI prom3_t<TK, TX, TP> hydro(const Kin<2, TK, TKP>& k, const TX*, const TP* par) {
+    const TP kappa = kappa_of(par[0], par[1]);
+    const TK J = det(add_diag(k.gu, 1.0));
+    return conv<prom3_t<TK, TX, TP>>(kappa / 2.0 * (J - 1.0 / J));
+  }
+  template <class TP> static C8_DI TP pscale(const TP* par) { return kappa_of(par[0], par[1]); }
+};
+
+// =============================================================================
+template <int DIM>
+struct HyperJ2PlaneStress {
+  static_assert(DIM == 2, "plane stress is 2-D");
+  // xi = zeta(00,01,11), Ie, lambda_z, alpha
+  static constexpr int NS = 3, NXI = 6, NPAR = 8, TYPE = L_HYPER_J2_PLANE_STRESS;
+  static constexpr bool FINITE = true, HAS_NEWTON = true, PLANE_STRESS = true;
+  static constexpr int Z_STRETCH = 4;  // packed index of lambda_z (residual index 2 in the reference)
+  static C8_DI void init(double* xi) {
+    xi[0] = xi[1] = xi[2] = 0.0; xi[3] = 1.0; xi[4] = 1.0; xi[5] = 0.0;
+  }
+  // src/hyper_J2_plane_stress.cpp:140-169 ; lambda_z is the CURRENT z stretch
+  template <class TK, class TKP, class TX, class TXP>
+  static C8_DI void trial(const Kin<2, TK, TKP>& k, const TXP* xip, const TX& lambda_z,
+                          Mat<prom4_t<TK, TKP, TX, TXP>, 2>& zeta_trial,
+                          prom4_t<TK, TKP, TX, TXP>& Ie_trial, TK& J2) {
+    using R = prom4_t<TK, TKP, TX, TXP>;
+    const Mat<TK, 2> F2 = add_diag(k.gu, 1.0);
+    J2 = det(F2);
+    const Mat<TKP, 2> Fp2 = add_diag(k.gup, 1.0);
+    Mat<prom_t<TK, TX>, 3> F3 = mat_conv<prom_t<TK, TX>>(embed3(F2));
+    F3(2, 2) = conv<prom_t<TK, TX>>(lambda_z);
+    Mat<prom_t<TKP, TXP>, 3> Fp3 = mat_conv<prom_t<TKP, TXP>>(embed3(Fp2));
+    Fp3(2, 2) = conv<prom_t<TKP, TXP>>(xip[4]);
+    const auto rF = F3 * inverse(Fp3);
+    const auto d13 = dcbrt(det(rF));
+    const auto rFb = scale(1.0 / d13, rF);
+    Mat<TXP, 3> core = embed3(unpack_sym<TXP, 2>(xip));
+    core(2, 2) = -(xip[0] + xip[2]);
+    const Mat<TXP, 3> corei = add_diag(core, xip[3]);
+    const Mat<R, 3> bt = mat_conv<R>(rFb * corei * transpose(rFb));
+    Ie_trial = trace(bt) / 3.0;
+    zeta_trial = extract2(bt);
+    zeta_trial(0, 0) -= Ie_trial; zeta_trial(1, 1) -= Ie_trial;
+  }
+  // initial guess: zeta, Ie from the trial state evaluated with the CURRENT-field lambda_z;
+  // lambda_z and alpha keep the values gathered from the current xi field (:176-200)
+  template <class K> static C8_DI void guess(const K& k, const double* xip, double* xi) {
+    Mat<double, 2> zt; double Iet, J2;
+    trial(k, xip, xi[4], zt, Iet, J2);
+    pack_sym<double, 2>(zt, xi);
+    xi[3] = Iet;
+  }
+  template <class TK, class TKP, class TX, class TXP, class TP>
+  static C8_DI int residual(const Kin<2, TK, TKP>& k, const TX* xi, const TXP* xip, const TP* par,
+                            double abs_tol, prom5_t<TK, TKP, TX, TXP, TP>* C) {
+    using R = prom5_t<TK, TKP, TX, TXP, TP>;
+    const double sqrt_23 = 0.81649658092772603, sqrt_32 = 1.2247448713915890;
+    const TP mu = mu_of(par[0], par[1]);
+    const TP kappa = kappa_of(par[0], par[1]);
+    const TX Ie = xi[3], lambda_z = xi[4], alpha = xi[5];
+    Mat<prom4_t<TK, TKP, TX, TXP>, 2> zt; prom4_t<TK, TKP, TX, TXP> Iet; TK J2;
+    trial(k, xip, lambda_z, zt, Iet, J2);
+    const Mat<TX, 2> zeta = unpack_sym<TX, 2>(xi);
+    Mat<TX, 3> z3 = embed3(zeta);
+    const TX zeta_zz = -(xi[0] + xi[2]);
+    z3(2, 2) = zeta_zz;
+    const auto s_mag = norm(scale(mu, z3));
+    const auto sy = hyper_yield<TX, TP>(alpha, par[2], par[3], par[4], par[5], par[6], par[7]);
+    const auto f = (s_mag - sqrt_23 * sy) / val(mu);
+    const TP mat_factor = kappa / (2.0 * mu);
+    // R_lambda_z = lambda_z - sqrt((1 - zeta_zz / (kappa/2mu)) / J2^2), :310-312
+    C[4] = conv<R>(lambda_z - dsqrt((1.0 - zeta_zz / mat_factor) / sqr(J2)));
+    if (is_plastic(val(f), abs_tol)) {
+      const auto dgam = sqrt_32 * (alpha - xip[5]);
+      const auto g = (2.0 * dgam * Ie) * mu / s_mag;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = i; j < 2; ++j) {
+          const int q = SymIdx<2>::idx(i, j);
+          C[q] = conv<R>(zeta.a[i][j] - zt.a[i][j] + g * zeta.a[i][j]);
+        }
+      C[3] = conv<R>(det(add_diag(z3, Ie)) - 1.0);
+      C[5] = conv<R>(f);
+      return PATH_PLASTIC;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = i; j < 2; ++j) {
+        const int q = SymIdx<2>::idx(i, j);
+        C[q] = conv<R>(zeta.a[i][j] - zt.a[i][j]);
+      }
+    C[3] = conv<R>(Ie - Iet);
+    C[5] = conv<R>(alpha - xip[5]);
+    return PATH_ELASTIC;
+  }
+  // sigma = mu zeta / J + kappa/2 (J - 1/J) I, J = det F2 * lambda_z, :361-375
+  template <class TK, class TKP, class TX, class TP>
+  static C8_DI Mat<prom3_t<TK, TX, TP>, 2> cauchy(const Kin<2, TK, TKP>& k, const TX* xi,
+                                                  const TP* par) {
+    using R = prom3_t<TK, TX, TP>;
+    const TP mu = mu_of(par[0], par[1]);
+    const TP kappa = kappa_of(par[0], par[1]);
+    const auto J = det(add_diag(k.gu, 1.0)) * xi[4];
+    Mat<R, 2> sig = mat_conv<R>(scale(mu / J, unpack_sym<TX, 2>(xi)));
+    const R h = kappa / 2.0 * (J - 1.0 / J);
+    sig(0, 0) += h; sig(1, 1) += h;
+    return sig;
+  }
+  template <class TP> static C8_DI TP pscale(const TP*) { return conv<TP>(0.0); }
+};
+
+}  // namespace c8

@@ -1,0 +1,122 @@
+/* c8b200.h -- C ABI of the B200-native calibr8 hot path.
+ *
+ * calibr8 has no plugin/FFI interface of its own; its seam for this path is the set of
+ * free functions of source/calibr8/src/evaluations.hpp:23-191 operating on State/Disc.
+ * Each entry point below names the reference function it replaces (file:line under
+ * /root/reference/source/calibr8/src).  A calibr8 maintainer binds them from C++ with a
+ * plain `extern "C"` include; see INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *   - return 0 on success, C8_ERR_LOCAL_SOLVE (-1) when at least one local constitutive
+ *     Newton did not converge (the reference's `return -1`, evaluations.cpp:95-97),
+ *     <= -2 on CUDA / usage errors (message via c8_last_error).
+ *   - all floating point is fp64, indices int32, as in the reference (defines.hpp:17-20).
+ *   - "dev" pointers are device pointers on the context's GPU; "host" pointers are host memory.
+ *   - nodal fields are node-interleaved [n_nodes][NB] (u_0..u_{dim-1}[, p]); local state is
+ *     structure-of-arrays [NXI][xi_ld]; the matrix is BSR with NB x NB blocks on the node graph
+ *     (c8_bsr_pattern).  c8_csr_block_* export the reference's per-block CSR view
+ *     (disc.cpp:356-459) for parity checks.
+ */
+#ifndef C8B200_H
+#define C8B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct c8_ctx c8_ctx;
+
+#define C8_OK 0
+#define C8_ERR_LOCAL_SOLVE (-1)
+#define C8_ERR_CUDA (-2)
+#define C8_ERR_USAGE (-3)
+
+/* global residual types: global_residual.cpp:619-630 */
+#define C8_MECHANICS 0
+#define C8_MECHANICS_PLANE_STRESS 1
+/* local residual types: local_residual.cpp:892-933 (in-scope subset) */
+#define C8_ELASTIC 0
+#define C8_SMALL_J2 1
+#define C8_SMALL_HILL 2
+#define C8_SMALL_HILL_PLANE_STRESS 3
+#define C8_HYPER_J2 4
+#define C8_HYPER_J2_PLANE_STRESS 5
+#define C8_SMALL_HILL_PLANE_STRAIN 6
+#define C8_HYPER_J2_PLANE_STRAIN 7
+
+/* ---- context / discretisation (replaces Disc::build_data, disc.cpp:563-583) ---- */
+c8_ctx* c8_create(int device);
+void c8_destroy(c8_ctx* ctx);
+const char* c8_last_error(c8_ctx* ctx);
+const char* c8_version(void);
+
+/* host arrays: conn [n_elems][dim+1], coords [n_nodes][3], elem_set [n_elems] or NULL */
+int c8_set_mesh(c8_ctx* ctx, int dim, int n_elems, int n_nodes, const int32_t* conn_host,
+                const double* coords_host, const int32_t* elem_set_host, int n_elem_sets);
+
+/* replaces create_global_residual / create_local_residual + LocalResidual::init_params;
+ * params_host [n_elem_sets][npar] in the model's parameter order */
+int c8_set_model(c8_ctx* ctx, int global_type, int local_type, const double* params_host,
+                 int local_max_iters, double local_abs_tol, double local_rel_tol,
+                 double stabilization_multiplier, double thickness);
+int c8_set_params(c8_ctx* ctx, const double* params_host); /* LocalResidual::set_params */
+
+/* out[0..11] = dim, nn, nb, nx, nxi, npar, n_elems, n_nodes, nnzb, n_dofs(=n_nodes*nb), group, xi_ld */
+int c8_info(c8_ctx* ctx, int64_t* out12);
+
+/* node-graph BSR pattern (host out): rowptr [n_nodes+1], colind [nnzb] */
+int c8_bsr_pattern(c8_ctx* ctx, int32_t* rowptr_host, int32_t* colind_host);
+/* device pointers of the resident pattern / element->block offsets (read-only) */
+int c8_bsr_pattern_dev(c8_ctx* ctx, const int32_t** rowptr_dev, const int32_t** colind_dev,
+                       const int32_t** eoff_dev);
+/* the reference's block (i,j) CSR (disc.cpp:356-387): sizes, pattern, and values gathered
+ * from a BSR value array on the device */
+int c8_csr_block_size(c8_ctx* ctx, int i, int j, int64_t* n_rows, int64_t* nnz);
+int c8_csr_block_pattern(c8_ctx* ctx, int i, int j, int32_t* rowptr_host, int32_t* colind_host);
+int c8_csr_block_values(c8_ctx* ctx, int i, int j, const double* bsr_vals_dev, double* vals_host);
+
+/* layout helpers between the reference's per-residual host arrays and the device layout */
+int c8_pack_x(c8_ctx* ctx, const double* u_host, const double* p_host, double* x_dev);
+int c8_unpack_x(c8_ctx* ctx, const double* x_dev, double* u_host, double* p_host);
+int c8_pack_xi(c8_ctx* ctx, const double* xi_host_aos, double* xi_dev_soa);
+int c8_unpack_xi(c8_ctx* ctx, const double* xi_dev_soa, double* xi_host_aos);
+/* LocalResidual::init_variables (local_residual.cpp:34-74): initial local state */
+int c8_init_xi(c8_ctx* ctx, double* xi_dev);
+
+/* ---- the hot path, device pointers ---- */
+/* eval_forward_jacobian, evaluations.cpp:12-154.  A_vals_dev / b_dev are accumulated into
+ * (zero them first, like LinearAlg::zero_all); xi_dev in: current-field values, out: solved.
+ * path_dev (int8 per element) and the element-level outputs may be NULL.
+ * n_failed (host out, may be NULL): number of local solves that failed. */
+int c8_forward_jacobian(c8_ctx* ctx, const double* x_dev, const double* x_prev_dev,
+                        const double* xi_prev_dev, double* xi_dev, double* A_vals_dev,
+                        double* b_dev, int8_t* path_dev, int* n_failed);
+/* same, also writing per-element Jacobians [n_elems][nx][nx] and residuals [n_elems][nx]
+ * in the reference's element dof order (global_residual.cpp:21-23) -- parity-test hook */
+int c8_forward_jacobian_elem(c8_ctx* ctx, const double* x_dev, const double* x_prev_dev,
+                             const double* xi_prev_dev, double* xi_dev, double* A_vals_dev,
+                             double* b_dev, int8_t* path_dev, double* elem_J_dev,
+                             double* elem_R_dev, int* n_failed);
+/* eval_global_residual, evaluations.cpp:156-259 (xi given, no local solve) */
+int c8_global_residual(c8_ctx* ctx, const double* x_dev, const double* x_prev_dev,
+                       const double* xi_dev, const double* xi_prev_dev, double* b_dev);
+
+/* ---- the hot path, HOST buffers (copies inside): the drop-in call a calibr8 caller makes ----
+ * u/p: the reference's per-residual nodal arrays; xi: [n_elems][nxi] packed like the apf IP
+ * fields; b_u/b_p out; the assembled matrix stays resident on the device (c8_resident_matrix)
+ * for the device-side linear solver, exactly where LinearAlg::A[GHOST] would be consumed. */
+int c8_forward_jacobian_host(c8_ctx* ctx, const double* u_host, const double* p_host,
+                             const double* u_prev_host, const double* p_prev_host,
+                             const double* xi_prev_host, double* xi_host, double* b_u_host,
+                             double* b_p_host, int* n_failed);
+int c8_resident_matrix(c8_ctx* ctx, double** A_vals_dev);
+
+/* stream control: all launches go to this stream (default: a context-owned stream) */
+int c8_set_stream(c8_ctx* ctx, void* cuda_stream);
+int c8_synchronize(c8_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* C8B200_H */

@@ -1,0 +1,88 @@
+"""Shared helpers for the CUDA-vs-oracle parity tests: the ten (mesh, mechanics, model)
+combinations the library is built for, seeded synthetic states, and comparison metrics."""
+import numpy as np
+
+from calibr8_b200 import meshgen
+from conftest import load_mesh
+
+HILL3D = dict(E=1000., nu=.25, Y=2., R00=1., R11=.9, R22=1.1, R01=1., R02=.95, R12=1.05, S=10., D=2.)
+HILL2D = dict(E=1000., nu=.25, Y=2., S=10., D=2., R00=1., R11=.9, R22=1.1, R01=.95)
+
+# name -> (dim, global_type, local_type, params, displacement amplitude of the synthetic state)
+COMBOS = {
+    "3d_elastic": (3, "mechanics", "elastic", dict(E=1000., nu=.25, cte=1e-3, delta_T=10.), 4e-3),
+    "3d_small_J2": (3, "mechanics", "small_J2", dict(E=1000., nu=.25, K=100., Y=2., cte=1e-4, delta_T=5.), 0.45e-3),
+    "3d_small_hill": (3, "mechanics", "small_hill", HILL3D, 0.45e-3),
+    "3d_hyper_J2": (3, "mechanics", "hyper_J2", dict(E=1000., nu=.25, Y=10., S=5., D=3., A=2., n=.5, K=100.), 2.2e-3),
+    "2d_elastic": (2, "mechanics", "elastic", dict(E=1000., nu=.25, cte=1e-3, delta_T=10.), 4e-3),
+    "2d_small_J2": (2, "mechanics", "small_J2", dict(E=1000., nu=.25, K=100., Y=2., cte=0., delta_T=0.), 0.45e-3),
+    "2d_small_hill_plane_strain": (2, "mechanics", "small_hill_plane_strain", HILL2D, 0.45e-3),
+    "2d_hyper_J2_plane_strain": (2, "mechanics", "hyper_J2_plane_strain",
+                                 dict(E=1000., nu=.25, K=100., Y=10., Y_inf=14., delta=5.), 2.2e-3),
+    "2d_small_hill_plane_stress": (2, "mechanics_plane_stress", "small_hill_plane_stress", HILL2D, 0.45e-3),
+    "2d_hyper_J2_plane_stress": (2, "mechanics_plane_stress", "hyper_J2_plane_stress",
+                                 dict(E=1000., nu=.25, Y=2., S=10., D=2., A=1., n=.5, K=20.), 0.45e-3),
+}
+LOCAL_TOL = dict(max_iters=60, abs_tol=1e-12, rel_tol=1e-12)
+
+
+def make_mesh(dim, size="small"):
+    if size == "ref":
+        return load_mesh("notch" if dim == 3 else "notch2D")
+    if dim == 3:
+        return meshgen.box_tets(4 if size == "small" else 8, notch_radius=0.3)
+    return meshgen.square_tris(8 if size == "small" else 24, notch_radius=0.3)
+
+
+def synthetic_fields(mesh, amp, mixed, seed=0):
+    """(u_prev, p_prev), (u, p): two smooth displacement states on one loading path."""
+    rng = np.random.RandomState(seed + 7)
+    base = meshgen.smooth_field(mesh, amp, seed=seed)
+    u1 = 1.45 * base
+    u2 = 1.8 * base + meshgen.smooth_field(mesh, 0.2 * amp, seed=seed + 1)
+    out = []
+    for u in (u1, u2):
+        p = rng.uniform(-1., 1., size=mesh.n_nodes) if mixed else None
+        out.append((u.reshape(-1).copy(), p))
+    return out
+
+
+def make_oracle(mesh, gtype, ltype, params, **kw):
+    from oracle.pyoracle import Oracle
+    return Oracle(mesh.dim, mesh.conn, mesh.coords, global_type=gtype, local_type=ltype,
+                  params=[params], max_iters=LOCAL_TOL["max_iters"], abs_tol=LOCAL_TOL["abs_tol"],
+                  rel_tol=LOCAL_TOL["rel_tol"], **kw)
+
+
+def make_context(mesh, gtype, ltype, params, device=0):
+    import torch
+    from calibr8_b200.capi import Context
+    ctx = Context(device)
+    ctx.set_mesh(mesh.dim, mesh.conn, mesh.coords)
+    ctx.set_model(gtype, ltype, params, **LOCAL_TOL)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    return ctx
+
+
+def xlist(u, p):
+    return [u] if p is None else [u, p]
+
+
+def rel_err_blockwise(a, b, axis):
+    """max over blocks of max|a-b| / max|b| (blocks = all entries sharing the leading index)."""
+    d = np.abs(a - b).reshape(a.shape[0], -1).max(axis=1)
+    s = np.abs(b).reshape(b.shape[0], -1).max(axis=1)
+    s = np.where(s > 0, s, 1.0)
+    return float((d / s).max())
+
+
+def rel_err_rows(vals_a, vals_b, rowptr):
+    """CSR values: max over rows of max|a-b| / max|b| in the row."""
+    worst = 0.0
+    d = np.abs(vals_a - vals_b)
+    m = np.abs(vals_b)
+    dmax = np.maximum.reduceat(d, rowptr[:-1])
+    mmax = np.maximum.reduceat(m, rowptr[:-1])
+    mmax = np.where(mmax > 0, mmax, 1.0)
+    worst = float((dmax / mmax).max())
+    return worst

@@ -1,0 +1,143 @@
+"""K1 / K2 parity: CUDA eval_forward_jacobian / eval_global_residual through the C ABI
+vs the CPU oracle on the same seeded inputs (residual/Jacobian entries to 1e-10 relative,
+CSR pattern bit-exact).  North-star tolerance: 1e-10 relative on entries (BASELINE.json)."""
+import numpy as np
+import pytest
+
+from parity_common import (COMBOS, make_context, make_mesh, make_oracle, rel_err_blockwise,
+                           rel_err_rows, synthetic_fields, xlist)
+
+TOL = 1e-10  # BASELINE.json north_star: residual/Jacobian entries within 1e-10 relative
+
+pytestmark = pytest.mark.gpu
+
+
+def run_pair(name, size="small"):
+    import torch
+    dim, gtype, ltype, params, amp = COMBOS[name]
+    mesh = make_mesh(dim, size)
+    mixed = gtype == "mechanics"
+    (u1, p1), (u2, p2) = synthetic_fields(mesh, amp, mixed)
+    orc = make_oracle(mesh, gtype, ltype, params)
+    ctx = make_context(mesh, gtype, ltype, params)
+    zero = orc.zeros_x()
+    xi0 = orc.init_xi()
+    # step A (oracle): a first state so that step B starts from a non-trivial history
+    rA = orc.forward_jacobian(xlist(u1, p1), zero, xi0, xi0, assemble=False)
+    assert rA["status"] == 0
+    xi1 = rA["xi"]
+    # step B, oracle
+    rB = orc.forward_jacobian(xlist(u2, p2), xlist(u1, p1), xi1, xi1, element_out=True)
+    assert rB["status"] == 0
+    # step B, CUDA
+    x = ctx.alloc("x"); xp = ctx.alloc("x"); xi = ctx.alloc("xi"); xip = ctx.alloc("xi")
+    A = ctx.alloc("A"); b = ctx.alloc("b"); path = ctx.alloc("path")
+    eJ = ctx.alloc("elem_J"); eR = ctx.alloc("elem_R")
+    ctx.pack_x(u2, p2, x); ctx.pack_x(u1, p1, xp)
+    ctx.pack_xi(xi1, xi); ctx.pack_xi(xi1, xip)
+    nf = ctx.forward_jacobian(x, xp, xip, xi, A, b, path, eJ, eR)
+    torch.cuda.synchronize()
+    return dict(mesh=mesh, orc=orc, ctx=ctx, rB=rB, nf=nf, x=x, xp=xp, xi=xi, xip=xip, A=A, b=b,
+                path=path, eJ=eJ, eR=eR, xi1=xi1, fields=((u1, p1), (u2, p2)))
+
+
+@pytest.mark.parametrize("name", list(COMBOS))
+def test_forward_jacobian_parity(name):
+    r = run_pair(name)
+    orc, ctx, rB = r["orc"], r["ctx"], r["rB"]
+    assert r["nf"] == 0
+    # branch per element is identical, and the state exercises both branches for plastic models
+    path = r["path"].cpu().numpy().astype(np.int32)
+    assert (path == rB["path"]).all()
+    if COMBOS[name][2] != "elastic":
+        assert 0 < path.sum() < path.size, "synthetic state should mix elastic and plastic points"
+    # local state
+    xi = ctx.unpack_xi(r["xi"])
+    assert rel_err_blockwise(xi, rB["xi"], 0) < TOL
+    # element Jacobians / residuals in the reference's dof order
+    n, nx = ctx.n_elems, ctx.nx
+    eJ = r["eJ"].cpu().numpy().reshape(n, nx, nx)
+    eR = r["eR"].cpu().numpy().reshape(n, nx)
+    assert rel_err_blockwise(eJ, rB["elem_dtotal"], 0) < TOL
+    assert rel_err_blockwise(eR, rB["elem_R"], 0) < TOL
+    # assembled system: pattern bit-exact, values to TOL per row
+    nr = orc.num_resid
+    for i in range(nr):
+        for j in range(nr):
+            rp_o, ci_o = orc.graph(i, j)
+            rp_c, ci_c = ctx.csr_block_pattern(i, j)
+            assert np.array_equal(rp_o, rp_c) and np.array_equal(ci_o, ci_c)
+            vals = ctx.csr_block_values(i, j, r["A"])
+            assert rel_err_rows(vals, rB["A"][i * nr + j], rp_o) < TOL
+    bs = ctx.unpack_x(r["b"])
+    for i in range(nr):
+        scale = np.abs(rB["b"][i]).max()
+        assert np.abs(bs[i] - rB["b"][i]).max() < TOL * scale
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["3d_small_J2", "3d_hyper_J2", "2d_small_hill_plane_stress",
+                                  "2d_hyper_J2_plane_stress"])
+def test_global_residual_parity(name):
+    import torch
+    r = run_pair(name)
+    orc, ctx, rB = r["orc"], r["ctx"], r["rB"]
+    (u1, p1), (u2, p2) = r["fields"]
+    b_o = orc.global_residual(xlist(u2, p2), xlist(u1, p1), rB["xi"], r["xi1"])
+    b = ctx.alloc("b")
+    ctx.global_residual(r["x"], r["xp"], r["xi"], r["xip"], b)
+    torch.cuda.synchronize()
+    bs = ctx.unpack_x(b)
+    for i in range(orc.num_resid):
+        assert np.abs(bs[i] - b_o[i]).max() < TOL * np.abs(b_o[i]).max()
+    # and the residual-only kernel agrees with the Jacobian kernel's residual
+    bj = ctx.unpack_x(r["b"])
+    for i in range(orc.num_resid):
+        assert np.abs(bs[i] - bj[i]).max() < TOL * np.abs(bj[i]).max()
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["3d_small_hill", "3d_hyper_J2", "2d_small_hill_plane_stress"])
+def test_forward_jacobian_reference_mesh(name):
+    """Same parity on the reference's own regression meshes (notch / notch2D)."""
+    r = run_pair(name, size="ref")
+    rB, ctx = r["rB"], r["ctx"]
+    assert r["nf"] == 0
+    n, nx = ctx.n_elems, ctx.nx
+    eJ = r["eJ"].cpu().numpy().reshape(n, nx, nx)
+    assert rel_err_blockwise(eJ, rB["elem_dtotal"], 0) < TOL
+    assert rel_err_blockwise(ctx.unpack_xi(r["xi"]), rB["xi"], 0) < TOL
+    ctx.close()
+
+
+def test_host_buffer_entry_point():
+    """c8_forward_jacobian_host (reference layouts, copies inside) == device-pointer path."""
+    name = "3d_small_J2"
+    r = run_pair(name)
+    ctx, rB = r["ctx"], r["rB"]
+    (u1, p1), (u2, p2) = r["fields"]
+    nf, xi, bs = ctx.forward_jacobian_host(u2, p2, u1, p1, r["xi1"], r["xi1"])
+    assert nf == 0
+    assert rel_err_blockwise(xi, rB["xi"], 0) < TOL
+    for i in range(2):
+        assert np.abs(bs[i] - rB["b"][i]).max() < TOL * np.abs(rB["b"][i]).max()
+    ctx.close()
+
+
+def test_local_solve_failure_is_reported():
+    """max_iters too small for a plastic step -> status -1 like the reference (evaluations.cpp:95-97)."""
+    import torch
+    from calibr8_b200.capi import Context
+    dim, gtype, ltype, params, amp = COMBOS["3d_small_J2"]
+    mesh = make_mesh(dim)
+    (u1, p1), (u2, p2) = synthetic_fields(mesh, amp, True)
+    ctx = Context(0)
+    ctx.set_mesh(mesh.dim, mesh.conn, mesh.coords)
+    ctx.set_model(gtype, ltype, params, max_iters=1, abs_tol=1e-12, rel_tol=1e-12)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    x = ctx.alloc("x"); xp = ctx.alloc("x"); xi = ctx.alloc("xi"); xip = ctx.alloc("xi")
+    ctx.pack_x(u2, p2, x)
+    ctx.init_xi(xi); ctx.init_xi(xip)
+    nf = ctx.forward_jacobian(x, xp, xip, xi, None, ctx.alloc("b"))
+    assert nf > 0
+    ctx.close()
