@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for the calibr8 hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm: CUDA through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  (CPU restatement of the reference)
+
+Workload (BASELINE.json configs[1]): 3-D finite-strain hyper-J2, mixed u-p mechanics, on a
+synthetic notched unit box of ~1M linear tets (56 cells/side, Kuhn split, quarter-circle notch
+r=0.2 removed).  A "step" is one pass of eval_forward_jacobian (local Newton per quadrature
+point + element residual/Jacobian + scatter into the BSR matrix) over the whole mesh at a
+synthetic state that puts roughly half the points on the plastic branch.
+
+metric  = QP residual+Jacobian evals/s (fp64)  [= elements / second; one coupled QP per element]
+value   = kernel-path throughput with inputs resident in HBM (memset A,b + K1 per step)
+e2e     = the same through c8_state_forward_jacobian with HOST nodal buffers
+          (H2D of the Newton iterate, assembly, D2H of the residual + status every step)
+N > 1   = the mesh is split into N element slabs (one rank per GPU, weak scaling: every rank
+          assembles its own ~1M-tet part; no data-path collective in this kernel-level bench).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "QP residual+Jacobian evals/s (fp64)"
+UNIT = "QP evals/s"
+PARAMS = dict(E=1000., nu=.25, Y=10., S=0., D=0., A=0., n=0., K=100.)   # test/primal/notch_hyper_J2.yaml.in:25-34
+LOCAL = dict(max_iters=500, abs_tol=1e-12, rel_tol=1e-12)             # same deck :20-24
+AMP = 2.2e-3
+N_CELLS = 56
+NOTCH = 0.2
+
+
+def workload_mesh(n_cells=N_CELLS):
+    from calibr8_b200 import meshgen
+    return meshgen.box_tets(n_cells, notch_radius=NOTCH)
+
+
+def workload_fields(mesh, seed=0):
+    from calibr8_b200 import meshgen
+    rng = np.random.RandomState(seed + 7)
+    base = meshgen.smooth_field(mesh, AMP, seed=seed)
+    u1 = (1.45 * base).reshape(-1)
+    u2 = (1.8 * base + meshgen.smooth_field(mesh, 0.2 * AMP, seed=seed + 1)).reshape(-1)
+    p1 = rng.uniform(-1., 1., size=mesh.n_nodes)
+    p2 = rng.uniform(-1., 1., size=mesh.n_nodes)
+    return (u1, p1), (u2, p2)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip().split(", "))
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[4 + k].strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return dict(sm_mhz=float(np.median(sm)) if sm else None,
+                    sm_max_mhz=float(np.max(mx)) if mx else None, samples=len(sm),
+                    reasons=sorted(reasons))
+
+
+# --------------------------------------------------------------------------------------
+def cpu_sample(n_threads, n_cells_sample=10, reps=1):
+    """Oracle (CPU restatement of the reference algorithm) on a bounded sample of the same
+    workload: each thread assembles its own n_cells_sample^3*6-tet notched box at the same
+    state (full eval_forward_jacobian incl. scatter into its private per-block CSR)."""
+    from oracle.pyoracle import Oracle
+    mesh = workload_mesh(n_cells_sample)
+    (u1, p1), (u2, p2) = workload_fields(mesh)
+    orcs = []
+    for _ in range(n_threads):
+        o = Oracle(mesh.dim, mesh.conn, mesh.coords, global_type="mechanics", local_type="hyper_J2",
+                   params=[PARAMS], **LOCAL)
+        xi0 = o.init_xi()
+        rA = o.forward_jacobian([u1, p1], o.zeros_x(), xi0, xi0, assemble=False)
+        orcs.append((o, rA["xi"]))
+    times = []
+    plastic = None
+    for _ in range(reps):
+        res = [None] * n_threads
+
+        def work(k):
+            o, xi1 = orcs[k]
+            res[k] = o.forward_jacobian([u2, p2], [u1, p1], xi1, xi1)
+
+        ths = [threading.Thread(target=work, args=(k,)) for k in range(n_threads)]
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        times.append(time.perf_counter() - t0)
+        plastic = float(res[0]["path"].mean())
+    t = min(times)
+    return dict(evals_per_s=mesh.n_elems * n_threads / t, seconds=t, n_elems=mesh.n_elems,
+                plastic_fraction=plastic)
+
+
+def flops_per_qp_reference(n_cells_sample=6):
+    """Algorithmic flops of the reference algorithm (16-wide AD on every operation) per QP on this
+    workload's state, from the op-counting oracle build."""
+    from oracle.pyoracle import Oracle
+    mesh = workload_mesh(n_cells_sample)
+    (u1, p1), (u2, p2) = workload_fields(mesh)
+    o = Oracle(mesh.dim, mesh.conn, mesh.coords, global_type="mechanics", local_type="hyper_J2",
+               params=[PARAMS], count_flops=True, **LOCAL)
+    xi0 = o.init_xi()
+    rA = o.forward_jacobian([u1, p1], o.zeros_x(), xi0, xi0, assemble=False)
+    o.flops_reset()
+    o.forward_jacobian([u2, p2], [u1, p1], rA["xi"], rA["xi"])
+    return o.flops_reset() / mesh.n_elems
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_cells_sample = 12
+    for _ in range(min(args.warmup, 1)):
+        cpu_sample(cores, n_cells_sample)
+    t0 = time.perf_counter()
+    vals = [cpu_sample(cores, n_cells_sample) for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    v = float(np.mean([r["evals_per_s"] for r in vals]))
+    sample = (f"{cores} threads x one {n_cells_sample}^3-cell notched box "
+              f"({vals[0]['n_elems']} tets each) of the same hyper-J2 state per step, "
+              f"full eval_forward_jacobian incl. CSR scatter")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * float(np.mean([r["seconds"] for r in vals])),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "3D finite-strain hyper_J2 mixed u-p, notched box tets (bounded sample)",
+                   "note": "CPU restatement of the reference algorithm (oracle/), not the Trilinos binary: "
+                           "the reference cannot be built offline (DESIGN.md)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": wall,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from calibr8_b200.capi import Context
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    mesh = workload_mesh()
+    (u1, p1), (u2, p2) = workload_fields(mesh, seed=rank)
+    ctx = Context(local_rank)
+    ctx.set_mesh(mesh.dim, mesh.conn, mesh.coords)
+    ctx.set_model("mechanics", "hyper_J2", PARAMS, **LOCAL)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    n = ctx.n_elems
+
+    # --- untimed set-up: history state xi_prev from one assembly at the previous synthetic state
+    x, xp, x0 = ctx.alloc("x"), ctx.alloc("x"), ctx.alloc("x")
+    xi0, xip, xi = ctx.alloc("xi"), ctx.alloc("xi"), ctx.alloc("xi")
+    A, b, path = ctx.alloc("A"), ctx.alloc("b"), ctx.alloc("path")
+    ctx.pack_x(u2, p2, x); ctx.pack_x(u1, p1, xp)
+    ctx.init_xi(xi0); ctx.init_xi(xip)
+    nf = ctx.forward_jacobian(xp, x0, xi0, xip, None, b)
+    assert nf == 0, "set-up assembly failed"
+    b.zero_()
+
+    def step():
+        A.zero_(); b.zero_()
+        xi.copy_(xip)                      # Disc::create_primal: the step starts from step-1's state
+        ctx.forward_jacobian(x, xp, xip, xi, A, b, path, check=False)
+
+    # roofline denominators measured on this box with the same timer
+    dfma_peak = ctx.bench_dfma(4096)
+    copy_peak = ctx.bench_copy()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    nf = ctx.forward_jacobian(x, xp, xip, xi, None, None, path)   # status check outside the timing
+    assert nf == 0
+    plastic = float(path.to(torch.float32).mean().item())
+
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    ev[0].record()
+    for k in range(args.steps):
+        A.zero_(); b.zero_(); xi.copy_(xip)
+        kev[k][0].record()
+        ctx.forward_jacobian(x, xp, xip, xi, A, b, path, check=False)
+        kev[k][1].record()
+        ev[k + 1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    k_ms = float(np.mean([a.elapsed_time(c) for a, c in kev]))
+
+    # --- e2e: host nodal buffers through the resident-state entry point
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    hu, hp_ = pin(u2), pin(p2)
+    hbu, hbp = torch.zeros(ctx.n_nodes * 3).double().pin_memory(), torch.zeros(ctx.n_nodes).double().pin_memory()
+    xi1_host = ctx.unpack_xi(xip)
+    ctx.state_set_prev(u1, p1, xi1_host)
+
+    hun, hpn, hbun, hbpn = hu.numpy(), hp_.numpy(), hbu.numpy(), hbp.numpy()
+
+    def e2e_step():
+        # hyper_J2's local Newton starts from the trial state of xi_prev, so the resident
+        # current-step xi needs no reset between repeated assemblies of the same iterate
+        return ctx.state_forward_jacobian(hun, hpn, hbun, hbpn)
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    h2d = (ctx.n_nodes * 4) * 8
+    d2h = (ctx.n_nodes * 4) * 8 + 4
+
+    # max over ranks
+    t = torch.tensor([total_ms, k_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, k_ms, e2e_s = [float(v) for v in t.tolist()]
+    ms_per_step = total_ms / args.steps
+    value = n * world / (ms_per_step * 1e-3)
+    e2e_value = n * world / e2e_s
+
+    if rank == 0:
+        flops_qp = flops_per_qp_reference()
+        achieved_tf = flops_qp * n / (k_ms * 1e-3) * 1e-12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        nnzb = ctx.nnzb
+        bytes_per_launch = (n * (16 + 64 + 64 + 64 + 64 + 1) + ctx.n_nodes * (24 + 32 + 32 + 32)
+                            + nnzb * 16 * 8)
+        cpu = None
+        if args.gpus == 1 and not args.no_cpu:
+            c1 = cpu_sample(1, 28)
+            cpu = {"value": c1["evals_per_s"], "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"one {c1['n_elems']}-tet notched box (28 cells/side) of the same hyper-J2 "
+                             f"state, full eval_forward_jacobian incl. CSR scatter, 1 thread, "
+                             f"{c1['seconds']:.1f} s"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"3D finite-strain hyper_J2 + mixed u-p mechanics, notched unit box, "
+                            f"{N_CELLS} cells/side Kuhn tets",
+                "n_elems_per_gpu": n, "n_nodes_per_gpu": ctx.n_nodes, "nnz_blocks_4x4": nnzb,
+                "plastic_fraction": plastic, "local_newton": LOCAL,
+                "timed_region": "memset(A,b) + xi<-xi_prev copy + K1 (eval_forward_jacobian) per step",
+                "l2_policy": "inputs larger than L2 (A 4x4-BSR values %.0f MB + state %.0f MB per step)"
+                             % (nnzb * 128 / 1e6, n * 8 * 8 * 3 / 1e6),
+                "parallelism": "1 rank/GPU, element slabs, no data-path collective" if world > 1 else "1 GPU",
+            },
+            "kernel_ms": k_ms,
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": dfma_peak, "unit": "TFLOP/s",
+                         "frac": achieved_tf / dfma_peak,
+                         "peak_source": "DFMA micro-benchmark measured in this run (c8_bench_dfma); "
+                                        "MEASURED_PEAKS.json has no fp64 entry",
+                         "algorithmic_flops_per_qp": flops_qp,
+                         "flops_definition": "reference algorithm's count (16-wide AD on every op, "
+                                             "op-counting oracle); the kernel executes fewer",
+                         "traffic": None},
+            "roofline_hbm": {"bound": "hbm", "achieved": bytes_per_launch / (k_ms * 1e-3) * 1e-9,
+                             "peak": hbm_peak, "unit": "GB/s",
+                             "frac": bytes_per_launch / (k_ms * 1e-3) * 1e-9 / hbm_peak,
+                             "algorithmic_bytes_per_launch": bytes_per_launch,
+                             "copy_gbs_measured_this_run": copy_peak, "traffic": None},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
+                    "api": "c8_state_forward_jacobian (host nodal iterate in, host residual + status out)"},
+            "gpu_launches": args.steps,
+            "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -39,7 +39,8 @@ SYMBOLS = [
     "c8_csr_block_pattern", "c8_csr_block_values", "c8_pack_x", "c8_unpack_x", "c8_pack_xi",
     "c8_unpack_xi", "c8_init_xi", "c8_forward_jacobian", "c8_forward_jacobian_elem",
     "c8_global_residual", "c8_forward_jacobian_host", "c8_resident_matrix", "c8_set_stream",
-    "c8_synchronize",
+    "c8_synchronize", "c8_state_set_prev", "c8_state_forward_jacobian", "c8_state_get_xi",
+    "c8_state_ptrs", "c8_bench_dfma", "c8_bench_copy",
 ]
 
 _lib = None
@@ -238,6 +239,41 @@ class Context:
                                                C.byref(nf))
         self._check(rc, allow_local_fail=True)
         return nf.value, xi, [bu, bp][: self.num_resid]
+
+    # ---- resident step state (host buffers in/out; what a calibr8 caller does per Newton iteration)
+    def state_set_prev(self, u_prev, p_prev, xi_prev):
+        c = np.ascontiguousarray
+        self._check(self.lib.c8_state_set_prev(self.h, _hp(c(u_prev)),
+                                               _hp(None if p_prev is None else c(p_prev)),
+                                               _hp(c(xi_prev))))
+
+    def state_forward_jacobian(self, u, p, b_u, b_p):
+        """u, p, b_u, b_p: C-contiguous float64 host arrays (pinned for full copy speed)."""
+        nf = C.c_int(0)
+        rc = self.lib.c8_state_forward_jacobian(self.h, _hp(u), _hp(p), _hp(b_u), _hp(b_p),
+                                                C.byref(nf))
+        self._check(rc, allow_local_fail=True)
+        return nf.value
+
+    def state_get_xi(self):
+        xi = np.zeros((self.n_elems, self.nxi))
+        self._check(self.lib.c8_state_get_xi(self.h, _hp(xi)))
+        return xi
+
+    def state_ptrs(self):
+        ps = [C.c_void_p() for _ in range(6)]
+        self._check(self.lib.c8_state_ptrs(self.h, *[C.byref(p) for p in ps]))
+        return dict(zip(["x", "x_prev", "xi", "xi_prev", "A", "b"], [p.value for p in ps]))
+
+    def bench_dfma(self, iters=4096):
+        v = C.c_double(0)
+        self._check(self.lib.c8_bench_dfma(self.h, iters, C.byref(v)))
+        return v.value
+
+    def bench_copy(self):
+        v = C.c_double(0)
+        self._check(self.lib.c8_bench_copy(self.h, C.byref(v)))
+        return v.value
 
     def resident_matrix_ptr(self):
         p = C.c_void_p()

@@ -112,6 +112,23 @@ int c8_forward_jacobian_host(c8_ctx* ctx, const double* u_host, const double* p_
                              double* b_p_host, int* n_failed);
 int c8_resident_matrix(c8_ctx* ctx, double** A_vals_dev);
 
+/* ---- resident step state: what Primal::solve_at_step (primal.cpp:31-208) iterates on ----
+ * c8_state_set_prev uploads the converged previous step (global + local fields) and starts the
+ * current step as its copy (Disc::create_primal, disc.cpp:643-683).  c8_state_forward_jacobian
+ * is one Newton-iteration's assembly: HOST nodal iterate in, HOST residual + status out; the
+ * local state, its history and the Jacobian stay resident on the device. */
+int c8_state_set_prev(c8_ctx* ctx, const double* u_prev_host, const double* p_prev_host,
+                      const double* xi_prev_host);
+int c8_state_forward_jacobian(c8_ctx* ctx, const double* u_host, const double* p_host,
+                              double* b_u_host, double* b_p_host, int* n_failed);
+int c8_state_get_xi(c8_ctx* ctx, double* xi_host);
+int c8_state_ptrs(c8_ctx* ctx, double** x_dev, double** x_prev_dev, double** xi_dev,
+                  double** xi_prev_dev, double** A_vals_dev, double** b_dev);
+
+/* ---- roofline denominators measured on the box with the same timer as the kernels ---- */
+int c8_bench_dfma(c8_ctx* ctx, int iters, double* tflops_out);
+int c8_bench_copy(c8_ctx* ctx, double* gbs_out);
+
 /* stream control: all launches go to this stream (default: a context-owned stream) */
 int c8_set_stream(c8_ctx* ctx, void* cuda_stream);
 int c8_synchronize(c8_ctx* ctx);
