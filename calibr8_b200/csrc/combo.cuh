@@ -20,7 +20,7 @@ struct Launch {
   static void forward_jacobian(const FwdArgs& a, cudaStream_t s) {
     if (a.mesh.n_elems == 0) return;
     const long long threads = (long long)a.mesh.n_elems * C::G;
-    const int block = 128;
+    const int block = C8_K1_BLOCK;
     k_forward_jacobian<C><<<(unsigned)((threads + block - 1) / block), block, 0, s>>>(a);
   }
   static void global_residual(const FwdArgs& a, cudaStream_t s) {

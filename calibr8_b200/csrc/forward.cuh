@@ -66,9 +66,15 @@ C8_DI void load_elem(const MeshArgs& m, const ModelArgs& md, const double* __res
 // xi: in = values gathered from the current xi field, out = converged state.
 // Cd: the last residual evaluation with xi seeded (value + this thread's dC/dxi columns).
 // Returns the branch (0/1) or -1 when not converged within max_iters.
+//
+// BLOCK-SYNCHRONOUS: every thread of the CTA must call this (inactive groups pass
+// active = false).  The iteration loop is driven by __syncthreads_or so that all warps of the
+// CTA walk the (large, fully unrolled) Newton body together: the kernel is instruction-fetch
+// bound when warps drift apart in a ~170 KB straight-line program (profiles/README.md).
 template <class C>
 C8_DI int local_newton(const Kin<C::D, double, double>& k0, const Elem<C>& E, const ModelArgs& md,
-                       double (&xi)[C::NXI], Dual<C::LXI> (&Cd)[C::NXI], unsigned mask, int t) {
+                       double (&xi)[C::NXI], Dual<C::LXI> (&Cd)[C::NXI], unsigned mask, int t,
+                       bool active) {
   using Model = typename C::Model;
   constexpr int NXI = C::NXI, LXI = C::LXI;
   if constexpr (!Model::HAS_NEWTON) {
@@ -81,31 +87,38 @@ C8_DI int local_newton(const Kin<C::D, double, double>& k0, const Elem<C>& E, co
     int path = 0, iter = 1;
     double R_norm_0 = 1.0;
     bool converged = false;
-    while (iter <= md.max_iters && !converged) {
-      Dual<LXI> xs[NXI];
+    while (true) {
+      const bool work = active && (iter <= md.max_iters) && !converged;
+      if (!__syncthreads_or(work)) break;
+      if (work) {
+        Dual<LXI> xs[NXI];
 #pragma unroll
-      for (int q = 0; q < NXI; ++q) xs[q] = seeded<LXI>(xi[q], q, t * LXI);
-      path = Model::residual(k0, xs, E.xip, E.par, md.abs_tol, Cd);
-      double nrm = 0.0;
+        for (int q = 0; q < NXI; ++q) xs[q] = seeded<LXI>(xi[q], q, t * LXI);
+        path = Model::residual(k0, xs, E.xip, E.par, md.abs_tol, Cd);
+        double nrm = 0.0;
 #pragma unroll
-      for (int q = 0; q < NXI; ++q) nrm += Cd[q].v * Cd[q].v;
-      const double R_norm = sqrt(nrm);
-      if (iter == 1) R_norm_0 = R_norm;
-      const double R_norm_rel = R_norm / R_norm_0;
-      if ((R_norm_rel < md.rel_tol) || (R_norm < md.abs_tol)) { converged = true; break; }
-      double Jc[NXI][LXI], rhs[NXI], dummy[NXI][1];
+        for (int q = 0; q < NXI; ++q) nrm += Cd[q].v * Cd[q].v;
+        const double R_norm = sqrt(nrm);
+        if (iter == 1) R_norm_0 = R_norm;
+        const double R_norm_rel = R_norm / R_norm_0;
+        if ((R_norm_rel < md.rel_tol) || (R_norm < md.abs_tol)) {
+          converged = true;
+        } else {
+          double Jc[NXI][LXI], rhs[NXI], dummy[NXI][1];
 #pragma unroll
-      for (int q = 0; q < NXI; ++q) {
-        rhs[q] = -Cd[q].v;
+          for (int q = 0; q < NXI; ++q) {
+            rhs[q] = -Cd[q].v;
 #pragma unroll
-        for (int s = 0; s < LXI; ++s) Jc[q][s] = Cd[q].d[s];
+            for (int s = 0; s < LXI; ++s) Jc[q][s] = Cd[q].d[s];
+          }
+          group_gauss_jordan<NXI, LXI, 0, C::G>(Jc, dummy, rhs, mask);
+#pragma unroll
+          for (int q = 0; q < NXI; ++q) xi[q] += rhs[q];
+          ++iter;
+        }
       }
-      group_gauss_jordan<NXI, LXI, 0, C::G>(Jc, dummy, rhs, mask);
-#pragma unroll
-      for (int q = 0; q < NXI; ++q) xi[q] += rhs[q];
-      ++iter;
     }
-    if (iter > md.max_iters && !converged) return -1;
+    if (active && !converged) return -1;
     return path;
   }
 }
@@ -175,8 +188,10 @@ struct Scatter {
   const Elem<C>& E;
   const XLanes<C::D, C::NB, C::LX>& xl;
   int e, t;
+  bool on;  // false: compute but store nothing (padding groups, failed local solves)
   C8_DI void row(int n, int eq, const Dual<C::LX>& r) const {
     constexpr int NB = C::NB, NN = C::NN, NX = C::NX;
+    if (!on) return;
     const int row_dof = n * NB + eq;
     if (a.b && (row_dof % C::G) == t) atomicAdd(&a.b[size_t(E.nodes[n]) * NB + eq], r.v);
     if (a.elem_R && (row_dof % C::G) == t) a.elem_R[size_t(e) * NX + C::ref_dof(n, eq)] = r.v;
@@ -199,13 +214,20 @@ struct Scatter {
   }
 };
 
+#ifndef C8_K1_BLOCK
+#define C8_K1_BLOCK 256
+#endif
+
 template <class C>
-__global__ void __launch_bounds__(128) k_forward_jacobian(const FwdArgs a) {
+__global__ void __launch_bounds__(C8_K1_BLOCK, 1) k_forward_jacobian(const FwdArgs a) {
   using Model = typename C::Model;
   constexpr int D = C::D, NN = C::NN, NB = C::NB, NXI = C::NXI, LX = C::LX, G = C::G;
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int e = gid / G, t = gid % G;
-  if (e >= a.mesh.n_elems) return;
+  const int t = gid % G;
+  const bool in_range = (gid / G) < a.mesh.n_elems;
+  // out-of-range groups recompute the last element (no stores) so that every thread of the CTA
+  // reaches the phase barriers below
+  const int e = in_range ? gid / G : a.mesh.n_elems - 1;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane / G * G));
 
@@ -219,18 +241,22 @@ __global__ void __launch_bounds__(128) k_forward_jacobian(const FwdArgs a) {
   k0.gu = grad_u_val<D, NB>(E.xn, E.g);
   k0.gup = grad_u_val<D, NB>(E.xpn, E.g);
 
-  // ---- P1: local Newton ---------------------------------------------------
+  // ---- P1: local Newton (block-synchronous) ---------------------------------
   Dual<C::LXI> Cd[NXI];
-  const int path = local_newton<C>(k0, E, a.model, xi, Cd, mask, t);
-  if (path < 0) {
+  const int path = local_newton<C>(k0, E, a.model, xi, Cd, mask, t, in_range);
+  const bool ok = in_range && path >= 0;
+  if (in_range && path < 0) {
+    // the reference aborts the assembly (src/evaluations.cpp:95-97): report, scatter nothing
     if (t == 0) atomicAdd(a.n_failed, 1);
     if (a.path && t == 0) a.path[e] = -1;
-    return;  // the reference aborts the assembly (src/evaluations.cpp:95-97)
   }
+  if (ok) {
 #pragma unroll
-  for (int q = 0; q < NXI; ++q)
-    if (q % G == t) a.xi[size_t(q) * a.xi_ld + e] = xi[q];
-  if (a.path && t == 0) a.path[e] = (signed char)path;
+    for (int q = 0; q < NXI; ++q)
+      if (q % G == t) a.xi[size_t(q) * a.xi_ld + e] = xi[q];
+    if (a.path && t == 0) a.path[e] = (signed char)path;
+  }
+  __syncthreads();
 
   // ---- P2: dC/dx, then dxi/dx ---------------------------------------------
   SeededX<C> sx;
@@ -242,6 +268,7 @@ __global__ void __launch_bounds__(128) k_forward_jacobian(const FwdArgs a) {
   {
     Dual<LX> C2[NXI];
     Model::residual(k2, xi, E.xip, E.par, a.model.abs_tol, C2);
+    __syncthreads();
     double Bc[NXI][LX];
 #pragma unroll
     for (int q = 0; q < NXI; ++q)
@@ -255,12 +282,14 @@ __global__ void __launch_bounds__(128) k_forward_jacobian(const FwdArgs a) {
       for (int s = 0; s < LX; ++s) xid[q].d[s] = Bc[q][s];
     }
   }
+  __syncthreads();
 
   // ---- P3: element residual and total Jacobian, scattered row by row ------
   const double wdv = quad1_weight<D>() * E.g.dv;
-  const Scatter<C> sc{a, E, sx.xl, e, t};
+  const Scatter<C> sc{a, E, sx.xl, e, t, ok};
   {
     const Mat<Dual<LX>, D> P = first_pk<D, C::M, Model>(k2, sx.p, xid, E.par, a.model.thickness);
+    __syncthreads();
 #pragma unroll
     for (int n = 0; n < NN; ++n)
 #pragma unroll
@@ -272,6 +301,7 @@ __global__ void __launch_bounds__(128) k_forward_jacobian(const FwdArgs a) {
       }
   }
   if constexpr (C::M == MECH_MIXED) {
+    __syncthreads();
     Dual<LX> Rp[NN];
     {
       Dual<LX> hp, sv[D];
