@@ -285,3 +285,196 @@ class Context:
 
     def synchronize(self):
         self._check(self.lib.c8_synchronize(self.h))
+
+
+# ======================================================================================
+# adjoint / QoI / linear-algebra entry points and the C++ host step solvers (c8h_*)
+SYMBOLS += [
+    "c8_adjoint_jacobian", "c8_adjoint_local", "c8_qoi_value", "c8_qoi_gradient", "c8_spmv",
+    "c8_dot", "c8_axpby", "c8_apply_dbc", "c8_gmres", "c8_linalg_release", "c8_get_coords",
+    "c8_get_conn", "c8_get_stream",
+]
+HOST_SYMBOLS = [
+    "c8h_create", "c8h_destroy", "c8h_last_error", "c8h_set_time", "c8h_add_dbc",
+    "c8h_finalize_dbcs", "c8h_set_solver", "c8h_set_qoi_avg_disp", "c8h_set_qoi_calibration",
+    "c8h_primal_solve", "c8h_adjoint_gradient", "c8h_get_step", "c8h_get_adjoint_step", "c8h_stats",
+]
+
+
+class C8Qoi(C.Structure):
+    """struct c8_qoi of include/c8b200.h"""
+    _fields_ = [("type", C.c_int), ("weights", C.c_double * 3), ("balance_factor", C.c_double),
+                ("dt_over_T", C.c_double), ("inv_area", C.c_double), ("load_mismatch", C.c_double),
+                ("coord_idx", C.c_int), ("coord_value", C.c_double), ("coord_tol", C.c_double),
+                ("reaction_force_comp", C.c_int), ("measured_dev", C.c_void_p),
+                ("facet_dev", C.c_void_p)]
+
+
+def make_qoi(kind="avg_disp", **kw):
+    q = C8Qoi()
+    q.type = 0 if kind == "avg_disp" else 1
+    w = kw.get("weights", (1., 1., 1.))
+    for k in range(3):
+        q.weights[k] = w[k] if k < len(w) else 1.0
+    q.balance_factor = kw.get("balance_factor", 1.0)
+    q.dt_over_T = kw.get("dt_over_T", 1.0)
+    q.inv_area = kw.get("inv_area", 1.0)
+    q.load_mismatch = kw.get("load_mismatch", 0.0)
+    q.coord_idx = kw.get("coord_idx", 0)
+    q.coord_value = kw.get("coord_value", 0.0)
+    q.coord_tol = kw.get("coord_tol", 1e-12)
+    q.reaction_force_comp = kw.get("reaction_force_comp", 0)
+    m = kw.get("measured")
+    q.measured_dev = None if m is None else m.data_ptr()
+    f = kw.get("facet")
+    q.facet_dev = None if f is None else f.data_ptr()
+    return q
+
+
+def _ctx_adjoint_jacobian(self, qoi, x, x_prev, xi, xi_prev, g, f, AT, rhs):
+    self._check(self.lib.c8_adjoint_jacobian(self.h, C.byref(qoi) if qoi is not None else None,
+                                             _dp(x), _dp(x_prev), _dp(xi), _dp(xi_prev), _dp(g),
+                                             _dp(f), _dp(AT), _dp(rhs)))
+
+
+def _ctx_adjoint_local(self, x, x_prev, xi, xi_prev, z, phi, g, f):
+    self._check(self.lib.c8_adjoint_local(self.h, _dp(x), _dp(x_prev), _dp(xi), _dp(xi_prev),
+                                          _dp(z), _dp(phi), _dp(g), _dp(f)))
+
+
+def _ctx_qoi_value(self, qoi, x, x_prev, xi, xi_prev, mode, scalars):
+    self._check(self.lib.c8_qoi_value(self.h, C.byref(qoi) if qoi is not None else None, _dp(x),
+                                      _dp(x_prev), _dp(xi), _dp(xi_prev), mode, _dp(scalars)))
+
+
+def _ctx_qoi_gradient(self, qoi, x, x_prev, xi, xi_prev, z, phi, grad):
+    self._check(self.lib.c8_qoi_gradient(self.h, C.byref(qoi) if qoi is not None else None, _dp(x),
+                                         _dp(x_prev), _dp(xi), _dp(xi_prev), _dp(z), _dp(phi),
+                                         _dp(grad)))
+
+
+def _ctx_spmv(self, A, x, y):
+    self._check(self.lib.c8_spmv(self.h, _dp(A), _dp(x), _dp(y)))
+
+
+def _ctx_dot(self, x, y):
+    v = C.c_double(0)
+    self._check(self.lib.c8_dot(self.h, _dp(x), _dp(y), C.byref(v)))
+    return v.value
+
+
+def _ctx_apply_dbc(self, A, R, x, nodes, eqs, vals, is_adjoint=False):
+    self._check(self.lib.c8_apply_dbc(self.h, _dp(A), _dp(R), _dp(x), _dp(nodes), _dp(eqs),
+                                      _dp(vals), int(nodes.numel()), int(is_adjoint)))
+
+
+def _ctx_gmres(self, A, b, x, restart=100, max_iters=5000, rel_tol=1e-10, abs_tol=0.0):
+    info = (C.c_double * 3)()
+    rc = self.lib.c8_gmres(self.h, _dp(A), _dp(b), _dp(x), restart, max_iters, C.c_double(rel_tol),
+                           C.c_double(abs_tol), info)
+    if rc not in (0, -4):
+        self._check(rc)
+    return dict(converged=(rc == 0), iters=int(info[0]), resid=info[1], resid0=info[2])
+
+
+Context.adjoint_jacobian = _ctx_adjoint_jacobian
+Context.adjoint_local = _ctx_adjoint_local
+Context.qoi_value = _ctx_qoi_value
+Context.qoi_gradient = _ctx_qoi_gradient
+Context.spmv = _ctx_spmv
+Context.dot = _ctx_dot
+Context.apply_dbc = _ctx_apply_dbc
+Context.gmres = _ctx_gmres
+
+
+class HostProblem:
+    """The C++ host step solvers (calibr8_b200/host): Primal / Adjoint above the C ABI."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.lib.c8h_create.restype = C.c_void_p
+        self.lib.c8h_last_error.restype = C.c_char_p
+        self.lib.c8h_last_error.argtypes = [C.c_void_p]
+        h = self.lib.c8h_create(ctx.h)
+        if not h:
+            raise C8Error("c8h_create failed")
+        self.h = C.c_void_p(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.c8h_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise C8Error("c8h: " + self.lib.c8h_last_error(self.h).decode())
+
+    def set_time(self, num_steps, step_size=1.0):
+        self.num_steps = num_steps
+        self._check(self.lib.c8h_set_time(self.h, num_steps, C.c_double(step_size)))
+
+    def add_dbc(self, resid, eq, nodes, expr):
+        nodes = np.ascontiguousarray(nodes, dtype=np.int32)
+        self._check(self.lib.c8h_add_dbc(self.h, resid, eq, _hp(nodes), int(nodes.size),
+                                         str(expr).encode()))
+
+    def finalize_dbcs(self):
+        self._check(self.lib.c8h_finalize_dbcs(self.h))
+
+    def set_solver(self, newton_max_iters=15, abs_tol=1e-8, rel_tol=1e-8, gmres_restart=100,
+                   gmres_max_iters=4000, linear_tol=1e-10, verbose=False):
+        self._check(self.lib.c8h_set_solver(self.h, newton_max_iters, C.c_double(abs_tol),
+                                            C.c_double(rel_tol), gmres_restart, gmres_max_iters,
+                                            C.c_double(linear_tol), int(verbose)))
+
+    def set_qoi_avg_disp(self):
+        self._check(self.lib.c8h_set_qoi_avg_disp(self.h))
+
+    def set_qoi_calibration(self, *, balance_factor, coord_idx, coord_value, coord_tol=1e-12,
+                            reaction_force_comp, weights, measured, load_data, area, facet=None):
+        w = np.ones(3); w[: len(weights)] = weights
+        measured = np.ascontiguousarray(measured, dtype=np.float64)
+        load_data = np.ascontiguousarray(load_data, dtype=np.float64)
+        fct = None if facet is None else np.ascontiguousarray(facet, dtype=np.int8)
+        self._check(self.lib.c8h_set_qoi_calibration(
+            self.h, C.c_double(balance_factor), coord_idx, C.c_double(coord_value),
+            C.c_double(coord_tol), reaction_force_comp, _hp(w), _hp(measured), _hp(load_data),
+            _hp(fct), C.c_double(area)))
+
+    def primal_solve(self):
+        J = C.c_double(0)
+        self._check(self.lib.c8h_primal_solve(self.h, C.byref(J)))
+        return J.value
+
+    def adjoint_gradient(self):
+        g = np.zeros(self.ctx.npar)
+        self._check(self.lib.c8h_adjoint_gradient(self.h, _hp(g)))
+        return g
+
+    def get_step(self, step):
+        c = self.ctx
+        u = np.zeros(c.n_nodes * c.dim)
+        p = np.zeros(c.n_nodes) if c.num_resid == 2 else None
+        xi = np.zeros((c.n_elems, c.nxi))
+        self._check(self.lib.c8h_get_step(self.h, step, _hp(u), _hp(p), _hp(xi)))
+        return [u, p][: c.num_resid], xi
+
+    def get_adjoint_step(self, step):
+        c = self.ctx
+        zu = np.zeros(c.n_nodes * c.dim)
+        zp = np.zeros(c.n_nodes) if c.num_resid == 2 else None
+        phi = np.zeros((c.n_elems, c.nxi))
+        self._check(self.lib.c8h_get_adjoint_step(self.h, step, _hp(zu), _hp(zp), _hp(phi)))
+        return [zu, zp][: c.num_resid], phi
+
+    def stats(self):
+        a, b = C.c_int(0), C.c_int(0)
+        self.lib.c8h_stats(self.h, C.byref(a), C.byref(b))
+        return dict(assemblies=a.value, linear_iters=b.value)

@@ -1,0 +1,43 @@
+// POD argument blocks of the adjoint / QoI kernels (shared with the host-side context).
+#pragma once
+#include "args.h"
+
+namespace c8 {
+
+enum QoiType { QOI_AVG_DISP = 0, QOI_CALIBRATION = 1 };
+
+struct QoiArgs {
+  int type;
+  // calibration
+  double weights[3];
+  double balance_factor;
+  double dt_over_T;        // m_dt / m_total_time
+  double inv_area;         // 1 / m_area
+  double load_mismatch;    // total_load - load_meas of the step (set after the preprocess pass)
+  int coord_idx;
+  double coord_value, coord_tol;
+  int reaction_force_comp;
+  const double* measured;      // [n_nodes][DIM] measured displacement of the step
+  const signed char* facet;    // 3-D: [n_elems][3] local vertex ids of the facet on the side set, -1 none
+};
+
+struct AdjArgs {
+  MeshArgs mesh;
+  ModelArgs model;
+  QoiArgs qoi;
+  const double* x;
+  const double* x_prev;
+  const double* xi;
+  const double* xi_prev;
+  long long xi_ld;
+  double* g;          // K3: in/out ; K4: in (g) / out (new g)
+  double* f;          // K3: in ; K4: out        [NX][xi_ld], element dofs node-interleaved
+  double* vals;       // K3: A^T (+=)
+  double* b;          // K3: rhs (+=)
+  const double* z;    // K4/K6: nodal adjoint [n_nodes][NB]
+  double* phi;        // K4: out ; K6: in
+  double* grad;       // K6: [n_es][NPAR] (+=), derivative w.r.t. EVERY parameter of the model
+  double* scalars;    // K5: [0] += J, [1] += total load
+};
+
+}  // namespace c8

@@ -1,0 +1,550 @@
+// K3-K6: the reverse-in-time adjoint element loops of the reference,
+//   K3 eval_adjoint_jacobian  src/evaluations.cpp:349-526  (A^T, rhs, g -= dJ/dxi)
+//   K4 solve_adjoint_local    src/evaluations.cpp:528-659  (phi, f, g)
+//   K5 eval_qoi / preprocess_qoi  src/evaluations.cpp:662-756, 261-347
+//   K6 eval_qoi_gradient      src/evaluations.cpp:758-925  (dC/dp^T phi + dJ/dp + dR/dp^T z)
+// Same thread-group / lane-split AD design as forward.cuh.  History arrays g [NXI][ld],
+// f [NX][ld], phi [NXI][ld] are structure-of-arrays like xi.
+#pragma once
+#include "forward.cuh"
+#include "qoi.cuh"
+
+namespace c8 {
+
+
+template <class C> C8_DI unsigned group_mask() {
+  const unsigned lane = threadIdx.x & 31u;
+  return (C::G == 32) ? 0xffffffffu : (((1u << C::G) - 1u) << (lane / C::G * C::G));
+}
+
+// nodal displacements as Dual<L> seeded w.r.t. the element dofs (for QoI derivatives)
+template <class C, int L>
+C8_DI void seeded_nodal_u(const Elem<C>& E, const XLanes<C::D, C::NB, L>& xl,
+                          Dual<L> (&un)[C::NN][C::D]) {
+#pragma unroll
+  for (int n = 0; n < C::NN; ++n)
+#pragma unroll
+    for (int i = 0; i < C::D; ++i) {
+      un[n][i].v = E.xn[n][i];
+#pragma unroll
+      for (int s = 0; s < L; ++s)
+        un[n][i].d[s] = (xl.nsel[s] != 0.0 && xl.node[s] == n && xl.eq[s] == i) ? 1.0 : 0.0;
+    }
+}
+
+template <class C>
+C8_DI void load_measured(const QoiArgs& q, const Elem<C>& E, double (&um)[C::NN][C::D],
+                         double (&X)[C::NN][C::D], const double* coords) {
+#pragma unroll
+  for (int n = 0; n < C::NN; ++n)
+#pragma unroll
+    for (int i = 0; i < C::D; ++i) {
+      um[n][i] = q.measured ? __ldg(&q.measured[size_t(E.nodes[n]) * C::D + i]) : 0.0;
+      X[n][i] = __ldg(&coords[size_t(E.nodes[n]) * C::D + i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3
+template <class C>
+__global__ void __launch_bounds__(128) k_adjoint_jacobian(const AdjArgs a) {
+  using Model = typename C::Model;
+  constexpr int D = C::D, NN = C::NN, NB = C::NB, NX = C::NX, NXI = C::NXI, LX = C::LX,
+                LXI = C::LXI, G = C::G;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = gid / G, t = gid % G;
+  if (e >= a.mesh.n_elems) return;
+  const unsigned mask = group_mask<C>();
+
+  Elem<C> E;
+  load_elem<C>(a.mesh, a.model, a.x, a.x_prev, a.xi_prev, a.xi_ld, e, E);
+  double xi[NXI];
+#pragma unroll
+  for (int q = 0; q < NXI; ++q) xi[q] = __ldg(&a.xi[size_t(q) * a.xi_ld + e]);
+  Kin<D, double, double> k0;
+  k0.gu = grad_u_val<D, NB>(E.xn, E.g);
+  k0.gup = grad_u_val<D, NB>(E.xpn, E.g);
+
+  // dC/dxi at the stored state (no Newton, src/evaluations.cpp:442-446)
+  Dual<LXI> xs[NXI], Cd[NXI];
+#pragma unroll
+  for (int q = 0; q < NXI; ++q) xs[q] = seeded<LXI>(xi[q], q, t * LXI);
+  Model::residual(k0, xs, E.xip, E.par, a.model.abs_tol, Cd);
+
+  SeededX<C> sx;
+  sx.init(E, k0.gu, t);
+  Kin<D, Dual<LX>, double> k2;
+  k2.gu = sx.gu;
+  k2.gup = k0.gup;
+  Dual<LX> xid[NXI];
+  double dxi_dx[NXI][LX];
+  {
+    Dual<LX> C2[NXI];
+    Model::residual(k2, xi, E.xip, E.par, a.model.abs_tol, C2);
+#pragma unroll
+    for (int q = 0; q < NXI; ++q)
+#pragma unroll
+      for (int s = 0; s < LX; ++s) dxi_dx[q][s] = C2[q].d[s];
+    local_sensitivity<C, LX>(Cd, dxi_dx, mask);
+#pragma unroll
+    for (int q = 0; q < NXI; ++q) {
+      xid[q].v = xi[q];
+#pragma unroll
+      for (int s = 0; s < LX; ++s) xid[q].d[s] = dxi_dx[q][s];
+    }
+  }
+
+  // total Jacobian, transposed scatter (matrix only)
+  const double wdv = quad1_weight<D>() * E.g.dv;
+  FwdArgs fa{};
+  fa.mesh = a.mesh;
+  fa.vals = a.vals;
+  fa.transpose = 1;
+  const Scatter<C> sc{fa, E, sx.xl, e, t, true};
+  {
+    const Mat<Dual<LX>, D> P = first_pk<D, C::M, Model>(k2, sx.p, xid, E.par, a.model.thickness);
+#pragma unroll
+    for (int n = 0; n < NN; ++n)
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        Dual<LX> r = P(i, 0) * (E.g.gN[n][0] * wdv);
+#pragma unroll
+        for (int j = 1; j < D; ++j) r += P(i, j) * (E.g.gN[n][j] * wdv);
+        sc.row(n, i, r);
+      }
+  }
+  if constexpr (C::M == MECH_MIXED) {
+    Dual<LX> Rp[NN];
+    {
+      Dual<LX> hp, sv[D];
+      pressure_terms<D, Model>(k2, sx.gp, xid, E.par, E.g.h, a.model.stab_mult, hp, sv);
+#pragma unroll
+      for (int n = 0; n < NN; ++n) {
+        Dual<LX> r = hp * ((1.0 / NN) * wdv);
+#pragma unroll
+        for (int i = 0; i < D; ++i) r += sv[i] * (E.g.gN[n][i] * wdv);
+        Rp[n] = -r;
+      }
+    }
+    const double ipk = 1.0 / Model::pscale(E.par);
+#pragma unroll
+    for (int q = 0; q < Quad2<D>::NPT; ++q) {
+      double N[NN];
+      Quad2<D>::basis(q, N);
+      Dual<LX> pq;
+      pq.v = 0.0;
+#pragma unroll
+      for (int n = 0; n < NN; ++n) pq.v += E.xn[n][D] * N[n];
+#pragma unroll
+      for (int s = 0; s < LX; ++s) {
+        double Ns = 0.0;
+#pragma unroll
+        for (int n = 0; n < NN; ++n) Ns = pick(sx.xl.node[s] == n, N[n], Ns);
+        pq.d[s] = (sx.xl.eq[s] == D) ? Ns : 0.0;
+      }
+      const double wq = Quad2<D>::weight() * E.g.dv;
+      const Dual<LX> pk = pq * ipk;
+#pragma unroll
+      for (int n = 0; n < NN; ++n) Rp[n] -= pk * (N[n] * wq);
+    }
+#pragma unroll
+    for (int n = 0; n < NN; ++n) sc.row(n, D, Rp[n]);
+  }
+
+  // QoI derivatives: dJ/dx (x seeded, xi NOT seeded) and dJ/dxi (xi seeded), :468-478
+  double dJ_dx[LX];
+#pragma unroll
+  for (int s = 0; s < LX; ++s) dJ_dx[s] = 0.0;
+  double gq[NXI];
+#pragma unroll
+  for (int q = 0; q < NXI; ++q) gq[q] = a.g[size_t(q) * a.xi_ld + e];
+  if (a.qoi.type == QOI_AVG_DISP) {
+#pragma unroll
+    for (int s = 0; s < LX; ++s)
+      dJ_dx[s] = (sx.xl.eq[s] < D) ? (1.0 / NN) * wdv / D : 0.0;
+  } else {
+    const bool in_obj = (D == 2) || (a.qoi.facet && a.qoi.facet[size_t(e) * 3] >= 0);
+    if (in_obj) {
+      Dual<LX> un[NN][D];
+      seeded_nodal_u<C, LX>(E, sx.xl, un);
+      double um[NN][D], X[NN][D];
+      load_measured<C>(a.qoi, E, um, X, a.mesh.coords);
+      const signed char* fv = (D == 3) ? &a.qoi.facet[size_t(e) * 3] : nullptr;
+      const Dual<LX> mm = calibration_disp_mismatch<D, Dual<LX>>(a.qoi, un, um, X, E.g.dv, fv);
+#pragma unroll
+      for (int s = 0; s < LX; ++s) dJ_dx[s] += mm.d[s];
+    }
+    const int nmask = load_node_mask<D>(a.qoi, a.mesh.coords, E.nodes);
+    if (nmask) {
+      const double coef = a.qoi.balance_factor * a.qoi.dt_over_T * a.qoi.load_mismatch;
+      {
+        const Mat<Dual<LX>, D> Px = first_pk<D, C::M, Model>(k2, sx.p, xi, E.par, a.model.thickness);
+        const Dual<LX> load = calibration_load<D>(a.qoi, Px, E.g, wdv, nmask);
+#pragma unroll
+        for (int s = 0; s < LX; ++s) dJ_dx[s] += coef * load.d[s];
+      }
+      {
+        double p0 = 0.0;
+        if constexpr (C::M == MECH_MIXED) {
+#pragma unroll
+          for (int n = 0; n < NN; ++n) p0 += E.xn[n][D] * (1.0 / NN);
+        }
+        const Mat<Dual<LXI>, D> Pxi = first_pk<D, C::M, Model>(k0, p0, xs, E.par, a.model.thickness);
+        const Dual<LXI> load = calibration_load<D>(a.qoi, Pxi, E.g, wdv, nmask);
+#pragma unroll
+        for (int q = 0; q < NXI; ++q) {
+          const double v = group_bcast<G>(mask, load.d[q % LXI], q / LXI);
+          gq[q] -= coef * v;
+        }
+      }
+    }
+  }
+  // g -= dJ/dxi (stored) ; rhs = -dJ/dx + f + dxi/dx^T g, :481-488
+#pragma unroll
+  for (int q = 0; q < NXI; ++q)
+    if (q % G == t) a.g[size_t(q) * a.xi_ld + e] = gq[q];
+#pragma unroll
+  for (int s = 0; s < LX; ++s) {
+    if (sx.xl.nsel[s] == 0.0) continue;
+    const int c = t * LX + s;
+    double r = -dJ_dx[s] + __ldg(&a.f[size_t(c) * a.xi_ld + e]);
+#pragma unroll
+    for (int q = 0; q < NXI; ++q) r = fma(dxi_dx[q][s], gq[q], r);
+    atomicAdd(&a.b[size_t(E.nodes[sx.xl.node[s]]) * NB + sx.xl.eq[s]], r);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K4
+template <class C>
+__global__ void __launch_bounds__(128) k_adjoint_local(const AdjArgs a) {
+  using Model = typename C::Model;
+  constexpr int D = C::D, NN = C::NN, NB = C::NB, NXI = C::NXI, LX = C::LX, LXI = C::LXI,
+                G = C::G;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = gid / G, t = gid % G;
+  if (e >= a.mesh.n_elems) return;
+  const unsigned mask = group_mask<C>();
+
+  Elem<C> E;
+  load_elem<C>(a.mesh, a.model, a.x, a.x_prev, a.xi_prev, a.xi_ld, e, E);
+  double xi[NXI];
+#pragma unroll
+  for (int q = 0; q < NXI; ++q) xi[q] = __ldg(&a.xi[size_t(q) * a.xi_ld + e]);
+  Kin<D, double, double> k0;
+  k0.gu = grad_u_val<D, NB>(E.xn, E.g);
+  k0.gup = grad_u_val<D, NB>(E.xpn, E.g);
+  const double wdv = quad1_weight<D>() * E.g.dv;
+  double z[NN][NB];
+#pragma unroll
+  for (int n = 0; n < NN; ++n)
+#pragma unroll
+    for (int q = 0; q < NB; ++q) z[n][q] = __ldg(&a.z[size_t(E.nodes[n]) * NB + q]);
+
+  // xi seeded: dC/dxi and dR/dxi (ip set 0 only, :613-621)
+  Dual<LXI> xs[NXI], Cd[NXI];
+#pragma unroll
+  for (int q = 0; q < NXI; ++q) xs[q] = seeded<LXI>(xi[q], q, t * LXI);
+  Model::residual(k0, xs, E.xip, E.par, a.model.abs_tol, Cd);
+  double rl[LXI];  // (dR/dxi^T z) for this thread's xi lanes
+#pragma unroll
+  for (int s = 0; s < LXI; ++s) rl[s] = 0.0;
+  {
+    double p0 = 0.0, gp0[D];
+    if constexpr (C::M == MECH_MIXED) {
+#pragma unroll
+      for (int n = 0; n < NN; ++n) p0 += E.xn[n][D] * (1.0 / NN);
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        gp0[j] = 0.0;
+#pragma unroll
+        for (int n = 0; n < NN; ++n) gp0[j] += E.xn[n][D] * E.g.gN[n][j];
+      }
+    }
+    const Mat<Dual<LXI>, D> P = first_pk<D, C::M, Model>(k0, p0, xs, E.par, a.model.thickness);
+#pragma unroll
+    for (int n = 0; n < NN; ++n)
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        Dual<LXI> r = P(i, 0) * (E.g.gN[n][0] * wdv);
+#pragma unroll
+        for (int j = 1; j < D; ++j) r += P(i, j) * (E.g.gN[n][j] * wdv);
+#pragma unroll
+        for (int s = 0; s < LXI; ++s) rl[s] = fma(r.d[s], z[n][i], rl[s]);
+      }
+    if constexpr (C::M == MECH_MIXED) {
+      Dual<LXI> hp, sv[D];
+      pressure_terms<D, Model>(k0, gp0, xs, E.par, E.g.h, a.model.stab_mult, hp, sv);
+#pragma unroll
+      for (int n = 0; n < NN; ++n) {
+        Dual<LXI> r = hp * ((1.0 / NN) * wdv);
+#pragma unroll
+        for (int i = 0; i < D; ++i) r += sv[i] * (E.g.gN[n][i] * wdv);
+#pragma unroll
+        for (int s = 0; s < LXI; ++s) rl[s] = fma(-r.d[s], z[n][D], rl[s]);
+      }
+    }
+  }
+  // rhs = g - dR/dxi^T z (replicated), J^T by an in-group transpose, phi = J^-T rhs
+  double rhs[NXI], JT[NXI][LXI], dummy[NXI][1];
+#pragma unroll
+  for (int q = 0; q < NXI; ++q) {
+    const double v = group_bcast<G>(mask, rl[q % LXI], q / LXI);
+    rhs[q] = __ldg(&a.g[size_t(q) * a.xi_ld + e]) - v;
+  }
+  // thread owns columns c = t*LXI+s of J (Cd[i].d[s] = J[i][c]); it needs columns c of J^T,
+  // i.e. JT[i][s] = J[c][i]: broadcast every J[r][i] and keep those with r == c
+#pragma unroll
+  for (int i = 0; i < NXI; ++i) {
+#pragma unroll
+    for (int s = 0; s < LXI; ++s) JT[i][s] = 0.0;
+  }
+#pragma unroll
+  for (int r = 0; r < NXI; ++r)
+#pragma unroll
+    for (int i = 0; i < NXI; ++i) {
+      const double v = group_bcast<G>(mask, Cd[r].d[i % LXI], i / LXI);  // J[r][i]
+#pragma unroll
+      for (int s = 0; s < LXI; ++s) JT[i][s] = pick(t * LXI + s == r, v, JT[i][s]);
+    }
+  group_gauss_jordan<NXI, LXI, 0, G>(JT, dummy, rhs, mask);  // rhs := phi
+#pragma unroll
+  for (int q = 0; q < NXI; ++q)
+    if (q % G == t) a.phi[size_t(q) * a.xi_ld + e] = rhs[q];
+
+  // f = -dC/dx_prev^T phi (x_prev seeded; non-zero only for finite-strain models), :626-632
+  {
+    XLanes<D, NB, LX> xl;
+    xl.init(t * LX, E.g);
+    Kin<D, double, Dual<LX>> kp;
+    kp.gu = k0.gu;
+    kp.gup = grad_u_seeded<D, NB, LX>(k0.gup, xl);
+    Dual<LX> Cp[NXI];
+    Model::residual(kp, xi, E.xip, E.par, a.model.abs_tol, Cp);
+#pragma unroll
+    for (int s = 0; s < LX; ++s) {
+      if (xl.nsel[s] == 0.0) continue;
+      double v = 0.0;
+#pragma unroll
+      for (int q = 0; q < NXI; ++q) v = fma(Cp[q].d[s], rhs[q], v);
+      a.f[size_t(t * LX + s) * a.xi_ld + e] = -v;
+    }
+  }
+  // g = -dC/dxi_prev^T phi (xi_prev seeded), :634-641
+  {
+    Dual<LXI> xps[NXI], Cq[NXI];
+#pragma unroll
+    for (int q = 0; q < NXI; ++q) xps[q] = seeded<LXI>(E.xip[q], q, t * LXI);
+    Model::residual(k0, xi, xps, E.par, a.model.abs_tol, Cq);
+#pragma unroll
+    for (int s = 0; s < LXI; ++s) {
+      const int c = t * LXI + s;
+      if (c >= NXI) continue;
+      double v = 0.0;
+#pragma unroll
+      for (int q = 0; q < NXI; ++q) v = fma(Cq[q].d[s], rhs[q], v);
+      a.g[size_t(c) * a.xi_ld + e] = -v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K6: every parameter of the model is seeded (lane k = parameter k); the host picks the
+// active ones (LocalResidual::seed_wrt_params seeds only those, src/local_residual.cpp:811-819;
+// lanes are independent so the active lanes are identical).
+template <class C>
+__global__ void __launch_bounds__(128) k_qoi_gradient(const AdjArgs a) {
+  using Model = typename C::Model;
+  constexpr int D = C::D, NN = C::NN, NB = C::NB, NXI = C::NXI, NPAR = C::NPAR, G = C::G;
+  constexpr int LP = (NPAR + G - 1) / G;
+  using TP = Dual<LP>;
+  __shared__ double sacc[128 / G][G * LP];  // per group in the block
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = gid / G, t = gid % G;
+  const int gl = threadIdx.x / G;
+  double acc[LP];
+#pragma unroll
+  for (int s = 0; s < LP; ++s) acc[s] = 0.0;
+  int es = 0;
+  if (e < a.mesh.n_elems) {
+    Elem<C> E;
+    load_elem<C>(a.mesh, a.model, a.x, a.x_prev, a.xi_prev, a.xi_ld, e, E);
+    es = a.mesh.elem_es ? a.mesh.elem_es[e] : 0;
+    double xi[NXI], phi[NXI];
+#pragma unroll
+    for (int q = 0; q < NXI; ++q) {
+      xi[q] = __ldg(&a.xi[size_t(q) * a.xi_ld + e]);
+      phi[q] = __ldg(&a.phi[size_t(q) * a.xi_ld + e]);
+    }
+    Kin<D, double, double> k0;
+    k0.gu = grad_u_val<D, NB>(E.xn, E.g);
+    k0.gup = grad_u_val<D, NB>(E.xpn, E.g);
+    const double wdv = quad1_weight<D>() * E.g.dv;
+    double z[NN][NB];
+#pragma unroll
+    for (int n = 0; n < NN; ++n)
+#pragma unroll
+      for (int q = 0; q < NB; ++q) z[n][q] = __ldg(&a.z[size_t(E.nodes[n]) * NB + q]);
+    TP par[NPAR];
+#pragma unroll
+    for (int k = 0; k < NPAR; ++k) par[k] = seeded<LP>(E.par[k], k, t * LP);
+    // dC/dp^T phi
+    {
+      TP Cp[NXI];
+      Model::residual(k0, xi, E.xip, par, a.model.abs_tol, Cp);
+#pragma unroll
+      for (int q = 0; q < NXI; ++q)
+#pragma unroll
+        for (int s = 0; s < LP; ++s) acc[s] = fma(Cp[q].d[s], phi[q], acc[s]);
+    }
+    // dR/dp^T z (all ip sets) and dJ/dp (calibration load term)
+    double p0 = 0.0, gp0[D];
+    if constexpr (C::M == MECH_MIXED) {
+#pragma unroll
+      for (int n = 0; n < NN; ++n) p0 += E.xn[n][D] * (1.0 / NN);
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        gp0[j] = 0.0;
+#pragma unroll
+        for (int n = 0; n < NN; ++n) gp0[j] += E.xn[n][D] * E.g.gN[n][j];
+      }
+    }
+    {
+      const Mat<TP, D> P = first_pk<D, C::M, Model>(k0, p0, xi, par, a.model.thickness);
+#pragma unroll
+      for (int n = 0; n < NN; ++n)
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          TP r = P(i, 0) * (E.g.gN[n][0] * wdv);
+#pragma unroll
+          for (int j = 1; j < D; ++j) r += P(i, j) * (E.g.gN[n][j] * wdv);
+#pragma unroll
+          for (int s = 0; s < LP; ++s) acc[s] = fma(r.d[s], z[n][i], acc[s]);
+        }
+      if (a.qoi.type == QOI_CALIBRATION) {
+        const int nmask = load_node_mask<D>(a.qoi, a.mesh.coords, E.nodes);
+        if (nmask) {
+          const double coef = a.qoi.balance_factor * a.qoi.dt_over_T * a.qoi.load_mismatch;
+          const TP load = calibration_load<D>(a.qoi, P, E.g, wdv, nmask);
+#pragma unroll
+          for (int s = 0; s < LP; ++s) acc[s] += coef * load.d[s];
+        }
+      }
+    }
+    if constexpr (C::M == MECH_MIXED) {
+      TP hp, sv[D];
+      pressure_terms<D, Model>(k0, gp0, xi, par, E.g.h, a.model.stab_mult, hp, sv);
+#pragma unroll
+      for (int n = 0; n < NN; ++n) {
+        TP r = hp * ((1.0 / NN) * wdv);
+#pragma unroll
+        for (int i = 0; i < D; ++i) r += sv[i] * (E.g.gN[n][i] * wdv);
+#pragma unroll
+        for (int s = 0; s < LP; ++s) acc[s] = fma(-r.d[s], z[n][D], acc[s]);
+      }
+      const TP ipk = 1.0 / Model::pscale(par);
+#pragma unroll
+      for (int q = 0; q < Quad2<D>::NPT; ++q) {
+        double N[NN];
+        Quad2<D>::basis(q, N);
+        double pq = 0.0;
+#pragma unroll
+        for (int n = 0; n < NN; ++n) pq += E.xn[n][D] * N[n];
+        const double wq = Quad2<D>::weight() * E.g.dv;
+        const TP pk = pq * ipk;
+#pragma unroll
+        for (int n = 0; n < NN; ++n) {
+          const TP r = pk * (N[n] * wq);
+#pragma unroll
+          for (int s = 0; s < LP; ++s) acc[s] = fma(-r.d[s], z[n][D], acc[s]);
+        }
+      }
+    }
+  }
+  // block reduction per element set is not needed when the block is single-set (the common
+  // case); otherwise fall back to direct global atomics
+  const bool multi_set = a.mesh.elem_es != nullptr;
+  if (multi_set) {
+    if (e < a.mesh.n_elems) {
+#pragma unroll
+      for (int s = 0; s < LP; ++s) {
+        const int k = t * LP + s;
+        if (k < NPAR) atomicAdd(&a.grad[es * NPAR + k], acc[s]);
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int s = 0; s < LP; ++s) sacc[gl][t * LP + s] = acc[s];
+  __syncthreads();
+  if (threadIdx.x < G * LP) {
+    double v = 0.0;
+    for (int g2 = 0; g2 < 128 / G; ++g2) v += sacc[g2][threadIdx.x];
+    if (threadIdx.x < NPAR) atomicAdd(&a.grad[threadIdx.x], v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K5: QoI value (and the calibration preprocess pass: total load on the coordinate plane).
+// T = double; one thread per element; block reduction then one atomic per block.
+//   mode 0: scalars[0] += sum of per-point QoI values   (eval_qoi main loop)
+//   mode 1: scalars[1] += load on the plane             (preprocess_qoi / Calibration::preprocess)
+template <class C>
+__global__ void __launch_bounds__(128) k_qoi_value(const AdjArgs a, int mode) {
+  using Model = typename C::Model;
+  constexpr int D = C::D, NN = C::NN, NB = C::NB, NXI = C::NXI;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (e < a.mesh.n_elems) {
+    Elem<C> E;
+    load_elem<C>(a.mesh, a.model, a.x, a.x_prev, a.xi_prev, a.xi_ld, e, E);
+    const double wdv = quad1_weight<D>() * E.g.dv;
+    if (mode == 0 && a.qoi.type == QOI_AVG_DISP) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double u = 0.0;
+#pragma unroll
+        for (int n = 0; n < NN; ++n) u += E.xn[n][i] * (1.0 / NN);
+        s += u * wdv;
+      }
+      v = s / D;
+    } else if (mode == 0) {
+      const bool in_obj = (D == 2) || (a.qoi.facet && a.qoi.facet[size_t(e) * 3] >= 0);
+      if (in_obj) {
+        double un[NN][D], um[NN][D], X[NN][D];
+#pragma unroll
+        for (int n = 0; n < NN; ++n)
+#pragma unroll
+          for (int i = 0; i < D; ++i) un[n][i] = E.xn[n][i];
+        load_measured<C>(a.qoi, E, um, X, a.mesh.coords);
+        const signed char* fv = (D == 3) ? &a.qoi.facet[size_t(e) * 3] : nullptr;
+        v = calibration_disp_mismatch<D, double>(a.qoi, un, um, X, E.g.dv, fv);
+      }
+    } else {
+      const int nmask = load_node_mask<D>(a.qoi, a.mesh.coords, E.nodes);
+      if (nmask) {
+        double xi[NXI];
+#pragma unroll
+        for (int q = 0; q < NXI; ++q) xi[q] = __ldg(&a.xi[size_t(q) * a.xi_ld + e]);
+        Kin<D, double, double> k0;
+        k0.gu = grad_u_val<D, NB>(E.xn, E.g);
+        k0.gup = grad_u_val<D, NB>(E.xpn, E.g);
+        double p0 = 0.0;
+        if constexpr (C::M == MECH_MIXED) {
+#pragma unroll
+          for (int n = 0; n < NN; ++n) p0 += E.xn[n][D] * (1.0 / NN);
+        }
+        const Mat<double, D> P = first_pk<D, C::M, Model>(k0, p0, xi, E.par, a.model.thickness);
+        v = calibration_load<D>(a.qoi, P, E.g, wdv, nmask);
+      }
+    }
+  }
+  __shared__ double sh[4];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(&a.scalars[mode], sh[0] + sh[1] + sh[2] + sh[3]);
+}
+
+}  // namespace c8

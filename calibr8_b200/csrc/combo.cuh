@@ -1,6 +1,6 @@
 // Instantiates every kernel of the hot path for one (DIM, MECH, Model, G) combination.
 #pragma once
-#include "forward.cuh"
+#include "adjoint.cuh"
 #include "kernel_table.h"
 
 namespace c8 {
@@ -32,6 +32,25 @@ struct Launch {
     if (n_elems == 0) return;
     k_init_xi<C><<<(n_elems + 255) / 256, 256, 0, s>>>(xi, xi_ld, n_elems);
   }
+  static void adjoint_jacobian(const AdjArgs& a, cudaStream_t s) {
+    if (a.mesh.n_elems == 0) return;
+    const long long threads = (long long)a.mesh.n_elems * C::G;
+    k_adjoint_jacobian<C><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(a);
+  }
+  static void adjoint_local(const AdjArgs& a, cudaStream_t s) {
+    if (a.mesh.n_elems == 0) return;
+    const long long threads = (long long)a.mesh.n_elems * C::G;
+    k_adjoint_local<C><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(a);
+  }
+  static void qoi_gradient(const AdjArgs& a, cudaStream_t s) {
+    if (a.mesh.n_elems == 0) return;
+    const long long threads = (long long)a.mesh.n_elems * C::G;
+    k_qoi_gradient<C><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(a);
+  }
+  static void qoi_value(const AdjArgs& a, int mode, cudaStream_t s) {
+    if (a.mesh.n_elems == 0) return;
+    k_qoi_value<C><<<(a.mesh.n_elems + 127) / 128, 128, 0, s>>>(a, mode);
+  }
   static KernelTable table() {
     KernelTable t;
     t.dim = C::D; t.mech = C::M; t.local_type = C::Model::TYPE;
@@ -40,6 +59,10 @@ struct Launch {
     t.forward_jacobian = &forward_jacobian;
     t.global_residual = &global_residual;
     t.init_xi = &init_xi;
+    t.adjoint_jacobian = &adjoint_jacobian;
+    t.adjoint_local = &adjoint_local;
+    t.qoi_gradient = &qoi_gradient;
+    t.qoi_value = &qoi_value;
     return t;
   }
 };

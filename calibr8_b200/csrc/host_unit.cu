@@ -1,0 +1,2 @@
+// Builds the C++ host layer (calibr8_b200/host) into libc8b200.so.
+#include "../host/host.cu"

@@ -3,6 +3,7 @@
 // (combo_*.cu) and looked up by the C-ABI context at c8_set_model time.
 #pragma once
 #include "args.h"
+#include "adj_args.h"
 
 namespace c8 {
 
@@ -13,6 +14,10 @@ struct KernelTable {
   void (*forward_jacobian)(const FwdArgs&, cudaStream_t);
   void (*global_residual)(const FwdArgs&, cudaStream_t);
   void (*init_xi)(double* xi, long long xi_ld, int n_elems, cudaStream_t);
+  void (*adjoint_jacobian)(const AdjArgs&, cudaStream_t);
+  void (*adjoint_local)(const AdjArgs&, cudaStream_t);
+  void (*qoi_gradient)(const AdjArgs&, cudaStream_t);
+  void (*qoi_value)(const AdjArgs&, int mode, cudaStream_t);
 };
 
 const KernelTable* find_kernel_table(int dim, int mech, int local_type);

@@ -1,0 +1,136 @@
+// Host-side mirror of calibr8's step solvers and objective for the hot path, in C++, ABOVE the
+// C ABI of include/c8b200.h (every device operation goes through a c8_* entry point).
+//
+//   Problem   <- State / Disc time + BC + QoI settings   src/state.cpp:33-46, src/disc.cpp:136-155
+//   Primal    <- Primal::solve_at_step                    src/primal.cpp:31-208 (+ line_search.hpp)
+//   Adjoint   <- Adjoint::solve_at_step + Adjoint_Objective::gradient
+//                                                         src/adjoint.cpp:76-189, adjoint_objective.cpp:48-118
+// The all-steps primal history (x[step], xi[step]) stays resident on the device for the reverse
+// sweep, like the apf fields of Disc::primal(step) in the reference (src/disc.cpp:643-683).
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "c8b200.h"
+#include "expr.hpp"
+
+namespace c8host {
+
+struct Dbc {  // "bc name: [resid_idx, eq, node_set_name, value]", src/dbcs.cpp:56-66
+  int resid, eq;
+  std::vector<int> nodes;
+  Expr expr;
+};
+
+struct SolverParams {
+  int newton_max_iters = 15;           // "nonlinear max iters"
+  double newton_abs_tol = 1e-8;        // "nonlinear absolute tol"
+  double newton_rel_tol = 1e-8;        // "nonlinear relative tol"
+  int gmres_restart = 100;
+  int gmres_max_iters = 4000;
+  double linear_tol = 1e-10;           // Belos "Convergence Tolerance" (relative)
+  // line search, src/line_search.hpp:24-31
+  double ls_c1 = 1e-4, ls_bmin = 0.5, ls_bmax = 0.9;
+  int ls_max_evals = 4;
+  bool print = false;
+};
+
+struct CalibrationQoi {
+  bool enabled = false;
+  double balance_factor = 1., coord_value = 0., coord_tol = 1e-12;
+  int coord_idx = -1, reaction_force_comp = -1;
+  double weights[3] = {1., 1., 1.};
+  std::vector<double> load_data;           // measured load per step ("load input file")
+  std::vector<double*> d_measured;         // per step (1..N) device [n_nodes][dim]
+  signed char* d_facet = nullptr;          // 3-D side-set facets
+  double area = 1.;
+};
+
+class DevVec {  // RAII device array
+ public:
+  DevVec() {}
+  explicit DevVec(size_t n) { resize(n); }
+  ~DevVec() { if (p_) cudaFree(p_); }
+  DevVec(const DevVec&) = delete;
+  DevVec& operator=(const DevVec&) = delete;
+  DevVec(DevVec&& o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+  void resize(size_t n) {
+    if (p_) cudaFree(p_);
+    p_ = nullptr; n_ = n;
+    if (n && cudaMalloc(&p_, n * sizeof(double)) != cudaSuccess) throw std::runtime_error("cudaMalloc");
+    if (n) cudaMemset(p_, 0, n * sizeof(double));
+  }
+  double* get() const { return p_; }
+  size_t size() const { return n_; }
+ private:
+  double* p_ = nullptr;
+  size_t n_ = 0;
+};
+
+class Problem {
+ public:
+  explicit Problem(c8_ctx* ctx);
+  ~Problem();
+  void check(int rc, const char* what) const;
+
+  c8_ctx* ctx;
+  int dim, nn, nb, nx, nxi, npar, n_elems, n_nodes, nnzb;
+  long long n_dofs, xi_ld;
+  std::vector<double> coords;  // [n_nodes][3] host copy for BC expressions
+  int num_steps = 0;
+  double step_size = 1.;
+  std::vector<Dbc> dbcs;
+  SolverParams sp;
+  int qoi_type = 0;  // 0 average displacement, 1 calibration
+  CalibrationQoi cal;
+
+  // history (device)
+  std::vector<DevVec> x, xi;   // [0..num_steps]
+  std::vector<DevVec> z, phi;  // adjoint fields per step
+  DevVec A, b, dx, Adx, saved_xi, work;
+  // flattened Dirichlet dofs
+  int n_dbc = 0;
+  int* d_dbc_node = nullptr;
+  int* d_dbc_eq = nullptr;
+  double* d_dbc_val = nullptr;
+  std::vector<double> h_dbc_val;
+  int n_assemblies = 0, n_linear_iters = 0;
+
+  double time(int step) const { return step * step_size; }
+  void set_time(int n_steps, double dt);
+  void add_dbc(int resid, int eq, const int* nodes, int n, const std::string& expr);
+  void finalize_dbcs();
+  void eval_dbc_values(double t);
+  void allocate_history();
+  double norm(const double* v) const;
+  double dot(const double* a, const double* c) const;
+  void axpy(double a, const double* xsrc, double* y) const;  // y += a x
+};
+
+class Primal {
+ public:
+  explicit Primal(Problem& p) : P(p) {}
+  void solve_at_step(int step);
+  double eval_qoi(int step);   // eval_qoi, src/evaluations.cpp:662-756
+  double solve_all();          // Solver::solve, src/main_primal.cpp:221-243
+ private:
+  bool assemble(int step, double* R_norm);  // K1 + DBC; false = local solve failed
+  Problem& P;
+};
+
+class Adjoint {
+ public:
+  explicit Adjoint(Problem& p) : P(p) {}
+  // Adjoint_Objective::gradient's reverse sweep: d J / d p for EVERY model parameter of
+  // element set 0..n_es-1 (the caller selects the active ones); grad [n_es][npar]
+  void gradient(std::vector<double>& grad);
+ private:
+  Problem& P;
+};
+
+}  // namespace c8host

@@ -1,0 +1,411 @@
+// Host-side step solvers above the C ABI (see calibr8_host.hpp) and their C driver API
+// (c8h_*) used by Python tests / bench through ctypes.
+#include "calibr8_host.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <limits>
+
+namespace c8host {
+
+#define C8H_CUDA(call)                                                          \
+  do {                                                                          \
+    cudaError_t e_ = (call);                                                    \
+    if (e_ != cudaSuccess)                                                      \
+      throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+Problem::Problem(c8_ctx* c) : ctx(c) {
+  int64_t info[12];
+  check(c8_info(ctx, info), "c8_info");
+  dim = int(info[0]); nn = int(info[1]); nb = int(info[2]); nx = int(info[3]); nxi = int(info[4]);
+  npar = int(info[5]); n_elems = int(info[6]); n_nodes = int(info[7]); nnzb = int(info[8]);
+  n_dofs = info[9]; xi_ld = info[11];
+  coords.resize(size_t(n_nodes) * 3);
+  c8_get_coords(ctx, coords.data());
+  A.resize(size_t(nnzb) * nb * nb);
+  b.resize(n_dofs); dx.resize(n_dofs); Adx.resize(n_dofs); work.resize(n_dofs);
+  saved_xi.resize(size_t(xi_ld) * nxi);
+}
+
+Problem::~Problem() {
+  if (d_dbc_node) cudaFree(d_dbc_node);
+  if (d_dbc_eq) cudaFree(d_dbc_eq);
+  if (d_dbc_val) cudaFree(d_dbc_val);
+  for (double* p : cal.d_measured) if (p) cudaFree(p);
+  if (cal.d_facet) cudaFree(cal.d_facet);
+}
+
+void Problem::check(int rc, const char* what) const {
+  if (rc != C8_OK) throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) +
+                                            "): " + c8_last_error(ctx));
+}
+
+void Problem::set_time(int n_steps, double dt) { num_steps = n_steps; step_size = dt; }
+
+void Problem::add_dbc(int resid, int eq, const int* nodes, int n, const std::string& expr) {
+  Dbc d{resid, eq, std::vector<int>(nodes, nodes + n), Expr(expr)};
+  dbcs.push_back(std::move(d));
+}
+
+void Problem::finalize_dbcs() {
+  std::vector<int> node, eq;
+  for (const Dbc& d : dbcs)
+    for (int nd : d.nodes) {
+      node.push_back(nd);
+      eq.push_back(d.resid == 0 ? d.eq : dim);  // residual 1 = pressure -> interleaved eq index dim
+    }
+  n_dbc = int(node.size());
+  h_dbc_val.assign(n_dbc, 0.0);
+  if (d_dbc_node) { cudaFree(d_dbc_node); cudaFree(d_dbc_eq); cudaFree(d_dbc_val); }
+  d_dbc_node = d_dbc_eq = nullptr; d_dbc_val = nullptr;
+  if (!n_dbc) return;
+  C8H_CUDA(cudaMalloc(&d_dbc_node, n_dbc * sizeof(int)));
+  C8H_CUDA(cudaMalloc(&d_dbc_eq, n_dbc * sizeof(int)));
+  C8H_CUDA(cudaMalloc(&d_dbc_val, n_dbc * sizeof(double)));
+  C8H_CUDA(cudaMemcpy(d_dbc_node, node.data(), n_dbc * sizeof(int), cudaMemcpyHostToDevice));
+  C8H_CUDA(cudaMemcpy(d_dbc_eq, eq.data(), n_dbc * sizeof(int), cudaMemcpyHostToDevice));
+}
+
+void Problem::eval_dbc_values(double t) {
+  size_t k = 0;
+  for (const Dbc& d : dbcs)
+    for (int nd : d.nodes) {
+      const double* X = &coords[size_t(nd) * 3];
+      h_dbc_val[k++] = d.expr(X[0], X[1], X[2], t);
+    }
+  if (n_dbc)
+    C8H_CUDA(cudaMemcpy(d_dbc_val, h_dbc_val.data(), n_dbc * sizeof(double), cudaMemcpyHostToDevice));
+}
+
+void Problem::allocate_history() {
+  x.clear(); xi.clear(); z.clear(); phi.clear();
+  for (int s = 0; s <= num_steps; ++s) {
+    x.emplace_back(size_t(n_dofs));
+    xi.emplace_back(size_t(xi_ld) * nxi);
+  }
+  check(c8_init_xi(ctx, xi[0].get()), "c8_init_xi");
+  check(c8_synchronize(ctx), "sync");
+}
+
+double Problem::dot(const double* a, const double* c) const {
+  double v = 0.0;
+  check(c8_dot(ctx, a, c, &v), "c8_dot");
+  return v;
+}
+double Problem::norm(const double* v) const { return std::sqrt(dot(v, v)); }
+void Problem::axpy(double a, const double* xs, double* y) const {
+  check(c8_axpby(ctx, a, xs, 1.0, y, n_dofs), "c8_axpby");
+}
+
+// ---------------------------------------------------------------------------------------------
+static c8_qoi make_qoi(const Problem& P, int step, double load_mismatch) {
+  c8_qoi q{};
+  q.type = P.qoi_type;
+  if (P.qoi_type == 1) {
+    for (int k = 0; k < 3; ++k) q.weights[k] = P.cal.weights[k];
+    q.balance_factor = P.cal.balance_factor;
+    q.dt_over_T = P.step_size / (P.num_steps * P.step_size);
+    q.inv_area = 1.0 / P.cal.area;
+    q.load_mismatch = load_mismatch;
+    q.coord_idx = P.cal.coord_idx;
+    q.coord_value = P.cal.coord_value;
+    q.coord_tol = P.cal.coord_tol;
+    q.reaction_force_comp = P.cal.reaction_force_comp;
+    q.measured_dev = (step >= 1 && step <= int(P.cal.d_measured.size())) ? P.cal.d_measured[step - 1] : nullptr;
+    q.facet_dev = (const int8_t*)P.cal.d_facet;
+  }
+  return q;
+}
+
+// preprocess_qoi + preprocess_finalize: total load on the plane -> load mismatch of the step
+static double preprocess_load_mismatch(Problem& P, int step, double* total_load_out = nullptr) {
+  if (P.qoi_type != 1) return 0.0;
+  c8_qoi q = make_qoi(P, step, 0.0);
+  cudaStream_t s = (cudaStream_t)c8_get_stream(P.ctx);
+  C8H_CUDA(cudaMemsetAsync(P.work.get(), 0, 2 * sizeof(double), s));
+  P.check(c8_qoi_value(P.ctx, &q, P.x[step].get(), P.x[step - 1].get(), P.xi[step].get(),
+                       P.xi[step - 1].get(), 1, P.work.get()), "c8_qoi_value(load)");
+  double h[2];
+  C8H_CUDA(cudaMemcpyAsync(h, P.work.get(), 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  C8H_CUDA(cudaStreamSynchronize(s));
+  const double meas = (step - 1 < int(P.cal.load_data.size())) ? P.cal.load_data[step - 1] : 0.0;
+  if (total_load_out) *total_load_out = h[1];
+  return h[1] - meas;
+}
+
+bool Primal::assemble(int step, double* R_norm) {
+  cudaStream_t s = (cudaStream_t)c8_get_stream(P.ctx);
+  C8H_CUDA(cudaMemsetAsync(P.A.get(), 0, P.A.size() * sizeof(double), s));
+  C8H_CUDA(cudaMemsetAsync(P.b.get(), 0, P.b.size() * sizeof(double), s));
+  int nf = 0;
+  const int rc = c8_forward_jacobian(P.ctx, P.x[step].get(), P.x[step - 1].get(),
+                                     P.xi[step - 1].get(), P.xi[step].get(), P.A.get(), P.b.get(),
+                                     nullptr, &nf);
+  ++P.n_assemblies;
+  if (rc == C8_ERR_LOCAL_SOLVE) return false;
+  P.check(rc, "c8_forward_jacobian");
+  P.check(c8_apply_dbc(P.ctx, P.A.get(), P.b.get(), P.x[step].get(), P.d_dbc_node, P.d_dbc_eq,
+                       P.d_dbc_val, P.n_dbc, 0), "c8_apply_dbc");
+  *R_norm = P.norm(P.b.get());
+  return true;
+}
+
+static double cubic_min(double phi_0, double dphi_0, double a, double phi, double slope_a) {
+  const double d1 = dphi_0 + slope_a - 3. * (phi_0 - phi) / (0. - a);
+  const double radicand = d1 * d1 - dphi_0 * slope_a;
+  if (radicand < 0.) return 0.5 * a;
+  const double d2 = std::sqrt(radicand);
+  const double denom = slope_a - dphi_0 + 2. * d2;
+  if (denom == 0.) return 0.5 * a;
+  return a - a * (slope_a + d2 - d1) / denom;
+}
+
+void Primal::solve_at_step(int step) {
+  cudaStream_t s = (cudaStream_t)c8_get_stream(P.ctx);
+  const size_t xb = P.n_dofs * sizeof(double), xib = size_t(P.xi_ld) * P.nxi * sizeof(double);
+  // create_primal(step): copy of step-1 (src/disc.cpp:643-683)
+  C8H_CUDA(cudaMemcpyAsync(P.x[step].get(), P.x[step - 1].get(), xb, cudaMemcpyDeviceToDevice, s));
+  C8H_CUDA(cudaMemcpyAsync(P.xi[step].get(), P.xi[step - 1].get(), xib, cudaMemcpyDeviceToDevice, s));
+  P.eval_dbc_values(P.time(step));
+  int iter = 1;
+  bool converged = false;
+  double resid_norm_0 = 1.;
+  const SolverParams& sp = P.sp;
+  while (iter <= sp.newton_max_iters && !converged) {
+    double rn = 0.;
+    if (!assemble(step, &rn))
+      throw std::runtime_error("primal: local solve failed at the base point (step " +
+                               std::to_string(step) + ")");
+    if (iter == 1) resid_norm_0 = rn;
+    const double rel = rn / resid_norm_0;
+    if (sp.print) std::printf("  step %d it %d |R| = %.6e rel %.3e\n", step, iter, rn, rel);
+    if (rn < sp.newton_abs_tol || rel < sp.newton_rel_tol) { converged = true; break; }
+    // solve A dx = -R
+    P.check(c8_axpby(P.ctx, -1.0, P.b.get(), 0.0, P.work.get(), P.n_dofs), "scale_b");
+    C8H_CUDA(cudaMemsetAsync(P.dx.get(), 0, xb, s));
+    double info[3];
+    int rc = c8_gmres(P.ctx, P.A.get(), P.work.get(), P.dx.get(), sp.gmres_restart, sp.gmres_max_iters,
+                      sp.linear_tol, 0.0, info);
+    P.n_linear_iters += int(info[0]);
+    if (rc != C8_OK && rc != C8_ERR_NOT_CONVERGED) P.check(rc, "c8_gmres");
+    if (sp.print) std::printf("    gmres its %d |r| %.3e -> %.3e\n", int(info[0]), info[2], info[1]);
+    P.axpy(1.0, P.dx.get(), P.x[step].get());  // add_to_soln
+    // line search (src/primal.cpp:141-201, src/line_search.hpp:85-135)
+    const double psi_0 = 0.5 * rn * rn, dpsi_0 = -2. * psi_0;
+    C8H_CUDA(cudaMemcpyAsync(P.saved_xi.get(), P.xi[step].get(), xib, cudaMemcpyDeviceToDevice, s));
+    double alpha_applied = 1.;
+    auto eval = [&](double alpha, double& phi, double& slope) -> bool {
+      C8H_CUDA(cudaMemcpyAsync(P.xi[step].get(), P.saved_xi.get(), xib, cudaMemcpyDeviceToDevice, s));
+      P.axpy(alpha - alpha_applied, P.dx.get(), P.x[step].get());
+      alpha_applied = alpha;
+      double ra = 0.;
+      if (!assemble(step, &ra)) return false;
+      phi = 0.5 * ra * ra;
+      P.check(c8_spmv(P.ctx, P.A.get(), P.dx.get(), P.Adx.get()), "c8_spmv");
+      slope = P.dot(P.b.get(), P.Adx.get());
+      return true;
+    };
+    const double armijo = sp.ls_c1 * dpsi_0;
+    double alpha = 1., best_alpha = 1., best_phi = std::numeric_limits<double>::max();
+    bool assembled_any = false, accepted = false;
+    for (int n = 1; n <= sp.ls_max_evals; ++n) {
+      double phi, slope;
+      if (!eval(alpha, phi, slope)) { alpha *= 0.5; continue; }
+      assembled_any = true;
+      if (phi < best_phi) { best_phi = phi; best_alpha = alpha; }
+      if (phi <= psi_0 + alpha * armijo) { accepted = true; break; }
+      const double am = cubic_min(psi_0, dpsi_0, alpha, phi, slope);
+      alpha = std::min(std::max(am, sp.ls_bmin * alpha), sp.ls_bmax * alpha);
+    }
+    if (!assembled_any) throw std::runtime_error("primal: line search could not assemble");
+    const double a_final = accepted ? alpha : best_alpha;
+    P.axpy(a_final - alpha_applied, P.dx.get(), P.x[step].get());
+    ++iter;
+  }
+  if (!converged) throw std::runtime_error("Newton's method failed in " +
+                                           std::to_string(sp.newton_max_iters) + " iterations");
+}
+
+double Primal::eval_qoi(int step) {
+  cudaStream_t s = (cudaStream_t)c8_get_stream(P.ctx);
+  const double mismatch = preprocess_load_mismatch(P, step);
+  c8_qoi q = make_qoi(P, step, mismatch);
+  C8H_CUDA(cudaMemsetAsync(P.work.get(), 0, 2 * sizeof(double), s));
+  P.check(c8_qoi_value(P.ctx, &q, P.x[step].get(), P.x[step - 1].get(), P.xi[step].get(),
+                       P.xi[step - 1].get(), 0, P.work.get()), "c8_qoi_value");
+  double h[2];
+  C8H_CUDA(cudaMemcpyAsync(h, P.work.get(), 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  C8H_CUDA(cudaStreamSynchronize(s));
+  double J = h[0];
+  if (P.qoi_type == 1)  // Calibration::postprocess, src/calibration.cpp:373-393 (single rank)
+    J += 0.5 * P.cal.balance_factor * q.dt_over_T * mismatch * mismatch;
+  return J;
+}
+
+double Primal::solve_all() {
+  P.allocate_history();
+  double J = 0.;
+  for (int step = 1; step <= P.num_steps; ++step) {
+    solve_at_step(step);
+    J += eval_qoi(step);
+  }
+  return J;
+}
+
+// ---------------------------------------------------------------------------------------------
+void Adjoint::gradient(std::vector<double>& grad) {
+  cudaStream_t s = (cudaStream_t)c8_get_stream(P.ctx);
+  const int N = P.num_steps;
+  const SolverParams& sp = P.sp;
+  const size_t xb = P.n_dofs * sizeof(double);
+  DevVec g(size_t(P.xi_ld) * P.nxi), f(size_t(P.xi_ld) * P.nx), rhs(P.n_dofs), d_grad(64);
+  P.z.clear(); P.phi.clear();
+  for (int k = 0; k <= N; ++k) { P.z.emplace_back(size_t(P.n_dofs)); P.phi.emplace_back(size_t(P.xi_ld) * P.nxi); }
+  int n_es = 1;
+  grad.assign(size_t(n_es) * P.npar, 0.0);
+  for (int step = N; step >= 1; --step) {
+    const double mismatch = preprocess_load_mismatch(P, step);
+    c8_qoi q = make_qoi(P, step, mismatch);
+    const double *x = P.x[step].get(), *xp = P.x[step - 1].get(), *xi = P.xi[step].get(),
+                 *xip = P.xi[step - 1].get();
+    C8H_CUDA(cudaMemsetAsync(P.A.get(), 0, P.A.size() * sizeof(double), s));
+    C8H_CUDA(cudaMemsetAsync(rhs.get(), 0, xb, s));
+    P.check(c8_adjoint_jacobian(P.ctx, &q, x, xp, xi, xip, g.get(), f.get(), P.A.get(), rhs.get()),
+            "c8_adjoint_jacobian");
+    double* z = P.z[step].get();
+    P.check(c8_apply_dbc(P.ctx, P.A.get(), rhs.get(), z, P.d_dbc_node, P.d_dbc_eq, P.d_dbc_val,
+                         P.n_dbc, 1), "c8_apply_dbc(adjoint)");
+    // iterative refinement of the linear adjoint solve, src/adjoint.cpp:113-180
+    int iter = 1;
+    double r0 = 1.;
+    while (true) {
+      C8H_CUDA(cudaMemsetAsync(P.dx.get(), 0, xb, s));
+      double info[3];
+      int rc = c8_gmres(P.ctx, P.A.get(), rhs.get(), P.dx.get(), sp.gmres_restart,
+                        sp.gmres_max_iters, 0.1 * sp.newton_rel_tol, 0.0, info);
+      P.n_linear_iters += int(info[0]);
+      if (rc != C8_OK && rc != C8_ERR_NOT_CONVERGED) P.check(rc, "c8_gmres(adjoint)");
+      P.axpy(1.0, P.dx.get(), z);
+      P.check(c8_spmv(P.ctx, P.A.get(), P.dx.get(), P.Adx.get()), "c8_spmv");
+      P.axpy(-1.0, P.Adx.get(), rhs.get());
+      const double rn = P.norm(rhs.get());
+      if (iter == 1) r0 = rn;
+      if (rn < sp.newton_abs_tol || (r0 > 0 && rn / r0 < sp.newton_rel_tol)) break;
+      if (++iter > sp.newton_max_iters) throw std::runtime_error("adjoint solve failed to converge");
+    }
+    P.check(c8_adjoint_local(P.ctx, x, xp, xi, xip, z, P.phi[step].get(), g.get(), f.get()),
+            "c8_adjoint_local");
+    C8H_CUDA(cudaMemsetAsync(d_grad.get(), 0, 64 * sizeof(double), s));
+    P.check(c8_qoi_gradient(P.ctx, &q, x, xp, xi, xip, z, P.phi[step].get(), d_grad.get()),
+            "c8_qoi_gradient");
+    double h[64];
+    C8H_CUDA(cudaMemcpyAsync(h, d_grad.get(), 64 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    C8H_CUDA(cudaStreamSynchronize(s));
+    for (int k = 0; k < n_es * P.npar; ++k) grad[k] += h[k];
+  }
+}
+
+}  // namespace c8host
+
+// =============================================================================================
+// C driver API over the host classes (for ctypes)
+using namespace c8host;
+
+struct c8h_problem {
+  Problem P;
+  std::string err;
+  explicit c8h_problem(c8_ctx* ctx) : P(ctx) {}
+};
+
+#define C8H_TRY(h, body)                                  \
+  try { body; return 0; }                                 \
+  catch (const std::exception& ex) { (h)->err = ex.what(); return -1; }
+
+extern "C" {
+
+c8h_problem* c8h_create(c8_ctx* ctx) {
+  try { return new c8h_problem(ctx); } catch (...) { return nullptr; }
+}
+void c8h_destroy(c8h_problem* h) { delete h; }
+const char* c8h_last_error(c8h_problem* h) { return h->err.c_str(); }
+
+int c8h_set_time(c8h_problem* h, int num_steps, double step_size) {
+  C8H_TRY(h, h->P.set_time(num_steps, step_size));
+}
+int c8h_add_dbc(c8h_problem* h, int resid, int eq, const int32_t* nodes, int n, const char* expr) {
+  C8H_TRY(h, h->P.add_dbc(resid, eq, nodes, n, expr));
+}
+int c8h_finalize_dbcs(c8h_problem* h) { C8H_TRY(h, h->P.finalize_dbcs()); }
+int c8h_set_solver(c8h_problem* h, int newton_max_iters, double abs_tol, double rel_tol,
+                   int gmres_restart, int gmres_max_iters, double linear_tol, int print) {
+  SolverParams& s = h->P.sp;
+  s.newton_max_iters = newton_max_iters; s.newton_abs_tol = abs_tol; s.newton_rel_tol = rel_tol;
+  s.gmres_restart = gmres_restart; s.gmres_max_iters = gmres_max_iters; s.linear_tol = linear_tol;
+  s.print = print != 0;
+  return 0;
+}
+int c8h_set_qoi_avg_disp(c8h_problem* h) { h->P.qoi_type = 0; return 0; }
+// measured_host: [num_steps][n_nodes][dim]; load_data [num_steps]; facet_host [n_elems][3] or NULL
+int c8h_set_qoi_calibration(c8h_problem* h, double balance_factor, int coord_idx,
+                            double coord_value, double coord_tol, int reaction_force_comp,
+                            const double* weights, const double* measured_host,
+                            const double* load_data, const int8_t* facet_host, double area) {
+  C8H_TRY(h, {
+    Problem& P = h->P;
+    P.qoi_type = 1;
+    CalibrationQoi& c = P.cal;
+    c.enabled = true;
+    c.balance_factor = balance_factor; c.coord_idx = coord_idx; c.coord_value = coord_value;
+    c.coord_tol = coord_tol; c.reaction_force_comp = reaction_force_comp; c.area = area;
+    for (int k = 0; k < 3; ++k) c.weights[k] = weights ? weights[k] : 1.0;
+    c.load_data.assign(load_data, load_data + P.num_steps);
+    for (double* p : c.d_measured) if (p) cudaFree(p);
+    c.d_measured.assign(P.num_steps, nullptr);
+    const size_t nm = size_t(P.n_nodes) * P.dim;
+    for (int s = 0; s < P.num_steps; ++s) {
+      C8H_CUDA(cudaMalloc(&c.d_measured[s], nm * sizeof(double)));
+      C8H_CUDA(cudaMemcpy(c.d_measured[s], measured_host + size_t(s) * nm, nm * sizeof(double),
+                          cudaMemcpyHostToDevice));
+    }
+    if (c.d_facet) { cudaFree(c.d_facet); c.d_facet = nullptr; }
+    if (facet_host) {
+      C8H_CUDA(cudaMalloc(&c.d_facet, size_t(P.n_elems) * 3));
+      C8H_CUDA(cudaMemcpy(c.d_facet, facet_host, size_t(P.n_elems) * 3, cudaMemcpyHostToDevice));
+    }
+  });
+}
+
+int c8h_primal_solve(c8h_problem* h, double* J_out) {
+  C8H_TRY(h, { Primal pr(h->P); *J_out = pr.solve_all(); });
+}
+int c8h_adjoint_gradient(c8h_problem* h, double* grad_out /* [npar] */) {
+  C8H_TRY(h, {
+    Adjoint ad(h->P);
+    std::vector<double> g;
+    ad.gradient(g);
+    std::memcpy(grad_out, g.data(), g.size() * sizeof(double));
+  });
+}
+// host copies of the stored history: u [n_nodes*dim], p [n_nodes] (or NULL), xi [n_elems][nxi]
+int c8h_get_step(c8h_problem* h, int step, double* u, double* p, double* xi) {
+  C8H_TRY(h, {
+    Problem& P = h->P;
+    if (u) P.check(c8_unpack_x(P.ctx, P.x[step].get(), u, p), "c8_unpack_x");
+    if (xi) P.check(c8_unpack_xi(P.ctx, P.xi[step].get(), xi), "c8_unpack_xi");
+  });
+}
+int c8h_get_adjoint_step(c8h_problem* h, int step, double* zu, double* zp, double* phi) {
+  C8H_TRY(h, {
+    Problem& P = h->P;
+    if (zu) P.check(c8_unpack_x(P.ctx, P.z[step].get(), zu, zp), "c8_unpack_x");
+    if (phi) P.check(c8_unpack_xi(P.ctx, P.phi[step].get(), phi), "c8_unpack_xi");
+  });
+}
+int c8h_stats(c8h_problem* h, int* n_assemblies, int* n_linear_iters) {
+  *n_assemblies = h->P.n_assemblies;
+  *n_linear_iters = h->P.n_linear_iters;
+  return 0;
+}
+
+}  // extern "C"

@@ -125,6 +125,61 @@ int c8_state_get_xi(c8_ctx* ctx, double* xi_host);
 int c8_state_ptrs(c8_ctx* ctx, double** x_dev, double** x_prev_dev, double** xi_dev,
                   double** xi_prev_dev, double** A_vals_dev, double** b_dev);
 
+/* ---- adjoint pass and objective integrands ----
+ * QoI description (QoI<T> of the reference; type 0 = "average displacement" avg_disp.cpp:15-33,
+ * type 1 = "calibration" calibration.cpp:414-478).  NULL = average displacement. */
+typedef struct c8_qoi {
+  int type;
+  double weights[3];        /* "displacement weights" */
+  double balance_factor;    /* "balance factor" */
+  double dt_over_T;         /* step size / total time */
+  double inv_area;          /* 1 / objective area */
+  double load_mismatch;     /* total load - measured load of the step (after the preprocess pass) */
+  int coord_idx;            /* "coordinate index" of the load plane */
+  double coord_value, coord_tol;
+  int reaction_force_comp;  /* "reaction force component" */
+  const double* measured_dev;  /* [n_nodes][dim] measured displacement of the step */
+  const int8_t* facet_dev;     /* 3-D: [n_elems][3] local vertex ids of the side-set facet or -1 */
+} c8_qoi;
+
+/* History arrays: g [nxi][xi_ld], f [nx][xi_ld] (element dofs node-interleaved), phi [nxi][xi_ld]. */
+/* eval_adjoint_jacobian, evaluations.cpp:349-526: AT_vals += dR/dx_total^T, rhs +=, g -= dJ/dxi */
+int c8_adjoint_jacobian(c8_ctx* ctx, const c8_qoi* qoi, const double* x_dev,
+                        const double* x_prev_dev, const double* xi_dev, const double* xi_prev_dev,
+                        double* g_dev, const double* f_dev, double* AT_vals_dev, double* rhs_dev);
+/* solve_adjoint_local, evaluations.cpp:528-659: phi, then f and g of the previous step */
+int c8_adjoint_local(c8_ctx* ctx, const double* x_dev, const double* x_prev_dev,
+                     const double* xi_dev, const double* xi_prev_dev, const double* z_dev,
+                     double* phi_dev, double* g_dev, double* f_dev);
+/* eval_qoi / preprocess_qoi, evaluations.cpp:662-756, 261-347.  mode 0: scalars_dev[0] += sum of
+ * the per-point QoI; mode 1: scalars_dev[1] += load on the coordinate plane (calibration) */
+int c8_qoi_value(c8_ctx* ctx, const c8_qoi* qoi, const double* x_dev, const double* x_prev_dev,
+                 const double* xi_dev, const double* xi_prev_dev, int mode, double* scalars_dev);
+/* eval_qoi_gradient, evaluations.cpp:758-925: grad_dev [n_elem_sets][npar] += derivative w.r.t.
+ * every model parameter (the caller selects the active ones) */
+int c8_qoi_gradient(c8_ctx* ctx, const c8_qoi* qoi, const double* x_dev, const double* x_prev_dev,
+                    const double* xi_dev, const double* xi_prev_dev, const double* z_dev,
+                    const double* phi_dev, double* grad_dev);
+
+/* ---- global linear algebra on the device (replaces linear_alg.cpp / linear_solve.cpp) ---- */
+#define C8_ERR_NOT_CONVERGED (-4)
+int c8_spmv(c8_ctx* ctx, const double* A_vals_dev, const double* x_dev, double* y_dev);
+int c8_dot(c8_ctx* ctx, const double* x_dev, const double* y_dev, double* out_host);
+int c8_axpby(c8_ctx* ctx, double a, const double* x_dev, double b, double* y_dev, int64_t n);
+/* apply_expression_primal_dbcs, dbcs.cpp:28-121: per constrained dof (node, eq) zero the row, keep
+ * the diagonal, R = diag*(x - value) (adjoint: R = 0) */
+int c8_apply_dbc(c8_ctx* ctx, double* A_vals_dev, double* R_dev, const double* x_dev,
+                 const int32_t* dbc_node_dev, const int32_t* dbc_eq_dev, const double* dbc_val_dev,
+                 int n_dbc, int is_adjoint);
+/* restarted GMRES(m) + block-Jacobi; info_host[3] = iterations, final |r|, initial |r| */
+int c8_gmres(c8_ctx* ctx, const double* A_vals_dev, const double* b_dev, double* x_dev,
+             int restart, int max_iters, double rel_tol, double abs_tol, double* info_host);
+void c8_linalg_release(c8_ctx* ctx);
+
+int c8_get_coords(c8_ctx* ctx, double* coords_host /* [n_nodes][3] */);
+int c8_get_conn(c8_ctx* ctx, int32_t* conn_host);
+void* c8_get_stream(c8_ctx* ctx);
+
 /* ---- roofline denominators measured on the box with the same timer as the kernels ---- */
 int c8_bench_dfma(c8_ctx* ctx, int iters, double* tflops_out);
 int c8_bench_copy(c8_ctx* ctx, double* gbs_out);
