@@ -40,4 +40,22 @@ struct AdjArgs {
   double* scalars;    // K5: [0] += J, [1] += total load
 };
 
+struct VfmArgs {
+  MeshArgs mesh;
+  ModelArgs model;
+  const double* x;        // measured displacement of the step
+  const double* x_prev;   // measured displacement of step-1
+  const double* xi_prev;
+  double* xi;             // K7: in (current-field values) / out ; K8: in
+  long long xi_ld;
+  double* b;              // K7: internal force residual (+=)
+  double* dR;             // K7 (grad): [NPAR][n_dofs] (+=) or nullptr
+  double* local_sens;     // K7 (grad): [NXI*NPAR][ld] in/out
+  int* n_failed;
+  const double* w;        // K8: virtual field [n_nodes][NB]
+  double* hist;           // K8: [NXI][ld] in/out
+  double s;               // K8: scaled virtual power mismatch
+  double* grad;           // K8: [NPAR] (+=)
+};
+
 }  // namespace c8

@@ -110,3 +110,50 @@ int c8_get_conn(c8_ctx* ctx, int32_t* conn_host) {
 void* c8_get_stream(c8_ctx* ctx) { return (void*)ctx->stream; }
 
 }  // extern "C"
+
+// ---- virtual fields method ---------------------------------------------------------------
+static VfmArgs vfm_args(c8_ctx* ctx, const double* x, const double* xp, const double* xip,
+                        double* xi) {
+  VfmArgs a{};
+  a.mesh = ctx->mesh_args();
+  a.model = ctx->model;
+  a.x = x; a.x_prev = xp; a.xi_prev = xip; a.xi = xi; a.xi_ld = ctx->xi_ld;
+  a.n_failed = ctx->d_nfailed;
+  return a;
+}
+
+extern "C" {
+
+int c8_vfm_forward(c8_ctx* ctx, const double* x_meas, const double* x_meas_prev,
+                   const double* xi_prev, double* xi, double* b, double* dR, double* local_sens,
+                   int* n_failed) {
+  C8_REQUIRE(ctx, ctx->kt != nullptr, "c8_set_model must be called first");
+  C8_REQUIRE(ctx, ctx->kt->vfm_forward != nullptr,
+             "virtual fields need a single-residual global residual (mechanics_plane_stress)");
+  VfmArgs a = vfm_args(ctx, x_meas, x_meas_prev, xi_prev, xi);
+  a.b = b; a.dR = dR; a.local_sens = local_sens;
+  C8_CUDA(ctx, cudaMemsetAsync(ctx->d_nfailed, 0, sizeof(int), ctx->stream));
+  ctx->kt->vfm_forward(a, ctx->stream);
+  C8_CUDA(ctx, cudaGetLastError());
+  if (n_failed) {
+    C8_CUDA(ctx, cudaMemcpyAsync(n_failed, ctx->d_nfailed, sizeof(int), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    C8_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return C8_OK;
+}
+
+int c8_vfm_adjoint(c8_ctx* ctx, const double* x_meas, const double* x_meas_prev,
+                   const double* xi, const double* xi_prev, const double* w, double s,
+                   double* hist, double* grad) {
+  C8_REQUIRE(ctx, ctx->kt != nullptr, "c8_set_model must be called first");
+  C8_REQUIRE(ctx, ctx->kt->vfm_adjoint != nullptr,
+             "virtual fields need a single-residual global residual (mechanics_plane_stress)");
+  VfmArgs a = vfm_args(ctx, x_meas, x_meas_prev, xi_prev, const_cast<double*>(xi));
+  a.w = w; a.s = s; a.hist = hist; a.grad = grad;
+  ctx->kt->vfm_adjoint(a, ctx->stream);
+  C8_CUDA(ctx, cudaGetLastError());
+  return C8_OK;
+}
+
+}  // extern "C"

@@ -1,6 +1,6 @@
 // Instantiates every kernel of the hot path for one (DIM, MECH, Model, G) combination.
 #pragma once
-#include "adjoint.cuh"
+#include "vfm.cuh"
 #include "kernel_table.h"
 
 namespace c8 {
@@ -51,6 +51,20 @@ struct Launch {
     if (a.mesh.n_elems == 0) return;
     k_qoi_value<C><<<(a.mesh.n_elems + 127) / 128, 128, 0, s>>>(a, mode);
   }
+  static void vfm_forward(const VfmArgs& a, cudaStream_t s) {
+    if constexpr (C::M == MECH_PLANE_STRESS) {
+      if (a.mesh.n_elems == 0) return;
+      const long long threads = (long long)a.mesh.n_elems * C::G;
+      k_vfm_forward<C><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(a);
+    }
+  }
+  static void vfm_adjoint(const VfmArgs& a, cudaStream_t s) {
+    if constexpr (C::M == MECH_PLANE_STRESS) {
+      if (a.mesh.n_elems == 0) return;
+      const long long threads = (long long)a.mesh.n_elems * C::G;
+      k_vfm_adjoint<C><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(a);
+    }
+  }
   static KernelTable table() {
     KernelTable t;
     t.dim = C::D; t.mech = C::M; t.local_type = C::Model::TYPE;
@@ -63,6 +77,8 @@ struct Launch {
     t.adjoint_local = &adjoint_local;
     t.qoi_gradient = &qoi_gradient;
     t.qoi_value = &qoi_value;
+    t.vfm_forward = (C::M == MECH_PLANE_STRESS) ? &vfm_forward : nullptr;
+    t.vfm_adjoint = (C::M == MECH_PLANE_STRESS) ? &vfm_adjoint : nullptr;
     return t;
   }
 };

@@ -18,6 +18,9 @@ struct KernelTable {
   void (*adjoint_local)(const AdjArgs&, cudaStream_t);
   void (*qoi_gradient)(const AdjArgs&, cudaStream_t);
   void (*qoi_value)(const AdjArgs&, int mode, cudaStream_t);
+  // virtual fields method: single-residual (plane stress) mechanics only, else nullptr
+  void (*vfm_forward)(const VfmArgs&, cudaStream_t);
+  void (*vfm_adjoint)(const VfmArgs&, cudaStream_t);
 };
 
 const KernelTable* find_kernel_table(int dim, int mech, int local_type);

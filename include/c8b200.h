@@ -161,6 +161,19 @@ int c8_qoi_gradient(c8_ctx* ctx, const c8_qoi* qoi, const double* x_dev, const d
                     const double* xi_dev, const double* xi_prev_dev, const double* z_dev,
                     const double* phi_dev, double* grad_dev);
 
+/* ---- virtual fields method (single-residual mechanics, i.e. mechanics_plane_stress) ----
+ * eval_measured_residual[_and_grad], evaluations.cpp:1750-1973: local solve at u = measured,
+ * b_dev += R; when dR_dev != NULL also the forward sensitivities: dR_dev [npar][n_dofs] +=
+ * dR/dp_total and local_sens_dev [nxi*npar][xi_ld] (dxi/dp, in/out), for EVERY model parameter. */
+int c8_vfm_forward(c8_ctx* ctx, const double* x_meas_dev, const double* x_meas_prev_dev,
+                   const double* xi_prev_dev, double* xi_dev, double* b_dev, double* dR_dev,
+                   double* local_sens_dev, int* n_failed);
+/* eval_vfm_adjoint_gradient, evaluations.cpp:1975-2143: hist_dev [nxi][xi_ld] in/out,
+ * grad_dev [npar] += s w^T dR/dp + phi^T dC/dp */
+int c8_vfm_adjoint(c8_ctx* ctx, const double* x_meas_dev, const double* x_meas_prev_dev,
+                   const double* xi_dev, const double* xi_prev_dev, const double* w_dev, double s,
+                   double* hist_dev, double* grad_dev);
+
 /* ---- global linear algebra on the device (replaces linear_alg.cpp / linear_solve.cpp) ---- */
 #define C8_ERR_NOT_CONVERGED (-4)
 int c8_spmv(c8_ctx* ctx, const double* A_vals_dev, const double* x_dev, double* y_dev);

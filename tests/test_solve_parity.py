@@ -96,3 +96,69 @@ def test_adjoint_gradient_vs_oracle(golden, name, active):
     assert abs(J - J_o) / abs(J_o) < J_TOL
     assert np.abs(g_gpu - g_o).max() < G_TOL * np.abs(g_o).max(), (g_gpu, g_o)
     hp.close(); ctx.close()
+
+
+def _calibration_setup(mesh):
+    """examples/synthetic_calibration: forward/notch2D_small_J2_plane_stress.yaml:14-52 and
+    inverse_pdeco/pdeco_notch2D_small_J2_plane_stress.yaml:25-68."""
+    truth = dict(E=1000., nu=.25, Y=2., S=10., D=50., R00=1., R11=1., R22=1., R01=1.)
+    start = dict(truth, Y=2.2, S=8., D=60.)
+    deck = dict(global_type="mechanics_plane_stress", local_type="small_hill_plane_stress",
+                params=truth, dbcs=[[0, 0, "xmin", "0.0"], [0, 1, "ymin", "0.0"], [0, 1, "ymax", "0.01 * t"]],
+                num_steps=4, global_max_iters=30, global_tol=1e-12, local_max_iters=20, local_tol=1e-12)
+    X = mesh.coords[mesh.conn]
+    area = 0.5 * np.abs((X[:, 1, 0] - X[:, 0, 0]) * (X[:, 2, 1] - X[:, 0, 1]) -
+                        (X[:, 1, 1] - X[:, 0, 1]) * (X[:, 2, 0] - X[:, 0, 0])).sum()
+    qoi = dict(balance_factor=1e2, coord_idx=1, coord_value=1.0, reaction_force_comp=1,
+               weights=(1e8, 1e8))
+    return truth, start, deck, area, qoi
+
+
+def test_calibration_objective_and_gradient(golden):
+    """BASELINE configs[0]: the shipped synthetic calibration (2-D plane-stress Hill, calibration
+    QoI = displacement mismatch + load mismatch): objective and adjoint gradient w.r.t. Y, S, D at
+    the inverse deck's starting point, GPU vs oracle."""
+    from oracle.driver import Adjoint
+    from oracle.pyoracle import PARAM_NAMES
+    mesh = load_mesh("notch2D")
+    truth, start, deck, area, qoi = _calibration_setup(mesh)
+    N = deck["num_steps"]
+    names = PARAM_NAMES[deck["local_type"]]
+    act = [names.index(a) for a in ("Y", "S", "D")]
+    # ---- synthetic data from the oracle's forward run at the true parameters
+    o, p = oracle_problem(deck, mesh)
+    o.set_qoi_calibration(**qoi)
+    zero_meas = np.zeros((mesh.n_nodes, 3))
+    loads = []
+
+    def setup_truth(step):
+        o.qoi_set_step(1.0, float(N), 0.0, zero_meas)
+    p.solve(setup_truth)
+    measured = []
+    for step in range(1, N + 1):
+        o.qoi_set_step(1.0, float(N), 0.0, zero_meas)
+        o.qoi(p.x[step], p.x[step - 1], p.xi[step], p.xi[step - 1], step)
+        loads.append(o.calibration_state()["total_load"])
+        m3 = np.zeros((mesh.n_nodes, 3)); m3[:, :2] = p.x[step][0].reshape(-1, 2)
+        measured.append(m3)
+    assert abs(o.calibration_state()["area"] - area) < 1e-12
+    # ---- oracle objective + gradient at the starting parameters
+    d2 = dict(deck, params=start)
+    o2, p2 = oracle_problem(d2, mesh, active=[act])
+    o2.set_qoi_calibration(**qoi)
+
+    def setup(step):
+        o2.qoi_set_step(1.0, float(N), loads[step - 1], measured[step - 1])
+    J_o = p2.solve(setup)
+    g_o = Adjoint(p2, max_iters=30, abs_tol=1e-14, rel_tol=1e-12).gradient(
+        [list(range(3))], 3, setup)
+    assert J_o > 0
+    # ---- GPU
+    ctx, hp = gpu_problem(d2, mesh, qoi=None)
+    meas2 = np.stack([m[:, :2] for m in measured])
+    hp.set_qoi_calibration(measured=meas2, load_data=loads, area=area, **qoi)
+    J = hp.primal_solve()
+    g = hp.adjoint_gradient()[act]
+    assert abs(J - J_o) / abs(J_o) < J_TOL, (J, J_o)
+    assert np.abs(g - g_o).max() < G_TOL * np.abs(g_o).max(), (g, g_o)
+    hp.close(); ctx.close()
