@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(128) k_adjoint_jacobian(const AdjArgs a) {
     double r = -dJ_dx[s] + __ldg(&a.f[size_t(c) * a.xi_ld + e]);
 #pragma unroll
     for (int q = 0; q < NXI; ++q) r = fma(dxi_dx[q][s], gq[q], r);
-    atomicAdd(&a.b[size_t(E.nodes[sx.xl.node[s]]) * NB + sx.xl.eq[s]], r);
+    if (E.nodes[sx.xl.node[s]] < a.mesh.n_row_nodes)
+      atomicAdd(&a.b[size_t(E.nodes[sx.xl.node[s]]) * NB + sx.xl.eq[s]], r);
   }
 }
 

@@ -68,6 +68,7 @@ int c8_qoi_value(c8_ctx* ctx, const c8_qoi* qoi, const double* x, const double* 
                  const double* xi, const double* xip, int mode, double* scalars_dev) {
   C8_REQUIRE(ctx, ctx->kt != nullptr, "c8_set_model must be called first");
   AdjArgs a = base_args(ctx, qoi, x, xp, xi, xip);
+  a.mesh.n_elems = ctx->n_owned_elems;  // every element is counted once across ranks
   a.scalars = scalars_dev;
   ctx->kt->qoi_value(a, mode, ctx->stream);
   C8_CUDA(ctx, cudaGetLastError());
@@ -79,6 +80,7 @@ int c8_qoi_gradient(c8_ctx* ctx, const c8_qoi* qoi, const double* x, const doubl
                     double* grad_dev) {
   C8_REQUIRE(ctx, ctx->kt != nullptr, "c8_set_model must be called first");
   AdjArgs a = base_args(ctx, qoi, x, xp, xi, xip);
+  a.mesh.n_elems = ctx->n_owned_elems;
   a.z = z; a.phi = const_cast<double*>(phi); a.grad = grad_dev;
   ctx->kt->qoi_gradient(a, ctx->stream);
   C8_CUDA(ctx, cudaGetLastError());
@@ -150,6 +152,7 @@ int c8_vfm_adjoint(c8_ctx* ctx, const double* x_meas, const double* x_meas_prev,
   C8_REQUIRE(ctx, ctx->kt->vfm_adjoint != nullptr,
              "virtual fields need a single-residual global residual (mechanics_plane_stress)");
   VfmArgs a = vfm_args(ctx, x_meas, x_meas_prev, xi_prev, const_cast<double*>(xi));
+  a.mesh.n_elems = ctx->n_owned_elems;
   a.w = w; a.s = s; a.hist = hist; a.grad = grad;
   ctx->kt->vfm_adjoint(a, ctx->stream);
   C8_CUDA(ctx, cudaGetLastError());

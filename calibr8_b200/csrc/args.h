@@ -14,6 +14,7 @@ namespace c8 {
 struct MeshArgs {
   int n_elems;
   int n_nodes;
+  int n_row_nodes;        // rows of nodes >= n_row_nodes are not scattered (ghost nodes of a partition)
   const int* conn;
   const double* coords;
   const int* elem_es;     // [n_elems] element-set id, or nullptr (all 0)

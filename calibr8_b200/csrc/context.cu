@@ -246,6 +246,8 @@ int c8_set_mesh(c8_ctx* ctx, int dim, int n_elems, int n_nodes, const int32_t* c
     if (ctx->d_elem_es) cudaFree(ctx->d_elem_es);
     ctx->d_elem_es = nullptr;
   }
+  ctx->n_owned_nodes = n_nodes;
+  ctx->n_owned_elems = n_elems;
   ctx->xi_ld = (long long)((n_elems + 31) / 32) * 32;  // 256-byte aligned component rows
   return C8_OK;
 }

@@ -26,6 +26,12 @@ struct c8_ctx {
   int* d_colind = nullptr;
   int* d_eoff = nullptr;
   long long xi_ld = 0;
+  // partition (multi-GPU): local nodes [0, n_owned_nodes) are owned, the rest are ghosts; local
+  // elements [0, n_owned_elems) are owned, the rest are halo elements computed redundantly
+  int n_owned_nodes = 0, n_owned_elems = 0;
+  void (*halo_cb)(void*, double*, int) = nullptr;
+  void (*allreduce_cb)(void*, double*, int) = nullptr;
+  void* comm_user = nullptr;
 
   // model
   const c8::KernelTable* kt = nullptr;
@@ -47,6 +53,7 @@ struct c8_ctx {
   c8::MeshArgs mesh_args() const {
     c8::MeshArgs m;
     m.n_elems = n_elems; m.n_nodes = n_nodes; m.conn = d_conn; m.coords = d_coords;
+    m.n_row_nodes = n_owned_nodes;
     m.elem_es = d_elem_es; m.eoff = d_eoff;
     return m;
   }

@@ -28,6 +28,13 @@ C8_DI double pick(int c, double a, double b) {
   return r;
 }
 
+C8_DI int picki(int c, int a, int b) {
+  int r;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.s32 %0, %1, %2, p;\n\t}"
+      : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+
 template <int L>
 struct Dual {
   double v;

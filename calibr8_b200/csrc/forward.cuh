@@ -192,8 +192,9 @@ struct Scatter {
   C8_DI void row(int n, int eq, const Dual<C::LX>& r) const {
     constexpr int NB = C::NB, NN = C::NN, NX = C::NX;
     if (!on) return;
+    const bool row_owned = E.nodes[n] < a.mesh.n_row_nodes;  // ghost rows belong to another rank
     const int row_dof = n * NB + eq;
-    if (a.b && (row_dof % C::G) == t) atomicAdd(&a.b[size_t(E.nodes[n]) * NB + eq], r.v);
+    if (a.b && row_owned && (row_dof % C::G) == t) atomicAdd(&a.b[size_t(E.nodes[n]) * NB + eq], r.v);
     if (a.elem_R && (row_dof % C::G) == t) a.elem_R[size_t(e) * NX + C::ref_dof(n, eq)] = r.v;
 #pragma unroll
     for (int s = 0; s < C::LX; ++s) {
@@ -201,9 +202,14 @@ struct Scatter {
       const int nc = xl.node[s], qc = xl.eq[s];
       if (a.vals) {
         if (!a.transpose) {
+          if (!row_owned) continue;
           const int blk = __ldg(&a.mesh.eoff[size_t(e) * NN * NN + n * NN + nc]);
           atomicAdd(&a.vals[size_t(blk) * NB * NB + eq * NB + qc], r.d[s]);
         } else {
+          int gn = 0;
+#pragma unroll
+          for (int n2 = 0; n2 < NN; ++n2) gn = picki(nc == n2, E.nodes[n2], gn);
+          if (gn >= a.mesh.n_row_nodes) continue;
           const int blk = __ldg(&a.mesh.eoff[size_t(e) * NN * NN + nc * NN + n]);
           atomicAdd(&a.vals[size_t(blk) * NB * NB + qc * NB + eq], r.d[s]);
         }
@@ -377,7 +383,7 @@ __global__ void __launch_bounds__(128) k_global_residual(const FwdArgs a) {
       double r = 0.0;
 #pragma unroll
       for (int j = 0; j < D; ++j) r += P(i, j) * (E.g.gN[n][j] * wdv);
-      atomicAdd(&a.b[size_t(E.nodes[n]) * NB + i], r);
+      if (E.nodes[n] < a.mesh.n_row_nodes) atomicAdd(&a.b[size_t(E.nodes[n]) * NB + i], r);
     }
   if constexpr (C::M == MECH_MIXED) {
     double hp, sv[D], Rp[NN];
@@ -402,7 +408,8 @@ __global__ void __launch_bounds__(128) k_global_residual(const FwdArgs a) {
       for (int n = 0; n < NN; ++n) Rp[n] -= pq * ipk * (N[n] * wq);
     }
 #pragma unroll
-    for (int n = 0; n < NN; ++n) atomicAdd(&a.b[size_t(E.nodes[n]) * NB + D], Rp[n]);
+    for (int n = 0; n < NN; ++n)
+      if (E.nodes[n] < a.mesh.n_row_nodes) atomicAdd(&a.b[size_t(E.nodes[n]) * NB + D], Rp[n]);
   }
 }
 

@@ -185,8 +185,14 @@ struct LinAlg {
   long long n;
   cudaStream_t s;
   explicit LinAlg(c8_ctx* c) : ctx(c) {
-    nb = c->kt->nb; n_nodes = c->n_nodes; n = (long long)n_nodes * nb; s = c->stream;
+    // rows = owned nodes (all nodes on one GPU); vectors are allocated for all local nodes so
+    // that SpMV can read ghost entries filled by the halo callback
+    nb = c->kt->nb; n_nodes = c->n_owned_nodes; n = (long long)n_nodes * nb; s = c->stream;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  }
+  void halo(double* x) const { if (ctx->halo_cb) ctx->halo_cb(ctx->comm_user, x, nb); }
+  void allreduce(double* buf_dev, int cnt) const {
+    if (ctx->allreduce_cb) ctx->allreduce_cb(ctx->comm_user, buf_dev, cnt);
   }
   void spmv(const double* A, const double* x, double* y) const {
     const int block = 128, grid = int((n + block - 1) / block);
@@ -219,6 +225,7 @@ struct LinAlg {
     dim3 grid(gx, nv < 64 ? nv : 64);
     k_multi_dot_partial<<<grid, DOT_BLOCK, 0, s>>>(V, ld, w, nv, n, partial);
     k_multi_dot_final<<<nv, 256, 0, s>>>(partial, gx, nv, out_dev);
+    allreduce(out_dev, nv);
   }
 };
 
@@ -237,7 +244,7 @@ struct c8_solver_ws {
 static c8_solver_ws g_ws_dummy;
 
 static int ensure_ws(c8_ctx* ctx, c8_solver_ws& ws, int m) {
-  const long long n = (long long)ctx->n_nodes * ctx->kt->nb;
+  const long long n = (long long)ctx->n_nodes * ctx->kt->nb;  // all local nodes incl. ghosts
   if (ws.m >= m && ws.n == n) return C8_OK;
   cudaFree(ws.V); cudaFree(ws.w); cudaFree(ws.z); cudaFree(ws.dinv); cudaFree(ws.partial);
   cudaFree(ws.dots); cudaFree(ws.coef);
@@ -264,6 +271,7 @@ extern "C" {
 int c8_spmv(c8_ctx* ctx, const double* A_vals_dev, const double* x_dev, double* y_dev) {
   C8_REQUIRE(ctx, ctx->kt != nullptr, "c8_set_model must be called first");
   LinAlg la(ctx);
+  la.halo(const_cast<double*>(x_dev));  // ghost entries of the input (no-op on one GPU)
   la.spmv(A_vals_dev, x_dev, y_dev);
   C8_CUDA(ctx, cudaGetLastError());
   return C8_OK;
@@ -308,7 +316,8 @@ int c8_gmres(c8_ctx* ctx, const double* A, const double* b, double* x, int resta
   int rc = ensure_ws(ctx, ws, m);
   if (rc != C8_OK) return rc;
   LinAlg la(ctx);
-  const long long n = la.n;
+  const long long n = la.n;      // owned dofs: the range every vector operation runs over
+  const long long ld = ws.n;     // allocation stride of a Krylov vector (owned + ghost)
   cudaStream_t s = ctx->stream;
   const int ag = grid_for(n, 256, la.sms);
   la.jacobi_setup(A, ws.dinv);
@@ -324,6 +333,7 @@ int c8_gmres(c8_ctx* ctx, const double* A, const double* b, double* x, int resta
   double beta0 = -1.0, beta = 0.0, target = 0.0;
   while (true) {
     // r = b - A x  -> V[0]
+    la.halo(x);
     la.spmv(A, x, ws.w);
     C8_CUDA(ctx, cudaMemcpyAsync(ws.V, b, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
     k_axpby<<<ag, 256, 0, s>>>(-1.0, ws.w, 1.0, ws.V, n);
@@ -335,13 +345,14 @@ int c8_gmres(c8_ctx* ctx, const double* A, const double* b, double* x, int resta
     g[0] = beta;
     int j = 0;
     for (; j < m && total < max_iters; ++j, ++total) {
-      double* vj1 = ws.V + size_t(j + 1) * n;
-      la.jacobi_apply(ws.dinv, ws.V + size_t(j) * n, ws.z);
+      double* vj1 = ws.V + size_t(j + 1) * ld;
+      la.jacobi_apply(ws.dinv, ws.V + size_t(j) * ld, ws.z);
+      la.halo(ws.z);
       la.spmv(A, ws.z, vj1);
       // classical Gram-Schmidt, two passes (CGS2) for orthogonality: h = V^T w ; w -= V h
       for (int pass = 0; pass < 2; ++pass) {
-        la.multi_dot(ws.V, n, vj1, j + 1, ws.partial, ws.dots);
-        k_multi_axpy_neg<<<ag, 256, 0, s>>>(ws.V, n, ws.dots, j + 1, n, vj1);
+        la.multi_dot(ws.V, ld, vj1, j + 1, ws.partial, ws.dots);
+        k_multi_axpy_neg<<<ag, 256, 0, s>>>(ws.V, ld, ws.dots, j + 1, n, vj1);
         C8_CUDA(ctx, cudaMemcpyAsync(ws.h_dots, ws.dots, (j + 1) * sizeof(double),
                                      cudaMemcpyDeviceToHost, s));
         C8_CUDA(ctx, cudaStreamSynchronize(s));
@@ -376,7 +387,7 @@ int c8_gmres(c8_ctx* ctx, const double* A, const double* b, double* x, int resta
     for (int i = 0; i < j; ++i) ws.h_dots[i] = y[i];
     C8_CUDA(ctx, cudaMemcpyAsync(ws.coef, ws.h_dots, j * sizeof(double), cudaMemcpyHostToDevice, s));
     C8_CUDA(ctx, cudaMemsetAsync(ws.w, 0, n * sizeof(double), s));
-    k_multi_axpy<<<ag, 256, 0, s>>>(ws.V, n, ws.coef, j, n, ws.w);
+    k_multi_axpy<<<ag, 256, 0, s>>>(ws.V, ld, ws.coef, j, n, ws.w);
     la.jacobi_apply(ws.dinv, ws.w, ws.z);
     k_axpby<<<ag, 256, 0, s>>>(1.0, ws.z, 1.0, x, n);
     C8_CUDA(ctx, cudaStreamSynchronize(s));
@@ -394,6 +405,36 @@ void c8_linalg_release(c8_ctx* ctx) {
   cudaFree(ws.dots); cudaFree(ws.coef);
   if (ws.h_dots) cudaFreeHost(ws.h_dots);
   g_ws.erase(it);
+}
+
+}  // extern "C"
+
+// ---- partition / communication hooks (multi-GPU) -------------------------------------------
+extern "C" {
+
+int c8_set_partition(c8_ctx* ctx, int n_owned_nodes, int n_owned_elems) {
+  C8_REQUIRE(ctx, n_owned_nodes <= ctx->n_nodes && n_owned_elems <= ctx->n_elems,
+             "owned counts exceed the local mesh");
+  ctx->n_owned_nodes = n_owned_nodes;
+  ctx->n_owned_elems = n_owned_elems;
+  return C8_OK;
+}
+
+int c8_set_comm(c8_ctx* ctx, c8_halo_fn halo, c8_allreduce_fn allreduce, void* user) {
+  ctx->halo_cb = halo;
+  ctx->allreduce_cb = allreduce;
+  ctx->comm_user = user;
+  return C8_OK;
+}
+
+int c8_halo(c8_ctx* ctx, double* vec_dev) {
+  if (ctx->halo_cb) ctx->halo_cb(ctx->comm_user, vec_dev, ctx->kt->nb);
+  return C8_OK;
+}
+
+int c8_allreduce(c8_ctx* ctx, double* buf_dev, int n) {
+  if (ctx->allreduce_cb) ctx->allreduce_cb(ctx->comm_user, buf_dev, n);
+  return C8_OK;
 }
 
 }  // extern "C"

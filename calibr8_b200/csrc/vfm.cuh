@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(128) k_vfm_forward(const VfmArgs a) {
         double r = 0.0;
 #pragma unroll
         for (int j = 0; j < D; ++j) r += P(i, j) * (E.g.gN[n][j] * wdv);
-        if ((n * NB + i) % G == t) atomicAdd(&a.b[size_t(E.nodes[n]) * NB + i], r);
+        if ((n * NB + i) % G == t && E.nodes[n] < a.mesh.n_row_nodes)
+          atomicAdd(&a.b[size_t(E.nodes[n]) * NB + i], r);
       }
   }
   if (!a.dR) return;
@@ -149,7 +150,8 @@ __global__ void __launch_bounds__(128) k_vfm_forward(const VfmArgs a) {
           double v = r.d[s];
 #pragma unroll
           for (int q = 0; q < NXI; ++q) v = fma(dR_dxi[n * NB + i][q], rhs[q][s], v);
-          atomicAdd(&a.dR[size_t(p) * n_dofs + size_t(E.nodes[n]) * NB + i], v);
+          if (E.nodes[n] < a.mesh.n_row_nodes)
+            atomicAdd(&a.dR[size_t(p) * n_dofs + size_t(E.nodes[n]) * NB + i], v);
         }
       }
   }

@@ -189,6 +189,23 @@ int c8_gmres(c8_ctx* ctx, const double* A_vals_dev, const double* b_dev, double*
              int restart, int max_iters, double rel_tol, double abs_tol, double* info_host);
 void c8_linalg_release(c8_ctx* ctx);
 
+/* ---- partition (one context per GPU; replaces the OWNED/GHOST maps of disc.cpp:271-314 and the
+ * import/export of linear_alg.cpp:53-86) ----
+ * The local mesh of a part lists its owned nodes first, then its ghost nodes; its owned elements
+ * first, then the halo elements (elements of other parts that touch an owned node).  Every part
+ * assembles the COMPLETE rows of its owned nodes (halo elements are evaluated redundantly), so no
+ * matrix or residual entries travel; only ghost entries of vectors (halo copy) and scalars do.
+ * Objective integrands run over owned elements only. */
+int c8_set_partition(c8_ctx* ctx, int n_owned_nodes, int n_owned_elems);
+/* communication hooks: halo(user, vec_dev, nb) fills the ghost entries of a nodal vector
+ * [n_nodes][nb]; allreduce(user, buf_dev, n) sums n doubles over the parts (both enqueue on the
+ * context's stream) */
+typedef void (*c8_halo_fn)(void* user, double* vec_dev, int nb);
+typedef void (*c8_allreduce_fn)(void* user, double* buf_dev, int n);
+int c8_set_comm(c8_ctx* ctx, c8_halo_fn halo, c8_allreduce_fn allreduce, void* user);
+int c8_halo(c8_ctx* ctx, double* vec_dev);
+int c8_allreduce(c8_ctx* ctx, double* buf_dev, int n);
+
 int c8_get_coords(c8_ctx* ctx, double* coords_host /* [n_nodes][3] */);
 int c8_get_conn(c8_ctx* ctx, int32_t* conn_host);
 void* c8_get_stream(c8_ctx* ctx);
