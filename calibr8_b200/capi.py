@@ -478,3 +478,80 @@ class HostProblem:
         a, b = C.c_int(0), C.c_int(0)
         self.lib.c8h_stats(self.h, C.byref(a), C.byref(b))
         return dict(assemblies=a.value, linear_iters=b.value)
+
+
+# ======================================================================================
+# partition / communication (one Context per GPU; calibr8_b200/partition.py builds the plan)
+SYMBOLS += [
+    "c8_set_partition", "c8_get_partition", "c8_set_comm", "c8_set_halo_plan", "c8_nccl_unique_id",
+    "c8_nccl_init", "c8_set_comm_host", "c8_halo", "c8_halo_nb", "c8_allreduce", "c8_comm_stats",
+    "c8_comm_release",
+]
+_EXCHANGE_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int)
+_HOST_ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_double), C.c_int)
+
+
+def _ctx_set_partition(self, part):
+    """part: calibr8_b200.partition.Part whose local mesh was given to set_mesh."""
+    assert part.n_nodes == self.n_nodes and part.n_elems == self.n_elems
+    self.part = part
+    self._check(self.lib.c8_set_partition(self.h, part.n_owned_nodes, part.n_owned_elems))
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    nbr, sp, sn, rp = i32(part.nbr_rank), i32(part.send_ptr), i32(part.send_nodes), i32(part.recv_ptr)
+    self._check(self.lib.c8_set_halo_plan(self.h, int(nbr.size), _hp(nbr), _hp(sp), _hp(sn), _hp(rp)))
+
+
+def _ctx_nccl_init(self, rank, nranks, broadcast_bytes):
+    """broadcast_bytes(b: bytes | None) -> bytes : distributes rank 0's 128-byte id"""
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        rc = self.lib.c8_nccl_unique_id(buf)
+        if rc != 0:
+            raise C8Error("c8_nccl_unique_id failed (libnccl.so.2 not loadable)")
+    raw = broadcast_bytes(buf.raw if rank == 0 else None)
+    self._check(self.lib.c8_nccl_init(self.h, C.create_string_buffer(raw, 128), rank, nranks))
+
+
+def _ctx_set_comm_host(self, exchanger):
+    """exchanger: object with .exchange(send[n_send][nb], nb) -> recv[n_ghost][nb] and
+    .allreduce(buf) -> summed buf (e.g. partition.HostExchange)"""
+    part = self.part
+    n_send, n_recv = int(part.send_ptr[-1]), int(part.recv_ptr[-1])
+
+    def ex(_user, send_p, recv_p, nb):
+        send = np.ctypeslib.as_array(send_p, shape=(max(n_send, 1) * nb,))[: n_send * nb]
+        recv = exchanger.exchange(send.reshape(n_send, nb), nb)
+        if n_recv:
+            np.ctypeslib.as_array(recv_p, shape=(n_recv * nb,))[:] = np.asarray(recv).reshape(-1)
+
+    def ar(_user, buf_p, n):
+        a = np.ctypeslib.as_array(buf_p, shape=(n,))
+        a[:] = exchanger.allreduce(a.copy())
+
+    self._cb = (_EXCHANGE_FN(ex), _HOST_ALLREDUCE_FN(ar))   # keep alive
+    self._check(self.lib.c8_set_comm_host(self.h, self._cb[0], self._cb[1], None))
+
+
+def _ctx_halo(self, vec, nb=None):
+    if nb is None:
+        self._check(self.lib.c8_halo(self.h, _dp(vec)))
+    else:
+        self._check(self.lib.c8_halo_nb(self.h, _dp(vec), nb))
+
+
+def _ctx_allreduce(self, buf):
+    self._check(self.lib.c8_allreduce(self.h, _dp(buf), int(buf.numel())))
+
+
+def _ctx_comm_stats(self):
+    out = (C.c_int64 * 3)()
+    self.lib.c8_comm_stats(self.h, out)
+    return dict(halo_calls=int(out[0]), allreduce_calls=int(out[1]), halo_bytes=int(out[2]))
+
+
+Context.set_partition = _ctx_set_partition
+Context.nccl_init = _ctx_nccl_init
+Context.set_comm_host = _ctx_set_comm_host
+Context.halo = _ctx_halo
+Context.allreduce = _ctx_allreduce
+Context.comm_stats = _ctx_comm_stats

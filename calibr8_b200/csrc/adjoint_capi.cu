@@ -138,9 +138,8 @@ int c8_vfm_forward(c8_ctx* ctx, const double* x_meas, const double* x_meas_prev,
   ctx->kt->vfm_forward(a, ctx->stream);
   C8_CUDA(ctx, cudaGetLastError());
   if (n_failed) {
-    C8_CUDA(ctx, cudaMemcpyAsync(n_failed, ctx->d_nfailed, sizeof(int), cudaMemcpyDeviceToHost,
-                                 ctx->stream));
-    C8_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int rc = c8::fetch_n_failed(ctx, n_failed);
+    if (rc != C8_OK) return rc;
   }
   return C8_OK;
 }

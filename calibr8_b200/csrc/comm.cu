@@ -1,0 +1,288 @@
+// Partition communication for one-context-per-GPU runs.  Replaces, for this path, the
+// OWNED<->GHOST Tpetra import/export of the reference (src/linear_alg.cpp:53-118) and its PCU
+// reductions (PCU_Add_Double / PCU_Add_Int on J, gradients and the local-solve status).
+//
+// Because every part assembles the complete rows of its owned nodes (halo elements are evaluated
+// redundantly), only two operations exist:
+//   halo copy   ghost entries of a nodal vector <- the owner's values (pack kernel -> neighbour
+//               exchange -> received straight into the contiguous ghost range of each neighbour)
+//   allreduce   fp64 sums of a few scalars
+// Transports:
+//   NCCL        ncclSend/ncclRecv grouped per neighbour + ncclAllReduce, enqueued on the context's
+//               stream (NVLink 5 / NVSwitch).  libnccl.so.2 is bound at run time with dlopen so
+//               that the library already loaded in the process (e.g. torch's) is the one used.
+//   host-staged pack -> pinned host -> caller's exchange function (MPI / gloo) -> ghost range.
+//               This is what a calibr8 MPI rank without NCCL binds (PCU/MPI callbacks).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "c8b200.h"
+#include "context.cuh"
+
+namespace c8 {
+
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string err;
+  bool load() {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) { err = std::string("dlopen(libnccl.so.2): ") + dlerror(); return false; }
+#define C8_SYM(field, name)                                                \
+  field = reinterpret_cast<decltype(field)>(dlsym(lib, name));             \
+  if (!field) { err = std::string("dlsym ") + name; lib = nullptr; return false; }
+    C8_SYM(GetUniqueId, "ncclGetUniqueId");
+    C8_SYM(CommInitRank, "ncclCommInitRank");
+    C8_SYM(CommDestroy, "ncclCommDestroy");
+    C8_SYM(AllReduce, "ncclAllReduce");
+    C8_SYM(Send, "ncclSend");
+    C8_SYM(Recv, "ncclRecv");
+    C8_SYM(GroupStart, "ncclGroupStart");
+    C8_SYM(GroupEnd, "ncclGroupEnd");
+    C8_SYM(GetErrorString, "ncclGetErrorString");
+#undef C8_SYM
+    return true;
+  }
+};
+static NcclApi g_nccl;
+
+struct Comm {
+  c8_ctx* ctx = nullptr;
+  // neighbour plan
+  int n_nbr = 0;
+  std::vector<int> nbr_rank, send_ptr, recv_ptr;  // node counts (prefix sums)
+  int n_send = 0, n_recv = 0;
+  int* d_send_nodes = nullptr;
+  double* d_sendbuf = nullptr;   // [n_send][NBMAX]
+  // NCCL transport
+  ncclComm_t nccl = nullptr;
+  int rank = 0, nranks = 1;
+  // host-staged transport
+  c8_host_exchange_fn exchange = nullptr;
+  c8_host_allreduce_fn host_allreduce = nullptr;
+  void* user = nullptr;
+  double* h_send = nullptr;
+  double* h_recv = nullptr;
+  std::string last;
+  // statistics
+  long long n_halo = 0, n_allreduce = 0, halo_bytes = 0;
+};
+static std::map<c8_ctx*, Comm> g_comm;
+static const int NBMAX = 4;
+
+__global__ void k_halo_pack(const double* __restrict__ v, const int* __restrict__ nodes,
+                            double* __restrict__ out, int n, int nb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * nb) return;
+  const int k = i / nb, c = i - k * nb;
+  out[i] = v[size_t(__ldg(&nodes[k])) * nb + c];
+}
+
+static void halo_nccl(void* user, double* vec, int nb) {
+  Comm& c = *static_cast<Comm*>(user);
+  if (c.n_nbr == 0) return;
+  cudaStream_t s = c.ctx->stream;
+  if (c.n_send)
+    k_halo_pack<<<(c.n_send * nb + 255) / 256, 256, 0, s>>>(vec, c.d_send_nodes, c.d_sendbuf, c.n_send, nb);
+  g_nccl.GroupStart();
+  for (int k = 0; k < c.n_nbr; ++k) {
+    const int ns = c.send_ptr[k + 1] - c.send_ptr[k], nr = c.recv_ptr[k + 1] - c.recv_ptr[k];
+    if (ns) g_nccl.Send(c.d_sendbuf + size_t(c.send_ptr[k]) * nb, size_t(ns) * nb, ncclDouble, c.nbr_rank[k], c.nccl, s);
+    if (nr)
+      g_nccl.Recv(vec + (size_t(c.ctx->n_owned_nodes) + c.recv_ptr[k]) * nb, size_t(nr) * nb, ncclDouble,
+                  c.nbr_rank[k], c.nccl, s);
+  }
+  ncclResult_t r = g_nccl.GroupEnd();
+  if (r != ncclSuccess) c.last = g_nccl.GetErrorString(r);
+  ++c.n_halo;
+  c.halo_bytes += (long long)(c.n_send + c.n_recv) * nb * 8;
+}
+
+static void allreduce_nccl(void* user, double* buf, int n) {
+  Comm& c = *static_cast<Comm*>(user);
+  ncclResult_t r = g_nccl.AllReduce(buf, buf, size_t(n), ncclDouble, ncclSum, c.nccl, c.ctx->stream);
+  if (r != ncclSuccess) c.last = g_nccl.GetErrorString(r);
+  ++c.n_allreduce;
+}
+
+static void halo_host(void* user, double* vec, int nb) {
+  Comm& c = *static_cast<Comm*>(user);
+  if (c.n_nbr == 0) return;
+  cudaStream_t s = c.ctx->stream;
+  if (c.n_send) {
+    k_halo_pack<<<(c.n_send * nb + 255) / 256, 256, 0, s>>>(vec, c.d_send_nodes, c.d_sendbuf, c.n_send, nb);
+    cudaMemcpyAsync(c.h_send, c.d_sendbuf, size_t(c.n_send) * nb * sizeof(double), cudaMemcpyDeviceToHost, s);
+  }
+  cudaStreamSynchronize(s);
+  c.exchange(c.user, c.h_send, c.h_recv, nb);
+  if (c.n_recv)
+    cudaMemcpyAsync(vec + size_t(c.ctx->n_owned_nodes) * nb, c.h_recv, size_t(c.n_recv) * nb * sizeof(double),
+                    cudaMemcpyHostToDevice, s);
+  cudaStreamSynchronize(s);  // h_recv is reused by the next call
+  ++c.n_halo;
+  c.halo_bytes += (long long)(c.n_send + c.n_recv) * nb * 8;
+}
+
+static void allreduce_host(void* user, double* buf, int n) {
+  Comm& c = *static_cast<Comm*>(user);
+  cudaStream_t s = c.ctx->stream;
+  std::vector<double> h(n);
+  cudaMemcpyAsync(h.data(), buf, n * sizeof(double), cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  c.host_allreduce(c.user, h.data(), n);
+  cudaMemcpyAsync(buf, h.data(), n * sizeof(double), cudaMemcpyHostToDevice, s);
+  cudaStreamSynchronize(s);
+  ++c.n_allreduce;
+}
+
+void comm_release(c8_ctx* ctx) {
+  auto it = g_comm.find(ctx);
+  if (it == g_comm.end()) return;
+  Comm& c = it->second;
+  if (c.nccl && g_nccl.lib) g_nccl.CommDestroy(c.nccl);
+  if (c.d_send_nodes) cudaFree(c.d_send_nodes);
+  if (c.d_sendbuf) cudaFree(c.d_sendbuf);
+  if (c.h_send) cudaFreeHost(c.h_send);
+  if (c.h_recv) cudaFreeHost(c.h_recv);
+  g_comm.erase(it);
+}
+
+}  // namespace c8
+
+using namespace c8;
+
+extern "C" {
+
+int c8_set_partition(c8_ctx* ctx, int n_owned_nodes, int n_owned_elems) {
+  C8_REQUIRE(ctx, n_owned_nodes >= 0 && n_owned_nodes <= ctx->n_nodes && n_owned_elems >= 0 &&
+                      n_owned_elems <= ctx->n_elems, "owned counts exceed the local mesh");
+  ctx->n_owned_nodes = n_owned_nodes;
+  ctx->n_owned_elems = n_owned_elems;
+  return C8_OK;
+}
+
+int c8_get_partition(c8_ctx* ctx, int* n_owned_nodes, int* n_owned_elems) {
+  if (n_owned_nodes) *n_owned_nodes = ctx->n_owned_nodes;
+  if (n_owned_elems) *n_owned_elems = ctx->n_owned_elems;
+  return C8_OK;
+}
+
+int c8_set_comm(c8_ctx* ctx, c8_halo_fn halo, c8_allreduce_fn allreduce, void* user) {
+  ctx->halo_cb = halo;
+  ctx->allreduce_cb = allreduce;
+  ctx->comm_user = user;
+  return C8_OK;
+}
+
+int c8_set_halo_plan(c8_ctx* ctx, int n_nbr, const int32_t* nbr_rank, const int32_t* send_ptr,
+                     const int32_t* send_nodes, const int32_t* recv_ptr) {
+  C8_REQUIRE(ctx, n_nbr >= 0, "negative neighbour count");
+  C8_CUDA(ctx, cudaSetDevice(ctx->device));
+  Comm& c = g_comm[ctx];
+  c.ctx = ctx;
+  c.n_nbr = n_nbr;
+  c.nbr_rank.assign(nbr_rank, nbr_rank + n_nbr);
+  c.send_ptr.assign(send_ptr, send_ptr + n_nbr + 1);
+  c.recv_ptr.assign(recv_ptr, recv_ptr + n_nbr + 1);
+  c.n_send = n_nbr ? send_ptr[n_nbr] : 0;
+  c.n_recv = n_nbr ? recv_ptr[n_nbr] : 0;
+  C8_REQUIRE(ctx, c.n_recv == ctx->n_nodes - ctx->n_owned_nodes,
+             "halo plan: received node count differs from the ghost count (c8_set_partition first)");
+  for (int i = 0; i < c.n_send; ++i)
+    C8_REQUIRE(ctx, send_nodes[i] >= 0 && send_nodes[i] < ctx->n_owned_nodes,
+               "halo plan: a send node is not owned");
+  if (c.d_send_nodes) cudaFree(c.d_send_nodes);
+  if (c.d_sendbuf) cudaFree(c.d_sendbuf);
+  if (c.h_send) cudaFreeHost(c.h_send);
+  if (c.h_recv) cudaFreeHost(c.h_recv);
+  c.d_send_nodes = nullptr; c.d_sendbuf = nullptr; c.h_send = c.h_recv = nullptr;
+  if (c.n_send) {
+    C8_CUDA(ctx, cudaMalloc(&c.d_send_nodes, c.n_send * sizeof(int)));
+    C8_CUDA(ctx, cudaMemcpy(c.d_send_nodes, send_nodes, c.n_send * sizeof(int), cudaMemcpyHostToDevice));
+    C8_CUDA(ctx, cudaMalloc(&c.d_sendbuf, size_t(c.n_send) * NBMAX * sizeof(double)));
+  }
+  C8_CUDA(ctx, cudaMallocHost(&c.h_send, size_t(c.n_send + 1) * NBMAX * sizeof(double)));
+  C8_CUDA(ctx, cudaMallocHost(&c.h_recv, size_t(c.n_recv + 1) * NBMAX * sizeof(double)));
+  return C8_OK;
+}
+
+int c8_nccl_unique_id(char* out128) {
+  if (!g_nccl.load()) return C8_ERR_USAGE;
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return C8_ERR_CUDA;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  std::memcpy(out128, &id, 128);
+  return C8_OK;
+}
+
+int c8_nccl_init(c8_ctx* ctx, const char* id128, int rank, int nranks) {
+  if (!g_nccl.load()) return fail(ctx, C8_ERR_USAGE, g_nccl.err);
+  auto it = g_comm.find(ctx);
+  C8_REQUIRE(ctx, it != g_comm.end(), "c8_set_halo_plan must be called before c8_nccl_init");
+  Comm& c = it->second;
+  C8_CUDA(ctx, cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  ncclResult_t r = g_nccl.CommInitRank(&c.nccl, nranks, id, rank);
+  if (r != ncclSuccess) return fail(ctx, C8_ERR_CUDA, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+  c.rank = rank; c.nranks = nranks;
+  return c8_set_comm(ctx, &halo_nccl, &allreduce_nccl, &c);
+}
+
+int c8_set_comm_host(c8_ctx* ctx, c8_host_exchange_fn exchange, c8_host_allreduce_fn allreduce,
+                     void* user) {
+  auto it = g_comm.find(ctx);
+  C8_REQUIRE(ctx, it != g_comm.end(), "c8_set_halo_plan must be called before c8_set_comm_host");
+  Comm& c = it->second;
+  c.exchange = exchange; c.host_allreduce = allreduce; c.user = user;
+  return c8_set_comm(ctx, &halo_host, &allreduce_host, &c);
+}
+
+int c8_halo(c8_ctx* ctx, double* vec_dev) {
+  C8_REQUIRE(ctx, ctx->kt != nullptr, "c8_set_model must be called first");
+  if (ctx->halo_cb) ctx->halo_cb(ctx->comm_user, vec_dev, ctx->kt->nb);
+  C8_CUDA(ctx, cudaGetLastError());
+  return C8_OK;
+}
+
+int c8_halo_nb(c8_ctx* ctx, double* vec_dev, int nb) {
+  C8_REQUIRE(ctx, nb >= 1 && nb <= NBMAX, "halo width must be 1..4");
+  if (ctx->halo_cb) ctx->halo_cb(ctx->comm_user, vec_dev, nb);
+  C8_CUDA(ctx, cudaGetLastError());
+  return C8_OK;
+}
+
+int c8_allreduce(c8_ctx* ctx, double* buf_dev, int n) {
+  if (ctx->allreduce_cb) ctx->allreduce_cb(ctx->comm_user, buf_dev, n);
+  C8_CUDA(ctx, cudaGetLastError());
+  return C8_OK;
+}
+
+int c8_comm_stats(c8_ctx* ctx, int64_t* out3) {
+  auto it = g_comm.find(ctx);
+  if (it == g_comm.end()) { out3[0] = out3[1] = out3[2] = 0; return C8_OK; }
+  out3[0] = it->second.n_halo; out3[1] = it->second.n_allreduce; out3[2] = it->second.halo_bytes;
+  return C8_OK;
+}
+
+void c8_comm_release(c8_ctx* ctx) { comm_release(ctx); }
+
+}  // extern "C"

@@ -131,6 +131,27 @@ static void residual_split(const c8_ctx* ctx, int i, int* eq0, int* neq) {
 }
 static int num_resid(const c8_ctx* ctx) { return (ctx->kt && ctx->kt->nb > ctx->dim) ? 2 : 1; }
 
+namespace c8 {
+__global__ void k_int_to_double(const int* i, double* d) { *d = double(*i); }
+
+// number of failed local solves over ALL parts (PCU_Add_Int of the status, src/primal.cpp:96)
+int fetch_n_failed(c8_ctx* ctx, int* out) {
+  if (ctx->allreduce_cb) {
+    if (!ctx->d_scalar) C8_CUDA(ctx, cudaMalloc(&ctx->d_scalar, 8 * sizeof(double)));
+    k_int_to_double<<<1, 1, 0, ctx->stream>>>(ctx->d_nfailed, ctx->d_scalar);
+    ctx->allreduce_cb(ctx->comm_user, ctx->d_scalar, 1);
+    double h = 0.0;
+    C8_CUDA(ctx, cudaMemcpyAsync(&h, ctx->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    C8_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = int(h + 0.5);
+  } else {
+    C8_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_nfailed, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    C8_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return C8_OK;
+}
+}  // namespace c8
+
 extern "C" {
 
 const char* c8_version(void) { return "calibr8_b200 0.1 (sm_100a)"; }
@@ -157,9 +178,11 @@ c8_ctx* c8_create(int device) {
 void c8_destroy(c8_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  c8_linalg_release(ctx);
+  c8_comm_release(ctx);
   void* ptrs[] = {ctx->d_conn, ctx->d_coords, ctx->d_elem_es, ctx->d_rowptr, ctx->d_colind,
                   ctx->d_eoff, ctx->d_params, ctx->d_nfailed, ctx->d_A, ctx->d_b, ctx->d_x,
-                  ctx->d_xp, ctx->d_xi, ctx->d_xip, ctx->d_stage};
+                  ctx->d_xp, ctx->d_xi, ctx->d_xip, ctx->d_stage, ctx->d_scalar};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -430,6 +453,7 @@ int c8_init_xi(c8_ctx* ctx, double* xi_dev) {
 }
 
 // ---- forward hot path -----------------------------------------------------------
+
 static int forward_impl(c8_ctx* ctx, const double* x, const double* xp, const double* xip,
                         double* xi, double* A, double* b, int8_t* path, double* eJ, double* eR,
                         int transpose, int* n_failed) {
@@ -445,9 +469,8 @@ static int forward_impl(c8_ctx* ctx, const double* x, const double* xp, const do
   C8_CUDA(ctx, cudaGetLastError());
   if (n_failed) {
     // the status is the reference's return value: the caller needs it before continuing
-    C8_CUDA(ctx, cudaMemcpyAsync(n_failed, ctx->d_nfailed, sizeof(int), cudaMemcpyDeviceToHost,
-                                 ctx->stream));
-    C8_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int rc = c8::fetch_n_failed(ctx, n_failed);
+    if (rc != C8_OK) return rc;
     if (*n_failed > 0) return C8_ERR_LOCAL_SOLVE;
   }
   return C8_OK;

@@ -41,6 +41,7 @@ struct c8_ctx {
 
   // scratch / resident system
   int* d_nfailed = nullptr;
+  double* d_scalar = nullptr;  // 8 doubles of device scratch for reduced scalars
   double* d_A = nullptr;       // resident BSR values [nnzb*nb*nb]
   double* d_b = nullptr;       // [n_nodes*nb]
   double* d_x = nullptr, *d_xp = nullptr;
@@ -64,6 +65,7 @@ int fail(c8_ctx* ctx, int code, const std::string& msg);
 bool cuda_ok(c8_ctx* ctx, cudaError_t e, const char* what);
 double* stage(c8_ctx* ctx, size_t bytes);
 double* pinned(c8_ctx* ctx, size_t bytes);
+int fetch_n_failed(c8_ctx* ctx, int* out);
 }  // namespace c8
 
 #define C8_CUDA(ctx, call)                                        \

@@ -408,33 +408,3 @@ void c8_linalg_release(c8_ctx* ctx) {
 }
 
 }  // extern "C"
-
-// ---- partition / communication hooks (multi-GPU) -------------------------------------------
-extern "C" {
-
-int c8_set_partition(c8_ctx* ctx, int n_owned_nodes, int n_owned_elems) {
-  C8_REQUIRE(ctx, n_owned_nodes <= ctx->n_nodes && n_owned_elems <= ctx->n_elems,
-             "owned counts exceed the local mesh");
-  ctx->n_owned_nodes = n_owned_nodes;
-  ctx->n_owned_elems = n_owned_elems;
-  return C8_OK;
-}
-
-int c8_set_comm(c8_ctx* ctx, c8_halo_fn halo, c8_allreduce_fn allreduce, void* user) {
-  ctx->halo_cb = halo;
-  ctx->allreduce_cb = allreduce;
-  ctx->comm_user = user;
-  return C8_OK;
-}
-
-int c8_halo(c8_ctx* ctx, double* vec_dev) {
-  if (ctx->halo_cb) ctx->halo_cb(ctx->comm_user, vec_dev, ctx->kt->nb);
-  return C8_OK;
-}
-
-int c8_allreduce(c8_ctx* ctx, double* buf_dev, int n) {
-  if (ctx->allreduce_cb) ctx->allreduce_cb(ctx->comm_user, buf_dev, n);
-  return C8_OK;
-}
-
-}  // extern "C"

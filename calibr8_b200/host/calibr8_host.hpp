@@ -80,6 +80,7 @@ class Problem {
 
   c8_ctx* ctx;
   int dim, nn, nb, nx, nxi, npar, n_elems, n_nodes, nnzb;
+  int n_owned_nodes = 0, n_owned_elems = 0;  // partition (== n_nodes / n_elems on one GPU)
   long long n_dofs, xi_ld;
   std::vector<double> coords;  // [n_nodes][3] host copy for BC expressions
   int num_steps = 0;

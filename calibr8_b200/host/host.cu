@@ -21,6 +21,7 @@ Problem::Problem(c8_ctx* c) : ctx(c) {
   dim = int(info[0]); nn = int(info[1]); nb = int(info[2]); nx = int(info[3]); nxi = int(info[4]);
   npar = int(info[5]); n_elems = int(info[6]); n_nodes = int(info[7]); nnzb = int(info[8]);
   n_dofs = info[9]; xi_ld = info[11];
+  check(c8_get_partition(ctx, &n_owned_nodes, &n_owned_elems), "c8_get_partition");
   coords.resize(size_t(n_nodes) * 3);
   c8_get_coords(ctx, coords.data());
   A.resize(size_t(nnzb) * nb * nb);
@@ -52,6 +53,7 @@ void Problem::finalize_dbcs() {
   std::vector<int> node, eq;
   for (const Dbc& d : dbcs)
     for (int nd : d.nodes) {
+      if (nd >= n_owned_nodes) continue;  // rows of ghost nodes belong to another part
       node.push_back(nd);
       eq.push_back(d.resid == 0 ? d.eq : dim);  // residual 1 = pressure -> interleaved eq index dim
     }
@@ -71,6 +73,7 @@ void Problem::eval_dbc_values(double t) {
   size_t k = 0;
   for (const Dbc& d : dbcs)
     for (int nd : d.nodes) {
+      if (nd >= n_owned_nodes) continue;
       const double* X = &coords[size_t(nd) * 3];
       h_dbc_val[k++] = d.expr(X[0], X[1], X[2], t);
     }
@@ -126,6 +129,7 @@ static double preprocess_load_mismatch(Problem& P, int step, double* total_load_
   C8H_CUDA(cudaMemsetAsync(P.work.get(), 0, 2 * sizeof(double), s));
   P.check(c8_qoi_value(P.ctx, &q, P.x[step].get(), P.x[step - 1].get(), P.xi[step].get(),
                        P.xi[step - 1].get(), 1, P.work.get()), "c8_qoi_value(load)");
+  P.check(c8_allreduce(P.ctx, P.work.get(), 2), "c8_allreduce");  // PCU_Add_Double, calibration.cpp:349-353
   double h[2];
   C8H_CUDA(cudaMemcpyAsync(h, P.work.get(), 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   C8H_CUDA(cudaStreamSynchronize(s));
@@ -139,6 +143,7 @@ bool Primal::assemble(int step, double* R_norm) {
   C8H_CUDA(cudaMemsetAsync(P.A.get(), 0, P.A.size() * sizeof(double), s));
   C8H_CUDA(cudaMemsetAsync(P.b.get(), 0, P.b.size() * sizeof(double), s));
   int nf = 0;
+  P.check(c8_halo(P.ctx, P.x[step].get()), "c8_halo");  // ghost entries of the Newton iterate
   const int rc = c8_forward_jacobian(P.ctx, P.x[step].get(), P.x[step - 1].get(),
                                      P.xi[step - 1].get(), P.xi[step].get(), P.A.get(), P.b.get(),
                                      nullptr, &nf);
@@ -234,6 +239,7 @@ double Primal::eval_qoi(int step) {
   C8H_CUDA(cudaMemsetAsync(P.work.get(), 0, 2 * sizeof(double), s));
   P.check(c8_qoi_value(P.ctx, &q, P.x[step].get(), P.x[step - 1].get(), P.xi[step].get(),
                        P.xi[step - 1].get(), 0, P.work.get()), "c8_qoi_value");
+  P.check(c8_allreduce(P.ctx, P.work.get(), 2), "c8_allreduce");
   double h[2];
   C8H_CUDA(cudaMemcpyAsync(h, P.work.get(), 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   C8H_CUDA(cudaStreamSynchronize(s));
@@ -294,11 +300,13 @@ void Adjoint::gradient(std::vector<double>& grad) {
       if (rn < sp.newton_abs_tol || (r0 > 0 && rn / r0 < sp.newton_rel_tol)) break;
       if (++iter > sp.newton_max_iters) throw std::runtime_error("adjoint solve failed to converge");
     }
+    P.check(c8_halo(P.ctx, z), "c8_halo");
     P.check(c8_adjoint_local(P.ctx, x, xp, xi, xip, z, P.phi[step].get(), g.get(), f.get()),
             "c8_adjoint_local");
     C8H_CUDA(cudaMemsetAsync(d_grad.get(), 0, 64 * sizeof(double), s));
     P.check(c8_qoi_gradient(P.ctx, &q, x, xp, xi, xip, z, P.phi[step].get(), d_grad.get()),
             "c8_qoi_gradient");
+    P.check(c8_allreduce(P.ctx, d_grad.get(), n_es * P.npar), "c8_allreduce");
     double h[64];
     C8H_CUDA(cudaMemcpyAsync(h, d_grad.get(), 64 * sizeof(double), cudaMemcpyDeviceToHost, s));
     C8H_CUDA(cudaStreamSynchronize(s));

@@ -54,6 +54,7 @@ class VirtualPower {
     P.check(c8_vfm_adjoint(P.ctx, meas[step].get(), meas[step - 1].get(), P.xi[step].get(),
                            P.xi[step - 1].get(), vf.get(), scaled_mismatch, hist.get(),
                            P.work.get()), "c8_vfm_adjoint");
+    P.check(c8_allreduce(P.ctx, P.work.get(), P.npar), "c8_allreduce");
     grad.assign(P.npar, 0.0);
     cudaMemcpyAsync(grad.data(), P.work.get(), P.npar * sizeof(double), cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);

@@ -203,8 +203,29 @@ int c8_set_partition(c8_ctx* ctx, int n_owned_nodes, int n_owned_elems);
 typedef void (*c8_halo_fn)(void* user, double* vec_dev, int nb);
 typedef void (*c8_allreduce_fn)(void* user, double* buf_dev, int n);
 int c8_set_comm(c8_ctx* ctx, c8_halo_fn halo, c8_allreduce_fn allreduce, void* user);
-int c8_halo(c8_ctx* ctx, double* vec_dev);
+int c8_get_partition(c8_ctx* ctx, int* n_owned_nodes, int* n_owned_elems);
+/* neighbour plan (host arrays): for neighbour k = 0..n_nbr-1 of rank nbr_rank[k], the owned local
+ * nodes send_nodes[send_ptr[k]..send_ptr[k+1]) are sent, and the ghost nodes
+ * n_owned_nodes + [recv_ptr[k], recv_ptr[k+1]) are received (ghosts are sorted by owner rank, then
+ * by the owner's ordering, so each neighbour fills one contiguous range) */
+int c8_set_halo_plan(c8_ctx* ctx, int n_nbr, const int32_t* nbr_rank, const int32_t* send_ptr,
+                     const int32_t* send_nodes, const int32_t* recv_ptr);
+/* transport 1: NCCL over NVLink (libnccl.so.2 bound at run time).  Rank 0 creates the id, the host
+ * program distributes the 128 bytes (MPI_Bcast / torch.distributed), every rank calls init. */
+int c8_nccl_unique_id(char* id_out128);
+int c8_nccl_init(c8_ctx* ctx, const char* id128, int rank, int nranks);
+/* transport 2: host-staged, for an MPI (PCU) or gloo host program without NCCL.
+ * exchange(user, send_host, recv_host, nb): send_host holds [n_send][nb] packed in send_ptr order,
+ * recv_host must be filled with [n_ghost][nb] in recv_ptr order; allreduce sums n host doubles. */
+typedef void (*c8_host_exchange_fn)(void* user, const double* send_host, double* recv_host, int nb);
+typedef void (*c8_host_allreduce_fn)(void* user, double* buf_host, int n);
+int c8_set_comm_host(c8_ctx* ctx, c8_host_exchange_fn exchange, c8_host_allreduce_fn allreduce,
+                     void* user);
+int c8_halo(c8_ctx* ctx, double* vec_dev);              /* nodal vector [n_nodes][NB] */
+int c8_halo_nb(c8_ctx* ctx, double* vec_dev, int nb);   /* nodal vector [n_nodes][nb], nb <= 4 */
 int c8_allreduce(c8_ctx* ctx, double* buf_dev, int n);
+int c8_comm_stats(c8_ctx* ctx, int64_t* out3 /* halo calls, allreduce calls, halo bytes */);
+void c8_comm_release(c8_ctx* ctx);
 
 int c8_get_coords(c8_ctx* ctx, double* coords_host /* [n_nodes][3] */);
 int c8_get_conn(c8_ctx* ctx, int32_t* conn_host);
