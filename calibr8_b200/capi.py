@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libc8b200.so")
+# C8B200_LIB selects an alternative build of the same library (kernel-tuning variants)
+LIB_PATH = os.environ.get("C8B200_LIB") or os.path.join(_HERE, "lib", "libc8b200.so")
 
 GLOBAL_TYPES = {"mechanics": 0, "mechanics_plane_stress": 1}
 LOCAL_TYPES = {

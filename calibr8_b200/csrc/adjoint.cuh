@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(128) k_adjoint_jacobian(const AdjArgs a) {
   fa.mesh = a.mesh;
   fa.vals = a.vals;
   fa.transpose = 1;
-  const Scatter<C> sc{fa, E, sx.xl, e, t, true};
+  Scatter<C, true, false> sc{fa, E, sx.xl, e, t, true};  // TODO(K3): FAST needs b
+  sc.init();
   {
     const Mat<Dual<LX>, D> P = first_pk<D, C::M, Model>(k2, sx.p, xid, E.par, a.model.thickness);
 #pragma unroll

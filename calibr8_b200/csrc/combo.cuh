@@ -21,7 +21,11 @@ struct Launch {
     if (a.mesh.n_elems == 0) return;
     const long long threads = (long long)a.mesh.n_elems * C::G;
     const int block = C8_K1_BLOCK;
-    k_forward_jacobian<C><<<(unsigned)((threads + block - 1) / block), block, 0, s>>>(a);
+    const unsigned grid = (unsigned)((threads + block - 1) / block);
+    // FAST: the production call (matrix + residual, no element-level output) is branch-free
+    const bool fast = a.vals && a.b && !a.elem_J && !a.elem_R;
+    if (fast) k_forward_jacobian<C, true><<<grid, block, 0, s>>>(a);
+    else k_forward_jacobian<C, false><<<grid, block, 0, s>>>(a);
   }
   static void global_residual(const FwdArgs& a, cudaStream_t s) {
     if (a.mesh.n_elems == 0) return;

@@ -35,6 +35,11 @@ C8_DI int picki(int c, int a, int b) {
   return r;
 }
 
+// fp64 reduction to global memory without a return value (RED.E.ADD.F64)
+C8_DI void red_add(double* addr, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" :: "l"(addr), "d"(v) : "memory");
+}
+
 template <int L>
 struct Dual {
   double v;
@@ -212,10 +217,9 @@ template <int L> C8_DI Dual<L> inv_sqr(const Dual<L>& a) {
 C8_DI double dpow(double a, double b) { return pow(a, b); }
 template <int L> C8_DI Dual<L> dpow(const Dual<L>& a, double b) {
   Dual<L> r; r.v = pow(a.v, b);
-  double s;
-  if (b == 1.0) s = 1.0;
-  else if (a.v == 0.0) s = 0.0;
-  else s = b / a.v * r.v;
+  // branch-free: s = 1 (b == 1), 0 (a == 0), b/a * a^b otherwise
+  double s = pick(a.v == 0.0, 0.0, b / a.v * r.v);
+  s = pick(b == 1.0, 1.0, s);
 #pragma unroll
   for (int i = 0; i < L; ++i) r.d[i] = s * a.d[i];
   return r;

@@ -87,36 +87,38 @@ C8_DI int local_newton(const Kin<C::D, double, double>& k0, const Elem<C>& E, co
     int path = 0, iter = 1;
     double R_norm_0 = 1.0;
     bool converged = false;
+    // WARP-UNIFORM body: every lane evaluates the residual and takes part in the solve (full-mask
+    // shuffles); lanes that are done re-evaluate at their unchanged xi, which reproduces the same
+    // Cd / path, and simply do not apply the update.
     while (true) {
       const bool work = active && (iter <= md.max_iters) && !converged;
       if (!__syncthreads_or(work)) break;
-      if (work) {
-        Dual<LXI> xs[NXI];
+      Dual<LXI> xs[NXI];
 #pragma unroll
-        for (int q = 0; q < NXI; ++q) xs[q] = seeded<LXI>(xi[q], q, t * LXI);
-        path = Model::residual(k0, xs, E.xip, E.par, md.abs_tol, Cd);
-        double nrm = 0.0;
+      for (int q = 0; q < NXI; ++q) xs[q] = seeded<LXI>(xi[q], q, t * LXI);
+      path = Model::residual(k0, xs, E.xip, E.par, md.abs_tol, Cd);
+      double nrm = 0.0;
 #pragma unroll
-        for (int q = 0; q < NXI; ++q) nrm += Cd[q].v * Cd[q].v;
-        const double R_norm = sqrt(nrm);
-        if (iter == 1) R_norm_0 = R_norm;
-        const double R_norm_rel = R_norm / R_norm_0;
-        if ((R_norm_rel < md.rel_tol) || (R_norm < md.abs_tol)) {
-          converged = true;
-        } else {
-          double Jc[NXI][LXI], rhs[NXI], dummy[NXI][1];
+      for (int q = 0; q < NXI; ++q) nrm += Cd[q].v * Cd[q].v;
+      const double R_norm = sqrt(nrm);
+      if (work && iter == 1) R_norm_0 = R_norm;
+      const double R_norm_rel = R_norm / R_norm_0;
+      const bool conv_now = (R_norm_rel < md.rel_tol) || (R_norm < md.abs_tol);
+      const bool update = work && !conv_now;
+      if (work && conv_now) converged = true;
+      if (__any_sync(0xffffffffu, update)) {
+        double Jc[NXI][LXI], rhs[NXI], dummy[NXI][1];
 #pragma unroll
-          for (int q = 0; q < NXI; ++q) {
-            rhs[q] = -Cd[q].v;
+        for (int q = 0; q < NXI; ++q) {
+          rhs[q] = -Cd[q].v;
 #pragma unroll
-            for (int s = 0; s < LXI; ++s) Jc[q][s] = Cd[q].d[s];
-          }
-          group_gauss_jordan<NXI, LXI, 0, C::G>(Jc, dummy, rhs, mask);
-#pragma unroll
-          for (int q = 0; q < NXI; ++q) xi[q] += rhs[q];
-          ++iter;
+          for (int s = 0; s < LXI; ++s) Jc[q][s] = Cd[q].d[s];
         }
+        group_gauss_jordan<NXI, LXI, 0, C::G, true>(Jc, dummy, rhs, mask);
+#pragma unroll
+        for (int q = 0; q < NXI; ++q) xi[q] = pick(update, xi[q] + rhs[q], xi[q]);
       }
+      if (update) ++iter;
     }
     if (active && !converged) return -1;
     return path;
@@ -124,7 +126,7 @@ C8_DI int local_newton(const Kin<C::D, double, double>& k0, const Elem<C>& E, co
 }
 
 // dxi/dx = -(dC/dxi)^-1 dC/dx for the columns this thread owns (Bc in: dC/dx, out: dxi/dx)
-template <class C, int LB>
+template <class C, int LB, bool FULL = false>
 C8_DI void local_sensitivity(const Dual<C::LXI> (&Cd)[C::NXI], double (&Bc)[C::NXI][LB],
                              unsigned mask) {
   if constexpr (!C::Model::HAS_NEWTON) {
@@ -143,7 +145,7 @@ C8_DI void local_sensitivity(const Dual<C::LXI> (&Cd)[C::NXI], double (&Bc)[C::N
 #pragma unroll
       for (int s = 0; s < LB; ++s) Bc[q][s] = -Bc[q][s];
     }
-    group_gauss_jordan<C::NXI, C::LXI, LB, C::G>(Jc, Bc, dummy, mask);
+    group_gauss_jordan<C::NXI, C::LXI, LB, C::G, FULL>(Jc, Bc, dummy, mask);
   }
 }
 
@@ -181,41 +183,83 @@ struct SeededX {
   }
 };
 
-// Scatter one element row (value + this thread's derivative lanes).
-template <class C>
+// Scatter one element row (value + this thread's derivative lanes) into the fixed BSR pattern.
+// TRANSPOSE: scatter dtotal^T (adjoint Jacobian).  FAST: vals and b are both given and no
+// element-level output is wanted -- the production case; it is completely branch-free: every lane
+// issues its reductions unconditionally and lanes that must not contribute (rows of ghost nodes,
+// which belong to another part; padding groups; failed local solves) add 0.0.  A conditional
+// atomicAdd compiles to a branch + reconvergence region each, 16 x (LX + 1) of them per thread.
+// !FAST: run-time checks for absent outputs and the element-level Jacobian / residual in the
+// reference's dof order (parity-test hook).
+template <class C, bool TRANSPOSE = false, bool FAST = false>
 struct Scatter {
   const FwdArgs& a;
   const Elem<C>& E;
   const XLanes<C::D, C::NB, C::LX>& xl;
   int e, t;
   bool on;  // false: compute but store nothing (padding groups, failed local solves)
-  C8_DI void row(int n, int eq, const Dual<C::LX>& r) const {
-    constexpr int NB = C::NB, NN = C::NN, NX = C::NX;
-    if (!on) return;
-    const bool row_owned = E.nodes[n] < a.mesh.n_row_nodes;  // ghost rows belong to another rank
-    const int row_dof = n * NB + eq;
-    if (a.b && row_owned && (row_dof % C::G) == t) atomicAdd(&a.b[size_t(E.nodes[n]) * NB + eq], r.v);
-    if (a.elem_R && (row_dof % C::G) == t) a.elem_R[size_t(e) * NX + C::ref_dof(n, eq)] = r.v;
+  bool lane_on[C::LX];
+  // residual entries this thread adds at the end: element dofs t, t+G, t+2G, ... (values are
+  // replicated over the group, so each thread just keeps its share -- no per-row branch)
+  static constexpr int NBACC = (C::NX + C::G - 1) / C::G;
+  double bacc[NBACC];
+  C8_DI void init() {
 #pragma unroll
     for (int s = 0; s < C::LX; ++s) {
-      if (xl.nsel[s] == 0.0) continue;
-      const int nc = xl.node[s], qc = xl.eq[s];
-      if (a.vals) {
-        if (!a.transpose) {
-          if (!row_owned) continue;
-          const int blk = __ldg(&a.mesh.eoff[size_t(e) * NN * NN + n * NN + nc]);
-          atomicAdd(&a.vals[size_t(blk) * NB * NB + eq * NB + qc], r.d[s]);
-        } else {
-          int gn = 0;
+      int gn = 0;
 #pragma unroll
-          for (int n2 = 0; n2 < NN; ++n2) gn = picki(nc == n2, E.nodes[n2], gn);
-          if (gn >= a.mesh.n_row_nodes) continue;
-          const int blk = __ldg(&a.mesh.eoff[size_t(e) * NN * NN + nc * NN + n]);
-          atomicAdd(&a.vals[size_t(blk) * NB * NB + qc * NB + eq], r.d[s]);
+      for (int n2 = 0; n2 < C::NN; ++n2) gn = picki(xl.node[s] == n2, E.nodes[n2], gn);
+      lane_on[s] = on && (xl.nsel[s] != 0.0) && (!TRANSPOSE || gn < a.mesh.n_row_nodes);
+    }
+#pragma unroll
+    for (int j = 0; j < NBACC; ++j) bacc[j] = 0.0;
+  }
+  // after the last row(): one reduction per kept residual entry
+  C8_DI void finish() const {
+    constexpr int NB = C::NB, NN = C::NN, NX = C::NX;
+    if (FAST || a.b != nullptr) {
+#pragma unroll
+      for (int j = 0; j < NBACC; ++j) {
+        const int dof = t + j * C::G;
+        const int dofc = dof < NX ? dof : NX - 1;
+        const int n = dofc / NB, eq = dofc - n * NB;
+        int gn = 0;
+#pragma unroll
+        for (int n2 = 0; n2 < NN; ++n2) gn = picki(n == n2, E.nodes[n2], gn);
+        const bool keep = on && dof < NX && gn < a.mesh.n_row_nodes;
+        red_add(&a.b[size_t(gn) * NB + eq], pick(keep, bacc[j], 0.0));
+      }
+    }
+  }
+  C8_DI void row(int n, int eq, const Dual<C::LX>& r) {
+    constexpr int NB = C::NB, NN = C::NN, NX = C::NX;
+    const bool row_on = on && E.nodes[n] < a.mesh.n_row_nodes;  // ghost rows belong to another rank
+    const int row_dof = n * NB + eq;
+    const int* eo = a.mesh.eoff + size_t(e) * NN * NN;
+    bacc[row_dof / C::G] = pick((row_dof % C::G) == t, r.v, bacc[row_dof / C::G]);
+    if constexpr (!FAST) {
+      if (on && a.elem_R && (row_dof % C::G) == t) a.elem_R[size_t(e) * NX + C::ref_dof(n, eq)] = r.v;
+    }
+    if (FAST || a.vals != nullptr) {
+#pragma unroll
+      for (int s = 0; s < C::LX; ++s) {
+        const int nc = xl.node[s], qc = xl.eq[s];
+        // padding lanes (2-D only) point at a valid slot and add 0
+        const int ncc = nc < NN ? nc : NN - 1, qcc = qc < NB ? qc : NB - 1;
+        if constexpr (!TRANSPOSE) {
+          const int blk = __ldg(&eo[n * NN + ncc]);
+          red_add(&a.vals[size_t(blk) * NB * NB + eq * NB + qcc], pick(lane_on[s] && row_on, r.d[s], 0.0));
+        } else {
+          const int blk = __ldg(&eo[ncc * NN + n]);
+          red_add(&a.vals[size_t(blk) * NB * NB + qcc * NB + eq], pick(lane_on[s], r.d[s], 0.0));
         }
       }
-      if (a.elem_J)
-        a.elem_J[(size_t(e) * NX + C::ref_dof(n, eq)) * NX + C::ref_dof(nc, qc)] = r.d[s];
+    }
+    if constexpr (!FAST) {
+#pragma unroll
+      for (int s = 0; s < C::LX; ++s)
+        if (on && a.elem_J && xl.nsel[s] != 0.0)
+          a.elem_J[(size_t(e) * NX + C::ref_dof(n, eq)) * NX + C::ref_dof(xl.node[s], xl.eq[s])] = r.d[s];
     }
   }
 };
@@ -223,9 +267,12 @@ struct Scatter {
 #ifndef C8_K1_BLOCK
 #define C8_K1_BLOCK 256
 #endif
+#ifndef C8_K1_MINB
+#define C8_K1_MINB 1
+#endif
 
-template <class C>
-__global__ void __launch_bounds__(C8_K1_BLOCK, 1) k_forward_jacobian(const FwdArgs a) {
+template <class C, bool FAST>
+__global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian(const FwdArgs a) {
   using Model = typename C::Model;
   constexpr int D = C::D, NN = C::NN, NB = C::NB, NXI = C::NXI, LX = C::LX, G = C::G;
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -280,7 +327,7 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, 1) k_forward_jacobian(const FwdAr
     for (int q = 0; q < NXI; ++q)
 #pragma unroll
       for (int s = 0; s < LX; ++s) Bc[q][s] = C2[q].d[s];
-    local_sensitivity<C, LX>(Cd, Bc, mask);
+    local_sensitivity<C, LX, true>(Cd, Bc, mask);
 #pragma unroll
     for (int q = 0; q < NXI; ++q) {
       xid[q].v = xi[q];
@@ -292,7 +339,8 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, 1) k_forward_jacobian(const FwdAr
 
   // ---- P3: element residual and total Jacobian, scattered row by row ------
   const double wdv = quad1_weight<D>() * E.g.dv;
-  const Scatter<C> sc{a, E, sx.xl, e, t, ok};
+  Scatter<C, false, FAST> sc{a, E, sx.xl, e, t, ok};
+  sc.init();
   {
     const Mat<Dual<LX>, D> P = first_pk<D, C::M, Model>(k2, sx.p, xid, E.par, a.model.thickness);
     __syncthreads();
@@ -346,6 +394,7 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, 1) k_forward_jacobian(const FwdAr
 #pragma unroll
     for (int n = 0; n < NN; ++n) sc.row(n, D, Rp[n]);
   }
+  sc.finish();
 }
 
 // K2: residual only (eval_global_residual): no Newton, xi given, T = double

@@ -26,12 +26,20 @@ C8_DI void cswap(int sw, double& a, double& b) {
 template <int G> C8_DI double group_bcast(unsigned mask, double v, int src) {
   return __shfl_sync(mask, v, src, G);
 }
+// Same, for call sites reached by ALL 32 lanes of the warp together (warp-uniform control flow):
+// with a compile-time full mask the shuffle is two plain SHFL.IDX; a run-time sub-warp mask makes
+// the compiler wrap every shuffle in a WARPSYNC / reconvergence sequence (about a quarter of K1's
+// static code before this, see profiles/README.md).
+template <int G> C8_DI double group_bcast_full(double v, int src) {
+  return __shfl_sync(0xffffffffu, v, src, G);
+}
 
 // J (N x N): column c lives in thread c / LJ, slot c % LJ  -> Jc[row][slot]
 // B (N x G*LB): thread owns LB columns                     -> Bc[row][slot]
 // b (N): replicated on every thread of the group
 // On return Bc = J^-1 B and b = J^-1 b (J is destroyed).
-template <int N, int LJ, int LB, int G>
+// FULL: the call site is warp-uniform (all 32 lanes arrive together) -> full-mask shuffles.
+template <int N, int LJ, int LB, int G, bool FULL = false>
 C8_DI void group_gauss_jordan(double (&Jc)[N][LJ], double (&Bc)[N][LB > 0 ? LB : 1],
                               double (&b)[N], unsigned mask) {
 #pragma unroll
@@ -39,7 +47,8 @@ C8_DI void group_gauss_jordan(double (&Jc)[N][LJ], double (&Bc)[N][LB > 0 ? LB :
     const int owner = k / LJ, slot = k % LJ;
     double col[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) col[i] = group_bcast<G>(mask, Jc[i][slot], owner);
+    for (int i = 0; i < N; ++i)
+      col[i] = FULL ? group_bcast_full<G>(Jc[i][slot], owner) : group_bcast<G>(mask, Jc[i][slot], owner);
     int p = k;
     double best = fabs(col[k]);
 #pragma unroll
@@ -47,7 +56,7 @@ C8_DI void group_gauss_jordan(double (&Jc)[N][LJ], double (&Bc)[N][LB > 0 ? LB :
       const double a = fabs(col[i]);
       if (a > best) { best = a; p = i; }
     }
-    if (p != k) {  // group-uniform (col is identical on all threads of the group)
+    if (__builtin_expect(p != k, 0)) {  // group-uniform (col is identical on all threads of the group)
 #pragma unroll
       for (int i = k + 1; i < N; ++i) {
         const int sw = (i == p) ? 1 : 0;
