@@ -1,5 +1,11 @@
 // Instantiates every kernel of the hot path for one (DIM, MECH, Model, G) combination.
 #pragma once
+// threads per quadrature point for the 3-D mixed u-p combinations (NX = 16 element dofs): 4 threads
+// x 4 derivative lanes measured fastest on B200 (profiles/README.md: fewer replicated value
+// instructions than 8 x 2, and a smaller program)
+#ifndef C8_G3D
+#define C8_G3D 4
+#endif
 #include "vfm.cuh"
 #include "kernel_table.h"
 

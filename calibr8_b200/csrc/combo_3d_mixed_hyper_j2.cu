@@ -1,5 +1,2 @@
-#ifndef C8_G3D
-#define C8_G3D 8
-#endif
 #include "combo.cuh"
 C8_DEFINE_COMBO(3d_mixed_hyper_j2, 3, MECH_MIXED, HyperJ2, C8_G3D)
