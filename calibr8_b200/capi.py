@@ -556,3 +556,25 @@ Context.set_comm_host = _ctx_set_comm_host
 Context.halo = _ctx_halo
 Context.allreduce = _ctx_allreduce
 Context.comm_stats = _ctx_comm_stats
+
+
+SYMBOLS += ["c8_set_preconditioner", "c8_preconditioner_info", "c8_linalg_invalidate"]
+
+
+def _ctx_set_preconditioner(self, kind="amg", nu_pre=2, nu_post=2, omega=0.7, over_correction=1.0,
+                            coarsest_max_nodes=40):
+    """right preconditioner of gmres(): 'amg' (aggregation multigrid, default) or 'block_jacobi'"""
+    opts = np.array([nu_pre, nu_post, omega, over_correction, coarsest_max_nodes], dtype=np.float64)
+    self._check(self.lib.c8_set_preconditioner(self.h, {"block_jacobi": 0, "amg": 1}[kind], _hp(opts),
+                                               int(opts.size)))
+
+
+def _ctx_preconditioner_info(self):
+    out = (C.c_double * 16)()
+    self._check(self.lib.c8_preconditioner_info(self.h, out, 16))
+    nl = int(out[0])
+    return dict(levels=nl, operator_complexity=out[1], nodes=[int(out[2 + l]) for l in range(nl)])
+
+
+Context.set_preconditioner = _ctx_set_preconditioner
+Context.preconditioner_info = _ctx_preconditioner_info

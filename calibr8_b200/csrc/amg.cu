@@ -1,0 +1,398 @@
+// Aggregation multigrid preconditioner (see amg.cuh).
+#include "amg.cuh"
+
+#include <algorithm>
+#include <cstdint>
+#include <numeric>
+
+namespace c8 {
+
+// r = b - A x ; one thread per scalar row
+template <int NB>
+__global__ void k_bsr_residual(const int* __restrict__ rowptr, const int* __restrict__ colind,
+                               const double* __restrict__ vals, const double* __restrict__ x,
+                               const double* __restrict__ b, double* __restrict__ r, int n_nodes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes * NB) return;
+  const int node = i / NB, row = i % NB;
+  double s = b[i];
+  const int b0 = rowptr[node], b1 = rowptr[node + 1];
+  for (int k = b0; k < b1; ++k) {
+    const double* a = vals + (size_t(k) * NB + row) * NB;
+    const double* xv = x + size_t(__ldg(&colind[k])) * NB;
+#pragma unroll
+    for (int c = 0; c < NB; ++c) s = fma(-__ldg(&a[c]), __ldg(&xv[c]), s);
+  }
+  r[i] = s;
+}
+
+// x = (zero_guess ? 0 : x) + omega * Dinv r
+template <int NB>
+__global__ void k_jacobi_update(const double* __restrict__ dinv, const double* __restrict__ r,
+                                double* __restrict__ x, double omega, int zero_guess, int n_nodes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes * NB) return;
+  const int node = i / NB, row = i % NB;
+  double s = 0.0;
+#pragma unroll
+  for (int c = 0; c < NB; ++c) s = fma(dinv[(size_t(node) * NB + row) * NB + c], r[size_t(node) * NB + c], s);
+  x[i] = (zero_guess ? 0.0 : x[i]) + omega * s;
+}
+
+// bc[I] = sum over the members of aggregate I
+template <int NB>
+__global__ void k_restrict(const int* __restrict__ aggptr, const int* __restrict__ aggmem,
+                           const double* __restrict__ r, double* __restrict__ bc, int nc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc * NB) return;
+  const int I = i / NB, c = i % NB;
+  double s = 0.0;
+  for (int k = aggptr[I]; k < aggptr[I + 1]; ++k) s += r[size_t(aggmem[k]) * NB + c];
+  bc[i] = s;
+}
+
+template <int NB>
+__global__ void k_prolong_add(const int* __restrict__ agg, const double* __restrict__ xc,
+                              double* __restrict__ x, double scale, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * NB) return;
+  const int node = i / NB, c = i % NB;
+  x[i] += scale * xc[size_t(agg[node]) * NB + c];
+}
+
+// coarse block values = sum of the fine blocks mapped to it; one thread per (coarse block, entry)
+template <int NB>
+__global__ void k_galerkin(const int* __restrict__ cptr, const int* __restrict__ cmem,
+                           const double* __restrict__ fine, double* __restrict__ coarse, int nnzb_c) {
+  constexpr int BB = NB * NB;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)nnzb_c * BB) return;
+  const int blk = int(i / BB), e = int(i % BB);
+  double s = 0.0;
+  for (int k = cptr[blk]; k < cptr[blk + 1]; ++k) s += fine[size_t(cmem[k]) * BB + e];
+  coarse[i] = s;
+}
+
+// dense [N][2N] = [A | I] from the coarsest BSR operator
+template <int NB>
+__global__ void k_dense_fill(const int* __restrict__ rowptr, const int* __restrict__ colind,
+                             const double* __restrict__ vals, double* __restrict__ M, int n_nodes) {
+  const int N = n_nodes * NB;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int node = i / NB, row = i % NB;
+  double* Mi = M + size_t(i) * 2 * N;
+  for (int c = 0; c < 2 * N; ++c) Mi[c] = (c == N + i) ? 1.0 : 0.0;
+  for (int k = rowptr[node]; k < rowptr[node + 1]; ++k)
+#pragma unroll
+    for (int c = 0; c < NB; ++c) Mi[colind[k] * NB + c] = vals[(size_t(k) * NB + row) * NB + c];
+}
+
+// Gauss-Jordan inverse with partial pivoting, one CTA, matrix in global memory (L2 resident)
+__global__ void __launch_bounds__(1024) k_dense_inverse(double* __restrict__ M, int N) {
+  extern __shared__ double colk[];  // N doubles
+  __shared__ double s_best[32];
+  __shared__ int s_idx[32];
+  __shared__ int s_p;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int W = 2 * N;
+  for (int k = 0; k < N; ++k) {
+    // pivot search
+    double best = -1.0;
+    int bi = k;
+    for (int i = k + tid; i < N; i += nt) {
+      const double a = fabs(M[size_t(i) * W + k]);
+      if (a > best) { best = a; bi = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_down_sync(0xffffffffu, best, o);
+      const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if ((tid & 31) == 0) { s_best[tid >> 5] = best; s_idx[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      double b = s_best[0];
+      int p = s_idx[0];
+      for (int w = 1; w < (nt >> 5); ++w)
+        if (s_best[w] > b || (s_best[w] == b && s_idx[w] < p)) { b = s_best[w]; p = s_idx[w]; }
+      s_p = p;
+      if (!(b > 0.0)) { M[size_t(k) * W + k] = 1.0; s_p = k; }  // empty row: identity
+    }
+    __syncthreads();
+    const int p = s_p;
+    if (p != k)
+      for (int c = tid; c < W; c += nt) {
+        const double t = M[size_t(k) * W + c];
+        M[size_t(k) * W + c] = M[size_t(p) * W + c];
+        M[size_t(p) * W + c] = t;
+      }
+    __syncthreads();
+    const double inv = 1.0 / M[size_t(k) * W + k];
+    for (int i = tid; i < N; i += nt) colk[i] = M[size_t(i) * W + k];
+    __syncthreads();
+    for (int c = tid; c < W; c += nt) M[size_t(k) * W + c] *= inv;
+    __syncthreads();
+    // eliminate column k from every other row; columns < k of the left half are already zero
+    const int c0 = k, ncol = W - c0;
+    const long long work = (long long)N * ncol;
+    for (long long q = tid; q < work; q += nt) {
+      const int i = int(q / ncol), c = c0 + int(q % ncol);
+      if (i == k) continue;
+      const double f = colk[i];
+      if (f != 0.0) M[size_t(i) * W + c] = fma(-f, M[size_t(k) * W + c], M[size_t(i) * W + c]);
+    }
+    __syncthreads();
+  }
+}
+
+// x = Ainv b with Ainv = right half of M
+__global__ void k_dense_apply(const double* __restrict__ M, const double* __restrict__ b,
+                              double* __restrict__ x, int N) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const double* row = M + size_t(warp) * 2 * N + N;
+  double s = 0.0;
+  for (int c = lane; c < N; c += 32) s = fma(row[c], b[c], s);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) x[warp] = s;
+}
+
+#define C8_NB_SWITCH(nb, CALL)  \
+  switch (nb) {                 \
+    case 2: { constexpr int NB = 2; CALL; } break; \
+    case 3: { constexpr int NB = 3; CALL; } break; \
+    default: { constexpr int NB = 4; CALL; } break; \
+  }
+
+// ---- host: aggregation ----------------------------------------------------------------------
+// Greedy aggregation on the node graph (root node + all its neighbours when none of them is
+// taken yet; leftovers join the neighbouring aggregate they are most connected to).
+static void aggregate(int n, const std::vector<int>& rowptr, const std::vector<int>& colind,
+                      std::vector<int>& agg, int& nc) {
+  agg.assign(n, -1);
+  nc = 0;
+  for (int i = 0; i < n; ++i) {
+    if (agg[i] != -1) continue;
+    bool free_nbrs = true;
+    for (int k = rowptr[i]; k < rowptr[i + 1] && free_nbrs; ++k)
+      if (agg[colind[k]] != -1) free_nbrs = false;
+    if (!free_nbrs) continue;
+    agg[i] = nc;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) agg[colind[k]] = nc;
+    ++nc;
+  }
+  std::vector<int> agg2 = agg, cnt;
+  for (int i = 0; i < n; ++i) {
+    if (agg[i] != -1) continue;
+    int best = -1, best_cnt = 0;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+      const int a = agg[colind[k]];
+      if (a == -1) continue;
+      int c = 0;
+      for (int k2 = rowptr[i]; k2 < rowptr[i + 1]; ++k2) c += (agg[colind[k2]] == a);
+      if (c > best_cnt || (c == best_cnt && a < best)) { best_cnt = c; best = a; }
+    }
+    agg2[i] = best;
+  }
+  agg.swap(agg2);
+  for (int i = 0; i < n; ++i) {
+    if (agg[i] != -1) continue;
+    agg[i] = nc;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k)
+      if (agg[colind[k]] == -1) agg[colind[k]] = nc;
+    ++nc;
+  }
+}
+
+template <class T>
+static int upload(c8_ctx* ctx, const std::vector<T>& h, T** d) {
+  *d = nullptr;
+  if (h.empty()) return C8_OK;
+  C8_CUDA(ctx, cudaMalloc(d, h.size() * sizeof(T)));
+  C8_CUDA(ctx, cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return C8_OK;
+}
+
+Amg::~Amg() {
+  for (AmgLevel& L : lv_) {
+    void* ptrs[] = {L.own_rowptr, L.own_colind, L.own_vals, L.dinv, L.x, L.b, L.r, L.agg, L.aggptr,
+                    L.aggmem, L.cptr, L.cmem};
+    for (void* p : ptrs)
+      if (p) cudaFree(p);
+  }
+  if (dense_) cudaFree(dense_);
+  if (r0_) cudaFree(r0_);
+}
+
+int Amg::build() {
+  nb_ = ctx_->kt->nb;
+  const int n0 = ctx_->n_owned_nodes;
+  // level-0 graph restricted to owned rows x owned columns (host copies of the context's pattern)
+  std::vector<int> rowptr(n0 + 1, 0), colind;
+  std::vector<int> blk;  // fine block id of each kept entry
+  colind.reserve(ctx_->h_colind.size());
+  blk.reserve(ctx_->h_colind.size());
+  for (int i = 0; i < n0; ++i) {
+    for (int k = ctx_->h_rowptr[i]; k < ctx_->h_rowptr[i + 1]; ++k) {
+      const int j = ctx_->h_colind[k];
+      if (j < n0) { colind.push_back(j); blk.push_back(k); }
+    }
+    rowptr[i + 1] = int(colind.size());
+  }
+  lv_.clear();
+  AmgLevel L0;
+  L0.n = n0; L0.nnzb = ctx_->nnzb; L0.ld = ctx_->n_nodes;
+  L0.rowptr = ctx_->d_rowptr; L0.colind = ctx_->d_colind;
+  lv_.push_back(L0);
+  int n = n0;
+  while (n > opt.coarsest_max_nodes && int(lv_.size()) < opt.max_levels) {
+    std::vector<int> agg;
+    int nc = 0;
+    aggregate(n, rowptr, colind, agg, nc);
+    if (nc >= n) break;  // no coarsening possible
+    // coarse pattern: unique (agg[i], agg[j]) pairs, and for each the fine blocks summed into it
+    std::vector<std::pair<uint64_t, int>> keys;
+    keys.reserve(colind.size());
+    for (int i = 0; i < n; ++i)
+      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k)
+        keys.emplace_back((uint64_t(uint32_t(agg[i])) << 32) | uint32_t(agg[colind[k]]), blk[k]);
+    std::sort(keys.begin(), keys.end());
+    std::vector<int> c_rowptr(nc + 1, 0), c_colind, cptr(1, 0), cmem;
+    cmem.reserve(keys.size());
+    for (size_t q = 0; q < keys.size();) {
+      size_t e = q;
+      while (e < keys.size() && keys[e].first == keys[q].first) { cmem.push_back(keys[e].second); ++e; }
+      const int I = int(keys[q].first >> 32), J = int(keys[q].first & 0xffffffffu);
+      c_colind.push_back(J);
+      c_rowptr[I + 1] += 1;
+      cptr.push_back(int(cmem.size()));
+      q = e;
+    }
+    for (int I = 0; I < nc; ++I) c_rowptr[I + 1] += c_rowptr[I];
+    std::vector<int> aggptr(nc + 1, 0), aggmem(n);
+    for (int i = 0; i < n; ++i) aggptr[agg[i] + 1] += 1;
+    for (int I = 0; I < nc; ++I) aggptr[I + 1] += aggptr[I];
+    {
+      std::vector<int> pos(aggptr.begin(), aggptr.end() - 1);
+      for (int i = 0; i < n; ++i) aggmem[pos[agg[i]]++] = i;
+    }
+    AmgLevel& F = lv_.back();
+    F.nc = nc;
+    F.n_cmem = int(cmem.size());
+    int rc;
+    if ((rc = upload(ctx_, agg, &F.agg)) != C8_OK) return rc;
+    if ((rc = upload(ctx_, aggptr, &F.aggptr)) != C8_OK) return rc;
+    if ((rc = upload(ctx_, aggmem, &F.aggmem)) != C8_OK) return rc;
+    if ((rc = upload(ctx_, cptr, &F.cptr)) != C8_OK) return rc;
+    if ((rc = upload(ctx_, cmem, &F.cmem)) != C8_OK) return rc;
+    AmgLevel C;
+    C.n = nc; C.ld = nc; C.nnzb = int(c_colind.size());
+    if ((rc = upload(ctx_, c_rowptr, &C.own_rowptr)) != C8_OK) return rc;
+    if ((rc = upload(ctx_, c_colind, &C.own_colind)) != C8_OK) return rc;
+    C.rowptr = C.own_rowptr; C.colind = C.own_colind;
+    const size_t nv = size_t(nc) * nb_;
+    C8_CUDA(ctx_, cudaMalloc(&C.own_vals, size_t(C.nnzb) * nb_ * nb_ * sizeof(double)));
+    C.vals = C.own_vals;
+    C8_CUDA(ctx_, cudaMalloc(&C.x, nv * sizeof(double)));
+    C8_CUDA(ctx_, cudaMalloc(&C.b, nv * sizeof(double)));
+    C8_CUDA(ctx_, cudaMalloc(&C.r, nv * sizeof(double)));
+    lv_.push_back(C);
+    // next level's graph: block ids are now the coarse blocks themselves
+    rowptr.swap(c_rowptr);
+    colind.swap(c_colind);
+    blk.resize(colind.size());
+    std::iota(blk.begin(), blk.end(), 0);
+    n = nc;
+  }
+  for (AmgLevel& L : lv_)
+    C8_CUDA(ctx_, cudaMalloc(&L.dinv, size_t(L.n > 0 ? L.n : 1) * nb_ * nb_ * sizeof(double)));
+  C8_CUDA(ctx_, cudaMalloc(&r0_, size_t(ctx_->n_nodes) * nb_ * sizeof(double)));
+  C8_CUDA(ctx_, cudaMemset(r0_, 0, size_t(ctx_->n_nodes) * nb_ * sizeof(double)));
+  nd_ = 0;
+  if (lv_.size() > 1 && lv_.back().n * nb_ <= 1024) {
+    nd_ = lv_.back().n * nb_;
+    C8_CUDA(ctx_, cudaMalloc(&dense_, size_t(nd_) * 2 * nd_ * sizeof(double)));
+  }
+  return C8_OK;
+}
+
+double Amg::operator_complexity() const {
+  double s = 0.0;
+  for (const AmgLevel& L : lv_) s += L.nnzb;
+  return lv_.empty() ? 0.0 : s / lv_[0].nnzb;
+}
+
+int Amg::setup(const double* A) {
+  cudaStream_t s = ctx_->stream;
+  lv_[0].vals = A;
+  for (size_t l = 0; l < lv_.size(); ++l) {
+    AmgLevel& L = lv_[l];
+    if (L.n == 0) continue;
+    const int gj = (L.n + 127) / 128;
+    C8_NB_SWITCH(nb_, (k_block_jacobi_setup<NB><<<gj, 128, 0, s>>>(L.rowptr, L.colind, L.vals, L.dinv, L.n)));
+    if (l + 1 < lv_.size()) {
+      AmgLevel& C = lv_[l + 1];
+      const long long work = (long long)C.nnzb * nb_ * nb_;
+      const unsigned g = unsigned((work + 255) / 256);
+      C8_NB_SWITCH(nb_, (k_galerkin<NB><<<g, 256, 0, s>>>(L.cptr, L.cmem, L.vals, C.own_vals, C.nnzb)));
+    }
+  }
+  if (nd_ > 0) {
+    const AmgLevel& C = lv_.back();
+    C8_NB_SWITCH(nb_, (k_dense_fill<NB><<<(nd_ + 127) / 128, 128, 0, s>>>(C.rowptr, C.colind, C.vals, dense_, C.n)));
+    k_dense_inverse<<<1, 1024, nd_ * sizeof(double), s>>>(dense_, nd_);
+  }
+  C8_CUDA(ctx_, cudaGetLastError());
+  return C8_OK;
+}
+
+void Amg::smooth(int l, const double* b, double* x, int sweeps, bool zero_guess) {
+  AmgLevel& L = lv_[l];
+  cudaStream_t s = ctx_->stream;
+  double* r = (l == 0) ? r0_ : L.r;
+  const int g = (L.n * nb_ + 127) / 128;
+  for (int k = 0; k < sweeps; ++k) {
+    if (k == 0 && zero_guess) {
+      C8_NB_SWITCH(nb_, (k_jacobi_update<NB><<<g, 128, 0, s>>>(L.dinv, b, x, opt.omega, 1, L.n)));
+    } else {
+      C8_NB_SWITCH(nb_, (k_bsr_residual<NB><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals, x, b, r, L.n)));
+      C8_NB_SWITCH(nb_, (k_jacobi_update<NB><<<g, 128, 0, s>>>(L.dinv, r, x, opt.omega, 0, L.n)));
+    }
+  }
+}
+
+void Amg::cycle(int l, const double* b, double* x) {
+  AmgLevel& L = lv_[l];
+  cudaStream_t s = ctx_->stream;
+  if (L.n == 0) return;
+  const bool coarsest = (l + 1 == int(lv_.size()));
+  if (coarsest) {
+    if (nd_ > 0 && l > 0) {
+      k_dense_apply<<<(nd_ * 32 + 255) / 256, 256, 0, s>>>(dense_, b, x, nd_);
+    } else {
+      smooth(l, b, x, 4 * (opt.nu_pre + opt.nu_post), true);
+    }
+    return;
+  }
+  smooth(l, b, x, opt.nu_pre, true);
+  double* r = (l == 0) ? r0_ : L.r;
+  const int g = (L.n * nb_ + 127) / 128;
+  C8_NB_SWITCH(nb_, (k_bsr_residual<NB><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals, x, b, r, L.n)));
+  AmgLevel& C = lv_[l + 1];
+  const int gc = (C.n * nb_ + 127) / 128;
+  C8_NB_SWITCH(nb_, (k_restrict<NB><<<gc, 128, 0, s>>>(L.aggptr, L.aggmem, r, C.b, C.n)));
+  cycle(l + 1, C.b, C.x);
+  C8_NB_SWITCH(nb_, (k_prolong_add<NB><<<g, 128, 0, s>>>(L.agg, C.x, x, opt.over_correction, L.n)));
+  smooth(l, b, x, opt.nu_post, false);
+}
+
+void Amg::apply(const double* r, double* z) {
+  // ghost entries of z stay zero: the preconditioner acts on the owned x owned block of the part
+  if (lv_[0].ld > lv_[0].n)
+    cudaMemsetAsync(z + size_t(lv_[0].n) * nb_, 0, size_t(lv_[0].ld - lv_[0].n) * nb_ * sizeof(double),
+                    ctx_->stream);
+  cycle(0, r, z);
+}
+
+}  // namespace c8

@@ -1,0 +1,75 @@
+// Aggregation multigrid preconditioner on the node graph (BSR, NB x NB blocks kept at every level).
+//
+// Replaces, for this path, the Teko block-Gauss-Seidel / MueLu smoothed-aggregation stack the
+// reference configures through Belos (src/linear_solve.cpp:74-105, decks
+// test/primal/notch_small_J2.yaml.in:54-98).  The hierarchy is plain (unsmoothed) aggregation:
+//   P        piecewise-constant per node block (every fine node injects into its aggregate with an
+//            identity NB x NB block), so the Galerkin operator P^T A P is the sum of the fine blocks
+//            of each aggregate pair and keeps the BSR format;
+//   pattern  of every level depends on the mesh only -> built once on the host; the numeric set-up
+//            per matrix is a gather-sum kernel per level (HBM-bound) + block-Jacobi inverses + a
+//            dense inverse of the coarsest operator (one CTA);
+//   smoother damped block-Jacobi (the NB x NB nodal block couples u and p of the stabilised mixed
+//            formulation), nu_pre / nu_post sweeps;
+//   cycle    V, optionally over-corrected.
+// The preconditioner is a fixed linear operator, so plain right-preconditioned GMRES applies.
+// In a partitioned run it acts on the owned x owned diagonal block of the part (no communication).
+#pragma once
+#include <vector>
+
+#include "linalg.cuh"
+
+namespace c8 {
+
+struct AmgLevel {
+  int n = 0;        // nodes = block rows
+  int nnzb = 0;
+  int ld = 0;       // nodes in a vector of this level (level 0: all local nodes incl. ghosts)
+  const int* rowptr = nullptr;   // device
+  const int* colind = nullptr;
+  const double* vals = nullptr;  // level 0: the caller's matrix
+  int* own_rowptr = nullptr;
+  int* own_colind = nullptr;
+  double* own_vals = nullptr;
+  double* dinv = nullptr;
+  double *x = nullptr, *b = nullptr, *r = nullptr;  // level >= 1 (level 0 uses the caller's x, b)
+  // transfer to the next coarser level
+  int nc = 0;
+  int* agg = nullptr;                      // [n] aggregate of a node
+  int *aggptr = nullptr, *aggmem = nullptr;  // members of an aggregate
+  int *cptr = nullptr, *cmem = nullptr;      // fine blocks summed into a coarse block
+  int n_cmem = 0;
+};
+
+struct AmgOptions {
+  int nu_pre = 2, nu_post = 2;
+  double omega = 0.7;          // block-Jacobi damping
+  double over_correction = 1.0;
+  int coarsest_max_nodes = 40;
+  int max_levels = 12;
+};
+
+class Amg {
+ public:
+  explicit Amg(c8_ctx* ctx) : ctx_(ctx) {}
+  ~Amg();
+  AmgOptions opt;
+  int build();                   // host: aggregates + coarse patterns from the context's BSR pattern
+  int setup(const double* A);    // device: Galerkin sums, block-Jacobi inverses, coarsest inverse
+  void apply(const double* r, double* z);  // z = M^-1 r, both [n_nodes_local][NB]
+  int num_levels() const { return int(lv_.size()); }
+  const std::vector<AmgLevel>& levels() const { return lv_; }
+  double operator_complexity() const;
+
+ private:
+  void cycle(int l, const double* b, double* x);
+  void smooth(int l, const double* b, double* x, int sweeps, bool zero_guess);
+  c8_ctx* ctx_;
+  int nb_ = 0;
+  std::vector<AmgLevel> lv_;
+  int nd_ = 0;                 // coarsest dense size (dofs)
+  double* dense_ = nullptr;    // [nd][2 nd] work, inverse in the right half
+  double* r0_ = nullptr;       // level-0 residual
+};
+
+}  // namespace c8

@@ -176,6 +176,7 @@ int c8_set_partition(c8_ctx* ctx, int n_owned_nodes, int n_owned_elems) {
                       n_owned_elems <= ctx->n_elems, "owned counts exceed the local mesh");
   ctx->n_owned_nodes = n_owned_nodes;
   ctx->n_owned_elems = n_owned_elems;
+  c8_linalg_invalidate(ctx);
   return C8_OK;
 }
 

@@ -271,6 +271,7 @@ int c8_set_mesh(c8_ctx* ctx, int dim, int n_elems, int n_nodes, const int32_t* c
   }
   ctx->n_owned_nodes = n_nodes;
   ctx->n_owned_elems = n_elems;
+  c8_linalg_invalidate(ctx);
   ctx->xi_ld = (long long)((n_elems + 31) / 32) * 32;  // 256-byte aligned component rows
   return C8_OK;
 }
@@ -284,6 +285,7 @@ int c8_set_model(c8_ctx* ctx, int global_type, int local_type, const double* par
   C8_REQUIRE(ctx, kt != nullptr,
              "no kernels for this (dim, global residual, local residual) combination");
   ctx->kt = kt;
+  c8_linalg_invalidate(ctx);
   ctx->global_type = global_type;
   ctx->local_type = local_type;
   ctx->model.npar = kt->npar;

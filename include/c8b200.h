@@ -184,10 +184,21 @@ int c8_axpby(c8_ctx* ctx, double a, const double* x_dev, double b, double* y_dev
 int c8_apply_dbc(c8_ctx* ctx, double* A_vals_dev, double* R_dev, const double* x_dev,
                  const int32_t* dbc_node_dev, const int32_t* dbc_eq_dev, const double* dbc_val_dev,
                  int n_dbc, int is_adjoint);
-/* restarted GMRES(m) + block-Jacobi; info_host[3] = iterations, final |r|, initial |r| */
+/* restarted GMRES(m), device-resident Arnoldi, right preconditioned (c8_set_preconditioner);
+ * info_host[3] = iterations, final |r|, initial |r| */
 int c8_gmres(c8_ctx* ctx, const double* A_vals_dev, const double* b_dev, double* x_dev,
              int restart, int max_iters, double rel_tol, double abs_tol, double* info_host);
 void c8_linalg_release(c8_ctx* ctx);
+void c8_linalg_invalidate(c8_ctx* ctx); /* after a mesh / partition / model change (called internally) */
+/* right preconditioner of c8_gmres (replaces the Teko/MueLu/Ifpack2 stack of linear_solve.cpp:74-105):
+ * block-Jacobi (one NB x NB inverse per node) or aggregation multigrid on the node graph with
+ * block-Jacobi smoothing (default).  opts (may be NULL): nu_pre, nu_post, omega, over_correction,
+ * coarsest_max_nodes. */
+#define C8_PC_BLOCK_JACOBI 0
+#define C8_PC_AMG 1
+int c8_set_preconditioner(c8_ctx* ctx, int type, const double* opts, int n_opts);
+/* out[0] = levels, out[1] = operator complexity, out[2..] = nodes per level */
+int c8_preconditioner_info(c8_ctx* ctx, double* out, int n_out);
 
 /* ---- partition (one context per GPU; replaces the OWNED/GHOST maps of disc.cpp:271-314 and the
  * import/export of linear_alg.cpp:53-86) ----
