@@ -299,6 +299,7 @@ HOST_SYMBOLS = [
     "c8h_create", "c8h_destroy", "c8h_last_error", "c8h_set_time", "c8h_add_dbc",
     "c8h_finalize_dbcs", "c8h_set_solver", "c8h_set_qoi_avg_disp", "c8h_set_qoi_calibration",
     "c8h_primal_solve", "c8h_adjoint_gradient", "c8h_get_step", "c8h_get_adjoint_step", "c8h_stats",
+    "c8h_profile",
 ]
 
 
@@ -474,6 +475,13 @@ class HostProblem:
         phi = np.zeros((c.n_elems, c.nxi))
         self._check(self.lib.c8h_get_adjoint_step(self.h, step, _hp(zu), _hp(zp), _hp(phi)))
         return [zu, zp][: c.num_resid], phi
+
+    def profile(self, enable=True):
+        """wall-clock seconds per phase (assembly, linear solves, K3, K4, K5/K6, line-search ops)"""
+        out = (C.c_double * 8)()
+        self.lib.c8h_profile(self.h, int(enable), out)
+        names = ["assemble", "linear_solve", "adjoint_jacobian", "adjoint_local", "qoi_gradient", "line_search"]
+        return {n: out[k] for k, n in enumerate(names)}
 
     def stats(self):
         a, b = C.c_int(0), C.c_int(0)

@@ -75,7 +75,20 @@ struct SolverState {
   std::unique_ptr<Amg> amg;
   bool amg_built = false;
   long long total_iters = 0, total_solves = 0;
+  // CUDA graphs of one Arnoldi iteration, one per column index j (the launch sequence of an
+  // iteration depends on j only through counts and pointers into the fixed workspace); valid for
+  // one matrix pointer / preconditioner configuration
+  std::vector<cudaGraphExec_t> iter_graph;
+  const double* graph_A = nullptr;
+  int graph_pc = -1;
+  bool use_graphs = true;
+  void drop_graphs() {
+    for (cudaGraphExec_t g : iter_graph) if (g) cudaGraphExecDestroy(g);
+    iter_graph.clear();
+    graph_A = nullptr; graph_pc = -1;
+  }
   void free_ws() {
+    drop_graphs();
     void* p[] = {V, w, z, dinv, partial, dots, dots2, nrm, coef, H, cs, sn, g, res};
     for (void* q : p) if (q) cudaFree(q);
     if (h_buf) cudaFreeHost(h_buf);
@@ -132,6 +145,7 @@ int c8_set_preconditioner(c8_ctx* ctx, int type, const double* opts, int n_opts)
   }
   const bool rebuild = o.coarsest_max_nodes != st.amg_opt.coarsest_max_nodes;
   st.amg_opt = o;
+  st.drop_graphs();
   if (st.amg) st.amg->opt = o;
   if (rebuild) { st.amg.reset(); st.amg_built = false; }
   return C8_OK;
@@ -192,6 +206,33 @@ int c8_gmres(c8_ctx* ctx, const double* A, const double* b, double* x, int resta
     return C8_OK;
   };
 
+  // one Arnoldi iteration for column j: a fixed launch sequence (captured into a CUDA graph on one
+  // GPU; a partitioned run launches directly because the transports enqueue host-side work)
+  auto iteration = [&](int j) {
+    double* vj1 = ws.V + size_t(j + 1) * ld;
+    precond(ws.V + size_t(j) * ld, ws.z);
+    la.halo(ws.z);
+    la.spmv(A, ws.z, vj1);
+    // classical Gram-Schmidt, two passes: h = V^T w ; w -= V h
+    la.multi_dot(ws.V, ld, vj1, j + 1, ws.partial, ws.dots);
+    k_multi_axpy_neg<<<ag, 256, 0, s>>>(ws.V, ld, ws.dots, j + 1, n, vj1);
+    la.multi_dot(ws.V, ld, vj1, j + 1, ws.partial, ws.dots2);
+    k_multi_axpy_neg<<<ag, 256, 0, s>>>(ws.V, ld, ws.dots2, j + 1, n, vj1);
+    la.multi_dot(vj1, 0, vj1, 1, ws.partial, ws.nrm);
+    k_givens<<<1, 32, 0, s>>>(ws.H, ldh, ws.cs, ws.sn, ws.g, ws.dots, ws.dots2, ws.nrm, j, ws.res);
+    k_normalize<<<ag, 256, 0, s>>>(vj1, ws.nrm, n, nullptr);
+  };
+  const bool graphs = ws.use_graphs && !ctx->halo_cb && !ctx->allreduce_cb && s != nullptr &&
+                      s != cudaStreamLegacy && s != cudaStreamPerThread;  // capture needs a real stream
+  if (graphs) {
+    const int pc_key = use_amg ? 1 : 0;
+    if (ws.graph_A != A || ws.graph_pc != pc_key || int(ws.iter_graph.size()) != ws.m) {
+      ws.drop_graphs();
+      ws.iter_graph.assign(ws.m, nullptr);
+      ws.graph_A = A; ws.graph_pc = pc_key;
+    }
+  }
+
   int total = 0;
   double beta0 = -1.0, beta = 0.0, target = 0.0;
   while (true) {
@@ -212,18 +253,19 @@ int c8_gmres(c8_ctx* ctx, const double* A, const double* b, double* x, int resta
     while (j < m && total < max_iters && !done) {
       const int j_end = std::min(std::min(j + check_every, m), j + (max_iters - total));
       for (; j < j_end; ++j, ++total) {
-        double* vj1 = ws.V + size_t(j + 1) * ld;
-        precond(ws.V + size_t(j) * ld, ws.z);
-        la.halo(ws.z);
-        la.spmv(A, ws.z, vj1);
-        // classical Gram-Schmidt, two passes: h = V^T w ; w -= V h
-        la.multi_dot(ws.V, ld, vj1, j + 1, ws.partial, ws.dots);
-        k_multi_axpy_neg<<<ag, 256, 0, s>>>(ws.V, ld, ws.dots, j + 1, n, vj1);
-        la.multi_dot(ws.V, ld, vj1, j + 1, ws.partial, ws.dots2);
-        k_multi_axpy_neg<<<ag, 256, 0, s>>>(ws.V, ld, ws.dots2, j + 1, n, vj1);
-        la.multi_dot(vj1, 0, vj1, 1, ws.partial, ws.nrm);
-        k_givens<<<1, 32, 0, s>>>(ws.H, ldh, ws.cs, ws.sn, ws.g, ws.dots, ws.dots2, ws.nrm, j, ws.res);
-        k_normalize<<<ag, 256, 0, s>>>(vj1, ws.nrm, n, nullptr);
+        if (graphs) {
+          if (!ws.iter_graph[j]) {
+            cudaGraph_t graph = nullptr;
+            C8_CUDA(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            iteration(j);
+            C8_CUDA(ctx, cudaStreamEndCapture(s, &graph));
+            C8_CUDA(ctx, cudaGraphInstantiate(&ws.iter_graph[j], graph, 0));
+            cudaGraphDestroy(graph);
+          }
+          C8_CUDA(ctx, cudaGraphLaunch(ws.iter_graph[j], s));
+        } else {
+          iteration(j);
+        }
       }
       // look at the residual estimates of the iterations just queued
       if ((rc = fetch(ws.res, j)) != C8_OK) return rc;

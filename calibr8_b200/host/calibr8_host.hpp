@@ -8,6 +8,7 @@
 // The all-steps primal history (x[step], xi[step]) stays resident on the device for the reverse
 // sweep, like the apf fields of Disc::primal(step) in the reference (src/disc.cpp:643-683).
 #pragma once
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <stdexcept>
@@ -101,6 +102,11 @@ class Problem {
   double* d_dbc_val = nullptr;
   std::vector<double> h_dbc_val;
   int n_assemblies = 0, n_linear_iters = 0;
+  // optional wall-clock profile (stream-synchronised around each phase when enabled):
+  // 0 forward assembly (K1 + Dirichlet rows + norm), 1 linear solves, 2 K3 adjoint Jacobian,
+  // 3 K4 adjoint local, 4 K5/K6 objective + gradient integrands, 5 line-search SpMV/dots
+  bool profile = false;
+  double t_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
   double time(int step) const { return step * step_size; }
   void set_time(int n_steps, double dt);
@@ -111,6 +117,14 @@ class Problem {
   double norm(const double* v) const;
   double dot(const double* a, const double* c) const;
   void axpy(double a, const double* xsrc, double* y) const;  // y += a x
+};
+
+struct PhaseTimer {  // adds the wall time of a scope to Problem::t_phase[id] when profiling
+  PhaseTimer(Problem& p, int id);
+  ~PhaseTimer();
+  Problem& P;
+  int id;
+  double t0 = 0.;
 };
 
 class Primal {

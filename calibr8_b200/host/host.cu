@@ -42,6 +42,16 @@ void Problem::check(int rc, const char* what) const {
                                             "): " + c8_last_error(ctx));
 }
 
+static double wall_now() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+PhaseTimer::PhaseTimer(Problem& p, int i) : P(p), id(i) {
+  if (P.profile) { c8_synchronize(P.ctx); t0 = wall_now(); }
+}
+PhaseTimer::~PhaseTimer() {
+  if (P.profile) { c8_synchronize(P.ctx); P.t_phase[id] += wall_now() - t0; }
+}
+
 void Problem::set_time(int n_steps, double dt) { num_steps = n_steps; step_size = dt; }
 
 void Problem::add_dbc(int resid, int eq, const int* nodes, int n, const std::string& expr) {
@@ -139,6 +149,7 @@ static double preprocess_load_mismatch(Problem& P, int step, double* total_load_
 }
 
 bool Primal::assemble(int step, double* R_norm) {
+  PhaseTimer pt(P, 0);
   cudaStream_t s = (cudaStream_t)c8_get_stream(P.ctx);
   C8H_CUDA(cudaMemsetAsync(P.A.get(), 0, P.A.size() * sizeof(double), s));
   C8H_CUDA(cudaMemsetAsync(P.b.get(), 0, P.b.size() * sizeof(double), s));
@@ -190,8 +201,10 @@ void Primal::solve_at_step(int step) {
     P.check(c8_axpby(P.ctx, -1.0, P.b.get(), 0.0, P.work.get(), P.n_dofs), "scale_b");
     C8H_CUDA(cudaMemsetAsync(P.dx.get(), 0, xb, s));
     double info[3];
+    PhaseTimer* pt1 = new PhaseTimer(P, 1);
     int rc = c8_gmres(P.ctx, P.A.get(), P.work.get(), P.dx.get(), sp.gmres_restart, sp.gmres_max_iters,
                       sp.linear_tol, 0.0, info);
+    delete pt1;
     P.n_linear_iters += int(info[0]);
     if (rc != C8_OK && rc != C8_ERR_NOT_CONVERGED) P.check(rc, "c8_gmres");
     if (sp.print) std::printf("    gmres its %d |r| %.3e -> %.3e\n", int(info[0]), info[2], info[1]);
@@ -207,6 +220,7 @@ void Primal::solve_at_step(int step) {
       double ra = 0.;
       if (!assemble(step, &ra)) return false;
       phi = 0.5 * ra * ra;
+      PhaseTimer pt5(P, 5);
       P.check(c8_spmv(P.ctx, P.A.get(), P.dx.get(), P.Adx.get()), "c8_spmv");
       slope = P.dot(P.b.get(), P.Adx.get());
       return true;
@@ -277,8 +291,11 @@ void Adjoint::gradient(std::vector<double>& grad) {
                  *xip = P.xi[step - 1].get();
     C8H_CUDA(cudaMemsetAsync(P.A.get(), 0, P.A.size() * sizeof(double), s));
     C8H_CUDA(cudaMemsetAsync(rhs.get(), 0, xb, s));
-    P.check(c8_adjoint_jacobian(P.ctx, &q, x, xp, xi, xip, g.get(), f.get(), P.A.get(), rhs.get()),
-            "c8_adjoint_jacobian");
+    {
+      PhaseTimer pt2(P, 2);
+      P.check(c8_adjoint_jacobian(P.ctx, &q, x, xp, xi, xip, g.get(), f.get(), P.A.get(), rhs.get()),
+              "c8_adjoint_jacobian");
+    }
     double* z = P.z[step].get();
     P.check(c8_apply_dbc(P.ctx, P.A.get(), rhs.get(), z, P.d_dbc_node, P.d_dbc_eq, P.d_dbc_val,
                          P.n_dbc, 1), "c8_apply_dbc(adjoint)");
@@ -288,8 +305,10 @@ void Adjoint::gradient(std::vector<double>& grad) {
     while (true) {
       C8H_CUDA(cudaMemsetAsync(P.dx.get(), 0, xb, s));
       double info[3];
+      PhaseTimer* pt1 = new PhaseTimer(P, 1);
       int rc = c8_gmres(P.ctx, P.A.get(), rhs.get(), P.dx.get(), sp.gmres_restart,
                         sp.gmres_max_iters, 0.1 * sp.newton_rel_tol, 0.0, info);
+      delete pt1;
       P.n_linear_iters += int(info[0]);
       if (rc != C8_OK && rc != C8_ERR_NOT_CONVERGED) P.check(rc, "c8_gmres(adjoint)");
       P.axpy(1.0, P.dx.get(), z);
@@ -301,8 +320,12 @@ void Adjoint::gradient(std::vector<double>& grad) {
       if (++iter > sp.newton_max_iters) throw std::runtime_error("adjoint solve failed to converge");
     }
     P.check(c8_halo(P.ctx, z), "c8_halo");
-    P.check(c8_adjoint_local(P.ctx, x, xp, xi, xip, z, P.phi[step].get(), g.get(), f.get()),
-            "c8_adjoint_local");
+    {
+      PhaseTimer pt3(P, 3);
+      P.check(c8_adjoint_local(P.ctx, x, xp, xi, xip, z, P.phi[step].get(), g.get(), f.get()),
+              "c8_adjoint_local");
+    }
+    PhaseTimer pt4(P, 4);
     C8H_CUDA(cudaMemsetAsync(d_grad.get(), 0, 64 * sizeof(double), s));
     P.check(c8_qoi_gradient(P.ctx, &q, x, xp, xi, xip, z, P.phi[step].get(), d_grad.get()),
             "c8_qoi_gradient");
@@ -409,6 +432,13 @@ int c8h_get_adjoint_step(c8h_problem* h, int step, double* zu, double* zp, doubl
     if (zu) P.check(c8_unpack_x(P.ctx, P.z[step].get(), zu, zp), "c8_unpack_x");
     if (phi) P.check(c8_unpack_xi(P.ctx, P.phi[step].get(), phi), "c8_unpack_xi");
   });
+}
+// enable != 0 switches the wall-clock phase profile on (adds stream syncs); out8 (may be NULL)
+// receives the accumulated seconds per phase, see Problem::t_phase
+int c8h_profile(c8h_problem* h, int enable, double* out8) {
+  h->P.profile = enable != 0;
+  if (out8) for (int k = 0; k < 8; ++k) out8[k] = h->P.t_phase[k];
+  return 0;
 }
 int c8h_stats(c8h_problem* h, int* n_assemblies, int* n_linear_iters) {
   *n_assemblies = h->P.n_assemblies;

@@ -18,6 +18,7 @@ ap.add_argument("--lin-tol", type=float, default=1e-8)
 ap.add_argument("--no-adjoint", action="store_true")
 ap.add_argument("--verbose", action="store_true")
 ap.add_argument("--pc", default="amg")
+ap.add_argument("--profile", action="store_true")
 ap.add_argument("--nu", type=int, default=2)
 ap.add_argument("--omega", type=float, default=0.7)
 ap.add_argument("--oc", type=float, default=1.0)
@@ -44,6 +45,7 @@ hp.set_solver(15, 1e-8, 1e-8, gmres_restart=a.restart, gmres_max_iters=20000, li
               verbose=a.verbose)
 hp.set_qoi_avg_disp()
 print(f"mesh {mesh.n_elems} tets {mesh.n_nodes} nodes, setup {time.time()-t0:.1f}s", flush=True)
+if a.profile: hp.profile(True)
 torch.cuda.synchronize(); t1 = time.time()
 J = hp.primal_solve()
 torch.cuda.synchronize(); t2 = time.time()
@@ -51,9 +53,17 @@ s1 = hp.stats()
 print("preconditioner", a.pc, ctx.preconditioner_info())
 print(f"forward: J={J:.12e} {t2-t1:.2f}s = {(t2-t1)/a.steps*1e3:.1f} ms/step  assemblies {s1['assemblies']} "
       f"krylov its {s1['linear_iters']}", flush=True)
+if a.profile: print("profile forward", {k: round(v, 4) for k, v in hp.profile(True).items()})
 if not a.no_adjoint:
     g = hp.adjoint_gradient()
     torch.cuda.synchronize(); t3 = time.time()
     s2 = hp.stats()
     print(f"adjoint: {t3-t2:.2f}s = {(t3-t2)/a.steps*1e3:.1f} ms/step krylov its {s2['linear_iters']-s1['linear_iters']} grad {g}", flush=True)
     print(f"forward+adjoint gradient wall-time/load step: {(t3-t1)/a.steps*1e3:.1f} ms")
+if not a.no_adjoint:
+    for rep in range(3):
+        t4 = time.time(); g = hp.adjoint_gradient(); torch.cuda.synchronize()
+        print(f"adjoint (call {rep+2}): {time.time()-t4:.2f}s")
+    t4 = time.time(); J = hp.primal_solve(); torch.cuda.synchronize()
+    print(f"forward (call 2): {time.time()-t4:.2f}s")
+if a.profile: print("profile total", {k: round(v, 4) for k, v in hp.profile(True).items()})
