@@ -32,7 +32,8 @@ struct AdjArgs {
   long long xi_ld;
   double* g;          // K3: in/out ; K4: in (g) / out (new g)
   double* f;          // K3: in ; K4: out        [NX][xi_ld], element dofs node-interleaved
-  double* vals;       // K3: A^T (+=)
+  double* vals;       // K3: A^T (overwritten)
+  double* emat;       // K3: element-matrix scratch of the two-phase assembly
   double* b;          // K3: rhs (+=)
   const double* z;    // K4/K6: nodal adjoint [n_nodes][NB]
   double* phi;        // K4: out ; K6: in

@@ -94,13 +94,13 @@ __global__ void __launch_bounds__(128) k_adjoint_jacobian(const AdjArgs a) {
     }
   }
 
-  // total Jacobian, transposed scatter (matrix only)
+  // total Jacobian -> element-matrix scratch; the gather pass transposes (matrix only)
   const double wdv = quad1_weight<D>() * E.g.dv;
   FwdArgs fa{};
   fa.mesh = a.mesh;
   fa.vals = a.vals;
-  fa.transpose = 1;
-  Scatter<C, true, false> sc{fa, E, sx.xl, e, t, true};  // TODO(K3): FAST needs b
+  fa.emat = a.emat;
+  Scatter<C, false> sc{fa, E, sx.xl, e, t, true};  // element matrix only; rhs is added below
   sc.init();
   {
     const Mat<Dual<LX>, D> P = first_pk<D, C::M, Model>(k2, sx.p, xid, E.par, a.model.thickness);

@@ -49,6 +49,10 @@ int c8_adjoint_jacobian(c8_ctx* ctx, const c8_qoi* qoi, const double* x, const d
   C8_REQUIRE(ctx, ctx->kt != nullptr, "c8_set_model must be called first");
   AdjArgs a = base_args(ctx, qoi, x, xp, xi, xip);
   a.g = g; a.f = const_cast<double*>(f); a.vals = AT_vals; a.b = rhs;
+  if (AT_vals) {
+    a.emat = element_scratch(ctx);
+    if (!a.emat) return C8_ERR_CUDA;
+  }
   ctx->kt->adjoint_jacobian(a, ctx->stream);
   C8_CUDA(ctx, cudaGetLastError());
   return C8_OK;

@@ -19,6 +19,10 @@ struct MeshArgs {
   const double* coords;
   const int* elem_es;     // [n_elems] element-set id, or nullptr (all 0)
   const int* eoff;
+  const int* gptr;        // [nnzb+1] gather plan of the two-phase assembly (inverse of eoff)
+  const int* gsrc;        // [n_elems*NN*NN] positions in eoff, sorted by block then element
+  int nnzb;
+  int n_row_blocks;       // blocks in the rows of nodes < n_row_nodes (= nnzb on one GPU)
 };
 
 struct ModelArgs {
@@ -38,13 +42,13 @@ struct FwdArgs {
   const double* xi_prev;
   double* xi;             // in: current-field values (initial guess for some models); out: solved
   long long xi_ld;
-  double* vals;           // BSR values (+=), may be nullptr
+  double* vals;           // BSR values (overwritten with the assembled matrix), may be nullptr
+  double* emat;           // element-matrix scratch [n_elems+1][NX][NX] (required when vals is given)
   double* b;              // residual (+=), may be nullptr
   signed char* path;      // per-element branch (0 elastic / 1 plastic), may be nullptr
   int* n_failed;          // device counter of failed local solves
   double* elem_J;         // optional [n_elems][NX][NX] element Jacobians (reference dof order)
   double* elem_R;         // optional [n_elems][NX]
-  int transpose;          // scatter dtotal^T (adjoint Jacobian)
 };
 
 }  // namespace c8

@@ -6,6 +6,7 @@
 #ifndef C8_G3D
 #define C8_G3D 4
 #endif
+#include <cstdio>
 #include "vfm.cuh"
 #include "kernel_table.h"
 
@@ -23,6 +24,14 @@ __global__ void k_init_xi(double* xi, long long xi_ld, int n_elems) {
 
 template <class C>
 struct Launch {
+  // phase 2 of the assembly (forward.cuh): BSR values of the owned rows <- element matrices
+  template <bool TRANSPOSE>
+  static void gather(const MeshArgs& m, const double* emat, double* vals, cudaStream_t s) {
+    const long long work = (long long)m.n_row_blocks * C::NB * C::NB;
+    if (work == 0) return;
+    k_bsr_gather<C::NB, C::NN, TRANSPOSE><<<(unsigned)((work + 255) / 256), 256, 0, s>>>(
+        m.gptr, m.gsrc, emat, vals, m.n_row_blocks);
+  }
   static void forward_jacobian(const FwdArgs& a, cudaStream_t s) {
     if (a.mesh.n_elems == 0) return;
     const long long threads = (long long)a.mesh.n_elems * C::G;
@@ -32,6 +41,20 @@ struct Launch {
     const bool fast = a.vals && a.b && !a.elem_J && !a.elem_R;
     if (fast) k_forward_jacobian<C, true><<<grid, block, 0, s>>>(a);
     else k_forward_jacobian<C, false><<<grid, block, 0, s>>>(a);
+    if (a.vals) gather<false>(a.mesh, a.emat, a.vals, s);
+#ifdef C8_K1_PHASE_CLOCKS
+    if (fast) {  // tuning builds: print and reset the per-phase warp-cycle counters
+      unsigned long long h[8], z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      cudaStreamSynchronize(s);
+      cudaMemcpyFromSymbol(h, g_k1_phase_clocks, sizeof(h));
+      cudaMemcpyToSymbol(g_k1_phase_clocks, z, sizeof(z));
+      double tot = 0;
+      for (int k = 0; k < 5; ++k) tot += double(h[k]);
+      fprintf(stderr, "K1 phases [load, P1 newton, P2 dC/dx+sens, P3 momentum, P3 pressure+scatter] %%:");
+      for (int k = 0; k < 5; ++k) fprintf(stderr, " %.1f", 100.0 * double(h[k]) / tot);
+      fprintf(stderr, "\n");
+    }
+#endif
   }
   static void global_residual(const FwdArgs& a, cudaStream_t s) {
     if (a.mesh.n_elems == 0) return;
@@ -46,6 +69,7 @@ struct Launch {
     if (a.mesh.n_elems == 0) return;
     const long long threads = (long long)a.mesh.n_elems * C::G;
     k_adjoint_jacobian<C><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(a);
+    if (a.vals) gather<true>(a.mesh, a.emat, a.vals, s);
   }
   static void adjoint_local(const AdjArgs& a, cudaStream_t s) {
     if (a.mesh.n_elems == 0) return;

@@ -132,6 +132,19 @@ static void residual_split(const c8_ctx* ctx, int i, int* eq0, int* neq) {
 static int num_resid(const c8_ctx* ctx) { return (ctx->kt && ctx->kt->nb > ctx->dim) ? 2 : 1; }
 
 namespace c8 {
+// element-matrix scratch of the two-phase assembly: [n_elems + 1][NX][NX] (the last slot is a
+// sink for thread groups that must not contribute)
+double* element_scratch(c8_ctx* ctx) {
+  const size_t need = size_t(ctx->n_elems) + 1;
+  if (ctx->d_emat && ctx->emat_elems >= need && ctx->emat_nx == ctx->kt->nx) return ctx->d_emat;
+  if (ctx->d_emat) cudaFree(ctx->d_emat);
+  ctx->d_emat = nullptr;
+  const size_t bytes = need * ctx->kt->nx * ctx->kt->nx * sizeof(double);
+  if (!cuda_ok(ctx, cudaMalloc(&ctx->d_emat, bytes), "cudaMalloc(element scratch)")) return nullptr;
+  ctx->emat_elems = need; ctx->emat_nx = ctx->kt->nx;
+  return ctx->d_emat;
+}
+
 __global__ void k_int_to_double(const int* i, double* d) { *d = double(*i); }
 
 // number of failed local solves over ALL parts (PCU_Add_Int of the status, src/primal.cpp:96)
@@ -182,7 +195,8 @@ void c8_destroy(c8_ctx* ctx) {
   c8_comm_release(ctx);
   void* ptrs[] = {ctx->d_conn, ctx->d_coords, ctx->d_elem_es, ctx->d_rowptr, ctx->d_colind,
                   ctx->d_eoff, ctx->d_params, ctx->d_nfailed, ctx->d_A, ctx->d_b, ctx->d_x,
-                  ctx->d_xp, ctx->d_xi, ctx->d_xip, ctx->d_stage, ctx->d_scalar};
+                  ctx->d_xp, ctx->d_xi, ctx->d_xip, ctx->d_stage, ctx->d_scalar, ctx->d_gptr,
+                  ctx->d_gsrc, ctx->d_emat};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -257,6 +271,18 @@ int c8_set_mesh(c8_ctx* ctx, int dim, int n_elems, int n_nodes, const int32_t* c
         eoff[(size_t(e) * nn + a) * nn + b] = int(it - ctx->h_colind.data());
       }
     }
+  // gather plan = the inverse of eoff: for every BSR block the (element, node pair) slots that
+  // contribute to it, sorted by element id (deterministic summation order)
+  {
+    std::vector<int> gptr(size_t(ctx->nnzb) + 1, 0), gsrc(eoff.size());
+    for (int v : eoff) gptr[v + 1]++;
+    for (int k = 0; k < ctx->nnzb; ++k) gptr[k + 1] += gptr[k];
+    std::vector<int> pos(gptr.begin(), gptr.end() - 1);
+    for (size_t q = 0; q < eoff.size(); ++q) gsrc[pos[eoff[q]]++] = int(q);
+    if (!upload(ctx, &ctx->d_gptr, gptr)) return C8_ERR_CUDA;
+    if (!upload(ctx, &ctx->d_gsrc, gsrc)) return C8_ERR_CUDA;
+  }
+  if (ctx->d_emat) { cudaFree(ctx->d_emat); ctx->d_emat = nullptr; ctx->emat_elems = 0; }
   if (!upload(ctx, &ctx->d_conn, ctx->h_conn)) return C8_ERR_CUDA;
   if (!upload(ctx, &ctx->d_coords, ctx->h_coords)) return C8_ERR_CUDA;
   if (!upload(ctx, &ctx->d_rowptr, ctx->h_rowptr)) return C8_ERR_CUDA;
@@ -465,7 +491,12 @@ static int forward_impl(c8_ctx* ctx, const double* x, const double* xp, const do
   a.model = ctx->model;
   a.x = x; a.x_prev = xp; a.xi_prev = xip; a.xi = xi; a.xi_ld = ctx->xi_ld;
   a.vals = A; a.b = b; a.path = (signed char*)path; a.n_failed = ctx->d_nfailed;
-  a.elem_J = eJ; a.elem_R = eR; a.transpose = transpose;
+  if (A) {
+    a.emat = element_scratch(ctx);
+    if (!a.emat) return C8_ERR_CUDA;
+  }
+  a.elem_J = eJ; a.elem_R = eR;
+  (void)transpose;
   C8_CUDA(ctx, cudaMemsetAsync(ctx->d_nfailed, 0, sizeof(int), ctx->stream));
   ctx->kt->forward_jacobian(a, ctx->stream);
   C8_CUDA(ctx, cudaGetLastError());

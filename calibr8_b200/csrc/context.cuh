@@ -25,6 +25,11 @@ struct c8_ctx {
   int* d_rowptr = nullptr;
   int* d_colind = nullptr;
   int* d_eoff = nullptr;
+  int* d_gptr = nullptr;       // gather plan: block -> contributing (element, node pair) slots
+  int* d_gsrc = nullptr;
+  double* d_emat = nullptr;    // element-matrix scratch [n_elems + 1][nx][nx]
+  size_t emat_elems = 0;
+  int emat_nx = 0;
   long long xi_ld = 0;
   // partition (multi-GPU): local nodes [0, n_owned_nodes) are owned, the rest are ghosts; local
   // elements [0, n_owned_elems) are owned, the rest are halo elements computed redundantly
@@ -55,7 +60,8 @@ struct c8_ctx {
     c8::MeshArgs m;
     m.n_elems = n_elems; m.n_nodes = n_nodes; m.conn = d_conn; m.coords = d_coords;
     m.n_row_nodes = n_owned_nodes;
-    m.elem_es = d_elem_es; m.eoff = d_eoff;
+    m.elem_es = d_elem_es; m.eoff = d_eoff; m.gptr = d_gptr; m.gsrc = d_gsrc; m.nnzb = nnzb;
+    m.n_row_blocks = h_rowptr.empty() ? 0 : h_rowptr[n_owned_nodes];
     return m;
   }
 };
@@ -66,6 +72,7 @@ bool cuda_ok(c8_ctx* ctx, cudaError_t e, const char* what);
 double* stage(c8_ctx* ctx, size_t bytes);
 double* pinned(c8_ctx* ctx, size_t bytes);
 int fetch_n_failed(c8_ctx* ctx, int* out);
+double* element_scratch(c8_ctx* ctx);
 }  // namespace c8
 
 #define C8_CUDA(ctx, call)                                        \

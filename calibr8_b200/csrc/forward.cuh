@@ -183,34 +183,34 @@ struct SeededX {
   }
 };
 
-// Scatter one element row (value + this thread's derivative lanes) into the fixed BSR pattern.
-// TRANSPOSE: scatter dtotal^T (adjoint Jacobian).  FAST: vals and b are both given and no
-// element-level output is wanted -- the production case; it is completely branch-free: every lane
-// issues its reductions unconditionally and lanes that must not contribute (rows of ghost nodes,
-// which belong to another part; padding groups; failed local solves) add 0.0.  A conditional
-// atomicAdd compiles to a branch + reconvergence region each, 16 x (LX + 1) of them per thread.
-// !FAST: run-time checks for absent outputs and the element-level Jacobian / residual in the
-// reference's dof order (parity-test hook).
-template <class C, bool TRANSPOSE = false, bool FAST = false>
+// Element row output (value + this thread's derivative lanes).
+//
+// Two-phase assembly into the fixed BSR pattern, replacing Tpetra's sumIntoLocalValues of the
+// reference (src/global_residual.cpp:556-586):
+//   phase 1 (here)        every thread group writes its element matrix row by row into a scratch
+//                         [n_elems+1][NX][NX] with plain vector stores (one base pointer, immediate
+//                         offsets; thread groups that must not contribute write to the sink slot);
+//   phase 2 (k_bsr_gather) every BSR block sums the element-matrix sub-blocks listed in the
+//                         precomputed gather plan, in element order -> bit-reproducible sums, no
+//                         fp64 atomics (256 per tet were the top stall of K1, profiles/README.md),
+//                         rows of ghost nodes (another part's rows) are simply not gathered.
+// The residual vector keeps reductions (16 per tet): each thread first collects the entries it
+// owns (values are replicated over the group), then adds them once in finish().
+// FAST: b is given and no element-level output is wanted (the production case, branch-free).
+template <class C, bool FAST = false>
 struct Scatter {
   const FwdArgs& a;
   const Elem<C>& E;
   const XLanes<C::D, C::NB, C::LX>& xl;
   int e, t;
   bool on;  // false: compute but store nothing (padding groups, failed local solves)
-  bool lane_on[C::LX];
-  // residual entries this thread adds at the end: element dofs t, t+G, t+2G, ... (values are
-  // replicated over the group, so each thread just keeps its share -- no per-row branch)
+  double* em = nullptr;    // this thread's columns of the element matrix: em[row*NX + s]
   static constexpr int NBACC = (C::NX + C::G - 1) / C::G;
   double bacc[NBACC];
   C8_DI void init() {
-#pragma unroll
-    for (int s = 0; s < C::LX; ++s) {
-      int gn = 0;
-#pragma unroll
-      for (int n2 = 0; n2 < C::NN; ++n2) gn = picki(xl.node[s] == n2, E.nodes[n2], gn);
-      lane_on[s] = on && (xl.nsel[s] != 0.0) && (!TRANSPOSE || gn < a.mesh.n_row_nodes);
-    }
+    constexpr int NX = C::NX;
+    if (a.vals != nullptr)
+      em = a.emat + size_t(on ? e : a.mesh.n_elems) * NX * NX + t * C::LX;
 #pragma unroll
     for (int j = 0; j < NBACC; ++j) bacc[j] = 0.0;
   }
@@ -232,37 +232,68 @@ struct Scatter {
     }
   }
   C8_DI void row(int n, int eq, const Dual<C::LX>& r) {
-    constexpr int NB = C::NB, NN = C::NN, NX = C::NX;
-    const bool row_on = on && E.nodes[n] < a.mesh.n_row_nodes;  // ghost rows belong to another rank
+    constexpr int NB = C::NB, NX = C::NX, LX = C::LX;
     const int row_dof = n * NB + eq;
-    const int* eo = a.mesh.eoff + size_t(e) * NN * NN;
     bacc[row_dof / C::G] = pick((row_dof % C::G) == t, r.v, bacc[row_dof / C::G]);
-    if constexpr (!FAST) {
-      if (on && a.elem_R && (row_dof % C::G) == t) a.elem_R[size_t(e) * NX + C::ref_dof(n, eq)] = r.v;
-    }
     if (FAST || a.vals != nullptr) {
+      double* dst = em + row_dof * NX;
+      if constexpr (LX % 2 == 0 && C::G * LX == NX) {
 #pragma unroll
-      for (int s = 0; s < C::LX; ++s) {
-        const int nc = xl.node[s], qc = xl.eq[s];
-        // padding lanes (2-D only) point at a valid slot and add 0
-        const int ncc = nc < NN ? nc : NN - 1, qcc = qc < NB ? qc : NB - 1;
-        if constexpr (!TRANSPOSE) {
-          const int blk = __ldg(&eo[n * NN + ncc]);
-          red_add(&a.vals[size_t(blk) * NB * NB + eq * NB + qcc], pick(lane_on[s] && row_on, r.d[s], 0.0));
-        } else {
-          const int blk = __ldg(&eo[ncc * NN + n]);
-          red_add(&a.vals[size_t(blk) * NB * NB + qcc * NB + eq], pick(lane_on[s], r.d[s], 0.0));
-        }
+        for (int s = 0; s < LX; s += 2)
+          *reinterpret_cast<double2*>(dst + s) = make_double2(r.d[s], r.d[s + 1]);
+      } else {
+#pragma unroll
+        for (int s = 0; s < LX; ++s)
+          if (t * LX + s < NX) dst[s] = r.d[s];
       }
     }
     if constexpr (!FAST) {
+      if (on && a.elem_R && (row_dof % C::G) == t) a.elem_R[size_t(e) * NX + C::ref_dof(n, eq)] = r.v;
 #pragma unroll
-      for (int s = 0; s < C::LX; ++s)
+      for (int s = 0; s < LX; ++s)
         if (on && a.elem_J && xl.nsel[s] != 0.0)
           a.elem_J[(size_t(e) * NX + C::ref_dof(n, eq)) * NX + C::ref_dof(xl.node[s], xl.eq[s])] = r.d[s];
     }
   }
 };
+
+// Phase 2 of the assembly: vals[block] = sum over the gather plan of the element sub-blocks
+// (TRANSPOSE: the transposed sub-block of the transposed pair -> dtotal^T for the adjoint).
+// One thread per (block, entry); rows of nodes >= n_row_nodes are left untouched.
+template <int NB, int NN, bool TRANSPOSE>
+__global__ void k_bsr_gather(const int* __restrict__ gptr, const int* __restrict__ gsrc,
+                             const double* __restrict__ emat, double* __restrict__ vals,
+                             int n_row_blocks) {
+  constexpr int BB = NB * NB, NX = NB * NN;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)n_row_blocks * BB) return;
+  const int blk = int(i / BB), ent = int(i % BB);
+  const int r = ent / NB, c = ent % NB;
+  double s = 0.0;
+  for (int k = gptr[blk]; k < gptr[blk + 1]; ++k) {
+    const int q = __ldg(&gsrc[k]);           // e*NN*NN + na*NN + nb : block (node na, node nb)
+    const int e = q / (NN * NN), rem = q - e * (NN * NN);
+    const int na = rem / NN, nb = rem - na * NN;
+    const double* m = emat + size_t(e) * NX * NX;
+    s += TRANSPOSE ? __ldg(&m[(nb * NB + c) * NX + na * NB + r]) : __ldg(&m[(na * NB + r) * NX + nb * NB + c]);
+  }
+  vals[i] = s;
+}
+
+// Optional per-phase cycle counters (tuning builds only: -DC8_K1_PHASE_CLOCKS)
+#ifdef C8_K1_PHASE_CLOCKS
+static __device__ unsigned long long g_k1_phase_clocks[8];
+#define C8_PHASE_MARK(k)                                                        \
+  do {                                                                          \
+    const long long now_ = clock64();                                           \
+    if ((threadIdx.x & 31) == 0) atomicAdd(&g_k1_phase_clocks[k], (unsigned long long)(now_ - tphase_)); \
+    tphase_ = now_;                                                             \
+  } while (0)
+#define C8_PHASE_START() long long tphase_ = clock64()
+#else
+#define C8_PHASE_MARK(k) do {} while (0)
+#define C8_PHASE_START() do {} while (0)
+#endif
 
 #ifndef C8_K1_BLOCK
 #define C8_K1_BLOCK 256
@@ -284,6 +315,7 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian(co
   const unsigned lane = threadIdx.x & 31u;
   const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane / G * G));
 
+  C8_PHASE_START();
   Elem<C> E;
   load_elem<C>(a.mesh, a.model, a.x, a.x_prev, a.xi_prev, a.xi_ld, e, E);
   double xi[NXI];
@@ -293,6 +325,7 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian(co
   Kin<D, double, double> k0;
   k0.gu = grad_u_val<D, NB>(E.xn, E.g);
   k0.gup = grad_u_val<D, NB>(E.xpn, E.g);
+  C8_PHASE_MARK(0);
 
   // ---- P1: local Newton (block-synchronous) ---------------------------------
   Dual<C::LXI> Cd[NXI];
@@ -310,6 +343,7 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian(co
     if (a.path && t == 0) a.path[e] = (signed char)path;
   }
   __syncthreads();
+  C8_PHASE_MARK(1);
 
   // ---- P2: dC/dx, then dxi/dx ---------------------------------------------
   SeededX<C> sx;
@@ -336,10 +370,11 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian(co
     }
   }
   __syncthreads();
+  C8_PHASE_MARK(2);
 
   // ---- P3: element residual and total Jacobian, scattered row by row ------
   const double wdv = quad1_weight<D>() * E.g.dv;
-  Scatter<C, false, FAST> sc{a, E, sx.xl, e, t, ok};
+  Scatter<C, FAST> sc{a, E, sx.xl, e, t, ok};
   sc.init();
   {
     const Mat<Dual<LX>, D> P = first_pk<D, C::M, Model>(k2, sx.p, xid, E.par, a.model.thickness);
@@ -354,6 +389,7 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian(co
         sc.row(n, i, r);
       }
   }
+  C8_PHASE_MARK(3);
   if constexpr (C::M == MECH_MIXED) {
     __syncthreads();
     Dual<LX> Rp[NN];
@@ -395,6 +431,7 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian(co
     for (int n = 0; n < NN; ++n) sc.row(n, D, Rp[n]);
   }
   sc.finish();
+  C8_PHASE_MARK(4);
 }
 
 // K2: residual only (eval_global_residual): no Newton, xi given, T = double

@@ -133,3 +133,4 @@ int c8_bench_copy(c8_ctx* ctx, double* gbs) {
 }
 
 }  // extern "C"
+

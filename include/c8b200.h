@@ -85,8 +85,10 @@ int c8_unpack_xi(c8_ctx* ctx, const double* xi_dev_soa, double* xi_host_aos);
 int c8_init_xi(c8_ctx* ctx, double* xi_dev);
 
 /* ---- the hot path, device pointers ---- */
-/* eval_forward_jacobian, evaluations.cpp:12-154.  A_vals_dev / b_dev are accumulated into
- * (zero them first, like LinearAlg::zero_all); xi_dev in: current-field values, out: solved.
+/* eval_forward_jacobian, evaluations.cpp:12-154.  A_vals_dev is OVERWRITTEN with the assembled
+ * Jacobian (two-phase assembly: element matrices -> scratch, then a deterministic gather per BSR
+ * block; rows of ghost nodes are left untouched); b_dev is accumulated into (zero it first, like
+ * LinearAlg::zero_all); xi_dev in: current-field values, out: solved.
  * path_dev (int8 per element) and the element-level outputs may be NULL.
  * n_failed (host out, may be NULL): number of local solves that failed. */
 int c8_forward_jacobian(c8_ctx* ctx, const double* x_dev, const double* x_prev_dev,
@@ -143,7 +145,8 @@ typedef struct c8_qoi {
 } c8_qoi;
 
 /* History arrays: g [nxi][xi_ld], f [nx][xi_ld] (element dofs node-interleaved), phi [nxi][xi_ld]. */
-/* eval_adjoint_jacobian, evaluations.cpp:349-526: AT_vals += dR/dx_total^T, rhs +=, g -= dJ/dxi */
+/* eval_adjoint_jacobian, evaluations.cpp:349-526: AT_vals = dR/dx_total^T (overwritten), rhs +=,
+ * g -= dJ/dxi */
 int c8_adjoint_jacobian(c8_ctx* ctx, const c8_qoi* qoi, const double* x_dev,
                         const double* x_prev_dev, const double* xi_dev, const double* xi_prev_dev,
                         double* g_dev, const double* f_dev, double* AT_vals_dev, double* rhs_dev);

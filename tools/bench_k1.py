@@ -23,7 +23,7 @@ def run(ltype, params, amp_scale, mesh, reps=10):
     assert ctx.forward_jacobian(xp, x0, xi0, xip, None, b) == 0
     ts = []
     for k in range(reps + 3):
-        A.zero_(); b.zero_(); xi.copy_(xip)
+        b.zero_(); xi.copy_(xip)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         ctx.forward_jacobian(x, xp, xip, xi, A, b, path, check=False)
