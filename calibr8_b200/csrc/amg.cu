@@ -308,7 +308,7 @@ int Amg::build() {
   for (AmgLevel& L : lv_)
     C8_CUDA(ctx_, cudaMalloc(&L.dinv, size_t(L.n > 0 ? L.n : 1) * nb_ * nb_ * sizeof(double)));
   C8_CUDA(ctx_, cudaMalloc(&r0_, size_t(ctx_->n_nodes) * nb_ * sizeof(double)));
-  C8_CUDA(ctx_, cudaMemset(r0_, 0, size_t(ctx_->n_nodes) * nb_ * sizeof(double)));
+  C8_CUDA(ctx_, cudaMemsetAsync(r0_, 0, size_t(ctx_->n_nodes) * nb_ * sizeof(double), ctx_->stream));
   nd_ = 0;
   if (lv_.size() > 1 && lv_.back().n * nb_ <= 1024) {
     nd_ = lv_.back().n * nb_;

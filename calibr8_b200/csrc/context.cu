@@ -329,7 +329,7 @@ int c8_set_model(c8_ctx* ctx, int global_type, int local_type, const double* par
     if (*bufs[k]) cudaFree(*bufs[k]);
     *bufs[k] = nullptr;
     C8_CUDA(ctx, cudaMalloc(bufs[k], std::max<size_t>(sizes[k], 1) * sizeof(double)));
-    C8_CUDA(ctx, cudaMemset(*bufs[k], 0, std::max<size_t>(sizes[k], 1) * sizeof(double)));
+    C8_CUDA(ctx, cudaMemsetAsync(*bufs[k], 0, std::max<size_t>(sizes[k], 1) * sizeof(double), ctx->stream));
   }
   return c8_set_params(ctx, params);
 }

@@ -67,10 +67,9 @@ C8_DI void load_elem(const MeshArgs& m, const ModelArgs& md, const double* __res
 // Cd: the last residual evaluation with xi seeded (value + this thread's dC/dxi columns).
 // Returns the branch (0/1) or -1 when not converged within max_iters.
 //
-// BLOCK-SYNCHRONOUS: every thread of the CTA must call this (inactive groups pass
-// active = false).  The iteration loop is driven by __syncthreads_or so that all warps of the
-// CTA walk the (large, fully unrolled) Newton body together: the kernel is instruction-fetch
-// bound when warps drift apart in a ~170 KB straight-line program (profiles/README.md).
+// WARP-SYNCHRONOUS: every thread of a warp must call this (inactive groups pass active = false);
+// the body is executed by all 32 lanes together so that the in-group solves can use full-mask
+// shuffles (profiles/README.md).
 template <class C>
 C8_DI int local_newton(const Kin<C::D, double, double>& k0, const Elem<C>& E, const ModelArgs& md,
                        double (&xi)[C::NXI], Dual<C::LXI> (&Cd)[C::NXI], unsigned mask, int t,
@@ -92,7 +91,13 @@ C8_DI int local_newton(const Kin<C::D, double, double>& k0, const Elem<C>& E, co
     // Cd / path, and simply do not apply the update.
     while (true) {
       const bool work = active && (iter <= md.max_iters) && !converged;
+      // warp-uniform loop: a warp leaves when its own quadrature points are done (the phase
+      // barriers of the caller re-align the CTA); -DC8_K1_BLOCK_NEWTON keeps the whole CTA together
+#ifdef C8_K1_BLOCK_NEWTON
       if (!__syncthreads_or(work)) break;
+#else
+      if (!__any_sync(0xffffffffu, work)) break;
+#endif
       Dual<LXI> xs[NXI];
 #pragma unroll
       for (int q = 0; q < NXI; ++q) xs[q] = seeded<LXI>(xi[q], q, t * LXI);

@@ -104,11 +104,11 @@ static int ensure_ws(c8_ctx* ctx, SolverState& ws, int m) {
   if (ws.m >= m && ws.n == n) return C8_OK;
   ws.free_ws();
   C8_CUDA(ctx, cudaMalloc(&ws.V, size_t(m + 1) * n * sizeof(double)));
-  C8_CUDA(ctx, cudaMemset(ws.V, 0, size_t(m + 1) * n * sizeof(double)));
+  C8_CUDA(ctx, cudaMemsetAsync(ws.V, 0, size_t(m + 1) * n * sizeof(double), ctx->stream));
   C8_CUDA(ctx, cudaMalloc(&ws.w, n * sizeof(double)));
   C8_CUDA(ctx, cudaMalloc(&ws.z, n * sizeof(double)));
-  C8_CUDA(ctx, cudaMemset(ws.w, 0, n * sizeof(double)));
-  C8_CUDA(ctx, cudaMemset(ws.z, 0, n * sizeof(double)));
+  C8_CUDA(ctx, cudaMemsetAsync(ws.w, 0, n * sizeof(double), ctx->stream));
+  C8_CUDA(ctx, cudaMemsetAsync(ws.z, 0, n * sizeof(double), ctx->stream));
   C8_CUDA(ctx, cudaMalloc(&ws.dinv, size_t(ctx->n_nodes) * ctx->kt->nb * ctx->kt->nb * sizeof(double)));
   C8_CUDA(ctx, cudaMalloc(&ws.partial, size_t(m + 2) * 256 * sizeof(double)));
   C8_CUDA(ctx, cudaMalloc(&ws.dots, size_t(m + 2) * sizeof(double)));

@@ -404,8 +404,20 @@ template <class TX, class TP>
 C8_DI prom_t<TX, TP> hyper_yield(const TX& alpha, const TP& Y, const TP& S, const TP& D,
                                        const TP& A, const TP& n, const TP& K) {
   // sigma_y = Y + S (1 - exp(-D alpha)) + A (alpha + 1e-12)^n + K alpha, src/hyper_J2.cpp:260-262
-  return conv<prom_t<TX, TP>>(Y + S * (1.0 - dexp(-D * alpha)) +
-                                    A * dpow(alpha + 1e-12, n) + K * alpha);
+  using R = prom_t<TX, TP>;
+  if constexpr (is_dual<TP>::value) {
+    return conv<R>(Y + S * (1.0 - dexp(-D * alpha)) + A * dpow(alpha + 1e-12, n) + K * alpha);
+  } else {
+    // Unseeded parameters: a saturation / power-law term whose coefficient is exactly zero
+    // contributes exactly zero (for a finite exp / pow), so its transcendental is skipped -- a
+    // parameter-uniform branch.  The sum keeps the reference's order, so non-zero terms are
+    // unchanged.  (The reference's own hyper-J2 deck, test/primal/notch_hyper_J2.yaml.in:25-34,
+    // has S = D = A = n = 0; pow() alone was ~1/6 of K1's instructions.)
+    R sat = conv<R>(0.0), pw = conv<R>(0.0);
+    if (S != 0.0) sat = conv<R>(S * (1.0 - dexp(-D * alpha)));
+    if (A != 0.0) pw = conv<R>(A * dpow(alpha + 1e-12, n));
+    return conv<R>(Y + sat + pw + K * alpha);
+  }
 }
 
 template <int DIM>

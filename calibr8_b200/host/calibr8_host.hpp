@@ -64,7 +64,10 @@ class DevVec {  // RAII device array
     if (p_) cudaFree(p_);
     p_ = nullptr; n_ = n;
     if (n && cudaMalloc(&p_, n * sizeof(double)) != cudaSuccess) throw std::runtime_error("cudaMalloc");
-    if (n) cudaMemset(p_, 0, n * sizeof(double));
+    if (n) {  // null-stream memset is not ordered with the context's non-blocking stream
+      cudaMemset(p_, 0, n * sizeof(double));
+      cudaDeviceSynchronize();
+    }
   }
   double* get() const { return p_; }
   size_t size() const { return n_; }
