@@ -222,6 +222,8 @@ def calibration_step_partitioned(mesh, load_steps, rank, world, local_rank):
     hp.finalize_dbcs()
     hp.set_solver(15, 1e-8, 1e-8, gmres_restart=100, gmres_max_iters=20000, linear_tol=1e-8)
     hp.set_qoi_avg_disp()
+    if os.environ.get("C8_BENCH_PROFILE"):
+        hp.profile(True)
     out = {}
     for rep in range(2):
         s0 = hp.stats()
@@ -245,7 +247,7 @@ def calibration_step_partitioned(mesh, load_steps, rank, world, local_rank):
                              "halo_elems_rank0": part.n_elems - part.n_owned_elems,
                              "ghost_nodes_rank0": part.n_nodes - part.n_owned_nodes,
                              "neighbours_rank0": int(part.nbr_rank.size)},
-               "comm_rank0": cs,
+               "comm_rank0": cs, "phase_seconds_cumulative": hp.profile(bool(os.environ.get("C8_BENCH_PROFILE"))),
                "note": "1M-tet mesh split over the ranks; NCCL halo copy of Krylov vectors / Newton iterate and "
                        "fp64 allreduce of dots, objective, gradient; AMG acts on each part's owned block"}
     hp.close(); ctx.close()

@@ -190,6 +190,7 @@ int c8_set_comm(c8_ctx* ctx, c8_halo_fn halo, c8_allreduce_fn allreduce, void* u
   ctx->halo_cb = halo;
   ctx->allreduce_cb = allreduce;
   ctx->comm_user = user;
+  ctx->comm_capturable = false;
   return C8_OK;
 }
 
@@ -245,7 +246,9 @@ int c8_nccl_init(c8_ctx* ctx, const char* id128, int rank, int nranks) {
   ncclResult_t r = g_nccl.CommInitRank(&c.nccl, nranks, id, rank);
   if (r != ncclSuccess) return fail(ctx, C8_ERR_CUDA, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
   c.rank = rank; c.nranks = nranks;
-  return c8_set_comm(ctx, &halo_nccl, &allreduce_nccl, &c);
+  const int rc = c8_set_comm(ctx, &halo_nccl, &allreduce_nccl, &c);
+  ctx->comm_capturable = true;
+  return rc;
 }
 
 int c8_set_comm_host(c8_ctx* ctx, c8_host_exchange_fn exchange, c8_host_allreduce_fn allreduce,

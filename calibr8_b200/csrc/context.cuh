@@ -37,6 +37,7 @@ struct c8_ctx {
   void (*halo_cb)(void*, double*, int) = nullptr;
   void (*allreduce_cb)(void*, double*, int) = nullptr;
   void* comm_user = nullptr;
+  bool comm_capturable = false;   // the hooks only enqueue stream work (CUDA-graph capturable)
 
   // model
   const c8::KernelTable* kt = nullptr;

@@ -222,8 +222,10 @@ int c8_gmres(c8_ctx* ctx, const double* A, const double* b, double* x, int resta
     k_givens<<<1, 32, 0, s>>>(ws.H, ldh, ws.cs, ws.sn, ws.g, ws.dots, ws.dots2, ws.nrm, j, ws.res);
     k_normalize<<<ag, 256, 0, s>>>(vj1, ws.nrm, n, nullptr);
   };
-  const bool graphs = ws.use_graphs && !ctx->halo_cb && !ctx->allreduce_cb && s != nullptr &&
-                      s != cudaStreamLegacy && s != cudaStreamPerThread;  // capture needs a real stream
+  // capture needs a real stream; a partitioned run captures too when its transport only enqueues
+  // stream work (NCCL), not when it stages through the host
+  bool graphs = ws.use_graphs && ((!ctx->halo_cb && !ctx->allreduce_cb) || ctx->comm_capturable) &&
+                s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
   if (graphs) {
     const int pc_key = use_amg ? 1 : 0;
     if (ws.graph_A != A || ws.graph_pc != pc_key || int(ws.iter_graph.size()) != ws.m) {
@@ -256,11 +258,21 @@ int c8_gmres(c8_ctx* ctx, const double* A, const double* b, double* x, int resta
         if (graphs) {
           if (!ws.iter_graph[j]) {
             cudaGraph_t graph = nullptr;
-            C8_CUDA(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            iteration(j);
-            C8_CUDA(ctx, cudaStreamEndCapture(s, &graph));
-            C8_CUDA(ctx, cudaGraphInstantiate(&ws.iter_graph[j], graph, 0));
-            cudaGraphDestroy(graph);
+            bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+              iteration(j);
+              ok = cudaStreamEndCapture(s, &graph) == cudaSuccess && graph != nullptr;
+            }
+            if (ok) ok = cudaGraphInstantiate(&ws.iter_graph[j], graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+            if (!ok) {  // capture not possible here (e.g. a transport that cannot be captured)
+              cudaGetLastError();
+              ws.iter_graph[j] = nullptr;
+              ws.use_graphs = false;
+              graphs = false;
+              iteration(j);
+              continue;
+            }
           }
           C8_CUDA(ctx, cudaGraphLaunch(ws.iter_graph[j], s));
         } else {
