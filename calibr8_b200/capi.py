@@ -204,7 +204,11 @@ class Context:
              "A": self.nnzb * self.nb * self.nb, "path": self.n_elems,
              "elem_J": self.n_elems * self.nx * self.nx, "elem_R": self.n_elems * self.nx}[kind]
         dt = torch.int8 if kind == "path" else torch.float64
-        return torch.zeros(n, dtype=dt, device=dev)
+        t = torch.zeros(n, dtype=dt, device=dev)
+        # the library launches on its own non-blocking stream unless set_stream() binds torch's:
+        # make sure the fill has landed before the tensor is handed to it
+        torch.cuda.current_stream(dev).synchronize()
+        return t
 
     # ---- hot path ----------------------------------------------------------------------
     def forward_jacobian(self, x, x_prev, xi_prev, xi, A=None, b=None, path=None, elem_J=None,
