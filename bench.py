@@ -169,6 +169,8 @@ def calibration_step(ctx, mesh, load_steps):
     hp.finalize_dbcs()
     hp.set_solver(15, 1e-8, 1e-8, gmres_restart=100, gmres_max_iters=20000, linear_tol=1e-8)
     hp.set_qoi_avg_disp()
+    if os.environ.get("C8_BENCH_PROFILE"):
+        hp.profile(True)
     out = {}
     for rep in range(2):   # the first pass builds the multigrid hierarchy and loads the kernels
         s0 = hp.stats()
@@ -186,6 +188,7 @@ def calibration_step(ctx, mesh, load_steps):
                "krylov_iterations": s1["linear_iters"] - s0["linear_iters"],
                "objective": J, "gradient": [float(v) for v in g],
                "preconditioner": ctx.preconditioner_info(),
+               "phase_seconds_cumulative": hp.profile(bool(os.environ.get("C8_BENCH_PROFILE"))),
                "note": "Newton tol 1e-8, GMRES(100) rel tol 1e-8, aggregation-AMG right preconditioner; "
                        "second of two passes (the first builds the hierarchy)"}
     hp.close()

@@ -169,20 +169,46 @@ __global__ void k_dense_apply(const double* __restrict__ M, const double* __rest
 // Greedy aggregation on the node graph (root node + all its neighbours when none of them is
 // taken yet; leftovers join the neighbouring aggregate they are most connected to).
 static void aggregate(int n, const std::vector<int>& rowptr, const std::vector<int>& colind,
-                      std::vector<int>& agg, int& nc) {
+                      std::vector<int>& agg, int& nc, int max_size) {
   agg.assign(n, -1);
   nc = 0;
-  for (int i = 0; i < n; ++i) {
-    if (agg[i] != -1) continue;
-    bool free_nbrs = true;
-    for (int k = rowptr[i]; k < rowptr[i + 1] && free_nbrs; ++k)
-      if (agg[colind[k]] != -1) free_nbrs = false;
-    if (!free_nbrs) continue;
-    agg[i] = nc;
-    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) agg[colind[k]] = nc;
-    ++nc;
+  if (max_size <= 0) {
+    // phase 1: a root and ALL its neighbours when none of them is taken yet
+    for (int i = 0; i < n; ++i) {
+      if (agg[i] != -1) continue;
+      bool free_nbrs = true;
+      for (int k = rowptr[i]; k < rowptr[i + 1] && free_nbrs; ++k)
+        if (agg[colind[k]] != -1) free_nbrs = false;
+      if (!free_nbrs) continue;
+      agg[i] = nc;
+      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) agg[colind[k]] = nc;
+      ++nc;
+    }
+  } else {
+    // bounded aggregates: a free root takes the free neighbours that share the most neighbours
+    // with it (a compact clump), up to max_size nodes
+    std::vector<std::pair<int, int>> cand;
+    std::vector<char> mark(n, 0);
+    for (int i = 0; i < n; ++i) {
+      if (agg[i] != -1) continue;
+      cand.clear();
+      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) mark[colind[k]] = 1;
+      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        const int j = colind[k];
+        if (j == i || agg[j] != -1) continue;
+        int common = 0;
+        for (int k2 = rowptr[j]; k2 < rowptr[j + 1]; ++k2) common += mark[colind[k2]];
+        cand.emplace_back(-common, j);
+      }
+      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) mark[colind[k]] = 0;
+      if (int(cand.size()) + 1 < (max_size + 1) / 2) continue;  // too few free neighbours: leftover
+      std::sort(cand.begin(), cand.end());
+      agg[i] = nc;
+      for (int q = 0; q < int(cand.size()) && q < max_size - 1; ++q) agg[cand[q].second] = nc;
+      ++nc;
+    }
   }
-  std::vector<int> agg2 = agg, cnt;
+  std::vector<int> agg2 = agg;
   for (int i = 0; i < n; ++i) {
     if (agg[i] != -1) continue;
     int best = -1, best_cnt = 0;
@@ -249,7 +275,7 @@ int Amg::build() {
   while (n > opt.coarsest_max_nodes && int(lv_.size()) < opt.max_levels) {
     std::vector<int> agg;
     int nc = 0;
-    aggregate(n, rowptr, colind, agg, nc);
+    aggregate(n, rowptr, colind, agg, nc, opt.max_aggregate_size);
     if (nc >= n) break;  // no coarsening possible
     // coarse pattern: unique (agg[i], agg[j]) pairs, and for each the fine blocks summed into it
     std::vector<std::pair<uint64_t, int>> keys;

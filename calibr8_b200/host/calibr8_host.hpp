@@ -98,6 +98,7 @@ class Problem {
   std::vector<DevVec> x, xi;   // [0..num_steps]
   std::vector<DevVec> z, phi;  // adjoint fields per step
   DevVec A, b, dx, Adx, saved_xi, work;
+  DevVec adj_g, adj_f, adj_rhs, adj_grad;  // reverse-sweep work arrays (reused)
   // flattened Dirichlet dofs
   int n_dbc = 0;
   int* d_dbc_node = nullptr;

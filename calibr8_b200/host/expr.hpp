@@ -79,6 +79,9 @@ class Expr {
         if (id == "cos") return std::cos(a);
         if (id == "tan") return std::tan(a);
         if (id == "atan") return std::atan(a);
+        if (id == "asin") return std::asin(a);
+        if (id == "acos") return std::acos(a);
+        if (id == "tanh") return std::tanh(a);
         if (id == "exp") return std::exp(a);
         if (id == "sqrt") return std::sqrt(a);
         if (id == "abs" || id == "fabs") return std::fabs(a);

@@ -91,12 +91,25 @@ void Problem::eval_dbc_values(double t) {
     C8H_CUDA(cudaMemcpy(d_dbc_val, h_dbc_val.data(), n_dbc * sizeof(double), cudaMemcpyHostToDevice));
 }
 
-void Problem::allocate_history() {
-  x.clear(); xi.clear(); z.clear(); phi.clear();
-  for (int s = 0; s <= num_steps; ++s) {
-    x.emplace_back(size_t(n_dofs));
-    xi.emplace_back(size_t(xi_ld) * nxi);
+// (re)size a per-step history to [0..num_steps] arrays of n doubles, zero-filled; arrays of the
+// right size are reused (cudaMalloc / cudaFree of ~100 MB blocks cost milliseconds each and an
+// objective is evaluated many times on one mesh)
+static void reset_history(Problem& P, std::vector<DevVec>& h, size_t n) {
+  cudaStream_t s = (cudaStream_t)c8_get_stream(P.ctx);
+  const size_t want = size_t(P.num_steps) + 1;
+  bool ok = h.size() == want;
+  for (size_t k = 0; ok && k < h.size(); ++k) ok = h[k].size() == n;
+  if (!ok) {
+    h.clear();
+    for (size_t k = 0; k < want; ++k) h.emplace_back(n);
+  } else {
+    for (DevVec& v : h) cudaMemsetAsync(v.get(), 0, n * sizeof(double), s);
   }
+}
+
+void Problem::allocate_history() {
+  reset_history(*this, x, size_t(n_dofs));
+  reset_history(*this, xi, size_t(xi_ld) * nxi);
   check(c8_init_xi(ctx, xi[0].get()), "c8_init_xi");
   check(c8_synchronize(ctx), "sync");
 }
@@ -279,9 +292,16 @@ void Adjoint::gradient(std::vector<double>& grad) {
   const int N = P.num_steps;
   const SolverParams& sp = P.sp;
   const size_t xb = P.n_dofs * sizeof(double);
-  DevVec g(size_t(P.xi_ld) * P.nxi), f(size_t(P.xi_ld) * P.nx), rhs(P.n_dofs), d_grad(64);
-  P.z.clear(); P.phi.clear();
-  for (int k = 0; k <= N; ++k) { P.z.emplace_back(size_t(P.n_dofs)); P.phi.emplace_back(size_t(P.xi_ld) * P.nxi); }
+  // reverse-sweep work arrays live in the Problem and are reused across gradient evaluations
+  auto fit = [&](DevVec& v, size_t n) {
+    if (v.size() != n) v.resize(n);
+    else cudaMemsetAsync(v.get(), 0, n * sizeof(double), s);
+  };
+  fit(P.adj_g, size_t(P.xi_ld) * P.nxi); fit(P.adj_f, size_t(P.xi_ld) * P.nx);
+  fit(P.adj_rhs, size_t(P.n_dofs)); fit(P.adj_grad, 64);
+  DevVec &g = P.adj_g, &f = P.adj_f, &rhs = P.adj_rhs, &d_grad = P.adj_grad;
+  reset_history(P, P.z, size_t(P.n_dofs));
+  reset_history(P, P.phi, size_t(P.xi_ld) * P.nxi);
   int n_es = 1;
   grad.assign(size_t(n_es) * P.npar, 0.0);
   for (int step = N; step >= 1; --step) {
