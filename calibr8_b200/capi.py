@@ -303,7 +303,7 @@ HOST_SYMBOLS = [
     "c8h_create", "c8h_destroy", "c8h_last_error", "c8h_set_time", "c8h_add_dbc",
     "c8h_finalize_dbcs", "c8h_set_solver", "c8h_set_qoi_avg_disp", "c8h_set_qoi_calibration",
     "c8h_primal_solve", "c8h_adjoint_gradient", "c8h_get_step", "c8h_get_adjoint_step", "c8h_stats",
-    "c8h_profile",
+    "c8h_profile", "c8h_eval_expr",
 ]
 
 
@@ -591,3 +591,16 @@ def _ctx_preconditioner_info(self):
 
 Context.set_preconditioner = _ctx_set_preconditioner
 Context.preconditioner_info = _ctx_preconditioner_info
+
+
+def eval_expr(expr, coords, t=0.0):
+    """Evaluate an expression in x, y, z, t (the grammar of calibr8_b200/host/expr.hpp, the role of the
+    reference's Pamgen RTC strings) at the rows of coords [n, 3] -- host only, no GPU needed."""
+    lib = load_library()
+    xyz = np.ascontiguousarray(coords, dtype=np.float64).reshape(-1, 3)
+    out = np.zeros(xyz.shape[0])
+    err = C.create_string_buffer(256)
+    rc = lib.c8h_eval_expr(str(expr).encode(), _hp(xyz), int(xyz.shape[0]), C.c_double(t), _hp(out), err, 256)
+    if rc != 0:
+        raise C8Error("expression: " + err.value.decode())
+    return out

@@ -1,0 +1,225 @@
+"""Process-boundary front end: the reference's `primal` and
+`objective` executables on top of the B200 hot path.
+
+    python -m calibr8_b200.cli primal    deck.yaml
+    python -m calibr8_b200.cli objective deck.yaml true|false [label]
+
+Same YAML deck schema as the reference (src/main_primal.cpp, src/main_objective.cpp:512-560):
+`problem`, `discretization`, `residuals`, `dirichlet bcs: expression`, `quantity of interest`,
+`inverse`, `virtual fields`.  Same text outputs, one `%.17e` per line:
+`objective_value[_label].txt`, `objective_gradient[_label].txt` (src/main_objective.cpp:199-219),
+the QoI side file `load out file` (src/reaction_mismatch.cpp:137-147).  The unmodified Python
+drivers of the reference (py/calibr8/util/driver_support.py) only need the executable names mapped.
+
+Differences, stated: the mesh may be a flat `.npz` (calibr8_b200.meshio) besides `.smb`+`.dmg`+assoc;
+`write synthetic: true` stores the measured displacement history as `<name>_synthetic/measured.npz`
+next to a copy of the mesh instead of SMB field tags; `linear algebra` is read for the convergence
+tolerance only (the solver is the library's AMG-GMRES).  No CPU path: needs the CUDA library.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+from . import meshio
+from .capi import PARAM_NAMES, Context, HostProblem, eval_expr, make_qoi
+
+
+def load_deck(path):
+    import yaml
+    with open(path) as f:
+        d = yaml.safe_load(f)
+    assert isinstance(d, dict) and len(d) == 1, "a deck has one top-level sublist"
+    name, body = next(iter(d.items()))
+    return name, body
+
+
+def _resolve(base, p):
+    return p if os.path.isabs(p) else os.path.normpath(os.path.join(base, p))
+
+
+def load_mesh(disc, base):
+    """-> (Mesh, measured [num_steps, n_nodes, dim] or None)"""
+    mf = _resolve(base, disc["mesh file"])
+    if os.path.isdir(mf) or mf.endswith("/"):
+        z = np.load(os.path.join(mf, "measured.npz"))
+        return meshio.load_npz(os.path.join(mf, "mesh.npz")), z["measured"]
+    if mf.endswith(".npz"):
+        return meshio.load_npz(mf), None
+    return meshio.load_calibr8_mesh(mf, _resolve(base, disc["geom file"]),
+                                    _resolve(base, disc["assoc file"])), None
+
+
+def _materials(local, mesh, override=None):
+    names = PARAM_NAMES[local["type"]]
+    out = []
+    for es in mesh.elem_set_names:
+        m = dict(local["materials"][es])
+        if override and es in override:
+            m.update(override[es])
+        out.append({k: float(m[k]) for k in names})
+    return out
+
+
+def build(deck, base, override=None, device=0):
+    disc = deck["discretization"]
+    mesh, measured = load_mesh(disc, base)
+    res = deck["residuals"]
+    g, l = res["global residual"], res["local residual"]
+    ctx = Context(device)
+    ctx.set_mesh(mesh.dim, mesh.conn, mesh.coords, mesh.elem_set, len(mesh.elem_set_names))
+    ctx.set_model(g["type"], l["type"], _materials(l, mesh, override),
+                  max_iters=int(l.get("nonlinear max iters", 0)),
+                  abs_tol=float(l.get("nonlinear absolute tol", 0.0)),
+                  rel_tol=float(l.get("nonlinear relative tol", 0.0)),
+                  stab_mult=float(g.get("stabilization multiplier", 1.0)),
+                  thickness=float(g.get("thickness", 1.0)))
+    hp = HostProblem(ctx)
+    nsteps = int(disc["num steps"])
+    hp.set_time(nsteps, float(disc.get("step size", 1.0)))
+    for _, bc in (deck.get("dirichlet bcs", {}).get("expression", {}) or {}).items():
+        hp.add_dbc(int(bc[0]), int(bc[1]), mesh.node_sets[str(bc[2])], str(bc[3]))
+    hp.finalize_dbcs()
+    lin_tol = 1e-10
+    try:
+        la = deck["linear algebra"]
+        st = la["Linear Solver Types"]["Belos"]["Solver Types"]
+        lin_tol = float(next(iter(st.values()))["Convergence Tolerance"])
+    except Exception:
+        pass
+    hp.set_solver(int(g.get("nonlinear max iters", 15)), float(g.get("nonlinear absolute tol", 1e-8)),
+                  float(g.get("nonlinear relative tol", 1e-8)), gmres_restart=200, gmres_max_iters=20000,
+                  linear_tol=max(lin_tol, 1e-13), verbose=bool(g.get("print convergence", False)))
+    return ctx, hp, mesh, measured
+
+
+def _area(mesh):
+    X = mesh.coords[mesh.conn]
+    return float(0.5 * np.abs((X[:, 1, 0] - X[:, 0, 0]) * (X[:, 2, 1] - X[:, 0, 1]) -
+                              (X[:, 1, 1] - X[:, 0, 1]) * (X[:, 2, 0] - X[:, 0, 0])).sum())
+
+
+def _loads_on_plane(ctx, hp, qoi_deck, nsteps):
+    """total reaction on the coordinate plane per step (QoI preprocess pass, reaction_mismatch.cpp:58-103)"""
+    import torch
+    q = make_qoi("calibration", coord_idx=int(qoi_deck["coordinate index"]),
+                 coord_value=float(qoi_deck["coordinate value"]),
+                 reaction_force_comp=int(qoi_deck["reaction force component"]))
+    out = []
+    xs = [hp.get_step(s) for s in range(nsteps + 1)]
+    dev = lambda: (ctx.alloc("x"), ctx.alloc("xi"))
+    (x0, xi0), (x1, xi1) = dev(), dev()
+    sc = torch.zeros(2, dtype=torch.float64, device=x0.device)
+    for s in range(1, nsteps + 1):
+        (xa, xia), (xb, xib) = xs[s], xs[s - 1]
+        ctx.pack_x(xa[0], xa[1] if len(xa) > 1 else None, x1); ctx.pack_xi(xia, xi1)
+        ctx.pack_x(xb[0], xb[1] if len(xb) > 1 else None, x0); ctx.pack_xi(xib, xi0)
+        sc.zero_(); torch.cuda.synchronize()
+        ctx.qoi_value(q, x1, x0, xi1, xi0, 1, sc)
+        ctx.synchronize()
+        out.append(float(sc[1].item()))
+    return out
+
+
+def _write_lines(path, values):
+    with open(path, "w") as f:
+        for v in values:
+            f.write("%.17e\n" % v)
+
+
+def run_primal(deck_path):
+    name, deck = load_deck(deck_path)
+    base = os.path.dirname(os.path.abspath(deck_path))
+    ctx, hp, mesh, _ = build(deck, base)
+    q = deck.get("quantity of interest", {"type": "average displacement"})
+    nsteps = int(deck["discretization"]["num steps"])
+    hp.set_qoi_avg_disp()
+    J = hp.primal_solve()
+    if q["type"] == "average displacement":
+        print("QoI (average displacement): %.17e" % J)
+    if q["type"] in ("reaction mismatch", "calibration") and q.get("load out file"):
+        loads = _loads_on_plane(ctx, hp, q, nsteps)
+        _write_lines(_resolve(os.getcwd(), q["load out file"]), loads)
+    if deck.get("problem", {}).get("write synthetic", False):
+        out = os.path.join(os.getcwd(), deck["problem"]["name"] + "_synthetic")
+        os.makedirs(out, exist_ok=True)
+        meshio.save_npz(mesh, os.path.join(out, "mesh.npz"))
+        meas = np.stack([hp.get_step(s)[0][0].reshape(-1, mesh.dim) for s in range(1, nsteps + 1)])
+        np.savez(os.path.join(out, "measured.npz"), measured=meas)
+    hp.close(); ctx.close()
+    return J
+
+
+def _active(deck, mesh, local_type):
+    """setup_opt_params, src/main_objective.cpp: active (elem set, parameter) pairs in order"""
+    names = PARAM_NAMES[local_type]
+    inv = deck["inverse"]["materials"]
+    act = []
+    for es_i, es in enumerate(mesh.elem_set_names):
+        for k, nm in enumerate(names):
+            if nm in (inv.get(es) or {}):
+                act.append((es_i, k))
+    return act
+
+
+def run_objective(deck_path, gradient, label=""):
+    name, deck = load_deck(deck_path)
+    base = os.path.dirname(os.path.abspath(deck_path))
+    ctx, hp, mesh, measured = build(deck, base)
+    inv = deck["inverse"]
+    otype = str(inv["objective type"]).lower()
+    nsteps = int(deck["discretization"]["num steps"])
+    ltype = deck["residuals"]["local residual"]["type"]
+    act = _active(deck, mesh, ltype)
+    assert all(e == 0 for e, _ in act) or ctx.n_es > 1
+    if otype in ("adjoint", "pdeco", "femu"):
+        q = deck["quantity of interest"]
+        if q["type"] == "calibration":
+            assert measured is not None, "the calibration objective needs a *_synthetic/ mesh directory"
+            loads = np.loadtxt(_resolve(base, q["load input file"])).reshape(-1)
+            w = [float(v) for v in q.get("displacement weights", [1.0] * mesh.dim)]
+            hp.set_qoi_calibration(balance_factor=float(q.get("balance factor", 1.0)),
+                                   coord_idx=int(q["coordinate index"]), coord_value=float(q["coordinate value"]),
+                                   reaction_force_comp=int(q["reaction force component"]), weights=w,
+                                   measured=measured, load_data=loads[:nsteps], area=_area(mesh))
+        else:
+            hp.set_qoi_avg_disp()
+        J = hp.primal_solve()
+        g = hp.adjoint_gradient() if gradient else None
+    elif otype in ("vfm", "fs_vfm", "adjoint_vfm"):
+        from .vfm import vfm_objective
+        assert measured is not None, "the VFM objective needs a *_synthetic/ mesh directory"
+        vf = deck["virtual fields"]
+        w = np.stack([eval_expr(vf["w_x"], mesh.coords), eval_expr(vf["w_y"], mesh.coords)], axis=1)
+        loads = np.loadtxt(_resolve(base, inv["load input file"])).reshape(-1)[:nsteps]
+        # load.dat is the external virtual power directly: the shipped virtual field is (0, 1) on the
+        # loaded edge; "internal power scale factor" multiplies the internal power like the thickness
+        scale = float(inv.get("internal power scale factor", 1.0))
+        J, g = vfm_objective(hp, "forward" if otype in ("vfm", "fs_vfm") else "adjoint", measured, w,
+                             loads, obj_scale_factor=float(inv.get("objective scale factor", 1.0)),
+                             thickness=float(inv.get("thickness", 1.0)) * scale)
+    else:
+        raise SystemExit(f"objective type '{otype}' is not implemented")
+    lab = ("_" + label) if label else ""
+    _write_lines("objective_value%s.txt" % lab, [J])
+    if gradient:
+        gall = np.asarray(g).reshape(-1)
+        _write_lines("objective_gradient%s.txt" % lab, [gall[k] for _, k in act])
+    hp.close(); ctx.close()
+    return J, (None if not gradient else np.array([np.asarray(g).reshape(-1)[k] for _, k in act]))
+
+
+def main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if len(argv) >= 2 and argv[0] == "primal":
+        run_primal(argv[1])
+    elif len(argv) >= 3 and argv[0] == "objective":
+        run_objective(argv[1], argv[2] == "true", argv[3] if len(argv) > 3 else "")
+    else:
+        raise SystemExit(__doc__)
+
+
+if __name__ == "__main__":
+    main()

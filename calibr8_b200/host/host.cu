@@ -460,6 +460,19 @@ int c8h_profile(c8h_problem* h, int enable, double* out8) {
   if (out8) for (int k = 0; k < 8; ++k) out8[k] = h->P.t_phase[k];
   return 0;
 }
+// evaluate a boundary-condition / virtual-field expression at n points (xyz [n][3]) and time t;
+// returns 0, or -1 with the message in err_out (may be NULL)
+int c8h_eval_expr(const char* expr, const double* xyz, int n, double t, double* out, char* err_out,
+                  int err_len) {
+  try {
+    Expr e(expr);
+    for (int i = 0; i < n; ++i) out[i] = e(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], t);
+    return 0;
+  } catch (const std::exception& ex) {
+    if (err_out && err_len > 0) { std::strncpy(err_out, ex.what(), err_len - 1); err_out[err_len - 1] = 0; }
+    return -1;
+  }
+}
 int c8h_stats(c8h_problem* h, int* n_assemblies, int* n_linear_iters) {
   *n_assemblies = h->P.n_assemblies;
   *n_linear_iters = h->P.n_linear_iters;
