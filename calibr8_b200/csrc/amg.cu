@@ -2,15 +2,18 @@
 #include "amg.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstdint>
 #include <numeric>
 
 namespace c8 {
 
-// r = b - A x ; one thread per scalar row
-template <int NB>
+// r = b - A x ; one thread per scalar row.  F = storage type of the matrix values: the fine level of
+// the preconditioner reads an fp32 copy (half the HBM traffic of the pass; the smoother then works
+// with a fixed, slightly perturbed linear operator, the Krylov residuals stay fp64)
+template <int NB, class F>
 __global__ void k_bsr_residual(const int* __restrict__ rowptr, const int* __restrict__ colind,
-                               const double* __restrict__ vals, const double* __restrict__ x,
+                               const F* __restrict__ vals, const double* __restrict__ x,
                                const double* __restrict__ b, double* __restrict__ r, int n_nodes) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_nodes * NB) return;
@@ -18,12 +21,63 @@ __global__ void k_bsr_residual(const int* __restrict__ rowptr, const int* __rest
   double s = b[i];
   const int b0 = rowptr[node], b1 = rowptr[node + 1];
   for (int k = b0; k < b1; ++k) {
-    const double* a = vals + (size_t(k) * NB + row) * NB;
+    const F* a = vals + (size_t(k) * NB + row) * NB;
     const double* xv = x + size_t(__ldg(&colind[k])) * NB;
 #pragma unroll
-    for (int c = 0; c < NB; ++c) s = fma(-__ldg(&a[c]), __ldg(&xv[c]), s);
+    for (int c = 0; c < NB; ++c) s = fma(-double(__ldg(&a[c])), __ldg(&xv[c]), s);
   }
   r[i] = s;
+}
+
+// One damped block-Jacobi sweep, out of place: xout = x' + omega Dinv (b - A x'), with
+// x' = xin (+ pscale * P xc when PROLONG: the coarse-grid correction is folded into the sweep).
+// Four lanes per node (lane r < NB owns row r); the node's residual rows meet through shuffles.
+template <int NB, class F, bool PROLONG>
+__global__ void k_smooth(const int* __restrict__ rowptr, const int* __restrict__ colind,
+                         const F* __restrict__ vals, const double* __restrict__ dinv,
+                         const double* __restrict__ b, const double* __restrict__ xin,
+                         double* __restrict__ xout, const int* __restrict__ agg,
+                         const double* __restrict__ xc, double pscale, double omega, int n) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  int node = gid >> 2;
+  const int lane4 = gid & 3;
+  const bool valid = node < n;
+  if (!valid) node = n - 1;            // keep every lane for the shuffles
+  const bool active = lane4 < NB;
+  const int row = active ? lane4 : 0;
+  double s = b[size_t(node) * NB + row];
+  const int b0 = rowptr[node], b1 = rowptr[node + 1];
+  for (int k = b0; k < b1; ++k) {
+    const int col = __ldg(&colind[k]);
+    const F* a = vals + (size_t(k) * NB + row) * NB;
+    const double* xv = xin + size_t(col) * NB;
+    // ghost columns of a partition (col >= n) carry no coarse correction; the index is clamped
+    // rather than branched around because the compiler may speculate a read-only load
+    const double ps = (PROLONG && col < n) ? pscale : 0.0;
+    const double* pc = PROLONG ? xc + size_t(agg[col < n ? col : 0]) * NB : nullptr;
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+      double v = __ldg(&xv[c]);
+      if (PROLONG) v = fma(ps, pc[c], v);
+      s = fma(-double(__ldg(&a[c])), v, s);
+    }
+  }
+  const int base = (threadIdx.x & 31) & ~3;
+  double upd = 0.0;
+#pragma unroll
+  for (int c = 0; c < NB; ++c) {
+    const double sc = __shfl_sync(0xffffffffu, s, base + c);
+    upd = fma(dinv[(size_t(node) * NB + row) * NB + c], sc, upd);
+  }
+  double xo = xin[size_t(node) * NB + row];
+  if (PROLONG) xo = fma(pscale, xc[size_t(agg[node]) * NB + row], xo);
+  if (valid && active) xout[size_t(node) * NB + row] = xo + omega * upd;
+}
+
+__global__ void k_to_float(const double* __restrict__ in, float* __restrict__ out, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = float(in[i]);
 }
 
 // x = (zero_guess ? 0 : x) + omega * Dinv r
@@ -158,6 +212,18 @@ __global__ void k_dense_apply(const double* __restrict__ M, const double* __rest
   if (lane == 0) x[warp] = s;
 }
 
+// C8_AMG_DEBUG=1: synchronise and report after every stage of the cycle (bad-access hunting)
+static void amg_dbg(cudaStream_t s, const char* what, int level) {
+  static const bool on = getenv("C8_AMG_DEBUG") != nullptr;
+  if (!on) return;
+  const cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "[amg] %s at level %d: %s\n", what, level, cudaGetErrorString(e));
+    fflush(stderr);
+    abort();
+  }
+}
+
 #define C8_NB_SWITCH(nb, CALL)  \
   switch (nb) {                 \
     case 2: { constexpr int NB = 2; CALL; } break; \
@@ -243,7 +309,7 @@ static int upload(c8_ctx* ctx, const std::vector<T>& h, T** d) {
 Amg::~Amg() {
   for (AmgLevel& L : lv_) {
     void* ptrs[] = {L.own_rowptr, L.own_colind, L.own_vals, L.dinv, L.x, L.b, L.r, L.agg, L.aggptr,
-                    L.aggmem, L.cptr, L.cmem};
+                    L.aggmem, L.cptr, L.cmem, L.xt, L.vals32};
     for (void* p : ptrs)
       if (p) cudaFree(p);
   }
@@ -331,8 +397,14 @@ int Amg::build() {
     std::iota(blk.begin(), blk.end(), 0);
     n = nc;
   }
-  for (AmgLevel& L : lv_)
+  for (AmgLevel& L : lv_) {
     C8_CUDA(ctx_, cudaMalloc(&L.dinv, size_t(L.n > 0 ? L.n : 1) * nb_ * nb_ * sizeof(double)));
+    const size_t nx = size_t(L.ld > 0 ? L.ld : 1) * nb_;
+    C8_CUDA(ctx_, cudaMalloc(&L.xt, nx * sizeof(double)));
+    C8_CUDA(ctx_, cudaMemsetAsync(L.xt, 0, nx * sizeof(double), ctx_->stream));
+  }
+  if (opt.fp32_fine_level && lv_.size() > 1)
+    C8_CUDA(ctx_, cudaMalloc(&lv_[0].vals32, size_t(lv_[0].nnzb) * nb_ * nb_ * sizeof(float)));
   C8_CUDA(ctx_, cudaMalloc(&r0_, size_t(ctx_->n_nodes) * nb_ * sizeof(double)));
   C8_CUDA(ctx_, cudaMemsetAsync(r0_, 0, size_t(ctx_->n_nodes) * nb_ * sizeof(double), ctx_->stream));
   nd_ = 0;
@@ -352,6 +424,8 @@ double Amg::operator_complexity() const {
 int Amg::setup(const double* A) {
   cudaStream_t s = ctx_->stream;
   lv_[0].vals = A;
+  if (lv_[0].vals32)
+    k_to_float<<<148 * 8, 256, 0, s>>>(A, lv_[0].vals32, size_t(lv_[0].nnzb) * nb_ * nb_);
   for (size_t l = 0; l < lv_.size(); ++l) {
     AmgLevel& L = lv_[l];
     if (L.n == 0) continue;
@@ -382,35 +456,66 @@ void Amg::smooth(int l, const double* b, double* x, int sweeps, bool zero_guess)
     if (k == 0 && zero_guess) {
       C8_NB_SWITCH(nb_, (k_jacobi_update<NB><<<g, 128, 0, s>>>(L.dinv, b, x, opt.omega, 1, L.n)));
     } else {
-      C8_NB_SWITCH(nb_, (k_bsr_residual<NB><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals, x, b, r, L.n)));
+      C8_NB_SWITCH(nb_, (k_bsr_residual<NB, double><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals, x, b, r, L.n)));
       C8_NB_SWITCH(nb_, (k_jacobi_update<NB><<<g, 128, 0, s>>>(L.dinv, r, x, opt.omega, 0, L.n)));
     }
   }
 }
 
-void Amg::cycle(int l, const double* b, double* x) {
+// one out-of-place sweep on level l (fp32 matrix copy on the fine level when present)
+void Amg::sweep(int l, const double* b, const double* xin, double* xout, const double* xc) {
+  AmgLevel& L = lv_[l];
+  cudaStream_t s = ctx_->stream;
+  const int g = (L.n * 4 + 127) / 128;
+  const double oc = opt.over_correction, om = opt.omega;
+  if (L.vals32) {
+    if (xc) { C8_NB_SWITCH(nb_, (k_smooth<NB, float, true><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals32, L.dinv, b, xin, xout, L.agg, xc, oc, om, L.n))); }
+    else { C8_NB_SWITCH(nb_, (k_smooth<NB, float, false><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals32, L.dinv, b, xin, xout, nullptr, nullptr, 0.0, om, L.n))); }
+  } else {
+    if (xc) { C8_NB_SWITCH(nb_, (k_smooth<NB, double, true><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, L.agg, xc, oc, om, L.n))); }
+    else { C8_NB_SWITCH(nb_, (k_smooth<NB, double, false><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, nullptr, nullptr, 0.0, om, L.n))); }
+  }
+}
+
+// V(nu_pre, nu_post) cycle; the result lands in xout.  Launches per level: nu_pre + nu_post sweeps
+// (the first from a zero guess is a block-diagonal product, the first after the coarse solve carries
+// the prolongation) + residual + restriction.
+void Amg::cycle(int l, const double* b, double* xout) {
   AmgLevel& L = lv_[l];
   cudaStream_t s = ctx_->stream;
   if (L.n == 0) return;
   const bool coarsest = (l + 1 == int(lv_.size()));
   if (coarsest) {
     if (nd_ > 0 && l > 0) {
-      k_dense_apply<<<(nd_ * 32 + 255) / 256, 256, 0, s>>>(dense_, b, x, nd_);
+      k_dense_apply<<<(nd_ * 32 + 255) / 256, 256, 0, s>>>(dense_, b, xout, nd_);
     } else {
-      smooth(l, b, x, 4 * (opt.nu_pre + opt.nu_post), true);
+      smooth(l, b, xout, 4 * (opt.nu_pre + opt.nu_post), true);
     }
     return;
   }
-  smooth(l, b, x, opt.nu_pre, true);
-  double* r = (l == 0) ? r0_ : L.r;
+  const int nu1 = opt.nu_pre < 1 ? 1 : opt.nu_pre, nu2 = opt.nu_post < 1 ? 1 : opt.nu_post;
+  const int writes = nu1 + nu2;
+  double* bufs[2] = {xout, L.xt};
+  auto buf = [&](int w) { return bufs[(writes - 1 - w) & 1]; };  // the last write goes to xout
   const int g = (L.n * nb_ + 127) / 128;
-  C8_NB_SWITCH(nb_, (k_bsr_residual<NB><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals, x, b, r, L.n)));
+  amg_dbg(s, "enter", l);
+  C8_NB_SWITCH(nb_, (k_jacobi_update<NB><<<g, 128, 0, s>>>(L.dinv, b, buf(0), opt.omega, 1, L.n)));
+  amg_dbg(s, "jacobi zero-guess", l);
+  for (int w = 1; w < nu1; ++w) { sweep(l, b, buf(w - 1), buf(w), nullptr); amg_dbg(s, "pre sweep", l); }
+  const double* cur = buf(nu1 - 1);
+  double* r = (l == 0) ? r0_ : L.r;
+  if (L.vals32) { C8_NB_SWITCH(nb_, (k_bsr_residual<NB, float><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals32, cur, b, r, L.n))); }
+  else { C8_NB_SWITCH(nb_, (k_bsr_residual<NB, double><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals, cur, b, r, L.n))); }
+  amg_dbg(s, "residual", l);
   AmgLevel& C = lv_[l + 1];
   const int gc = (C.n * nb_ + 127) / 128;
   C8_NB_SWITCH(nb_, (k_restrict<NB><<<gc, 128, 0, s>>>(L.aggptr, L.aggmem, r, C.b, C.n)));
+  amg_dbg(s, "restrict", l);
   cycle(l + 1, C.b, C.x);
-  C8_NB_SWITCH(nb_, (k_prolong_add<NB><<<g, 128, 0, s>>>(L.agg, C.x, x, opt.over_correction, L.n)));
-  smooth(l, b, x, opt.nu_post, false);
+  amg_dbg(s, "coarse cycle", l);
+  sweep(l, b, cur, buf(nu1), C.x);
+  amg_dbg(s, "prolong sweep", l);
+  for (int w = nu1 + 1; w < writes; ++w) { sweep(l, b, buf(w - 1), buf(w), nullptr); amg_dbg(s, "post sweep", l); }
 }
 
 void Amg::apply(const double* r, double* z) {

@@ -33,6 +33,8 @@ struct AmgLevel {
   double* own_vals = nullptr;
   double* dinv = nullptr;
   double *x = nullptr, *b = nullptr, *r = nullptr;  // level >= 1 (level 0 uses the caller's x, b)
+  double* xt = nullptr;          // ping-pong partner of x for the out-of-place sweeps
+  float* vals32 = nullptr;       // fp32 copy of the fine-level values (level 0 only)
   // transfer to the next coarser level
   int nc = 0;
   int* agg = nullptr;                      // [n] aggregate of a node
@@ -47,6 +49,7 @@ struct AmgOptions {
   double over_correction = 1.6; // plain aggregation under-corrects; measured best 1.5-1.8
   int coarsest_max_nodes = 40;
   int max_levels = 12;
+  bool fp32_fine_level = true;  // the fine-level sweeps read an fp32 copy of the matrix
   int max_aggregate_size = 8;  // bounded compact aggregates (0: root + all neighbours, ~25 nodes in 3-D)
 };
 
@@ -65,6 +68,7 @@ class Amg {
  private:
   void cycle(int l, const double* b, double* x);
   void smooth(int l, const double* b, double* x, int sweeps, bool zero_guess);
+  void sweep(int l, const double* b, const double* xin, double* xout, const double* xc);
   c8_ctx* ctx_;
   int nb_ = 0;
   std::vector<AmgLevel> lv_;

@@ -146,7 +146,7 @@ def _run_parts(world, transport, case):
     procs = [mpc.Process(target=_worker, args=(r, world, port, transport, case, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=900) for _ in range(world)]
+    res = [q.get(timeout=240) for _ in range(world)]
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
