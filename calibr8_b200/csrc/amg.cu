@@ -20,6 +20,7 @@ __global__ void k_bsr_residual(const int* __restrict__ rowptr, const int* __rest
   const int node = i / NB, row = i % NB;
   double s = b[i];
   const int b0 = rowptr[node], b1 = rowptr[node + 1];
+#pragma unroll 4
   for (int k = b0; k < b1; ++k) {
     const F* a = vals + (size_t(k) * NB + row) * NB;
     const double* xv = x + size_t(__ldg(&colind[k])) * NB;
@@ -47,6 +48,7 @@ __global__ void k_smooth(const int* __restrict__ rowptr, const int* __restrict__
   const int row = active ? lane4 : 0;
   double s = b[size_t(node) * NB + row];
   const int b0 = rowptr[node], b1 = rowptr[node + 1];
+#pragma unroll 4
   for (int k = b0; k < b1; ++k) {
     const int col = __ldg(&colind[k]);
     const F* a = vals + (size_t(k) * NB + row) * NB;
@@ -72,6 +74,59 @@ __global__ void k_smooth(const int* __restrict__ rowptr, const int* __restrict__
   double xo = xin[size_t(node) * NB + row];
   if (PROLONG) xo = fma(pscale, xc[size_t(agg[node]) * NB + row], xo);
   if (valid && active) xout[size_t(node) * NB + row] = xo + omega * upd;
+}
+
+// Coarse levels: rows are long (the coarse graphs fill in) and few, so one thread per scalar row is
+// a serial chain of dependent gathers (measured ~17 us per launch whatever the level size).  Here a
+// WARP owns a node: the lanes split the row's blocks, partial sums meet in a shuffle reduction.
+// RESID_ONLY: r = b - A x' instead of the Jacobi update.
+template <int NB, bool PROLONG, bool RESID_ONLY>
+__global__ void k_smooth_warp(const int* __restrict__ rowptr, const int* __restrict__ colind,
+                              const double* __restrict__ vals, const double* __restrict__ dinv,
+                              const double* __restrict__ b, const double* __restrict__ xin,
+                              double* __restrict__ xout, const int* __restrict__ agg,
+                              const double* __restrict__ xc, double pscale, double omega, int n) {
+  const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (node >= n) return;  // the whole warp leaves together
+  double s[NB];
+#pragma unroll
+  for (int r = 0; r < NB; ++r) s[r] = 0.0;
+  for (int k = rowptr[node] + lane; k < rowptr[node + 1]; k += 32) {
+    const int col = colind[k];
+    double xv[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) xv[c] = xin[size_t(col) * NB + c];
+    if (PROLONG) {
+      const double* pc = xc + size_t(agg[col]) * NB;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) xv[c] = fma(pscale, pc[c], xv[c]);
+    }
+    const double* a = vals + size_t(k) * NB * NB;
+#pragma unroll
+    for (int r = 0; r < NB; ++r)
+#pragma unroll
+      for (int c = 0; c < NB; ++c) s[r] = fma(-a[r * NB + c], xv[c], s[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < NB; ++r) {
+    for (int o = 16; o > 0; o >>= 1) s[r] += __shfl_down_sync(0xffffffffu, s[r], o);
+    s[r] = __shfl_sync(0xffffffffu, s[r], 0) + b[size_t(node) * NB + r];
+  }
+  if (lane < NB) {
+    if (RESID_ONLY) {
+      double v = s[0];
+#pragma unroll
+      for (int r = 1; r < NB; ++r) v = (lane == r) ? s[r] : v;
+      xout[size_t(node) * NB + lane] = v;
+    } else {
+      double upd = 0.0;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) upd = fma(dinv[(size_t(node) * NB + lane) * NB + c], s[c], upd);
+      double xo = xin[size_t(node) * NB + lane];
+      if (PROLONG) xo = fma(pscale, xc[size_t(agg[node]) * NB + lane], xo);
+      xout[size_t(node) * NB + lane] = xo + omega * upd;
+    }
+  }
 }
 
 __global__ void k_to_float(const double* __restrict__ in, float* __restrict__ out, size_t n) {
@@ -341,7 +396,7 @@ int Amg::build() {
   while (n > opt.coarsest_max_nodes && int(lv_.size()) < opt.max_levels) {
     std::vector<int> agg;
     int nc = 0;
-    aggregate(n, rowptr, colind, agg, nc, opt.max_aggregate_size);
+    aggregate(n, rowptr, colind, agg, nc, lv_.size() == 1 ? opt.max_aggregate_size : opt.coarse_aggregate_size);
     if (nc >= n) break;  // no coarsening possible
     // coarse pattern: unique (agg[i], agg[j]) pairs, and for each the fine blocks summed into it
     std::vector<std::pair<uint64_t, int>> keys;
@@ -468,6 +523,12 @@ void Amg::sweep(int l, const double* b, const double* xin, double* xout, const d
   cudaStream_t s = ctx_->stream;
   const int g = (L.n * 4 + 127) / 128;
   const double oc = opt.over_correction, om = opt.omega;
+  if (l > 0) {  // coarse levels: a warp per node
+    const int gw = (L.n * 32 + 127) / 128;
+    if (xc) { C8_NB_SWITCH(nb_, (k_smooth_warp<NB, true, false><<<gw, 128, 0, s>>>(L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, L.agg, xc, oc, om, L.n))); }
+    else { C8_NB_SWITCH(nb_, (k_smooth_warp<NB, false, false><<<gw, 128, 0, s>>>(L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, nullptr, nullptr, 0.0, om, L.n))); }
+    return;
+  }
   if (L.vals32) {
     if (xc) { C8_NB_SWITCH(nb_, (k_smooth<NB, float, true><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals32, L.dinv, b, xin, xout, L.agg, xc, oc, om, L.n))); }
     else { C8_NB_SWITCH(nb_, (k_smooth<NB, float, false><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals32, L.dinv, b, xin, xout, nullptr, nullptr, 0.0, om, L.n))); }
@@ -504,7 +565,8 @@ void Amg::cycle(int l, const double* b, double* xout) {
   for (int w = 1; w < nu1; ++w) { sweep(l, b, buf(w - 1), buf(w), nullptr); amg_dbg(s, "pre sweep", l); }
   const double* cur = buf(nu1 - 1);
   double* r = (l == 0) ? r0_ : L.r;
-  if (L.vals32) { C8_NB_SWITCH(nb_, (k_bsr_residual<NB, float><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals32, cur, b, r, L.n))); }
+  if (l > 0) { C8_NB_SWITCH(nb_, (k_smooth_warp<NB, false, true><<<(L.n * 32 + 127) / 128, 128, 0, s>>>(L.rowptr, L.colind, L.vals, nullptr, b, cur, r, nullptr, nullptr, 0.0, 0.0, L.n))); }
+  else if (L.vals32) { C8_NB_SWITCH(nb_, (k_bsr_residual<NB, float><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals32, cur, b, r, L.n))); }
   else { C8_NB_SWITCH(nb_, (k_bsr_residual<NB, double><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals, cur, b, r, L.n))); }
   amg_dbg(s, "residual", l);
   AmgLevel& C = lv_[l + 1];

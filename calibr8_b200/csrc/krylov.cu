@@ -143,9 +143,11 @@ int c8_set_preconditioner(c8_ctx* ctx, int type, const double* opts, int n_opts)
     if (n_opts > 3) o.over_correction = opts[3];
     if (n_opts > 4) o.coarsest_max_nodes = int(opts[4]);
     if (n_opts > 5) o.max_aggregate_size = int(opts[5]);
+    if (n_opts > 6) o.coarse_aggregate_size = int(opts[6]);
   }
   const bool rebuild = o.coarsest_max_nodes != st.amg_opt.coarsest_max_nodes ||
-                       o.max_aggregate_size != st.amg_opt.max_aggregate_size;
+                       o.max_aggregate_size != st.amg_opt.max_aggregate_size ||
+                       o.coarse_aggregate_size != st.amg_opt.coarse_aggregate_size;
   st.amg_opt = o;
   st.drop_graphs();
   if (st.amg) st.amg->opt = o;
