@@ -264,15 +264,19 @@ struct Scatter {
 
 // Phase 2 of the assembly: vals[block] = sum over the gather plan of the element sub-blocks
 // (TRANSPOSE: the transposed sub-block of the transposed pair -> dtotal^T for the adjoint).
-// One thread per (block, entry); rows of nodes >= n_row_nodes are left untouched.
+// Rows of nodes >= n_row_nodes are left untouched.  Non-transposed blocks with an even NB are
+// gathered two entries per thread (16-byte loads / stores); the additions stay in plan order, so
+// the sum is bit-reproducible.
 template <int NB, int NN, bool TRANSPOSE>
 __global__ void k_bsr_gather(const int* __restrict__ gptr, const int* __restrict__ gsrc,
                              const double* __restrict__ emat, double* __restrict__ vals,
                              int n_row_blocks) {
   constexpr int BB = NB * NB, NX = NB * NN;
+  constexpr bool VEC2 = !TRANSPOSE && (NB % 2 == 0);
+  constexpr int EPT = VEC2 ? 2 : 1;                 // entries per thread
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= (long long)n_row_blocks * BB) return;
-  const int blk = int(i / BB), ent = int(i % BB);
+  if (i >= (long long)n_row_blocks * (BB / EPT)) return;
+  const int blk = int(i / (BB / EPT)), ent = int(i % (BB / EPT)) * EPT;
   const int r = ent / NB, c = ent % NB;
   auto src = [&](int k) -> const double* {
     const int q = __ldg(&gsrc[k]);           // e*NN*NN + na*NN + nb : block (node na, node nb)
@@ -281,19 +285,25 @@ __global__ void k_bsr_gather(const int* __restrict__ gptr, const int* __restrict
     const double* m = emat + size_t(e) * NX * NX;
     return TRANSPOSE ? &m[(nb * NB + c) * NX + na * NB + r] : &m[(na * NB + r) * NX + nb * NB + c];
   };
-  double s = 0.0;
   int k = gptr[blk];
   const int k1 = gptr[blk + 1];
-  // four independent loads in flight per thread (the kernel is latency-bound otherwise); the
-  // additions stay in plan order, so the sum is bit-reproducible
-  for (; k + 4 <= k1; k += 4) {
-    const double* p0 = src(k); const double* p1 = src(k + 1);
-    const double* p2 = src(k + 2); const double* p3 = src(k + 3);
-    const double v0 = __ldg(p0), v1 = __ldg(p1), v2 = __ldg(p2), v3 = __ldg(p3);
-    s += v0; s += v1; s += v2; s += v3;
+  if constexpr (VEC2) {
+    double s0 = 0.0, s1 = 0.0;
+    for (; k + 2 <= k1; k += 2) {
+      const double2 v0 = __ldg(reinterpret_cast<const double2*>(src(k)));
+      const double2 v1 = __ldg(reinterpret_cast<const double2*>(src(k + 1)));
+      s0 += v0.x; s1 += v0.y; s0 += v1.x; s1 += v1.y;
+    }
+    for (; k < k1; ++k) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(src(k)));
+      s0 += v.x; s1 += v.y;
+    }
+    *reinterpret_cast<double2*>(vals + size_t(blk) * BB + ent) = make_double2(s0, s1);
+  } else {
+    double s = 0.0;
+    for (; k < k1; ++k) s += __ldg(src(k));
+    vals[size_t(blk) * BB + ent] = s;
   }
-  for (; k < k1; ++k) s += __ldg(src(k));
-  vals[i] = s;
 }
 
 // Optional per-phase cycle counters (tuning builds only: -DC8_K1_PHASE_CLOCKS)
