@@ -36,7 +36,7 @@ PARAM_NAMES = {
 # every symbol include/c8b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "c8_create", "c8_destroy", "c8_last_error", "c8_version", "c8_set_mesh", "c8_set_model",
-    "c8_set_params", "c8_info", "c8_bsr_pattern", "c8_bsr_pattern_dev", "c8_csr_block_size",
+    "c8_set_params", "c8_get_params", "c8_info", "c8_bsr_pattern", "c8_bsr_pattern_dev", "c8_csr_block_size",
     "c8_csr_block_pattern", "c8_csr_block_values", "c8_pack_x", "c8_unpack_x", "c8_pack_xi",
     "c8_unpack_xi", "c8_init_xi", "c8_forward_jacobian", "c8_forward_jacobian_elem",
     "c8_global_residual", "c8_forward_jacobian_host", "c8_resident_matrix", "c8_set_stream",
@@ -605,3 +605,74 @@ def eval_expr(expr, coords, t=0.0):
     if rc != 0:
         raise C8Error("expression: " + err.value.decode())
     return out
+
+
+# ======================================================================================
+# Objective on canonical [-1, 1] parameters (calibr8_b200/host/objective.cu)
+HOST_SYMBOLS += ["c8h_objective_create", "c8h_objective_destroy", "c8h_objective_error",
+                 "c8h_objective_value", "c8h_objective_gradient", "c8h_objective_transform",
+                 "c8h_objective_active_params", "c8h_vfm_objective"]
+
+
+class Objective:
+    """value(p) / gradient(p) of a calibration objective on canonical parameters -- the role of the
+    reference's ROL::Objective subclasses (Adjoint_Objective, FS_VFM_Objective, Adjoint_VFM_Objective)."""
+    TYPES = {"adjoint": 0, "pdeco": 0, "fs_vfm": 1, "vfm": 1, "adjoint_vfm": 2}
+
+    def __init__(self, host_problem, kind, active, lower, upper, *, measured=None, w=None, loads=None,
+                 obj_scale_factor=1.0, thickness=1.0):
+        self.hp, self.lib = host_problem, host_problem.lib
+        self.n = len(active)
+        act = np.ascontiguousarray(active, dtype=np.int32)
+        lo = np.ascontiguousarray(lower, dtype=np.float64)
+        hi = np.ascontiguousarray(upper, dtype=np.float64)
+        c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        self._keep = (c(measured), c(w), c(loads))
+        self.lib.c8h_objective_create.restype = C.c_void_p
+        self.lib.c8h_objective_error.restype = C.c_char_p
+        self.lib.c8h_objective_error.argtypes = [C.c_void_p]
+        h = self.lib.c8h_objective_create(host_problem.h, self.TYPES[kind.lower()], self.n, _hp(act), _hp(lo),
+                                          _hp(hi), _hp(self._keep[0]), _hp(self._keep[1]), _hp(self._keep[2]),
+                                          C.c_double(obj_scale_factor), C.c_double(thickness))
+        self.h = C.c_void_p(h)
+        err = self.lib.c8h_objective_error(self.h).decode()
+        if err:
+            raise C8Error("objective: " + err)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise C8Error("objective: " + self.lib.c8h_objective_error(self.h).decode())
+
+    def value(self, p):
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        J = C.c_double(0)
+        self._check(self.lib.c8h_objective_value(self.h, _hp(p), self.n, C.byref(J)))
+        return J.value
+
+    def gradient(self, p):
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        g = np.zeros(self.n)
+        self._check(self.lib.c8h_objective_gradient(self.h, _hp(p), self.n, _hp(g)))
+        return g
+
+    def to_canonical(self, phys):
+        out = np.zeros(self.n)
+        self._check(self.lib.c8h_objective_transform(self.h, _hp(np.ascontiguousarray(phys, dtype=np.float64)),
+                                                     self.n, 1, _hp(out)))
+        return out
+
+    def to_physical(self, can):
+        out = np.zeros(self.n)
+        self._check(self.lib.c8h_objective_transform(self.h, _hp(np.ascontiguousarray(can, dtype=np.float64)),
+                                                     self.n, 0, _hp(out)))
+        return out
+
+    def active_params(self):
+        out = np.zeros(self.n)
+        self._check(self.lib.c8h_objective_active_params(self.h, _hp(out), self.n))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.c8h_objective_destroy(self.h)
+            self.h = None

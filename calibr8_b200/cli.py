@@ -3,6 +3,7 @@
 
     python -m calibr8_b200.cli primal    deck.yaml
     python -m calibr8_b200.cli objective deck.yaml true|false [label]
+    python -m calibr8_b200.cli inverse   deck.yaml          (src/main_inverse.cpp: the in-process optimiser)
 
 Same YAML deck schema as the reference (src/main_primal.cpp, src/main_objective.cpp:512-560):
 `problem`, `discretization`, `residuals`, `dirichlet bcs: expression`, `quantity of interest`,
@@ -211,12 +212,86 @@ def run_objective(deck_path, gradient, label=""):
     return J, (None if not gradient else np.array([np.asarray(g).reshape(-1)[k] for _, k in act]))
 
 
+def _setup_objective(deck, base):
+    """-> (ctx, hp, Objective, names of the active parameters, start point in canonical coordinates)"""
+    from .capi import Objective
+    ctx, hp, mesh, measured = build(deck, base)
+    inv = deck["inverse"]
+    otype = str(inv["objective type"]).lower()
+    nsteps = int(deck["discretization"]["num steps"])
+    ltype = deck["residuals"]["local residual"]["type"]
+    act = _active(deck, mesh, ltype)
+    assert all(e == 0 for e, _ in act), "one element set"
+    names = [PARAM_NAMES[ltype][k] for _, k in act]
+    bounds = inv["materials"][mesh.elem_set_names[0]]
+    lo = [float(bounds[n][0]) for n in names]
+    hi = [float(bounds[n][1]) for n in names]
+    kw = {}
+    if otype in ("adjoint", "pdeco", "femu"):
+        q = deck["quantity of interest"]
+        if q["type"] == "calibration":
+            loads = np.loadtxt(_resolve(base, q["load input file"])).reshape(-1)
+            w = [float(v) for v in q.get("displacement weights", [1.0] * mesh.dim)]
+            hp.set_qoi_calibration(balance_factor=float(q.get("balance factor", 1.0)),
+                                   coord_idx=int(q["coordinate index"]), coord_value=float(q["coordinate value"]),
+                                   reaction_force_comp=int(q["reaction force component"]), weights=w,
+                                   measured=measured, load_data=loads[:nsteps], area=_area(mesh))
+        else:
+            hp.set_qoi_avg_disp()
+        kind = "adjoint"
+    else:
+        vf = deck["virtual fields"]
+        kw = dict(measured=measured,
+                  w=np.stack([eval_expr(vf["w_x"], mesh.coords), eval_expr(vf["w_y"], mesh.coords)], axis=1),
+                  loads=np.loadtxt(_resolve(base, inv["load input file"])).reshape(-1)[:nsteps],
+                  obj_scale_factor=float(inv.get("objective scale factor", 1.0)),
+                  thickness=float(inv.get("thickness", 1.0)) * float(inv.get("internal power scale factor", 1.0)))
+        kind = "adjoint_vfm" if otype == "adjoint_vfm" else "fs_vfm"
+    obj = Objective(hp, kind, [k for _, k in act], lo, hi, **kw)
+    p0 = obj.to_canonical(obj.active_params())
+    return ctx, hp, obj, names, p0
+
+
+def run_inverse(deck_path):
+    """The `inverse` executable (src/main_inverse.cpp:21-162): bound-constrained quasi-Newton on the
+    canonical box [-1, 1]^n from the deck's material values; writes the iterate log to ROL_out.txt
+    and the calibrated physical parameters to inverse_result.txt (one `%.17e` per line)."""
+    from scipy.optimize import minimize
+    name, deck = load_deck(deck_path)
+    base = os.path.dirname(os.path.abspath(deck_path))
+    ctx, hp, obj, names, p0 = _setup_objective(deck, base)
+    inv = deck["inverse"]
+    log = []
+
+    def fun(p):
+        J, g = obj.value(p), obj.gradient(p)
+        log.append((J, float(np.abs(g).max()), obj.to_physical(p)))
+        return J, g
+
+    res = minimize(fun, p0, jac=True, method="L-BFGS-B", bounds=[(-1.0, 1.0)] * len(p0),
+                   options=dict(maxiter=int(inv.get("iteration limit", 50)),
+                                gtol=float(inv.get("gradient tolerance", 1e-8)), ftol=1e-30,
+                                maxls=int(inv.get("max line search evals", 20))))
+    phys = obj.to_physical(res.x)
+    with open("ROL_out.txt", "w") as f:
+        f.write("# eval  objective  |grad|_inf  " + "  ".join(names) + "\n")
+        for k, (J, gn, pp) in enumerate(log):
+            f.write("%4d  %.12e  %.6e  %s\n" % (k, J, gn, "  ".join("%.10e" % v for v in pp)))
+    _write_lines("inverse_result.txt", phys)
+    for n, v in zip(names, phys):
+        print("%s = %.12e" % (n, v))
+    obj.close(); hp.close(); ctx.close()
+    return dict(zip(names, phys)), res.fun, len(log)
+
+
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     if len(argv) >= 2 and argv[0] == "primal":
         run_primal(argv[1])
     elif len(argv) >= 3 and argv[0] == "objective":
         run_objective(argv[1], argv[2] == "true", argv[3] if len(argv) > 3 else "")
+    elif len(argv) >= 2 and argv[0] == "inverse":
+        run_inverse(argv[1])
     else:
         raise SystemExit(__doc__)
 

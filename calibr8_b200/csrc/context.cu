@@ -342,6 +342,13 @@ int c8_set_params(c8_ctx* ctx, const double* params) {
                                ctx->stream));
   C8_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->model.params = ctx->d_params;
+  ctx->h_params.assign(params, params + n);
+  return C8_OK;
+}
+
+int c8_get_params(c8_ctx* ctx, double* params_host) {
+  C8_REQUIRE(ctx, ctx->kt != nullptr, "c8_set_model must be called first");
+  std::memcpy(params_host, ctx->h_params.data(), ctx->h_params.size() * sizeof(double));
   return C8_OK;
 }
 

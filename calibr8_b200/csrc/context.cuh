@@ -44,6 +44,7 @@ struct c8_ctx {
   int global_type = -1, local_type = -1;
   c8::ModelArgs model{};
   double* d_params = nullptr;
+  std::vector<double> h_params;   // [n_es][npar] host copy
 
   // scratch / resident system
   int* d_nfailed = nullptr;

@@ -152,4 +152,35 @@ class Adjoint {
   Problem& P;
 };
 
+// Objective on canonical [-1, 1] parameters (the ROL::Objective<double> role of the reference,
+// src/objective.hpp:15-60): value(p) / gradient(g, p), parameter scaling, re-use of the forward
+// solve when the parameters did not change (param_diff).
+class Objective {
+ public:
+  Objective(Problem& p, const std::vector<int>& active, const std::vector<double>& lower,
+            const std::vector<double>& upper);
+  virtual ~Objective() {}
+  virtual double value(const std::vector<double>& p_canonical) = 0;
+  virtual void gradient(std::vector<double>& g, const std::vector<double>& p_canonical) = 0;
+  std::vector<double> transform_params(const std::vector<double>& p, bool scale_to_canonical) const;
+  std::vector<double> transform_gradient(const std::vector<double>& g) const;
+  std::vector<double> active_params() const;   // physical values of the active parameters
+  int num_opt_params() const { return int(m_active.size()); }
+ protected:
+  bool param_diff(const std::vector<double>& p) const;
+  void set_params_from_canonical(const std::vector<double>& p);
+  Problem& P;
+  std::vector<int> m_active;          // parameter indices (element set 0)
+  std::vector<double> m_lower, m_upper, m_base, m_p_old;
+  double m_J_old = 0.;
+  const double m_difftol = 1.0e-15;
+};
+
+class AdjointObjective : public Objective {  // src/adjoint_objective.cpp:24-118
+ public:
+  using Objective::Objective;
+  double value(const std::vector<double>& p) override;
+  void gradient(std::vector<double>& g, const std::vector<double>& p) override;
+};
+
 }  // namespace c8host

@@ -369,6 +369,8 @@ struct c8h_problem {
   explicit c8h_problem(c8_ctx* ctx) : P(ctx) {}
 };
 
+c8host::Problem& c8h_problem_ref(c8h_problem* h) { return h->P; }
+
 #define C8H_TRY(h, body)                                  \
   try { body; return 0; }                                 \
   catch (const std::exception& ex) { (h)->err = ex.what(); return -1; }

@@ -75,41 +75,93 @@ class VirtualPower {
 
 }  // namespace c8host
 
+namespace c8host {
+
+// mode 0: forward-sensitivity objective (FS_VFM), mode 1: adjoint-sensitivity objective.
+// load_data [num_steps] = external virtual power per step; grad [npar] (all model parameters)
+void vfm_evaluate(Problem& P, int mode, const double* measured_host, const double* w_host,
+                  const double* load_data, double obj_scale_factor, double thickness, double& J,
+                  std::vector<double>& grad) {
+  VirtualPower vp(P, measured_host, w_host);
+  const int N = P.num_steps;
+  const double total_time = P.time(N) - P.time(0), dt = P.step_size;
+  std::vector<double> gs;
+  grad.assign(P.npar, 0.0);
+  J = 0.0;
+  if (mode == 0) {
+    for (int step = 1; step <= N; ++step) {
+      double ivp;
+      vp.compute_at_step_forward_sens(step, ivp, gs);
+      const double mismatch = thickness * ivp - load_data[step - 1];
+      J += 0.5 * obj_scale_factor * dt / total_time * mismatch * mismatch;
+      for (int p = 0; p < P.npar; ++p) grad[p] += gs[p] * mismatch * obj_scale_factor * dt / total_time;
+    }
+  } else {
+    std::vector<double> ivp(N);
+    for (int step = 1; step <= N; ++step) ivp[step - 1] = vp.compute_at_step(step);
+    for (int step = N; step > 0; --step) {
+      const double mismatch = ivp[step - 1] * thickness - load_data[step - 1];
+      const double scaled = mismatch * obj_scale_factor * dt / total_time;
+      J += 0.5 * mismatch * scaled;
+      vp.compute_at_step_adjoint(step, scaled, gs);
+      for (int p = 0; p < P.npar; ++p) grad[p] += gs[p];
+    }
+  }
+}
+
+// FS_VFM_Objective / Adjoint_VFM_Objective on canonical parameters
+class VfmObjective : public Objective {
+ public:
+  VfmObjective(Problem& p, int mode, const std::vector<int>& active, const std::vector<double>& lo,
+               const std::vector<double>& hi, const double* measured, const double* w,
+               const double* loads, double scale, double thickness)
+      : Objective(p, active, lo, hi), m_mode(mode), m_scale(scale), m_thickness(thickness) {
+    const size_t nd = size_t(P.n_nodes) * P.dim;
+    m_measured.assign(measured, measured + size_t(P.num_steps) * nd);
+    m_w.assign(w, w + nd);
+    m_loads.assign(loads, loads + P.num_steps);
+  }
+  double value(const std::vector<double>& p) override { evaluate(p); return m_J_old; }
+  void gradient(std::vector<double>& g, const std::vector<double>& p) override {
+    evaluate(p);
+    std::vector<double> act(m_active.size());
+    for (size_t i = 0; i < m_active.size(); ++i) act[i] = m_grad[m_active[i]];
+    g = transform_gradient(act);
+  }
+ private:
+  void evaluate(const std::vector<double>& p) {
+    if (!param_diff(p)) return;
+    set_params_from_canonical(p);
+    vfm_evaluate(P, m_mode, m_measured.data(), m_w.data(), m_loads.data(), m_scale, m_thickness, m_J_old,
+                 m_grad);
+    m_p_old = p;
+  }
+  int m_mode;
+  double m_scale, m_thickness;
+  std::vector<double> m_measured, m_w, m_loads, m_grad;
+};
+
+}  // namespace c8host
+
 using namespace c8host;
+
+c8host::Objective* c8h_make_vfm_objective(c8host::Problem& P, int mode, const std::vector<int>& active,
+                                          const std::vector<double>& lo, const std::vector<double>& hi,
+                                          const double* measured, const double* w, const double* loads,
+                                          double scale, double thickness) {
+  return new VfmObjective(P, mode, active, lo, hi, measured, w, loads, scale, thickness);
+}
 
 extern "C" {
 
-// mode 0: forward-sensitivity objective (FS_VFM), mode 1: adjoint-sensitivity objective.
-// load_data [num_steps] = external virtual power per step; grad_out [npar] (all model parameters)
 int c8h_vfm_objective(c8h_problem* h, int mode, const double* measured_host, const double* w_host,
                       const double* load_data, double obj_scale_factor, double thickness,
                       double* J_out, double* grad_out) {
   try {
     Problem& P = h->P;
-    VirtualPower vp(P, measured_host, w_host);
-    const int N = P.num_steps;
-    const double total_time = P.time(N) - P.time(0), dt = P.step_size;
-    std::vector<double> grad(P.npar, 0.0), gs;
+    std::vector<double> grad;
     double J = 0.0;
-    if (mode == 0) {
-      for (int step = 1; step <= N; ++step) {
-        double ivp;
-        vp.compute_at_step_forward_sens(step, ivp, gs);
-        const double mismatch = thickness * ivp - load_data[step - 1];
-        J += 0.5 * obj_scale_factor * dt / total_time * mismatch * mismatch;
-        for (int p = 0; p < P.npar; ++p) grad[p] += gs[p] * mismatch * obj_scale_factor * dt / total_time;
-      }
-    } else {
-      std::vector<double> ivp(N);
-      for (int step = 1; step <= N; ++step) ivp[step - 1] = vp.compute_at_step(step);
-      for (int step = N; step > 0; --step) {
-        const double mismatch = ivp[step - 1] * thickness - load_data[step - 1];
-        const double scaled = mismatch * obj_scale_factor * dt / total_time;
-        J += 0.5 * mismatch * scaled;
-        vp.compute_at_step_adjoint(step, scaled, gs);
-        for (int p = 0; p < P.npar; ++p) grad[p] += gs[p];
-      }
-    }
+    vfm_evaluate(P, mode, measured_host, w_host, load_data, obj_scale_factor, thickness, J, grad);
     *J_out = J;
     for (int p = 0; p < P.npar; ++p) grad_out[p] = grad[p];
     return 0;

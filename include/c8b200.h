@@ -61,6 +61,7 @@ int c8_set_model(c8_ctx* ctx, int global_type, int local_type, const double* par
                  int local_max_iters, double local_abs_tol, double local_rel_tol,
                  double stabilization_multiplier, double thickness);
 int c8_set_params(c8_ctx* ctx, const double* params_host); /* LocalResidual::set_params */
+int c8_get_params(c8_ctx* ctx, double* params_host);       /* LocalResidual::params, [n_elem_sets][npar] */
 
 /* out[0..11] = dim, nn, nb, nx, nxi, npar, n_elems, n_nodes, nnzb, n_dofs(=n_nodes*nb), group, xi_ld */
 int c8_info(c8_ctx* ctx, int64_t* out12);

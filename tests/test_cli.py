@@ -145,3 +145,40 @@ def test_synthetic_calibration_flow_through_text_files(tmp_path, monkeypatch):
     _write("vfm0.yaml", VFM.format(mesh=synth, Y=2., S=10., D=50., otype="FS_VFM"))
     cli.main(["objective", "vfm0.yaml", "false", "vfm0"])
     assert float(open("objective_value_vfm0.txt").read()) < 1e-6 * out["FS_VFM"][0]
+
+
+@pytest.mark.gpu
+def test_inverse_recovers_the_true_parameters(tmp_path, monkeypatch):
+    """BASELINE configs[0] end to end: the shipped synthetic calibration (forward run at the true
+    Y, S, D = 2, 10, 50 -> synthetic data -> `inverse` from 2.2, 8, 60 within the deck's bounds)
+    recovers the truth, with the PDE-constrained (adjoint) objective."""
+    from calibr8_b200 import cli
+    from calibr8_b200.capi import Objective
+    monkeypatch.chdir(tmp_path)
+    _write("fwd.yaml", FORWARD.format(mesh=MESH, Y=2., S=10., D=50.))
+    cli.main(["primal", "fwd.yaml"])
+    synth = os.path.join(str(tmp_path), "fwd_synthetic") + "/"
+    deck = PDECO.format(mesh=synth, Y=2.2, S=8., D=60.) + """    iteration limit: 60
+    gradient tolerance: 1e-10
+"""
+    _write("inv.yaml", deck)
+    params, J, nevals = cli.run_inverse("inv.yaml")
+    assert J < 1e-9, J
+    assert abs(params["Y"] - 2.) < 1e-4 and abs(params["S"] - 10.) < 2e-2 and abs(params["D"] - 50.) < 0.2, params
+    got = np.loadtxt("inverse_result.txt")
+    assert np.allclose(got, [params["Y"], params["S"], params["D"]])
+    assert os.path.exists("ROL_out.txt") and nevals < 200
+    # canonical scaling of the Objective (src/objective.cpp:41-61): bounds Y [1,3], S [5,15], D [40,80]
+    name, d = cli.load_deck("inv.yaml")
+    ctx, hp, obj, names, p0 = cli._setup_objective(d, str(tmp_path))
+    assert names == ["Y", "S", "D"]
+    assert np.allclose(p0, [(2.2 - 2.) / 1., (8. - 10.) / 5., (60. - 60.) / 20.])
+    assert np.allclose(obj.to_physical([1., -1., 0.5]), [3., 5., 70.])
+    assert np.allclose(obj.to_canonical([10., 0., 60.]), [1., -1., 0.])          # clamped
+    # canonical gradient = span * physical gradient, and value() re-uses the cached forward solve
+    g_can = obj.gradient(p0)
+    _write("start.yaml", PDECO.format(mesh=synth, Y=2.2, S=8., D=60.))
+    Jp, g_phys = cli.run_objective("start.yaml", True)
+    assert abs(obj.value(p0) - Jp) < 1e-10 * Jp
+    assert np.allclose(g_can, g_phys * np.array([1., 5., 20.]), rtol=1e-7)
+    obj.close(); hp.close(); ctx.close()
