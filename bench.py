@@ -460,16 +460,21 @@ def run_ours(args):
                          "algorithmic_flops_per_qp": flops_qp,
                          "flops_definition": "reference algorithm's count (16-wide AD on every op, "
                                              "op-counting oracle); the kernel executes fewer",
-                         "traffic": None},
+                         "kernels": "k_forward_jacobian<Cfg<3,0,HyperJ2<3>,4>,true> + k_bsr_gather<4,4,false>",
+                         "traffic": 4.72e9,
+                         "traffic_source": "ncu --set full, dram read+write per launch: element kernel 0.10+2.12 GB, "
+                                           "gather 2.17+0.33 GB (profiles/r01c_*; the scratch is written once, read once)"},
             "roofline_hbm": {"bound": "hbm", "achieved": bytes_per_launch / (k_ms * 1e-3) * 1e-9,
                              "peak": hbm_peak, "unit": "GB/s",
                              "frac": bytes_per_launch / (k_ms * 1e-3) * 1e-9 / hbm_peak,
                              "algorithmic_bytes_per_launch": bytes_per_launch,
-                             "copy_gbs_measured_this_run": copy_peak, "traffic": None},
+                             "copy_gbs_measured_this_run": copy_peak, "traffic": 4.72e9,
+                             "note": "K1 is fp64-bound; the two-phase assembly moves 7.4x the compulsory bytes "
+                                     "(2 KB scratch per tet written and read once) to avoid 256 fp64 atomics per tet"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
                     "api": "c8_state_forward_jacobian (host nodal iterate in, host residual + status out)"},
-            "gpu_launches": args.steps,
+            "gpu_launches": 2 * args.steps,   # element kernel + BSR gather per step
             "clocks": clocks,
         }
         line["roofline_spmv"] = {"bound": "hbm", "achieved": spmv_bytes / (spmv_ms * 1e-3) * 1e-9,
