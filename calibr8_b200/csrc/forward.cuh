@@ -77,12 +77,12 @@ C8_DI int local_newton(const Kin<C::D, double, double>& k0, const Elem<C>& E, co
   using Model = typename C::Model;
   constexpr int NXI = C::NXI, LXI = C::LXI;
   if constexpr (!Model::HAS_NEWTON) {
-    Model::guess(k0, E.xip, xi);
+    Model::guess(k0, E.xip, E.par, md.abs_tol, xi);
 #pragma unroll
     for (int q = 0; q < NXI; ++q) Cd[q] = make_dual<LXI>(0.0);
     return 0;
   } else {
-    Model::guess(k0, E.xip, xi);
+    Model::guess(k0, E.xip, E.par, md.abs_tol, xi);
     int path = 0, iter = 1;
     double R_norm_0 = 1.0;
     bool converged = false;

@@ -126,7 +126,7 @@ struct Elastic {
   static constexpr bool FINITE = false, HAS_NEWTON = false, PLANE_STRESS = false;
   static constexpr int Z_STRETCH = -1;
   static C8_DI void init(double* xi) { xi[0] = 0.0; }
-  template <class K> static C8_DI void guess(const K&, const double*, double* xi) { xi[0] = 0.0; }
+  template <class K> static C8_DI void guess(const K&, const double*, const double*, double, double* xi) { xi[0] = 0.0; }
   template <class TK, class TKP, class TX, class TXP, class TP>
   static C8_DI int residual(const Kin<DIM, TK, TKP>&, const TX*, const TXP*, const TP*, double,
                             prom5_t<TK, TKP, TX, TXP, TP>* C) {
@@ -160,9 +160,29 @@ struct SmallJ2 {
 #pragma unroll
     for (int i = 0; i < NXI; ++i) xi[i] = 0.0;
   }
-  template <class K> static C8_DI void guess(const K&, const double* xip, double* xi) {
+  // Initial guess of the local Newton.  The reference starts from xi_prev ("pick an initial guess",
+  // src/small_J2.cpp:126-135); with linear hardening the radial return is closed form, so a yielding
+  // point starts AT the solution of the same residual (the Newton then only confirms |C| < tol):
+  //   dgam = (|s_tr| - sqrt(2/3) sigma_y(alpha_old)) / (2 mu + 2/3 K),  n = s_tr / |s_tr|,
+  //   pstrain = pstrain_old + dgam n,  alpha = alpha_old + sqrt(2/3) dgam.
+  template <class K> static C8_DI void guess(const K& k, const double* xip, const double* par, double abs_tol,
+                                             double* xi) {
 #pragma unroll
     for (int i = 0; i < NXI; ++i) xi[i] = xip[i];
+    const double sqrt_23 = 0.81649658092772603;
+    const double mu = mu_of(par[0], par[1]);
+    const Mat<double, DIM> s = small_dev_stress<DIM>(k.gu, xip, par[0], par[1]);
+    const double s_mag = norm(s);
+    const double f = (s_mag - sqrt_23 * (par[3] + par[2] * xip[NS])) / mu;
+    if (is_plastic(f, abs_tol) && s_mag > 0.0) {
+      const double dgam = mu * f / (2.0 * mu + (2.0 / 3.0) * par[2]);
+      const double g = dgam / s_mag;
+#pragma unroll
+      for (int i = 0; i < DIM; ++i)
+#pragma unroll
+        for (int j = i; j < DIM; ++j) xi[SymIdx<DIM>::idx(i, j)] = xip[SymIdx<DIM>::idx(i, j)] + g * s.a[i][j];
+      xi[NS] = xip[NS] + sqrt_23 * dgam;
+    }
   }
   template <class TK, class TKP, class TX, class TXP, class TP>
   static C8_DI int residual(const Kin<DIM, TK, TKP>& k, const TX* xi, const TXP* xip,
@@ -217,7 +237,8 @@ struct SmallHill {
 #pragma unroll
     for (int i = 0; i < NXI; ++i) xi[i] = 0.0;
   }
-  template <class K> static C8_DI void guess(const K&, const double* xip, double* xi) {
+  template <class K> static C8_DI void guess(const K&, const double* xip, const double* par, double abs_tol,
+                                                  double* xi) {
 #pragma unroll
     for (int i = 0; i < NXI; ++i) xi[i] = xip[i];
   }
@@ -273,7 +294,8 @@ struct SmallHillPlaneStress {
 #pragma unroll
     for (int i = 0; i < NXI; ++i) xi[i] = 0.0;
   }
-  template <class K> static C8_DI void guess(const K&, const double* xip, double* xi) {
+  template <class K> static C8_DI void guess(const K&, const double* xip, const double* par, double abs_tol,
+                                                  double* xi) {
 #pragma unroll
     for (int i = 0; i < NXI; ++i) xi[i] = xip[i];
   }
@@ -335,7 +357,8 @@ struct SmallHillPlaneStrain {
 #pragma unroll
     for (int i = 0; i < NXI; ++i) xi[i] = 0.0;
   }
-  template <class K> static C8_DI void guess(const K&, const double* xip, double* xi) {
+  template <class K> static C8_DI void guess(const K&, const double* xip, const double* par, double abs_tol,
+                                                  double* xi) {
 #pragma unroll
     for (int i = 0; i < NXI; ++i) xi[i] = xip[i];
   }
@@ -431,14 +454,60 @@ struct HyperJ2 {
     for (int i = 0; i < NS; ++i) xi[i] = 0.0;
     xi[NS] = 1.0; xi[NS + 1] = 0.0;
   }
-  // trial-state initial guess, src/hyper_J2.cpp:167-179
-  template <class K> static C8_DI void guess(const K& k, const double* xip, double* xi) {
+  // trial-state initial guess, src/hyper_J2.cpp:167-179.  For a yielding point with linear hardening
+  // (S = A = 0) the flow rule and the yield condition of the SAME residual are solved in closed form
+  // at Ie = Ie_trial (zeta stays parallel to dev be_bar_trial):
+  //   dgam = mu f_tr / (2 mu Ie + 2/3 K),  |zeta| = |dev bt| - 2 Ie dgam,  alpha = alpha_old + sqrt(2/3) dgam
+  // and Ie follows from det(zeta + Ie I) = 1 by a scalar Newton: the full local Newton then starts at
+  // the solution (1 evaluation to confirm |C| < tol instead of 4-5 iterations).
+  template <class K> static C8_DI void guess(const K& k, const double* xip, const double* par, double abs_tol,
+                                             double* xi) {
     const Mat<double, DIM> zo = unpack_sym<double, DIM>(xip);
     const Mat<double, DIM> bt = be_bar_trial<DIM>(k, zo, xip[NS]);
-    const Mat<double, DIM> z = dev(bt);
+    Mat<double, DIM> z = dev(bt);
+    double Ie = trace(bt) / 3.0;
+    double alpha = xip[NS + 1];
+    if (par[3] == 0.0 && par[5] == 0.0) {
+      const double sqrt_23 = 0.81649658092772603;
+      const double mu = mu_of(par[0], par[1]);
+      const double z_mag = norm(z);
+      const double f = (mu * z_mag - sqrt_23 * (par[2] + par[7] * alpha)) / mu;
+      if (is_plastic(f, abs_tol) && z_mag > 0.0) {
+        // zeta = nhat m(Ie), m = |dev bt| - 2 Ie dgam(Ie); Ie from the isochoric constraint
+        // det(zeta + Ie I) = 1 by a scalar Newton in plain doubles (a few dozen flops per step,
+        // against ~10^3 for one AD evaluation + 8x8 solve of the full local Newton)
+        const Mat<double, DIM> nhat = scale(1.0 / z_mag, z);
+        const double c0 = mu * f, kk = (2.0 / 3.0) * par[7];
+        double m = 0.0, dgam = 0.0;
+#pragma unroll 1
+        for (int it = 0; it < 8; ++it) {
+          const double den = 2.0 * mu * Ie + kk;
+          dgam = c0 / den;
+          m = z_mag - 2.0 * Ie * dgam;
+          if constexpr (DIM == 3) {
+            const Mat<double, DIM> Amat = add_diag(scale(m, nhat), Ie);
+            const double g = det(Amat) - 1.0;
+            if (fabs(g) < 1e-15) break;
+            const double ddgam = -c0 * 2.0 * mu / (den * den);
+            const double dm = -2.0 * dgam - 2.0 * Ie * ddgam;
+            const Mat<double, DIM> adj = cofactor_T(Amat);
+            double dg = 0.0;
+#pragma unroll
+            for (int i = 0; i < DIM; ++i)
+#pragma unroll
+              for (int j = 0; j < DIM; ++j) dg += adj(j, i) * (dm * nhat(i, j) + (i == j ? 1.0 : 0.0));
+            Ie -= g / dg;
+          } else {
+            break;
+          }
+        }
+        z = scale(m, nhat);
+        alpha += sqrt_23 * dgam;
+      }
+    }
     pack_sym<double, DIM>(z, xi);
-    xi[NS] = trace(bt) / 3.0;
-    xi[NS + 1] = xip[NS + 1];
+    xi[NS] = Ie;
+    xi[NS + 1] = alpha;
   }
   template <class TK, class TKP, class TX, class TXP, class TP>
   static C8_DI int residual(const Kin<DIM, TK, TKP>& k, const TX* xi, const TXP* xip,
@@ -519,7 +588,8 @@ struct HyperJ2PlaneStrain {
     zeta_trial = b2;
     zeta_trial(0, 0) -= Ie_trial; zeta_trial(1, 1) -= Ie_trial;
   }
-  template <class K> static C8_DI void guess(const K& k, const double* xip, double* xi) {
+  template <class K> static C8_DI void guess(const K& k, const double* xip, const double* par, double abs_tol,
+                                                  double* xi) {
     Mat<double, 2> zt; double Iet;
     trial(k, xip, zt, Iet);
     pack_sym<double, 2>(zt, xi);
@@ -619,7 +689,8 @@ struct HyperJ2PlaneStress {
   }
   // initial guess: zeta, Ie from the trial state evaluated with the CURRENT-field lambda_z;
   // lambda_z and alpha keep the values gathered from the current xi field (:176-200)
-  template <class K> static C8_DI void guess(const K& k, const double* xip, double* xi) {
+  template <class K> static C8_DI void guess(const K& k, const double* xip, const double* par, double abs_tol,
+                                                  double* xi) {
     Mat<double, 2> zt; double Iet, J2;
     trial(k, xip, xi[4], zt, Iet, J2);
     pack_sym<double, 2>(zt, xi);
