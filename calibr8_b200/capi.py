@@ -574,10 +574,10 @@ SYMBOLS += ["c8_set_preconditioner", "c8_preconditioner_info", "c8_linalg_invali
 
 
 def _ctx_set_preconditioner(self, kind="amg", nu_pre=2, nu_post=2, omega=0.7, over_correction=1.6,
-                            coarsest_max_nodes=40, max_aggregate_size=8, coarse_aggregate_size=8):
+                            coarsest_max_nodes=40, max_aggregate_size=8, coarse_aggregate_size=8, coarse_nu=0):
     """right preconditioner of gmres(): 'amg' (aggregation multigrid, default) or 'block_jacobi'"""
     opts = np.array([nu_pre, nu_post, omega, over_correction, coarsest_max_nodes, max_aggregate_size,
-                     coarse_aggregate_size],
+                     coarse_aggregate_size, coarse_nu],
                     dtype=np.float64)
     self._check(self.lib.c8_set_preconditioner(self.h, {"block_jacobi": 0, "amg": 1}[kind], _hp(opts),
                                                int(opts.size)))

@@ -554,7 +554,8 @@ void Amg::cycle(int l, const double* b, double* xout) {
     }
     return;
   }
-  const int nu1 = opt.nu_pre < 1 ? 1 : opt.nu_pre, nu2 = opt.nu_post < 1 ? 1 : opt.nu_post;
+  int nu1 = opt.nu_pre < 1 ? 1 : opt.nu_pre, nu2 = opt.nu_post < 1 ? 1 : opt.nu_post;
+  if (l > 0 && opt.coarse_nu > 0) nu1 = nu2 = opt.coarse_nu;  // cheaper cycle below the fine level
   const int writes = nu1 + nu2;
   double* bufs[2] = {xout, L.xt};
   auto buf = [&](int w) { return bufs[(writes - 1 - w) & 1]; };  // the last write goes to xout

@@ -50,6 +50,7 @@ struct AmgOptions {
   int coarsest_max_nodes = 40;
   int max_levels = 12;
   int coarse_aggregate_size = 8;  // aggregate bound on the coarse levels (0: root + all neighbours)
+  int coarse_nu = 0;            // sweeps per side on levels >= 1 (0: same as the fine level)
   bool fp32_fine_level = true;  // the fine-level sweeps read an fp32 copy of the matrix
   int max_aggregate_size = 8;  // bounded compact aggregates (0: root + all neighbours, ~25 nodes in 3-D)
 };

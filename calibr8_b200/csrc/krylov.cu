@@ -144,6 +144,7 @@ int c8_set_preconditioner(c8_ctx* ctx, int type, const double* opts, int n_opts)
     if (n_opts > 4) o.coarsest_max_nodes = int(opts[4]);
     if (n_opts > 5) o.max_aggregate_size = int(opts[5]);
     if (n_opts > 6) o.coarse_aggregate_size = int(opts[6]);
+    if (n_opts > 7) o.coarse_nu = int(opts[7]);
   }
   const bool rebuild = o.coarsest_max_nodes != st.amg_opt.coarsest_max_nodes ||
                        o.max_aggregate_size != st.amg_opt.max_aggregate_size ||

@@ -141,3 +141,86 @@ def test_local_solve_failure_is_reported():
     nf = ctx.forward_jacobian(x, xp, xip, xi, None, ctx.alloc("b"))
     assert nf > 0
     ctx.close()
+
+
+def test_two_element_sets_with_different_materials():
+    """Two element sets with their own material parameters (`materials: {es: {...}}` of the reference
+    decks, LocalResidual::init_params per element set): K1 parity against the oracle."""
+    import torch
+    from calibr8_b200.capi import Context
+    from oracle.pyoracle import Oracle
+    dim, gtype, ltype, params, amp = COMBOS["3d_small_J2"]
+    mesh = make_mesh(dim)
+    cx = mesh.coords[mesh.conn].mean(axis=1)[:, 0]
+    es = (cx > 0.5).astype(np.int32)
+    assert 0 < es.sum() < es.size
+    pars = [dict(params), dict(params, Y=3.0, K=40.0, E=800.0)]
+    (u1, p1), (u2, p2) = synthetic_fields(mesh, amp, True)
+    orc = Oracle(mesh.dim, mesh.conn, mesh.coords, es, 2, global_type=gtype, local_type=ltype,
+                 params=pars, max_iters=60, abs_tol=1e-12, rel_tol=1e-12)
+    xi0 = orc.init_xi()
+    rA = orc.forward_jacobian(xlist(u1, p1), orc.zeros_x(), xi0, xi0, assemble=False)
+    rB = orc.forward_jacobian(xlist(u2, p2), xlist(u1, p1), rA["xi"], rA["xi"], element_out=True)
+    ctx = Context(0)
+    ctx.set_mesh(mesh.dim, mesh.conn, mesh.coords, es, 2)
+    ctx.set_model(gtype, ltype, pars, max_iters=60, abs_tol=1e-12, rel_tol=1e-12)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    x, xp, xi, xip = ctx.alloc("x"), ctx.alloc("x"), ctx.alloc("xi"), ctx.alloc("xi")
+    A, b, path, eJ = ctx.alloc("A"), ctx.alloc("b"), ctx.alloc("path"), ctx.alloc("elem_J")
+    ctx.pack_x(u2, p2, x); ctx.pack_x(u1, p1, xp)
+    ctx.pack_xi(rA["xi"], xi); ctx.pack_xi(rA["xi"], xip)
+    assert ctx.forward_jacobian(x, xp, xip, xi, A, b, path, eJ, None) == 0
+    torch.cuda.synchronize()
+    assert (path.cpu().numpy().astype(np.int32) == rB["path"]).all()
+    n, nx = ctx.n_elems, ctx.nx
+    assert rel_err_blockwise(eJ.cpu().numpy().reshape(n, nx, nx), rB["elem_dtotal"], 0) < TOL
+    assert rel_err_blockwise(ctx.unpack_xi(xi), rB["xi"], 0) < TOL
+    # the two sets really behave differently
+    assert rB["path"][es == 0].mean() != rB["path"][es == 1].mean()
+    ctx.close()
+
+
+@pytest.mark.parametrize("n_elems", [1, 3, 9])
+def test_tiny_and_ragged_meshes(n_elems):
+    """Edge cases of the launch geometry: fewer elements than one warp's worth of thread groups,
+    element counts that are not a multiple of the groups per CTA."""
+    import torch
+    from calibr8_b200.capi import Context
+    from oracle.pyoracle import Oracle
+    dim, gtype, ltype, params, amp = COMBOS["3d_hyper_J2"]
+    full = make_mesh(dim)
+    conn = full.conn[:n_elems]
+    used = np.unique(conn)
+    remap = -np.ones(full.n_nodes, dtype=np.int64); remap[used] = np.arange(used.size)
+    conn = remap[conn].astype(np.int32)
+    coords = np.ascontiguousarray(full.coords[used])
+    rng = np.random.RandomState(3)
+    u1 = rng.uniform(-1, 1, size=coords.shape[0] * 3) * amp
+    u2 = u1 * 1.3 + rng.uniform(-1, 1, size=u1.size) * 0.2 * amp
+    p1 = rng.uniform(-1, 1, size=coords.shape[0]); p2 = rng.uniform(-1, 1, size=coords.shape[0])
+    orc = Oracle(3, conn, coords, global_type=gtype, local_type=ltype, params=[params], max_iters=60,
+                 abs_tol=1e-12, rel_tol=1e-12)
+    xi0 = orc.init_xi()
+    rA = orc.forward_jacobian([u1, p1], orc.zeros_x(), xi0, xi0, assemble=False)
+    rB = orc.forward_jacobian([u2, p2], [u1, p1], rA["xi"], rA["xi"])
+    ctx = Context(0)
+    ctx.set_mesh(3, conn, coords)
+    ctx.set_model(gtype, ltype, params, max_iters=60, abs_tol=1e-12, rel_tol=1e-12)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    x, xp, xi, xip = ctx.alloc("x"), ctx.alloc("x"), ctx.alloc("xi"), ctx.alloc("xi")
+    A, b = ctx.alloc("A"), ctx.alloc("b")
+    ctx.pack_x(u2, p2, x); ctx.pack_x(u1, p1, xp)
+    ctx.pack_xi(rA["xi"], xi); ctx.pack_xi(rA["xi"], xip)
+    assert ctx.forward_jacobian(x, xp, xip, xi, A, b) == 0
+    torch.cuda.synchronize()
+    bu, bp = ctx.unpack_x(b)
+    scale = max(np.abs(rB["b"][0]).max(), 1e-300)
+    assert np.abs(bu - rB["b"][0]).max() < TOL * scale
+    for i in range(2):
+        for j in range(2):
+            rp, ci = ctx.csr_block_pattern(i, j)
+            assert np.array_equal(ci, orc.graph(i, j)[1])
+            v = ctx.csr_block_values(i, j, A)
+            ref = rB["A"][i * 2 + j]
+            assert np.abs(v - ref).max() < TOL * max(np.abs(ref).max(), 1e-300)
+    ctx.close()

@@ -25,6 +25,7 @@ ap.add_argument("--oc", type=float, default=1.6)
 ap.add_argument("--agg", type=int, default=8)
 ap.add_argument("--cagg", type=int, default=8)
 ap.add_argument("--cmax", type=int, default=40)
+ap.add_argument("--cnu", type=int, default=0)
 a = ap.parse_args()
 
 PAR = {"small_J2": dict(E=1000., nu=.25, K=100., Y=2., cte=0., delta_T=0.),
@@ -36,7 +37,7 @@ mesh = meshgen.box_tets(a.cells, notch_radius=0.2)
 ctx = Context(0)
 ctx.set_mesh(3, mesh.conn, mesh.coords)
 ctx.set_model("mechanics", a.model, PAR[a.model], max_iters=500, abs_tol=1e-12, rel_tol=1e-12)
-ctx.set_preconditioner(a.pc, nu_pre=a.nu, nu_post=a.nu, omega=a.omega, over_correction=a.oc, max_aggregate_size=a.agg, coarse_aggregate_size=a.cagg, coarsest_max_nodes=a.cmax)
+ctx.set_preconditioner(a.pc, nu_pre=a.nu, nu_post=a.nu, omega=a.omega, over_correction=a.oc, max_aggregate_size=a.agg, coarse_aggregate_size=a.cagg, coarsest_max_nodes=a.cmax, coarse_nu=a.cnu)
 hp = HostProblem(ctx)
 hp.set_time(a.steps, 1.0)
 hp.add_dbc(0, 0, mesh.node_sets["xmin"], "0.0")
