@@ -303,7 +303,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
 
     mesh = workload_mesh()
-    (u1, p1), (u2, p2) = workload_fields(mesh, seed=rank)
+    (u1, p1), (u2, p2) = workload_fields(mesh, seed=0)   # identical per-GPU work on every rank (weak scaling)
     ctx = Context(local_rank)
     ctx.set_mesh(mesh.dim, mesh.conn, mesh.coords)
     ctx.set_model("mechanics", "hyper_J2", PARAMS, **LOCAL)

@@ -38,6 +38,7 @@ struct SolverParams {
   // line search, src/line_search.hpp:24-31
   double ls_c1 = 1e-4, ls_bmin = 0.5, ls_bmax = 0.9;
   int ls_max_evals = 4;
+  bool reuse_accepted_assembly = true;  // do not re-assemble the state the line search just accepted
   bool print = false;
 };
 

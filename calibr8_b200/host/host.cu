@@ -201,11 +201,20 @@ void Primal::solve_at_step(int step) {
   bool converged = false;
   double resid_norm_0 = 1.;
   const SolverParams& sp = P.sp;
+  // When the line search accepts the step it evaluated last, A and R already hold the assembly at the
+  // accepted point; the reference re-assembles the identical state at the top of the next iteration
+  // (src/primal.cpp:95) -- skipped here (SolverParams::reuse_accepted_assembly).
+  bool have_assembly = false;
+  double rn_kept = 0.;
   while (iter <= sp.newton_max_iters && !converged) {
     double rn = 0.;
-    if (!assemble(step, &rn))
+    if (have_assembly) {
+      rn = rn_kept;
+      have_assembly = false;
+    } else if (!assemble(step, &rn)) {
       throw std::runtime_error("primal: local solve failed at the base point (step " +
                                std::to_string(step) + ")");
+    }
     if (iter == 1) resid_norm_0 = rn;
     const double rel = rn / resid_norm_0;
     if (sp.print) std::printf("  step %d it %d |R| = %.6e rel %.3e\n", step, iter, rn, rel);
@@ -226,12 +235,16 @@ void Primal::solve_at_step(int step) {
     const double psi_0 = 0.5 * rn * rn, dpsi_0 = -2. * psi_0;
     C8H_CUDA(cudaMemcpyAsync(P.saved_xi.get(), P.xi[step].get(), xib, cudaMemcpyDeviceToDevice, s));
     double alpha_applied = 1.;
+    bool last_eval_ok = false;
+    double last_eval_rn = 0.;
     auto eval = [&](double alpha, double& phi, double& slope) -> bool {
       C8H_CUDA(cudaMemcpyAsync(P.xi[step].get(), P.saved_xi.get(), xib, cudaMemcpyDeviceToDevice, s));
       P.axpy(alpha - alpha_applied, P.dx.get(), P.x[step].get());
       alpha_applied = alpha;
       double ra = 0.;
+      last_eval_ok = false;
       if (!assemble(step, &ra)) return false;
+      last_eval_ok = true; last_eval_rn = ra;
       phi = 0.5 * ra * ra;
       PhaseTimer pt5(P, 5);
       P.check(c8_spmv(P.ctx, P.A.get(), P.dx.get(), P.Adx.get()), "c8_spmv");
@@ -252,6 +265,10 @@ void Primal::solve_at_step(int step) {
     }
     if (!assembled_any) throw std::runtime_error("primal: line search could not assemble");
     const double a_final = accepted ? alpha : best_alpha;
+    if (sp.reuse_accepted_assembly && last_eval_ok && a_final == alpha_applied) {
+      have_assembly = true;       // x, xi, A, R are exactly the state of the last trial
+      rn_kept = last_eval_rn;
+    }
     P.axpy(a_final - alpha_applied, P.dx.get(), P.x[step].get());
     ++iter;
   }
