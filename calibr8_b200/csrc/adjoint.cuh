@@ -52,8 +52,11 @@ __global__ void __launch_bounds__(128) k_adjoint_jacobian(const AdjArgs a) {
   constexpr int D = C::D, NN = C::NN, NB = C::NB, NX = C::NX, NXI = C::NXI, LX = C::LX,
                 LXI = C::LXI, G = C::G;
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int e = gid / G, t = gid % G;
-  if (e >= a.mesh.n_elems) return;
+  const int t = gid % G;
+  // padding groups recompute the last element and store nothing, so that every lane of a warp
+  // reaches the in-group solves (full-mask shuffles, see groupsolve.cuh)
+  const bool in_range = (gid / G) < a.mesh.n_elems;
+  const int e = in_range ? gid / G : a.mesh.n_elems - 1;
   const unsigned mask = group_mask<C>();
 
   Elem<C> E;
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(128) k_adjoint_jacobian(const AdjArgs a) {
     for (int q = 0; q < NXI; ++q)
 #pragma unroll
       for (int s = 0; s < LX; ++s) dxi_dx[q][s] = C2[q].d[s];
-    local_sensitivity<C, LX>(Cd, dxi_dx, mask);
+    local_sensitivity<C, LX, true>(Cd, dxi_dx, mask);
 #pragma unroll
     for (int q = 0; q < NXI; ++q) {
       xid[q].v = xi[q];
@@ -100,7 +103,7 @@ __global__ void __launch_bounds__(128) k_adjoint_jacobian(const AdjArgs a) {
   fa.mesh = a.mesh;
   fa.vals = a.vals;
   fa.emat = a.emat;
-  Scatter<C, false> sc{fa, E, sx.xl, e, t, true};  // element matrix only; rhs is added below
+  Scatter<C, false> sc{fa, E, sx.xl, e, t, in_range};  // element matrix only; rhs is added below
   sc.init();
   {
     const Mat<Dual<LX>, D> P = first_pk<D, C::M, Model>(k2, sx.p, xid, E.par, a.model.thickness);
@@ -201,6 +204,7 @@ __global__ void __launch_bounds__(128) k_adjoint_jacobian(const AdjArgs a) {
     }
   }
   // g -= dJ/dxi (stored) ; rhs = -dJ/dx + f + dxi/dx^T g, :481-488
+  if (!in_range) return;  // no shuffles below
 #pragma unroll
   for (int q = 0; q < NXI; ++q)
     if (q % G == t) a.g[size_t(q) * a.xi_ld + e] = gq[q];
@@ -224,8 +228,9 @@ __global__ void __launch_bounds__(128) k_adjoint_local(const AdjArgs a) {
   constexpr int D = C::D, NN = C::NN, NB = C::NB, NXI = C::NXI, LX = C::LX, LXI = C::LXI,
                 G = C::G;
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int e = gid / G, t = gid % G;
-  if (e >= a.mesh.n_elems) return;
+  const int t = gid % G;
+  const bool in_range = (gid / G) < a.mesh.n_elems;   // padding groups: compute, store nothing
+  const int e = in_range ? gid / G : a.mesh.n_elems - 1;
   const unsigned mask = group_mask<C>();
 
   Elem<C> E;
@@ -291,7 +296,7 @@ __global__ void __launch_bounds__(128) k_adjoint_local(const AdjArgs a) {
   double rhs[NXI], JT[NXI][LXI], dummy[NXI][1];
 #pragma unroll
   for (int q = 0; q < NXI; ++q) {
-    const double v = group_bcast<G>(mask, rl[q % LXI], q / LXI);
+    const double v = group_bcast_full<G>(rl[q % LXI], q / LXI);
     rhs[q] = __ldg(&a.g[size_t(q) * a.xi_ld + e]) - v;
   }
   // thread owns columns c = t*LXI+s of J (Cd[i].d[s] = J[i][c]); it needs columns c of J^T,
@@ -305,11 +310,12 @@ __global__ void __launch_bounds__(128) k_adjoint_local(const AdjArgs a) {
   for (int r = 0; r < NXI; ++r)
 #pragma unroll
     for (int i = 0; i < NXI; ++i) {
-      const double v = group_bcast<G>(mask, Cd[r].d[i % LXI], i / LXI);  // J[r][i]
+      const double v = group_bcast_full<G>(Cd[r].d[i % LXI], i / LXI);  // J[r][i]
 #pragma unroll
       for (int s = 0; s < LXI; ++s) JT[i][s] = pick(t * LXI + s == r, v, JT[i][s]);
     }
-  group_gauss_jordan<NXI, LXI, 0, G>(JT, dummy, rhs, mask);  // rhs := phi
+  group_gauss_jordan<NXI, LXI, 0, G, true>(JT, dummy, rhs, mask);  // rhs := phi
+  if (!in_range) return;  // no shuffles below
 #pragma unroll
   for (int q = 0; q < NXI; ++q)
     if (q % G == t) a.phi[size_t(q) * a.xi_ld + e] = rhs[q];

@@ -27,7 +27,7 @@ struct Launch {
   // phase 2 of the assembly (forward.cuh): BSR values of the owned rows <- element matrices
   template <bool TRANSPOSE>
   static void gather(const MeshArgs& m, const double* emat, double* vals, cudaStream_t s) {
-    constexpr int EPT = (!TRANSPOSE && C::NB % 2 == 0) ? 2 : 1;  // entries per thread (forward.cuh)
+    constexpr int EPT = (C::NB % 2 == 0) ? 2 : 1;  // entries per thread (forward.cuh)
     const long long work = (long long)m.n_row_blocks * (C::NB * C::NB / EPT);
     if (work == 0) return;
     k_bsr_gather<C::NB, C::NN, TRANSPOSE><<<(unsigned)((work + 255) / 256), 256, 0, s>>>(

@@ -272,12 +272,14 @@ __global__ void k_bsr_gather(const int* __restrict__ gptr, const int* __restrict
                              const double* __restrict__ emat, double* __restrict__ vals,
                              int n_row_blocks) {
   constexpr int BB = NB * NB, NX = NB * NN;
-  constexpr bool VEC2 = !TRANSPOSE && (NB % 2 == 0);
+  constexpr bool VEC2 = (NB % 2 == 0);
   constexpr int EPT = VEC2 ? 2 : 1;                 // entries per thread
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)n_row_blocks * (BB / EPT)) return;
   const int blk = int(i / (BB / EPT)), ent = int(i % (BB / EPT)) * EPT;
-  const int r = ent / NB, c = ent % NB;
+  // the pair of entries a thread owns is contiguous in the ELEMENT matrix: (r, c), (r, c+1) of the
+  // output block when not transposing; (r, c), (r+1, c) when transposing
+  const int r = TRANSPOSE ? ent % NB : ent / NB, c = TRANSPOSE ? ent / NB : ent % NB;
   auto src = [&](int k) -> const double* {
     const int q = __ldg(&gsrc[k]);           // e*NN*NN + na*NN + nb : block (node na, node nb)
     const int e = q / (NN * NN), rem = q - e * (NN * NN);
@@ -298,11 +300,16 @@ __global__ void k_bsr_gather(const int* __restrict__ gptr, const int* __restrict
       const double2 v = __ldg(reinterpret_cast<const double2*>(src(k)));
       s0 += v.x; s1 += v.y;
     }
-    *reinterpret_cast<double2*>(vals + size_t(blk) * BB + ent) = make_double2(s0, s1);
+    if constexpr (TRANSPOSE) {
+      vals[size_t(blk) * BB + r * NB + c] = s0;
+      vals[size_t(blk) * BB + (r + 1) * NB + c] = s1;
+    } else {
+      *reinterpret_cast<double2*>(vals + size_t(blk) * BB + ent) = make_double2(s0, s1);
+    }
   } else {
     double s = 0.0;
     for (; k < k1; ++k) s += __ldg(src(k));
-    vals[size_t(blk) * BB + ent] = s;
+    vals[size_t(blk) * BB + r * NB + c] = s;
   }
 }
 

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(128) k_vfm_adjoint(const VfmArgs a) {
     double rhs[NXI], JT[NXI][LXI], dummy[NXI][1];
 #pragma unroll
     for (int q = 0; q < NXI; ++q) {
-      const double v = group_bcast<G>(mask, rl[q % LXI], q / LXI);
+      const double v = group_bcast_full<G>(rl[q % LXI], q / LXI);
       rhs[q] = a.s * -v - a.hist[size_t(q) * a.xi_ld + e];
     }
 #pragma unroll
@@ -224,11 +224,11 @@ __global__ void __launch_bounds__(128) k_vfm_adjoint(const VfmArgs a) {
     for (int r = 0; r < NXI; ++r)
 #pragma unroll
       for (int i = 0; i < NXI; ++i) {
-        const double v = group_bcast<G>(mask, Cd[r].d[i % LXI], i / LXI);
+        const double v = group_bcast_full<G>(Cd[r].d[i % LXI], i / LXI);
 #pragma unroll
         for (int s = 0; s < LXI; ++s) JT[i][s] = pick(t * LXI + s == r, v, JT[i][s]);
       }
-    group_gauss_jordan<NXI, LXI, 0, G>(JT, dummy, rhs, mask);  // rhs := phi
+    group_gauss_jordan<NXI, LXI, 0, G, true>(JT, dummy, rhs, mask);  // rhs := phi
     // h <- dC/dxi_prev^T phi
     {
       Dual<LXI> xps[NXI], Cq[NXI];
