@@ -303,7 +303,7 @@ HOST_SYMBOLS = [
     "c8h_create", "c8h_destroy", "c8h_last_error", "c8h_set_time", "c8h_add_dbc",
     "c8h_finalize_dbcs", "c8h_set_solver", "c8h_set_qoi_avg_disp", "c8h_set_qoi_calibration",
     "c8h_primal_solve", "c8h_adjoint_gradient", "c8h_get_step", "c8h_get_adjoint_step", "c8h_stats",
-    "c8h_profile", "c8h_eval_expr",
+    "c8h_profile", "c8h_eval_expr", "c8h_describe_residuals",
 ]
 
 
@@ -676,3 +676,15 @@ class Objective:
         if getattr(self, "h", None):
             self.lib.c8h_objective_destroy(self.h)
             self.h = None
+
+
+def describe_residuals(local_type, global_type, ndims):
+    """create_local_residual / create_global_residual metadata of the host layer (names, variable
+    types, equation counts, parameter order) -- host only, no GPU needed."""
+    import json
+    lib = load_library()
+    buf = C.create_string_buffer(2048)
+    rc = lib.c8h_describe_residuals(local_type.encode(), global_type.encode(), int(ndims), buf, 2048)
+    if rc != 0:
+        raise C8Error(buf.value.decode())
+    return json.loads(buf.value.decode())

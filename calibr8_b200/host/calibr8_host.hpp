@@ -19,6 +19,7 @@
 
 #include "c8b200.h"
 #include "expr.hpp"
+#include "residuals.hpp"
 
 namespace c8host {
 

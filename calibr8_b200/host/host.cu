@@ -479,6 +479,36 @@ int c8h_profile(c8h_problem* h, int enable, double* out8) {
   if (out8) for (int k = 0; k < 8; ++k) out8[k] = h->P.t_phase[k];
   return 0;
 }
+// JSON description of create_local_residual(local_type, ndims) + create_global_residual(global_type, ndims)
+// (host only; returns 0, or -1 with the message in out)
+int c8h_describe_residuals(const char* local_type, const char* global_type, int ndims, char* out, int len) {
+  auto put = [&](const std::string& s) { std::strncpy(out, s.c_str(), len - 1); out[len - 1] = 0; };
+  try {
+    const LocalResidual l = create_local_residual(local_type, ndims);
+    const GlobalResidual g = create_global_residual(global_type, ndims);
+    auto strs = [](const std::vector<std::string>& v) {
+      std::string s = "[";
+      for (size_t i = 0; i < v.size(); ++i) s += (i ? ", \"" : "\"") + v[i] + "\"";
+      return s + "]";
+    };
+    auto ints = [](const std::vector<int>& v) {
+      std::string s = "[";
+      for (size_t i = 0; i < v.size(); ++i) s += (i ? ", " : "") + std::to_string(v[i]);
+      return s + "]";
+    };
+    put("{\"local\": {\"c8_type\": " + std::to_string(l.c8_type) + ", \"resid_names\": " + strs(l.resid_names) +
+        ", \"var_types\": " + ints(l.var_types) + ", \"num_eqs\": " + ints(l.num_eqs) + ", \"num_dofs\": " +
+        std::to_string(l.num_dofs()) + ", \"param_names\": " + strs(l.param_names) + ", \"finite_deformation\": " +
+        (l.finite_deformation ? "true" : "false") + ", \"z_stretch_idx\": " + std::to_string(l.z_stretch_idx) +
+        "}, \"global\": {\"c8_type\": " + std::to_string(g.c8_type) + ", \"resid_names\": " + strs(g.resid_names) +
+        ", \"num_eqs\": " + ints(g.num_eqs) + ", \"num_ip_sets\": " + std::to_string(g.num_ip_sets) + "}}");
+    return 0;
+  } catch (const std::exception& ex) {
+    put(ex.what());
+    return -1;
+  }
+}
+
 // evaluate a boundary-condition / virtual-field expression at n points (xyz [n][3]) and time t;
 // returns 0, or -1 with the message in err_out (may be NULL)
 int c8h_eval_expr(const char* expr, const double* xyz, int n, double t, double* out, char* err_out,

@@ -82,3 +82,30 @@ def test_mesh_generators():
     assert m2.n_elems == 98 and m2.n_nodes == 64
     # the 1M-tet configuration of BASELINE.json has exactly this many tets before the notch
     assert 55 ** 3 * 6 == 998250
+
+
+def test_residual_factories_match_the_reference_metadata():
+    """create_local_residual / create_global_residual (host C++): names, variable types, equation counts
+    and parameter order as the reference's constructors set them (e.g. src/small_J2.cpp:36-60,
+    src/hyper_J2_plane_stress.cpp:43-63), and the Python tables agree with them."""
+    import pytest
+    from calibr8_b200 import capi
+    cases = {("small_J2", "mechanics", 3): (["pstrain", "alpha"], [6, 1]),
+             ("small_hill", "mechanics", 3): (["pstrain", "alpha"], [6, 1]),
+             ("hyper_J2", "mechanics", 3): (["zeta", "Ie", "alpha"], [6, 1, 1]),
+             ("elastic", "mechanics", 2): (["dummy"], [1]),
+             ("small_hill_plane_stress", "mechanics_plane_stress", 2): (["pstrain", "alpha"], [3, 1]),
+             ("hyper_J2_plane_stress", "mechanics_plane_stress", 2): (["zeta", "Ie", "lambda_z", "alpha"], [3, 1, 1, 1]),
+             ("hyper_J2_plane_strain", "mechanics", 2): (["zeta", "Ie", "alpha"], [3, 1, 1])}
+    for (lt, gt, nd), (names, neq) in cases.items():
+        d = capi.describe_residuals(lt, gt, nd)
+        assert d["local"]["resid_names"] == names and d["local"]["num_eqs"] == neq
+        assert d["local"]["param_names"] == capi.PARAM_NAMES[lt]
+        assert d["local"]["c8_type"] == capi.LOCAL_TYPES[lt] and d["global"]["c8_type"] == capi.GLOBAL_TYPES[gt]
+        assert d["global"]["resid_names"] == (["u", "p"] if gt == "mechanics" else ["u"])
+        assert d["global"]["num_ip_sets"] == (2 if gt == "mechanics" else 1)
+    assert capi.describe_residuals("hyper_J2_plane_stress", "mechanics_plane_stress", 2)["local"]["z_stretch_idx"] == 2
+    with pytest.raises(capi.C8Error):
+        capi.describe_residuals("hypo_hill", "mechanics", 3)          # out of the hot-path scope
+    with pytest.raises(capi.C8Error):
+        capi.describe_residuals("small_hill_plane_stress", "mechanics_plane_stress", 3)
