@@ -131,9 +131,21 @@ C8_DI int local_newton(const Kin<C::D, double, double>& k0, const Elem<C>& E, co
 }
 
 // dxi/dx = -(dC/dxi)^-1 dC/dx for the columns this thread owns (Bc in: dC/dx, out: dxi/dx)
+// path: the branch of this point (used at warp-uniform call sites only): when every point of the warp
+// is elastic and the model's elastic Jacobian is the identity, -(I)^-1 B = -B needs no solve (the
+// reference's LU of an identity matrix is exact, so the result is bit-identical).
 template <class C, int LB, bool FULL = false>
 C8_DI void local_sensitivity(const Dual<C::LXI> (&Cd)[C::NXI], double (&Bc)[C::NXI][LB],
-                             unsigned mask) {
+                             unsigned mask, int path = -1) {
+  if constexpr (C::Model::HAS_NEWTON && C::Model::ELASTIC_J_IDENTITY && FULL) {
+    if (__all_sync(0xffffffffu, path == PATH_ELASTIC)) {
+#pragma unroll
+      for (int q = 0; q < C::NXI; ++q)
+#pragma unroll
+        for (int s = 0; s < LB; ++s) Bc[q][s] = -Bc[q][s];
+      return;
+    }
+  }
   if constexpr (!C::Model::HAS_NEWTON) {
     // Elastic: C == 0 identically, the reference's LU of a zero matrix returns 0
 #pragma unroll
@@ -391,21 +403,38 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian(co
   k2.gu = sx.gu;
   k2.gup = k0.gup;
   Dual<LX> xid[NXI];
+  // With one thread per node (G == NN, LX == NB) in the mixed formulation, lane LX-1 of every thread
+  // is the node's PRESSURE dof, and the constitutive residual does not depend on the pressure: P2 and
+  // the sensitivity solve run on the LX-1 displacement lanes only, dxi/dp = 0 exactly.
+  constexpr bool DROP_P_LANE = (C::M == MECH_MIXED) && (G == NN) && (LX == NB);
+  constexpr int L2 = DROP_P_LANE ? LX - 1 : LX;
   {
-    Dual<LX> C2[NXI];
-    Model::residual(k2, xi, E.xip, E.par, a.model.abs_tol, C2);
+    Kin<D, Dual<L2>, double> k2n;
+    k2n.gup = k0.gup;
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        k2n.gu(i, j).v = k2.gu(i, j).v;
+#pragma unroll
+        for (int s = 0; s < L2; ++s) k2n.gu(i, j).d[s] = k2.gu(i, j).d[s];
+      }
+    Dual<L2> C2[NXI];
+    Model::residual(k2n, xi, E.xip, E.par, a.model.abs_tol, C2);
     C8_PHASE_SYNC();
-    double Bc[NXI][LX];
+    double Bc[NXI][L2];
 #pragma unroll
     for (int q = 0; q < NXI; ++q)
 #pragma unroll
-      for (int s = 0; s < LX; ++s) Bc[q][s] = C2[q].d[s];
-    local_sensitivity<C, LX, true>(Cd, Bc, mask);
+      for (int s = 0; s < L2; ++s) Bc[q][s] = C2[q].d[s];
+    local_sensitivity<C, L2, true>(Cd, Bc, mask, in_range ? path : PATH_ELASTIC);
 #pragma unroll
     for (int q = 0; q < NXI; ++q) {
       xid[q].v = xi[q];
 #pragma unroll
-      for (int s = 0; s < LX; ++s) xid[q].d[s] = Bc[q][s];
+      for (int s = 0; s < L2; ++s) xid[q].d[s] = Bc[q][s];
+#pragma unroll
+      for (int s = L2; s < LX; ++s) xid[q].d[s] = 0.0;
     }
   }
   C8_PHASE_SYNC();

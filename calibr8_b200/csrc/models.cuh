@@ -124,6 +124,8 @@ template <int DIM>
 struct Elastic {
   static constexpr int NXI = 1, NPAR = 4, TYPE = L_ELASTIC;
   static constexpr bool FINITE = false, HAS_NEWTON = false, PLANE_STRESS = false;
+  // on the elastic branch C = xi - (a function of xi_prev and the kinematics): dC/dxi = I
+  static constexpr bool ELASTIC_J_IDENTITY = false;
   static constexpr int Z_STRETCH = -1;
   static C8_DI void init(double* xi) { xi[0] = 0.0; }
   template <class K> static C8_DI void guess(const K&, const double*, const double*, double, double* xi) { xi[0] = 0.0; }
@@ -155,6 +157,8 @@ struct SmallJ2 {
   static constexpr int NS = SymIdx<DIM>::n;
   static constexpr int NXI = NS + 1, NPAR = 6, TYPE = L_SMALL_J2;
   static constexpr bool FINITE = false, HAS_NEWTON = true, PLANE_STRESS = false;
+  // on the elastic branch C = xi - (a function of xi_prev and the kinematics): dC/dxi = I
+  static constexpr bool ELASTIC_J_IDENTITY = true;
   static constexpr int Z_STRETCH = -1;
   static C8_DI void init(double* xi) {
 #pragma unroll
@@ -232,6 +236,8 @@ struct SmallHill {
   static_assert(DIM == 3, "small_hill is a 3-D model");
   static constexpr int NS = 6, NXI = 7, NPAR = 11, TYPE = L_SMALL_HILL;
   static constexpr bool FINITE = false, HAS_NEWTON = true, PLANE_STRESS = false;
+  // on the elastic branch C = xi - (a function of xi_prev and the kinematics): dC/dxi = I
+  static constexpr bool ELASTIC_J_IDENTITY = true;
   static constexpr int Z_STRETCH = -1;
   static C8_DI void init(double* xi) {
 #pragma unroll
@@ -289,6 +295,8 @@ struct SmallHillPlaneStress {
   static_assert(DIM == 2, "plane stress is 2-D");
   static constexpr int NS = 3, NXI = 4, NPAR = 9, TYPE = L_SMALL_HILL_PLANE_STRESS;
   static constexpr bool FINITE = false, HAS_NEWTON = true, PLANE_STRESS = true;
+  // on the elastic branch C = xi - (a function of xi_prev and the kinematics): dC/dxi = I
+  static constexpr bool ELASTIC_J_IDENTITY = true;
   static constexpr int Z_STRETCH = -1;
   static C8_DI void init(double* xi) {
 #pragma unroll
@@ -352,6 +360,8 @@ struct SmallHillPlaneStrain {
   static_assert(DIM == 2, "plane strain is 2-D");
   static constexpr int NS = 3, NXI = 4, NPAR = 9, TYPE = L_SMALL_HILL_PLANE_STRAIN;
   static constexpr bool FINITE = false, HAS_NEWTON = true, PLANE_STRESS = false;
+  // on the elastic branch C = xi - (a function of xi_prev and the kinematics): dC/dxi = I
+  static constexpr bool ELASTIC_J_IDENTITY = true;
   static constexpr int Z_STRETCH = -1;
   static C8_DI void init(double* xi) {
 #pragma unroll
@@ -448,6 +458,8 @@ struct HyperJ2 {
   static constexpr int NS = SymIdx<DIM>::n;
   static constexpr int NXI = NS + 2, NPAR = 8, TYPE = L_HYPER_J2;
   static constexpr bool FINITE = true, HAS_NEWTON = true, PLANE_STRESS = false;
+  // on the elastic branch C = xi - (a function of xi_prev and the kinematics): dC/dxi = I
+  static constexpr bool ELASTIC_J_IDENTITY = true;
   static constexpr int Z_STRETCH = -1;
   static C8_DI void init(double* xi) {
 #pragma unroll
@@ -572,6 +584,8 @@ struct HyperJ2PlaneStrain {
   static_assert(DIM == 2, "plane strain is 2-D");
   static constexpr int NS = 3, NXI = 5, NPAR = 6, TYPE = L_HYPER_J2_PLANE_STRAIN;
   static constexpr bool FINITE = true, HAS_NEWTON = true, PLANE_STRESS = false;
+  // on the elastic branch C = xi - (a function of xi_prev and the kinematics): dC/dxi = I
+  static constexpr bool ELASTIC_J_IDENTITY = false;
   static constexpr int Z_STRETCH = -1;
   static C8_DI void init(double* xi) {
     xi[0] = xi[1] = xi[2] = 0.0; xi[3] = 1.0; xi[4] = 0.0;
@@ -659,6 +673,8 @@ struct HyperJ2PlaneStress {
   // xi = zeta(00,01,11), Ie, lambda_z, alpha
   static constexpr int NS = 3, NXI = 6, NPAR = 8, TYPE = L_HYPER_J2_PLANE_STRESS;
   static constexpr bool FINITE = true, HAS_NEWTON = true, PLANE_STRESS = true;
+  // on the elastic branch C = xi - (a function of xi_prev and the kinematics): dC/dxi = I
+  static constexpr bool ELASTIC_J_IDENTITY = false;
   static constexpr int Z_STRETCH = 4;  // packed index of lambda_z (residual index 2 in the reference)
   static C8_DI void init(double* xi) {
     xi[0] = xi[1] = xi[2] = 0.0; xi[3] = 1.0; xi[4] = 1.0; xi[5] = 0.0;
