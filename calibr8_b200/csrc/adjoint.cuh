@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128) k_adjoint_jacobian(const AdjArgs a) {
   Dual<LXI> xs[NXI], Cd[NXI];
 #pragma unroll
   for (int q = 0; q < NXI; ++q) xs[q] = seeded<LXI>(xi[q], q, t * LXI);
-  Model::residual(k0, xs, E.xip, E.par, a.model.abs_tol, Cd);
+  const int path = Model::residual(k0, xs, E.xip, E.par, a.model.abs_tol, Cd);
 
   SeededX<C> sx;
   sx.init(E, k0.gu, t);
@@ -82,18 +82,36 @@ __global__ void __launch_bounds__(128) k_adjoint_jacobian(const AdjArgs a) {
   Dual<LX> xid[NXI];
   double dxi_dx[NXI][LX];
   {
-    Dual<LX> C2[NXI];
-    Model::residual(k2, xi, E.xip, E.par, a.model.abs_tol, C2);
+    // as in K1 (forward.cuh): the pressure lane carries no constitutive derivative, and an
+    // all-elastic warp needs no solve
+    constexpr bool DROP_P_LANE = (C::M == MECH_MIXED) && (G == NN) && (LX == NB);
+    constexpr int L2 = DROP_P_LANE ? LX - 1 : LX;
+    Kin<D, Dual<L2>, double> k2n;
+    k2n.gup = k0.gup;
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        k2n.gu(i, j).v = k2.gu(i, j).v;
+#pragma unroll
+        for (int s = 0; s < L2; ++s) k2n.gu(i, j).d[s] = k2.gu(i, j).d[s];
+      }
+    Dual<L2> C2[NXI];
+    Model::residual(k2n, xi, E.xip, E.par, a.model.abs_tol, C2);
+    double Bc[NXI][L2];
 #pragma unroll
     for (int q = 0; q < NXI; ++q)
 #pragma unroll
-      for (int s = 0; s < LX; ++s) dxi_dx[q][s] = C2[q].d[s];
-    local_sensitivity<C, LX, true>(Cd, dxi_dx, mask);
+      for (int s = 0; s < L2; ++s) Bc[q][s] = C2[q].d[s];
+    local_sensitivity<C, L2, true>(Cd, Bc, mask, in_range ? path : PATH_ELASTIC);
 #pragma unroll
     for (int q = 0; q < NXI; ++q) {
       xid[q].v = xi[q];
 #pragma unroll
-      for (int s = 0; s < LX; ++s) xid[q].d[s] = dxi_dx[q][s];
+      for (int s = 0; s < LX; ++s) {
+        dxi_dx[q][s] = s < L2 ? Bc[q][s < L2 ? s : 0] : 0.0;
+        xid[q].d[s] = dxi_dx[q][s];
+      }
     }
   }
 
