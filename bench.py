@@ -405,10 +405,14 @@ def run_ours(args):
     # same mesh and model, a bounded number of load steps
     cal = None
     if not args.no_solve:
-        if world == 1:
-            cal = calibration_step(ctx, mesh, args.load_steps)
-        else:
-            cal = calibration_step_partitioned(mesh, args.load_steps, rank, world, local_rank)
+        # secondary leg: a failure here must not lose the headline line
+        try:
+            if world == 1:
+                cal = calibration_step(ctx, mesh, args.load_steps)
+            else:
+                cal = calibration_step_partitioned(mesh, args.load_steps, rank, world, local_rank)
+        except Exception as ex:   # noqa: BLE001
+            cal = {"metric": "forward+adjoint gradient wall-time/load step", "error": repr(ex)[:300]}
 
     # max over ranks
     t = torch.tensor([total_ms, k_ms, e2e_s], dtype=torch.float64, device=dev)
@@ -435,6 +439,7 @@ def run_ours(args):
         if args.gpus == 1 and not args.no_cpu:
             c1 = cpu_sample(1, 28)
             cpu = {"value": c1["evals_per_s"], "unit": UNIT, "cores": 1, "kind": "port",
+                   "host_cores_available": os.cpu_count(),
                    "sample": f"one {c1['n_elems']}-tet notched box (28 cells/side) of the same hyper-J2 "
                              f"state, full eval_forward_jacobian incl. CSR scatter, 1 thread, "
                              f"{c1['seconds']:.1f} s"}
