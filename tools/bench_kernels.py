@@ -22,27 +22,11 @@ def timeit(fn, pre=lambda: None, reps=6):
     return float(np.median(ts))
 
 
-def ref_flops_3d(n_cells=6):
-    """flops per QP of the reference algorithm for K1..K6 on the bench state (counting oracle)"""
-    from oracle.pyoracle import Oracle
-    mesh = bench.workload_mesh(n_cells)
-    (u1, p1), (u2, p2) = bench.workload_fields(mesh)
-    o = Oracle(3, mesh.conn, mesh.coords, global_type="mechanics", local_type="hyper_J2", params=[bench.PARAMS],
-               count_flops=True, active=[[0, 1, 2, 7]], **bench.LOCAL)
-    o.set_qoi_avg_disp()
-    xi0 = o.init_xi()
-    rA = o.forward_jacobian([u1, p1], o.zeros_x(), xi0, xi0, assemble=False)
-    n = mesh.n_elems
-    out = {}
-    o.flops_reset(); rB = o.forward_jacobian([u2, p2], [u1, p1], rA["xi"], rA["xi"]); out["K1"] = o.flops_reset() / n
-    o.flops_reset(); o.global_residual([u2, p2], [u1, p1], rB["xi"], rA["xi"]); out["K2"] = o.flops_reset() / n
-    g = np.zeros((n, o.n_xi)); f = np.zeros((n, o.n_x))
-    o.flops_reset(); o.adjoint_jacobian([u2, p2], [u1, p1], rB["xi"], rA["xi"], g, f, 1); out["K3"] = o.flops_reset() / n
-    z = [np.random.RandomState(1).randn(mesh.n_nodes * 3), np.random.RandomState(2).randn(mesh.n_nodes)]
-    o.flops_reset(); phi = o.adjoint_local([u2, p2], [u1, p1], rB["xi"], rA["xi"], z, g, f); out["K4"] = o.flops_reset() / n
-    o.flops_reset(); o.qoi([u2, p2], [u1, p1], rB["xi"], rA["xi"], 1); out["K5"] = o.flops_reset() / n
-    o.flops_reset(); o.qoi_gradient([u2, p2], [u1, p1], rB["xi"], rA["xi"], z, phi, [[0, 1, 2, 3]], 4, 1); out["K6"] = o.flops_reset() / n
-    return out
+def ref_flops_3d():
+    """flops per QP of the reference algorithm for K1..K6 on the bench state (counted by
+    tests/golden/make_flop_counts.py with the op-counting oracle build)"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return json.load(open(os.path.join(root, "tests", "golden", "flop_counts.json")))
 
 
 res = {}
