@@ -497,7 +497,7 @@ class HostProblem:
 # partition / communication (one Context per GPU; calibr8_b200/partition.py builds the plan)
 SYMBOLS += [
     "c8_set_partition", "c8_get_partition", "c8_set_comm", "c8_set_halo_plan", "c8_nccl_unique_id",
-    "c8_nccl_init", "c8_set_comm_host", "c8_halo", "c8_halo_nb", "c8_allreduce", "c8_comm_stats",
+    "c8_nccl_init", "c8_set_comm_host", "c8_set_comm_rank", "c8_halo", "c8_halo_nb", "c8_allreduce", "c8_comm_stats",
     "c8_comm_release",
 ]
 _EXCHANGE_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int)
@@ -543,6 +543,8 @@ def _ctx_set_comm_host(self, exchanger):
 
     self._cb = (_EXCHANGE_FN(ex), _HOST_ALLREDUCE_FN(ar))   # keep alive
     self._check(self.lib.c8_set_comm_host(self.h, self._cb[0], self._cb[1], None))
+    if getattr(exchanger, "world", 1) > 1:   # lets the multigrid preconditioner span the parts
+        self._check(self.lib.c8_set_comm_rank(self.h, int(exchanger.rank), int(exchanger.world)))
 
 
 def _ctx_halo(self, vec, nb=None):
@@ -574,10 +576,13 @@ SYMBOLS += ["c8_set_preconditioner", "c8_preconditioner_info", "c8_linalg_invali
 
 
 def _ctx_set_preconditioner(self, kind="amg", nu_pre=2, nu_post=2, omega=0.7, over_correction=1.6,
-                            coarsest_max_nodes=40, max_aggregate_size=8, coarse_aggregate_size=8, coarse_nu=0):
-    """right preconditioner of gmres(): 'amg' (aggregation multigrid, default) or 'block_jacobi'"""
+                            coarsest_max_nodes=40, max_aggregate_size=8, coarse_aggregate_size=8, coarse_nu=0,
+                            distributed=True, replicate_max_nodes=30000):
+    """right preconditioner of gmres(): 'amg' (aggregation multigrid, default) or 'block_jacobi'.
+    distributed: on a partitioned run the hierarchy spans the parts (False: each part's owned block);
+    replicate_max_nodes: a level with at most this many nodes globally is replicated on every part"""
     opts = np.array([nu_pre, nu_post, omega, over_correction, coarsest_max_nodes, max_aggregate_size,
-                     coarse_aggregate_size, coarse_nu],
+                     coarse_aggregate_size, coarse_nu, 1.0 if distributed else 0.0, replicate_max_nodes],
                     dtype=np.float64)
     self._check(self.lib.c8_set_preconditioner(self.h, {"block_jacobi": 0, "amg": 1}[kind], _hp(opts),
                                                int(opts.size)))

@@ -1,5 +1,6 @@
 // Aggregation multigrid preconditioner (see amg.cuh).
 #include "amg.cuh"
+#include "comm.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -38,7 +39,7 @@ __global__ void k_smooth(const int* __restrict__ rowptr, const int* __restrict__
                          const F* __restrict__ vals, const double* __restrict__ dinv,
                          const double* __restrict__ b, const double* __restrict__ xin,
                          double* __restrict__ xout, const int* __restrict__ agg,
-                         const double* __restrict__ xc, double pscale, double omega, int n) {
+                         const double* __restrict__ xc, double pscale, double omega, int n, int npc) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int node = gid >> 2;
   const int lane4 = gid & 3;
@@ -53,10 +54,11 @@ __global__ void k_smooth(const int* __restrict__ rowptr, const int* __restrict__
     const int col = __ldg(&colind[k]);
     const F* a = vals + (size_t(k) * NB + row) * NB;
     const double* xv = xin + size_t(col) * NB;
-    // ghost columns of a partition (col >= n) carry no coarse correction; the index is clamped
-    // rather than branched around because the compiler may speculate a read-only load
-    const double ps = (PROLONG && col < n) ? pscale : 0.0;
-    const double* pc = PROLONG ? xc + size_t(agg[col < n ? col : 0]) * NB : nullptr;
+    // columns >= npc carry no coarse correction (the ghost columns of a part whose hierarchy acts
+    // on its owned block only; npc = all columns when the hierarchy spans the parts); the index is
+    // clamped rather than branched around because the compiler may speculate a read-only load
+    const double ps = (PROLONG && col < npc) ? pscale : 0.0;
+    const double* pc = PROLONG ? xc + size_t(agg[col < npc ? col : 0]) * NB : nullptr;
 #pragma unroll
     for (int c = 0; c < NB; ++c) {
       double v = __ldg(&xv[c]);
@@ -286,72 +288,6 @@ static void amg_dbg(cudaStream_t s, const char* what, int level) {
     default: { constexpr int NB = 4; CALL; } break; \
   }
 
-// ---- host: aggregation ----------------------------------------------------------------------
-// Greedy aggregation on the node graph (root node + all its neighbours when none of them is
-// taken yet; leftovers join the neighbouring aggregate they are most connected to).
-static void aggregate(int n, const std::vector<int>& rowptr, const std::vector<int>& colind,
-                      std::vector<int>& agg, int& nc, int max_size) {
-  agg.assign(n, -1);
-  nc = 0;
-  if (max_size <= 0) {
-    // phase 1: a root and ALL its neighbours when none of them is taken yet
-    for (int i = 0; i < n; ++i) {
-      if (agg[i] != -1) continue;
-      bool free_nbrs = true;
-      for (int k = rowptr[i]; k < rowptr[i + 1] && free_nbrs; ++k)
-        if (agg[colind[k]] != -1) free_nbrs = false;
-      if (!free_nbrs) continue;
-      agg[i] = nc;
-      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) agg[colind[k]] = nc;
-      ++nc;
-    }
-  } else {
-    // bounded aggregates: a free root takes the free neighbours that share the most neighbours
-    // with it (a compact clump), up to max_size nodes
-    std::vector<std::pair<int, int>> cand;
-    std::vector<char> mark(n, 0);
-    for (int i = 0; i < n; ++i) {
-      if (agg[i] != -1) continue;
-      cand.clear();
-      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) mark[colind[k]] = 1;
-      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
-        const int j = colind[k];
-        if (j == i || agg[j] != -1) continue;
-        int common = 0;
-        for (int k2 = rowptr[j]; k2 < rowptr[j + 1]; ++k2) common += mark[colind[k2]];
-        cand.emplace_back(-common, j);
-      }
-      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) mark[colind[k]] = 0;
-      if (int(cand.size()) + 1 < (max_size + 1) / 2) continue;  // too few free neighbours: leftover
-      std::sort(cand.begin(), cand.end());
-      agg[i] = nc;
-      for (int q = 0; q < int(cand.size()) && q < max_size - 1; ++q) agg[cand[q].second] = nc;
-      ++nc;
-    }
-  }
-  std::vector<int> agg2 = agg;
-  for (int i = 0; i < n; ++i) {
-    if (agg[i] != -1) continue;
-    int best = -1, best_cnt = 0;
-    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
-      const int a = agg[colind[k]];
-      if (a == -1) continue;
-      int c = 0;
-      for (int k2 = rowptr[i]; k2 < rowptr[i + 1]; ++k2) c += (agg[colind[k2]] == a);
-      if (c > best_cnt || (c == best_cnt && a < best)) { best_cnt = c; best = a; }
-    }
-    agg2[i] = best;
-  }
-  agg.swap(agg2);
-  for (int i = 0; i < n; ++i) {
-    if (agg[i] != -1) continue;
-    agg[i] = nc;
-    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k)
-      if (agg[colind[k]] == -1) agg[colind[k]] = nc;
-    ++nc;
-  }
-}
-
 template <class T>
 static int upload(c8_ctx* ctx, const std::vector<T>& h, T** d) {
   *d = nullptr;
@@ -372,87 +308,99 @@ Amg::~Amg() {
   if (r0_) cudaFree(r0_);
 }
 
+// the build's collectives on top of the context's transport: host vectors staged through a device buffer
+struct DeviceCollectives : AmgCollectives {
+  c8_ctx* ctx = nullptr;
+  double* d = nullptr;
+  size_t cap = 0;
+  bool ok = true;
+  ~DeviceCollectives() override { if (d) cudaFree(d); }
+  double* buf(size_t n) {
+    if (n > cap) {
+      if (d) cudaFree(d);
+      d = nullptr; cap = 0;
+      if (cudaMalloc(&d, (n + 1024) * sizeof(double)) != cudaSuccess) { ok = false; return nullptr; }
+      cap = n + 1024;
+    }
+    return d;
+  }
+  template <class F>
+  void round_trip(std::vector<double>& v, F&& op) {
+    if (v.empty()) return;   // the same on every part
+    double* p = buf(v.size());
+    if (!p) return;
+    cudaStream_t s = ctx->stream;
+    cudaMemcpyAsync(p, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice, s);
+    op(p);
+    cudaMemcpyAsync(v.data(), p, v.size() * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) ok = false;
+  }
+  void allreduce(std::vector<double>& v) override {
+    round_trip(v, [&](double* p) { ctx->allreduce_cb(ctx->comm_user, p, int(v.size())); });
+  }
+  void halo(int level, std::vector<double>& v) override {
+    round_trip(v, [&](double* p) { comm_halo_level(ctx, level, p, 1); });
+  }
+  int add_level(const HaloPlanHost& plan) override {
+    const int id = comm_add_level(ctx, plan);
+    if (id < 0) ok = false;
+    return id;
+  }
+  HaloPlanHost plan(int level) const override { return comm_plan(ctx, level); }
+};
+
 int Amg::build() {
   nb_ = ctx_->kt->nb;
   const int n0 = ctx_->n_owned_nodes;
-  // level-0 graph restricted to owned rows x owned columns (host copies of the context's pattern)
-  std::vector<int> rowptr(n0 + 1, 0), colind;
-  std::vector<int> blk;  // fine block id of each kept entry
-  colind.reserve(ctx_->h_colind.size());
-  blk.reserve(ctx_->h_colind.size());
-  for (int i = 0; i < n0; ++i) {
-    for (int k = ctx_->h_rowptr[i]; k < ctx_->h_rowptr[i + 1]; ++k) {
-      const int j = ctx_->h_colind[k];
-      if (j < n0) { colind.push_back(j); blk.push_back(k); }
-    }
-    rowptr[i + 1] = int(colind.size());
-  }
+  // the hierarchy spans the parts when one of the library's transports is bound (amg_host.hpp);
+  // with the caller's own hooks it acts on the owned x owned block of the part
+  dist_ = opt.distributed && comm_library_transport(ctx_);
+  comm_drop_levels(ctx_);
+  DeviceCollectives dc;
+  dc.ctx = ctx_; dc.rank = comm_rank(ctx_); dc.nranks = comm_nranks(ctx_);
+  AmgBuildOptions bo;
+  bo.coarsest_max_nodes = opt.coarsest_max_nodes; bo.max_levels = opt.max_levels;
+  bo.max_aggregate_size = opt.max_aggregate_size; bo.coarse_aggregate_size = opt.coarse_aggregate_size;
+  bo.replicate_max_nodes = opt.replicate_max_nodes;
+  std::vector<AmgLevelHost> hl;
+  amg_build_host(n0, ctx_->n_nodes, ctx_->h_rowptr.data(), ctx_->h_colind.data(), dist_ ? &dc : nullptr, 0, bo, hl);
+  if (!dc.ok) return fail(ctx_, C8_ERR_CUDA, "multigrid build: a collective of the hierarchy build failed");
   lv_.clear();
-  AmgLevel L0;
-  L0.n = n0; L0.nnzb = ctx_->nnzb; L0.ld = ctx_->n_nodes;
-  L0.rowptr = ctx_->d_rowptr; L0.colind = ctx_->d_colind;
-  lv_.push_back(L0);
-  int n = n0;
-  while (n > opt.coarsest_max_nodes && int(lv_.size()) < opt.max_levels) {
-    std::vector<int> agg;
-    int nc = 0;
-    aggregate(n, rowptr, colind, agg, nc, lv_.size() == 1 ? opt.max_aggregate_size : opt.coarse_aggregate_size);
-    if (nc >= n) break;  // no coarsening possible
-    // coarse pattern: unique (agg[i], agg[j]) pairs, and for each the fine blocks summed into it
-    std::vector<std::pair<uint64_t, int>> keys;
-    keys.reserve(colind.size());
-    for (int i = 0; i < n; ++i)
-      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k)
-        keys.emplace_back((uint64_t(uint32_t(agg[i])) << 32) | uint32_t(agg[colind[k]]), blk[k]);
-    std::sort(keys.begin(), keys.end());
-    std::vector<int> c_rowptr(nc + 1, 0), c_colind, cptr(1, 0), cmem;
-    cmem.reserve(keys.size());
-    for (size_t q = 0; q < keys.size();) {
-      size_t e = q;
-      while (e < keys.size() && keys[e].first == keys[q].first) { cmem.push_back(keys[e].second); ++e; }
-      const int I = int(keys[q].first >> 32), J = int(keys[q].first & 0xffffffffu);
-      c_colind.push_back(J);
-      c_rowptr[I + 1] += 1;
-      cptr.push_back(int(cmem.size()));
-      q = e;
+  lv_.resize(hl.size());
+  int rc;
+  for (size_t l = 0; l < hl.size(); ++l) {
+    AmgLevel& L = lv_[l];
+    const AmgLevelHost& H = hl[l];
+    L.n = H.n; L.halo_level = H.halo_level;
+    if (l == 0) {
+      L.ld = ctx_->n_nodes; L.nnzb = ctx_->nnzb;
+      L.rowptr = ctx_->d_rowptr; L.colind = ctx_->d_colind;
+    } else {
+      L.ld = H.ld; L.nnzb = H.nnzb;
+      if ((rc = upload(ctx_, H.rowptr, &L.own_rowptr)) != C8_OK) return rc;
+      if ((rc = upload(ctx_, H.colind, &L.own_colind)) != C8_OK) return rc;
+      L.rowptr = L.own_rowptr; L.colind = L.own_colind;
+      const size_t nv = size_t(L.ld > 0 ? L.ld : 1) * nb_;
+      C8_CUDA(ctx_, cudaMalloc(&L.own_vals, size_t(L.nnzb > 0 ? L.nnzb : 1) * nb_ * nb_ * sizeof(double)));
+      L.vals = L.own_vals;
+      C8_CUDA(ctx_, cudaMalloc(&L.x, nv * sizeof(double)));
+      C8_CUDA(ctx_, cudaMalloc(&L.b, nv * sizeof(double)));
+      C8_CUDA(ctx_, cudaMalloc(&L.r, nv * sizeof(double)));
+      C8_CUDA(ctx_, cudaMemsetAsync(L.x, 0, nv * sizeof(double), ctx_->stream));
+      C8_CUDA(ctx_, cudaMemsetAsync(L.b, 0, nv * sizeof(double), ctx_->stream));
+      C8_CUDA(ctx_, cudaMemsetAsync(L.r, 0, nv * sizeof(double), ctx_->stream));
     }
-    for (int I = 0; I < nc; ++I) c_rowptr[I + 1] += c_rowptr[I];
-    std::vector<int> aggptr(nc + 1, 0), aggmem(n);
-    for (int i = 0; i < n; ++i) aggptr[agg[i] + 1] += 1;
-    for (int I = 0; I < nc; ++I) aggptr[I + 1] += aggptr[I];
-    {
-      std::vector<int> pos(aggptr.begin(), aggptr.end() - 1);
-      for (int i = 0; i < n; ++i) aggmem[pos[agg[i]]++] = i;
+    if (l + 1 < hl.size()) {
+      L.nc = H.nc_rows;
+      L.npc = int(H.agg.size());
+      L.coarse_replicated = H.coarse_replicated;
+      L.n_cmem = int(H.cmem.size());
+      if ((rc = upload(ctx_, H.agg, &L.agg)) != C8_OK) return rc;
+      if ((rc = upload(ctx_, H.aggptr, &L.aggptr)) != C8_OK) return rc;
+      if ((rc = upload(ctx_, H.aggmem, &L.aggmem)) != C8_OK) return rc;
+      if ((rc = upload(ctx_, H.cptr, &L.cptr)) != C8_OK) return rc;
+      if ((rc = upload(ctx_, H.cmem, &L.cmem)) != C8_OK) return rc;
     }
-    AmgLevel& F = lv_.back();
-    F.nc = nc;
-    F.n_cmem = int(cmem.size());
-    int rc;
-    if ((rc = upload(ctx_, agg, &F.agg)) != C8_OK) return rc;
-    if ((rc = upload(ctx_, aggptr, &F.aggptr)) != C8_OK) return rc;
-    if ((rc = upload(ctx_, aggmem, &F.aggmem)) != C8_OK) return rc;
-    if ((rc = upload(ctx_, cptr, &F.cptr)) != C8_OK) return rc;
-    if ((rc = upload(ctx_, cmem, &F.cmem)) != C8_OK) return rc;
-    AmgLevel C;
-    C.n = nc; C.ld = nc; C.nnzb = int(c_colind.size());
-    if ((rc = upload(ctx_, c_rowptr, &C.own_rowptr)) != C8_OK) return rc;
-    if ((rc = upload(ctx_, c_colind, &C.own_colind)) != C8_OK) return rc;
-    C.rowptr = C.own_rowptr; C.colind = C.own_colind;
-    const size_t nv = size_t(nc) * nb_;
-    C8_CUDA(ctx_, cudaMalloc(&C.own_vals, size_t(C.nnzb) * nb_ * nb_ * sizeof(double)));
-    C.vals = C.own_vals;
-    C8_CUDA(ctx_, cudaMalloc(&C.x, nv * sizeof(double)));
-    C8_CUDA(ctx_, cudaMalloc(&C.b, nv * sizeof(double)));
-    C8_CUDA(ctx_, cudaMalloc(&C.r, nv * sizeof(double)));
-    lv_.push_back(C);
-    // next level's graph: block ids are now the coarse blocks themselves
-    rowptr.swap(c_rowptr);
-    colind.swap(c_colind);
-    blk.resize(colind.size());
-    std::iota(blk.begin(), blk.end(), 0);
-    n = nc;
-  }
-  for (AmgLevel& L : lv_) {
     C8_CUDA(ctx_, cudaMalloc(&L.dinv, size_t(L.n > 0 ? L.n : 1) * nb_ * nb_ * sizeof(double)));
     const size_t nx = size_t(L.ld > 0 ? L.ld : 1) * nb_;
     C8_CUDA(ctx_, cudaMalloc(&L.xt, nx * sizeof(double)));
@@ -463,7 +411,7 @@ int Amg::build() {
   C8_CUDA(ctx_, cudaMalloc(&r0_, size_t(ctx_->n_nodes) * nb_ * sizeof(double)));
   C8_CUDA(ctx_, cudaMemsetAsync(r0_, 0, size_t(ctx_->n_nodes) * nb_ * sizeof(double), ctx_->stream));
   nd_ = 0;
-  if (lv_.size() > 1 && lv_.back().n * nb_ <= 1024) {
+  if (lv_.size() > 1 && lv_.back().halo_level < 0 && lv_.back().n > 0 && lv_.back().n * nb_ <= 1024) {
     nd_ = lv_.back().n * nb_;
     C8_CUDA(ctx_, cudaMalloc(&dense_, size_t(nd_) * 2 * nd_ * sizeof(double)));
   }
@@ -483,14 +431,19 @@ int Amg::setup(const double* A) {
     k_to_float<<<148 * 8, 256, 0, s>>>(A, lv_[0].vals32, size_t(lv_[0].nnzb) * nb_ * nb_);
   for (size_t l = 0; l < lv_.size(); ++l) {
     AmgLevel& L = lv_[l];
-    if (L.n == 0) continue;
-    const int gj = (L.n + 127) / 128;
-    C8_NB_SWITCH(nb_, (k_block_jacobi_setup<NB><<<gj, 128, 0, s>>>(L.rowptr, L.colind, L.vals, L.dinv, L.n)));
+    if (L.n > 0) {
+      const int gj = (L.n + 127) / 128;
+      C8_NB_SWITCH(nb_, (k_block_jacobi_setup<NB><<<gj, 128, 0, s>>>(L.rowptr, L.colind, L.vals, L.dinv, L.n)));
+    }
     if (l + 1 < lv_.size()) {
       AmgLevel& C = lv_[l + 1];
       const long long work = (long long)C.nnzb * nb_ * nb_;
-      const unsigned g = unsigned((work + 255) / 256);
-      C8_NB_SWITCH(nb_, (k_galerkin<NB><<<g, 256, 0, s>>>(L.cptr, L.cmem, L.vals, C.own_vals, C.nnzb)));
+      if (work > 0) {
+        const unsigned g = unsigned((work + 255) / 256);
+        C8_NB_SWITCH(nb_, (k_galerkin<NB><<<g, 256, 0, s>>>(L.cptr, L.cmem, L.vals, C.own_vals, C.nnzb)));
+        // a replicated level: every part computed the blocks of its own rows (zeros elsewhere)
+        if (L.coarse_replicated) ctx_->allreduce_cb(ctx_->comm_user, C.own_vals, int(work));
+      }
     }
   }
   if (nd_ > 0) {
@@ -502,6 +455,11 @@ int Amg::setup(const double* A) {
   return C8_OK;
 }
 
+// fills the ghost entries of a level's vector (no-op on serial / replicated levels)
+void Amg::halo(int l, const double* v) {
+  if (lv_[l].halo_level >= 0) comm_halo_level(ctx_, lv_[l].halo_level, const_cast<double*>(v), nb_);
+}
+
 void Amg::smooth(int l, const double* b, double* x, int sweeps, bool zero_guess) {
   AmgLevel& L = lv_[l];
   cudaStream_t s = ctx_->stream;
@@ -509,17 +467,21 @@ void Amg::smooth(int l, const double* b, double* x, int sweeps, bool zero_guess)
   const int g = (L.n * nb_ + 127) / 128;
   for (int k = 0; k < sweeps; ++k) {
     if (k == 0 && zero_guess) {
-      C8_NB_SWITCH(nb_, (k_jacobi_update<NB><<<g, 128, 0, s>>>(L.dinv, b, x, opt.omega, 1, L.n)));
+      if (L.n > 0) { C8_NB_SWITCH(nb_, (k_jacobi_update<NB><<<g, 128, 0, s>>>(L.dinv, b, x, opt.omega, 1, L.n))); }
     } else {
+      halo(l, x);
+      if (L.n == 0) continue;
       C8_NB_SWITCH(nb_, (k_bsr_residual<NB, double><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals, x, b, r, L.n)));
       C8_NB_SWITCH(nb_, (k_jacobi_update<NB><<<g, 128, 0, s>>>(L.dinv, r, x, opt.omega, 0, L.n)));
     }
   }
 }
 
-// one out-of-place sweep on level l (fp32 matrix copy on the fine level when present)
+// one out-of-place sweep on level l (fp32 matrix copy on the fine level when present); the ghost
+// entries of xin (and of xc) must be current
 void Amg::sweep(int l, const double* b, const double* xin, double* xout, const double* xc) {
   AmgLevel& L = lv_[l];
+  if (L.n == 0) return;
   cudaStream_t s = ctx_->stream;
   const int g = (L.n * 4 + 127) / 128;
   const double oc = opt.over_correction, om = opt.omega;
@@ -530,21 +492,24 @@ void Amg::sweep(int l, const double* b, const double* xin, double* xout, const d
     return;
   }
   if (L.vals32) {
-    if (xc) { C8_NB_SWITCH(nb_, (k_smooth<NB, float, true><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals32, L.dinv, b, xin, xout, L.agg, xc, oc, om, L.n))); }
-    else { C8_NB_SWITCH(nb_, (k_smooth<NB, float, false><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals32, L.dinv, b, xin, xout, nullptr, nullptr, 0.0, om, L.n))); }
+    if (xc) { C8_NB_SWITCH(nb_, (k_smooth<NB, float, true><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals32, L.dinv, b, xin, xout, L.agg, xc, oc, om, L.n, L.npc))); }
+    else { C8_NB_SWITCH(nb_, (k_smooth<NB, float, false><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals32, L.dinv, b, xin, xout, nullptr, nullptr, 0.0, om, L.n, 0))); }
   } else {
-    if (xc) { C8_NB_SWITCH(nb_, (k_smooth<NB, double, true><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, L.agg, xc, oc, om, L.n))); }
-    else { C8_NB_SWITCH(nb_, (k_smooth<NB, double, false><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, nullptr, nullptr, 0.0, om, L.n))); }
+    if (xc) { C8_NB_SWITCH(nb_, (k_smooth<NB, double, true><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, L.agg, xc, oc, om, L.n, L.npc))); }
+    else { C8_NB_SWITCH(nb_, (k_smooth<NB, double, false><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, nullptr, nullptr, 0.0, om, L.n, 0))); }
   }
 }
 
 // V(nu_pre, nu_post) cycle; the result lands in xout.  Launches per level: nu_pre + nu_post sweeps
 // (the first from a zero guess is a block-diagonal product, the first after the coarse solve carries
-// the prolongation) + residual + restriction.
+// the prolongation) + residual + restriction.  On a partitioned level every sweep / residual is
+// preceded by the halo copy of its input vector; the restricted right-hand side of a replicated
+// coarse level is summed over the parts (each part fills the rows of its own aggregates).
 void Amg::cycle(int l, const double* b, double* xout) {
   AmgLevel& L = lv_[l];
   cudaStream_t s = ctx_->stream;
-  if (L.n == 0) return;
+  const bool part = L.halo_level >= 0;
+  if (L.n == 0 && !part) return;
   const bool coarsest = (l + 1 == int(lv_.size()));
   if (coarsest) {
     if (nd_ > 0 && l > 0) {
@@ -561,28 +526,36 @@ void Amg::cycle(int l, const double* b, double* xout) {
   auto buf = [&](int w) { return bufs[(writes - 1 - w) & 1]; };  // the last write goes to xout
   const int g = (L.n * nb_ + 127) / 128;
   amg_dbg(s, "enter", l);
-  C8_NB_SWITCH(nb_, (k_jacobi_update<NB><<<g, 128, 0, s>>>(L.dinv, b, buf(0), opt.omega, 1, L.n)));
+  if (L.n > 0) { C8_NB_SWITCH(nb_, (k_jacobi_update<NB><<<g, 128, 0, s>>>(L.dinv, b, buf(0), opt.omega, 1, L.n))); }
   amg_dbg(s, "jacobi zero-guess", l);
-  for (int w = 1; w < nu1; ++w) { sweep(l, b, buf(w - 1), buf(w), nullptr); amg_dbg(s, "pre sweep", l); }
+  for (int w = 1; w < nu1; ++w) { halo(l, buf(w - 1)); sweep(l, b, buf(w - 1), buf(w), nullptr); amg_dbg(s, "pre sweep", l); }
   const double* cur = buf(nu1 - 1);
+  halo(l, cur);
   double* r = (l == 0) ? r0_ : L.r;
-  if (l > 0) { C8_NB_SWITCH(nb_, (k_smooth_warp<NB, false, true><<<(L.n * 32 + 127) / 128, 128, 0, s>>>(L.rowptr, L.colind, L.vals, nullptr, b, cur, r, nullptr, nullptr, 0.0, 0.0, L.n))); }
-  else if (L.vals32) { C8_NB_SWITCH(nb_, (k_bsr_residual<NB, float><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals32, cur, b, r, L.n))); }
-  else { C8_NB_SWITCH(nb_, (k_bsr_residual<NB, double><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals, cur, b, r, L.n))); }
+  if (L.n > 0) {
+    if (l > 0) { C8_NB_SWITCH(nb_, (k_smooth_warp<NB, false, true><<<(L.n * 32 + 127) / 128, 128, 0, s>>>(L.rowptr, L.colind, L.vals, nullptr, b, cur, r, nullptr, nullptr, 0.0, 0.0, L.n))); }
+    else if (L.vals32) { C8_NB_SWITCH(nb_, (k_bsr_residual<NB, float><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals32, cur, b, r, L.n))); }
+    else { C8_NB_SWITCH(nb_, (k_bsr_residual<NB, double><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals, cur, b, r, L.n))); }
+  }
   amg_dbg(s, "residual", l);
   AmgLevel& C = lv_[l + 1];
-  const int gc = (C.n * nb_ + 127) / 128;
-  C8_NB_SWITCH(nb_, (k_restrict<NB><<<gc, 128, 0, s>>>(L.aggptr, L.aggmem, r, C.b, C.n)));
+  if (C.n > 0) {
+    const int gc = (C.n * nb_ + 127) / 128;
+    C8_NB_SWITCH(nb_, (k_restrict<NB><<<gc, 128, 0, s>>>(L.aggptr, L.aggmem, r, C.b, C.n)));
+    if (L.coarse_replicated) ctx_->allreduce_cb(ctx_->comm_user, C.b, C.n * nb_);
+  }
   amg_dbg(s, "restrict", l);
   cycle(l + 1, C.b, C.x);
+  halo(l + 1, C.x);   // the prolongation reads the aggregates of ghost columns
   amg_dbg(s, "coarse cycle", l);
-  sweep(l, b, cur, buf(nu1), C.x);
+  sweep(l, b, cur, buf(nu1), C.x);   // the ghost entries of cur are still current
   amg_dbg(s, "prolong sweep", l);
-  for (int w = nu1 + 1; w < writes; ++w) { sweep(l, b, buf(w - 1), buf(w), nullptr); amg_dbg(s, "post sweep", l); }
+  for (int w = nu1 + 1; w < writes; ++w) { halo(l, buf(w - 1)); sweep(l, b, buf(w - 1), buf(w), nullptr); amg_dbg(s, "post sweep", l); }
 }
 
 void Amg::apply(const double* r, double* z) {
-  // ghost entries of z stay zero: the preconditioner acts on the owned x owned block of the part
+  // ghost entries of z: zero when the hierarchy acts on the owned block only; GMRES refreshes them
+  // by its own halo copy before the SpMV either way
   if (lv_[0].ld > lv_[0].n)
     cudaMemsetAsync(z + size_t(lv_[0].n) * nb_, 0, size_t(lv_[0].ld - lv_[0].n) * nb_ * sizeof(double),
                     ctx_->stream);

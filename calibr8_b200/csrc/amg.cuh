@@ -13,7 +13,10 @@
 //            formulation), nu_pre / nu_post sweeps;
 //   cycle    V, optionally over-corrected.
 // The preconditioner is a fixed linear operator, so plain right-preconditioned GMRES applies.
-// In a partitioned run it acts on the owned x owned diagonal block of the part (no communication).
+// In a partitioned run with one of the library's transports (NCCL / host-staged) the hierarchy
+// spans the parts: aggregates stay inside a part, every level keeps an owned + ghost numbering with
+// its own halo plan, and once a level is small it is replicated on every part (amg_host.hpp).  With
+// the caller's own communication hooks it acts on the owned x owned block of the part.
 #pragma once
 #include <vector>
 
@@ -24,7 +27,8 @@ namespace c8 {
 struct AmgLevel {
   int n = 0;        // nodes = block rows
   int nnzb = 0;
-  int ld = 0;       // nodes in a vector of this level (level 0: all local nodes incl. ghosts)
+  int ld = 0;       // nodes in a vector of this level (owned + ghost)
+  int halo_level = -1;   // >= 0: partitioned level, plan id for comm_halo_level
   const int* rowptr = nullptr;   // device
   const int* colind = nullptr;
   const double* vals = nullptr;  // level 0: the caller's matrix
@@ -36,8 +40,10 @@ struct AmgLevel {
   double* xt = nullptr;          // ping-pong partner of x for the out-of-place sweeps
   float* vals32 = nullptr;       // fp32 copy of the fine-level values (level 0 only)
   // transfer to the next coarser level
-  int nc = 0;
-  int* agg = nullptr;                      // [n] aggregate of a node
+  int nc = 0;                              // rows of the coarse level
+  int npc = 0;                             // columns with an aggregate (n, or ld when the hierarchy spans the parts)
+  bool coarse_replicated = false;          // coarse level global + replicated: values and rhs summed over the parts
+  int* agg = nullptr;                      // [npc] aggregate of a node = index into the coarse vector
   int *aggptr = nullptr, *aggmem = nullptr;  // members of an aggregate
   int *cptr = nullptr, *cmem = nullptr;      // fine blocks summed into a coarse block
   int n_cmem = 0;
@@ -53,6 +59,8 @@ struct AmgOptions {
   int coarse_nu = 0;            // sweeps per side on levels >= 1 (0: same as the fine level)
   bool fp32_fine_level = true;  // the fine-level sweeps read an fp32 copy of the matrix
   int max_aggregate_size = 8;  // bounded compact aggregates (0: root + all neighbours, ~25 nodes in 3-D)
+  bool distributed = true;      // partitioned run: hierarchy across the parts (library transports only)
+  int replicate_max_nodes = 30000;  // a level with at most this many nodes GLOBALLY is replicated
 };
 
 class Amg {
@@ -66,13 +74,16 @@ class Amg {
   int num_levels() const { return int(lv_.size()); }
   const std::vector<AmgLevel>& levels() const { return lv_; }
   double operator_complexity() const;
+  bool distributed() const { return dist_; }
 
  private:
   void cycle(int l, const double* b, double* x);
   void smooth(int l, const double* b, double* x, int sweeps, bool zero_guess);
   void sweep(int l, const double* b, const double* xin, double* xout, const double* xc);
+  void halo(int l, const double* v);
   c8_ctx* ctx_;
   int nb_ = 0;
+  bool dist_ = false;
   std::vector<AmgLevel> lv_;
   int nd_ = 0;                 // coarsest dense size (dofs)
   double* dense_ = nullptr;    // [nd][2 nd] work, inverse in the right half

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "c8b200.h"
+#include "comm.cuh"
 #include "context.cuh"
 
 namespace c8 {
@@ -82,6 +83,13 @@ struct Comm {
   double* h_send = nullptr;
   double* h_recv = nullptr;
   std::string last;
+  // plans of the coarser multigrid levels (amg_host.hpp); level l >= 1 is levels[l - 1].  They share
+  // the neighbour list and the send/staging buffers of the level-0 plan (a coarse level never sends
+  // more nodes to a neighbour than the fine level does)
+  HaloPlanHost plan0;
+  struct Level { HaloPlanHost plan; int* d_send_nodes = nullptr; };
+  std::vector<Level> levels;
+  bool library_transport = false;   // NCCL or host-staged (not the caller's own c8_set_comm hooks)
   // statistics
   long long n_halo = 0, n_allreduce = 0, halo_bytes = 0;
 };
@@ -96,24 +104,30 @@ __global__ void k_halo_pack(const double* __restrict__ v, const int* __restrict_
   out[i] = v[size_t(__ldg(&nodes[k])) * nb + c];
 }
 
-static void halo_nccl(void* user, double* vec, int nb) {
-  Comm& c = *static_cast<Comm*>(user);
+// one halo copy over NCCL for any level's plan: pack -> grouped send/recv straight into the ghost range
+static void halo_nccl_plan(Comm& c, const int* d_send_nodes, const std::vector<int>& send_ptr,
+                           const std::vector<int>& recv_ptr, int n_owned, double* vec, int nb) {
   if (c.n_nbr == 0) return;
   cudaStream_t s = c.ctx->stream;
-  if (c.n_send)
-    k_halo_pack<<<(c.n_send * nb + 255) / 256, 256, 0, s>>>(vec, c.d_send_nodes, c.d_sendbuf, c.n_send, nb);
+  const int n_send = send_ptr[c.n_nbr], n_recv = recv_ptr[c.n_nbr];
+  if (n_send)
+    k_halo_pack<<<(n_send * nb + 255) / 256, 256, 0, s>>>(vec, d_send_nodes, c.d_sendbuf, n_send, nb);
   g_nccl.GroupStart();
   for (int k = 0; k < c.n_nbr; ++k) {
-    const int ns = c.send_ptr[k + 1] - c.send_ptr[k], nr = c.recv_ptr[k + 1] - c.recv_ptr[k];
-    if (ns) g_nccl.Send(c.d_sendbuf + size_t(c.send_ptr[k]) * nb, size_t(ns) * nb, ncclDouble, c.nbr_rank[k], c.nccl, s);
+    const int ns = send_ptr[k + 1] - send_ptr[k], nr = recv_ptr[k + 1] - recv_ptr[k];
+    if (ns) g_nccl.Send(c.d_sendbuf + size_t(send_ptr[k]) * nb, size_t(ns) * nb, ncclDouble, c.nbr_rank[k], c.nccl, s);
     if (nr)
-      g_nccl.Recv(vec + (size_t(c.ctx->n_owned_nodes) + c.recv_ptr[k]) * nb, size_t(nr) * nb, ncclDouble,
-                  c.nbr_rank[k], c.nccl, s);
+      g_nccl.Recv(vec + (size_t(n_owned) + recv_ptr[k]) * nb, size_t(nr) * nb, ncclDouble, c.nbr_rank[k], c.nccl, s);
   }
   ncclResult_t r = g_nccl.GroupEnd();
   if (r != ncclSuccess) c.last = g_nccl.GetErrorString(r);
   ++c.n_halo;
-  c.halo_bytes += (long long)(c.n_send + c.n_recv) * nb * 8;
+  c.halo_bytes += (long long)(n_send + n_recv) * nb * 8;
+}
+
+static void halo_nccl(void* user, double* vec, int nb) {
+  Comm& c = *static_cast<Comm*>(user);
+  halo_nccl_plan(c, c.d_send_nodes, c.send_ptr, c.recv_ptr, c.ctx->n_owned_nodes, vec, nb);
 }
 
 static void allreduce_nccl(void* user, double* buf, int n) {
@@ -153,10 +167,81 @@ static void allreduce_host(void* user, double* buf, int n) {
   ++c.n_allreduce;
 }
 
+// a coarse level through the host-staged transport: the caller's exchange function only knows the
+// level-0 message sizes, so the (shorter) coarse messages travel in the leading part of each
+// neighbour's level-0 slot
+static void halo_host_level(Comm& c, const Comm::Level& L, double* vec, int nb) {
+  if (c.n_nbr == 0) return;
+  cudaStream_t s = c.ctx->stream;
+  const HaloPlanHost& P = L.plan;
+  const int n_send = P.n_send(), n_recv = P.n_recv();
+  std::vector<double> tmp(size_t(std::max(n_send, n_recv) + 1) * nb);
+  if (n_send) {
+    k_halo_pack<<<(n_send * nb + 255) / 256, 256, 0, s>>>(vec, L.d_send_nodes, c.d_sendbuf, n_send, nb);
+    cudaMemcpyAsync(tmp.data(), c.d_sendbuf, size_t(n_send) * nb * sizeof(double), cudaMemcpyDeviceToHost, s);
+  }
+  cudaStreamSynchronize(s);
+  for (int k = 0; k < c.n_nbr; ++k)
+    std::memcpy(c.h_send + size_t(c.send_ptr[k]) * nb, tmp.data() + size_t(P.send_ptr[k]) * nb,
+                size_t(P.send_ptr[k + 1] - P.send_ptr[k]) * nb * sizeof(double));
+  c.exchange(c.user, c.h_send, c.h_recv, nb);
+  for (int k = 0; k < c.n_nbr; ++k)
+    std::memcpy(tmp.data() + size_t(P.recv_ptr[k]) * nb, c.h_recv + size_t(c.recv_ptr[k]) * nb,
+                size_t(P.recv_ptr[k + 1] - P.recv_ptr[k]) * nb * sizeof(double));
+  if (n_recv)
+    cudaMemcpyAsync(vec + size_t(P.n_owned) * nb, tmp.data(), size_t(n_recv) * nb * sizeof(double),
+                    cudaMemcpyHostToDevice, s);
+  cudaStreamSynchronize(s);
+  ++c.n_halo;
+  c.halo_bytes += (long long)(n_send + n_recv) * nb * 8;
+}
+
+static void drop_levels(Comm& c) {
+  for (Comm::Level& L : c.levels)
+    if (L.d_send_nodes) cudaFree(L.d_send_nodes);
+  c.levels.clear();
+}
+
+// ---- services for the partitioned multigrid (comm.cuh)
+bool comm_library_transport(c8_ctx* ctx) {
+  auto it = g_comm.find(ctx);
+  return it != g_comm.end() && it->second.library_transport && it->second.nranks > 1 &&
+         ctx->halo_cb != nullptr && ctx->allreduce_cb != nullptr;
+}
+int comm_rank(c8_ctx* ctx) { auto it = g_comm.find(ctx); return it == g_comm.end() ? 0 : it->second.rank; }
+int comm_nranks(c8_ctx* ctx) { auto it = g_comm.find(ctx); return it == g_comm.end() ? 1 : it->second.nranks; }
+HaloPlanHost comm_plan(c8_ctx* ctx, int level) {
+  Comm& c = g_comm[ctx];
+  return level == 0 ? c.plan0 : c.levels[level - 1].plan;
+}
+int comm_add_level(c8_ctx* ctx, const HaloPlanHost& plan) {
+  Comm& c = g_comm[ctx];
+  Comm::Level L;
+  L.plan = plan;
+  if (plan.n_send()) {
+    if (cudaMalloc(&L.d_send_nodes, plan.n_send() * sizeof(int)) != cudaSuccess) return -1;
+    cudaMemcpy(L.d_send_nodes, plan.send_nodes.data(), plan.n_send() * sizeof(int), cudaMemcpyHostToDevice);
+  }
+  c.levels.push_back(L);
+  return int(c.levels.size());
+}
+void comm_drop_levels(c8_ctx* ctx) {
+  auto it = g_comm.find(ctx);
+  if (it != g_comm.end()) drop_levels(it->second);
+}
+void comm_halo_level(c8_ctx* ctx, int level, double* vec, int nb) {
+  if (level == 0) { if (ctx->halo_cb) ctx->halo_cb(ctx->comm_user, vec, nb); return; }
+  Comm& c = g_comm[ctx];
+  const Comm::Level& L = c.levels[level - 1];
+  if (c.nccl) halo_nccl_plan(c, L.d_send_nodes, L.plan.send_ptr, L.plan.recv_ptr, L.plan.n_owned, vec, nb);
+  else halo_host_level(c, L, vec, nb);
+}
+
 void comm_release(c8_ctx* ctx) {
   auto it = g_comm.find(ctx);
   if (it == g_comm.end()) return;
   Comm& c = it->second;
+  drop_levels(c);
   if (c.nccl && g_nccl.lib) g_nccl.CommDestroy(c.nccl);
   if (c.d_send_nodes) cudaFree(c.d_send_nodes);
   if (c.d_sendbuf) cudaFree(c.d_sendbuf);
@@ -191,6 +276,9 @@ int c8_set_comm(c8_ctx* ctx, c8_halo_fn halo, c8_allreduce_fn allreduce, void* u
   ctx->allreduce_cb = allreduce;
   ctx->comm_user = user;
   ctx->comm_capturable = false;
+  auto it = g_comm.find(ctx);
+  if (it != g_comm.end()) it->second.library_transport = false;   // the caller's own hooks
+  c8_linalg_invalidate(ctx);
   return C8_OK;
 }
 
@@ -206,6 +294,15 @@ int c8_set_halo_plan(c8_ctx* ctx, int n_nbr, const int32_t* nbr_rank, const int3
   c.recv_ptr.assign(recv_ptr, recv_ptr + n_nbr + 1);
   c.n_send = n_nbr ? send_ptr[n_nbr] : 0;
   c.n_recv = n_nbr ? recv_ptr[n_nbr] : 0;
+  c.send_ptr.resize(n_nbr + 1, 0);   // n_nbr == 0: one zero entry
+  c.recv_ptr.resize(n_nbr + 1, 0);
+  drop_levels(c);
+  c.plan0.n_owned = ctx->n_owned_nodes;
+  c.plan0.nbr_rank = c.nbr_rank;
+  c.plan0.send_ptr = c.send_ptr;
+  c.plan0.recv_ptr = c.recv_ptr;
+  c.plan0.send_nodes.assign(send_nodes, send_nodes + c.n_send);
+  c8_linalg_invalidate(ctx);
   C8_REQUIRE(ctx, c.n_recv == ctx->n_nodes - ctx->n_owned_nodes,
              "halo plan: received node count differs from the ghost count (c8_set_partition first)");
   for (int i = 0; i < c.n_send; ++i)
@@ -248,6 +345,7 @@ int c8_nccl_init(c8_ctx* ctx, const char* id128, int rank, int nranks) {
   c.rank = rank; c.nranks = nranks;
   const int rc = c8_set_comm(ctx, &halo_nccl, &allreduce_nccl, &c);
   ctx->comm_capturable = true;
+  c.library_transport = true;
   return rc;
 }
 
@@ -257,7 +355,18 @@ int c8_set_comm_host(c8_ctx* ctx, c8_host_exchange_fn exchange, c8_host_allreduc
   C8_REQUIRE(ctx, it != g_comm.end(), "c8_set_halo_plan must be called before c8_set_comm_host");
   Comm& c = it->second;
   c.exchange = exchange; c.host_allreduce = allreduce; c.user = user;
-  return c8_set_comm(ctx, &halo_host, &allreduce_host, &c);
+  const int rc = c8_set_comm(ctx, &halo_host, &allreduce_host, &c);
+  c.library_transport = true;
+  return rc;
+}
+
+int c8_set_comm_rank(c8_ctx* ctx, int rank, int nranks) {
+  C8_REQUIRE(ctx, nranks >= 1 && rank >= 0 && rank < nranks, "rank must be in [0, nranks)");
+  auto it = g_comm.find(ctx);
+  C8_REQUIRE(ctx, it != g_comm.end(), "c8_set_halo_plan must be called before c8_set_comm_rank");
+  it->second.rank = rank; it->second.nranks = nranks;
+  c8_linalg_invalidate(ctx);
+  return C8_OK;
 }
 
 int c8_halo(c8_ctx* ctx, double* vec_dev) {

@@ -145,10 +145,14 @@ int c8_set_preconditioner(c8_ctx* ctx, int type, const double* opts, int n_opts)
     if (n_opts > 5) o.max_aggregate_size = int(opts[5]);
     if (n_opts > 6) o.coarse_aggregate_size = int(opts[6]);
     if (n_opts > 7) o.coarse_nu = int(opts[7]);
+    if (n_opts > 8) o.distributed = opts[8] != 0.0;
+    if (n_opts > 9) o.replicate_max_nodes = int(opts[9]);
   }
   const bool rebuild = o.coarsest_max_nodes != st.amg_opt.coarsest_max_nodes ||
                        o.max_aggregate_size != st.amg_opt.max_aggregate_size ||
-                       o.coarse_aggregate_size != st.amg_opt.coarse_aggregate_size;
+                       o.coarse_aggregate_size != st.amg_opt.coarse_aggregate_size ||
+                       o.distributed != st.amg_opt.distributed ||
+                       o.replicate_max_nodes != st.amg_opt.replicate_max_nodes;
   st.amg_opt = o;
   st.drop_graphs();
   if (st.amg) st.amg->opt = o;

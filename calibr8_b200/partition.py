@@ -176,6 +176,7 @@ class HostExchange:
     def __init__(self, part: Part, group=None):
         import torch.distributed as dist
         self.part, self.dist, self.group = part, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
 
     def exchange(self, send: np.ndarray, nb: int) -> np.ndarray:
         """send: [n_send][nb] packed in send_ptr order; returns [n_ghost][nb] in recv_ptr order"""

@@ -236,6 +236,10 @@ typedef void (*c8_host_exchange_fn)(void* user, const double* send_host, double*
 typedef void (*c8_host_allreduce_fn)(void* user, double* buf_host, int n);
 int c8_set_comm_host(c8_ctx* ctx, c8_host_exchange_fn exchange, c8_host_allreduce_fn allreduce,
                      void* user);
+/* rank of this part and number of parts, for the host-staged transport (c8_nccl_init takes them
+ * itself): lets the multigrid preconditioner span the parts (per-level halo copies, replicated
+ * coarse levels) instead of acting on each part's owned block only */
+int c8_set_comm_rank(c8_ctx* ctx, int rank, int nranks);
 int c8_halo(c8_ctx* ctx, double* vec_dev);              /* nodal vector [n_nodes][NB] */
 int c8_halo_nb(c8_ctx* ctx, double* vec_dev, int nb);   /* nodal vector [n_nodes][nb], nb <= 4 */
 int c8_allreduce(c8_ctx* ctx, double* buf_dev, int n);
