@@ -245,7 +245,9 @@ def calibration_step_partitioned(mesh, load_steps, rank, world, local_rank):
                              "neighbours_rank0": int(part.nbr_rank.size)},
                "comm_rank0": cs, "phase_seconds_cumulative": hp.profile(bool(os.environ.get("C8_BENCH_PROFILE"))),
                "note": "1M-tet mesh split over the ranks; NCCL halo copy of Krylov vectors / Newton iterate and "
-                       "fp64 allreduce of dots, objective, gradient; AMG acts on each part's owned block"}
+                       "fp64 allreduce of dots, objective, gradient; the multigrid hierarchy spans the parts "
+                       "(halo copy per sweep on the partitioned levels, coarse levels replicated)",
+               "preconditioner": ctx.preconditioner_info()}
     hp.close(); ctx.close()
     return out
 
