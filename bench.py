@@ -34,6 +34,7 @@ METRIC = "QP residual+Jacobian evals/s (fp64)"
 UNIT = "QP evals/s"
 PARAMS = dict(E=1000., nu=.25, Y=10., S=0., D=0., A=0., n=0., K=100.)   # test/primal/notch_hyper_J2.yaml.in:25-34
 LOCAL = dict(max_iters=500, abs_tol=1e-12, rel_tol=1e-12)             # same deck :20-24
+LINEAR_TOL = 1e-6   # Belos "Convergence Tolerance" of the same deck (:59); Newton tolerances 1e-8 (:16-18)
 AMP = 2.2e-3
 N_CELLS = 56
 NOTCH = 0.2
@@ -160,7 +161,7 @@ def calibration_step(ctx, mesh, load_steps):
     hp.add_dbc(0, 2, mesh.node_sets["zmin"], "0.0")
     hp.add_dbc(0, 1, mesh.node_sets["ymax"], "0.001 * t")
     hp.finalize_dbcs()
-    hp.set_solver(15, 1e-8, 1e-8, gmres_restart=100, gmres_max_iters=20000, linear_tol=1e-8)
+    hp.set_solver(15, 1e-8, 1e-8, gmres_restart=100, gmres_max_iters=20000, linear_tol=LINEAR_TOL)
     hp.set_qoi_avg_disp()
     if os.environ.get("C8_BENCH_PROFILE"):
         hp.profile(True)
@@ -182,7 +183,8 @@ def calibration_step(ctx, mesh, load_steps):
                "objective": J, "gradient": [float(v) for v in g],
                "preconditioner": ctx.preconditioner_info(),
                "phase_seconds_cumulative": hp.profile(bool(os.environ.get("C8_BENCH_PROFILE"))),
-               "note": "Newton tol 1e-8, GMRES(100) rel tol 1e-8, aggregation-AMG right preconditioner; "
+               "note": "Newton tol 1e-8 and GMRES rel tol 1e-6 as in the reference deck (test/primal/notch_hyper_J2.yaml.in), "
+                       "GMRES(100), aggregation-AMG right preconditioner; "
                        "second of two passes (the first builds the hierarchy)"}
     hp.close()
     return out
@@ -216,7 +218,7 @@ def calibration_step_partitioned(mesh, load_steps, rank, world, local_rank):
     hp.add_dbc(0, 2, part.node_sets["zmin"], "0.0")
     hp.add_dbc(0, 1, part.node_sets["ymax"], "0.001 * t")
     hp.finalize_dbcs()
-    hp.set_solver(15, 1e-8, 1e-8, gmres_restart=100, gmres_max_iters=20000, linear_tol=1e-8)
+    hp.set_solver(15, 1e-8, 1e-8, gmres_restart=100, gmres_max_iters=20000, linear_tol=LINEAR_TOL)
     hp.set_qoi_avg_disp()
     if os.environ.get("C8_BENCH_PROFILE"):
         hp.profile(True)

@@ -16,6 +16,7 @@ template <int NB, class F>
 __global__ void k_bsr_residual(const int* __restrict__ rowptr, const int* __restrict__ colind,
                                const F* __restrict__ vals, const double* __restrict__ x,
                                const double* __restrict__ b, double* __restrict__ r, int n_nodes) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_nodes * NB) return;
   const int node = i / NB, row = i % NB;
@@ -23,10 +24,11 @@ __global__ void k_bsr_residual(const int* __restrict__ rowptr, const int* __rest
   const int b0 = rowptr[node], b1 = rowptr[node + 1];
 #pragma unroll 4
   for (int k = b0; k < b1; ++k) {
-    const F* a = vals + (size_t(k) * NB + row) * NB;
-    const double* xv = x + size_t(__ldg(&colind[k])) * NB;
+    double a[NB], xv[NB];
+    ld_row<NB, F>(vals + (size_t(k) * NB + row) * NB, a);
+    ld_row<NB, double>(x + size_t(__ldg(&colind[k])) * NB, xv);
 #pragma unroll
-    for (int c = 0; c < NB; ++c) s = fma(-double(__ldg(&a[c])), __ldg(&xv[c]), s);
+    for (int c = 0; c < NB; ++c) s = fma(-a[c], xv[c], s);
   }
   r[i] = s;
 }
@@ -40,6 +42,7 @@ __global__ void k_smooth(const int* __restrict__ rowptr, const int* __restrict__
                          const double* __restrict__ b, const double* __restrict__ xin,
                          double* __restrict__ xout, const int* __restrict__ agg,
                          const double* __restrict__ xc, double pscale, double omega, int n, int npc) {
+  pdl_wait();
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int node = gid >> 2;
   const int lane4 = gid & 3;
@@ -52,19 +55,22 @@ __global__ void k_smooth(const int* __restrict__ rowptr, const int* __restrict__
 #pragma unroll 4
   for (int k = b0; k < b1; ++k) {
     const int col = __ldg(&colind[k]);
-    const F* a = vals + (size_t(k) * NB + row) * NB;
-    const double* xv = xin + size_t(col) * NB;
+    double a[NB], xv[NB];
+    ld_row<NB, F>(vals + (size_t(k) * NB + row) * NB, a);
+    ld_row<NB, double>(xin + size_t(col) * NB, xv);
     // columns >= npc carry no coarse correction (the ghost columns of a part whose hierarchy acts
     // on its owned block only; npc = all columns when the hierarchy spans the parts); the index is
     // clamped rather than branched around because the compiler may speculate a read-only load
     const double ps = (PROLONG && col < npc) ? pscale : 0.0;
     const double* pc = PROLONG ? xc + size_t(agg[col < npc ? col : 0]) * NB : nullptr;
+    if (PROLONG) {
+      double pv[NB];
+      ld_row<NB, double>(pc, pv);
 #pragma unroll
-    for (int c = 0; c < NB; ++c) {
-      double v = __ldg(&xv[c]);
-      if (PROLONG) v = fma(ps, pc[c], v);
-      s = fma(-double(__ldg(&a[c])), v, s);
+      for (int c = 0; c < NB; ++c) xv[c] = fma(ps, pv[c], xv[c]);
     }
+#pragma unroll
+    for (int c = 0; c < NB; ++c) s = fma(-a[c], xv[c], s);
   }
   const int base = (threadIdx.x & 31) & ~3;
   double upd = 0.0;
@@ -88,6 +94,7 @@ __global__ void k_smooth_warp(const int* __restrict__ rowptr, const int* __restr
                               const double* __restrict__ b, const double* __restrict__ xin,
                               double* __restrict__ xout, const int* __restrict__ agg,
                               const double* __restrict__ xc, double pscale, double omega, int n) {
+  pdl_wait();
   const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (node >= n) return;  // the whole warp leaves together
   double s[NB];
@@ -141,6 +148,7 @@ __global__ void k_to_float(const double* __restrict__ in, float* __restrict__ ou
 template <int NB>
 __global__ void k_jacobi_update(const double* __restrict__ dinv, const double* __restrict__ r,
                                 double* __restrict__ x, double omega, int zero_guess, int n_nodes) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_nodes * NB) return;
   const int node = i / NB, row = i % NB;
@@ -154,6 +162,7 @@ __global__ void k_jacobi_update(const double* __restrict__ dinv, const double* _
 template <int NB>
 __global__ void k_restrict(const int* __restrict__ aggptr, const int* __restrict__ aggmem,
                            const double* __restrict__ r, double* __restrict__ bc, int nc) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nc * NB) return;
   const int I = i / NB, c = i % NB;
@@ -260,6 +269,7 @@ __global__ void __launch_bounds__(1024) k_dense_inverse(double* __restrict__ M, 
 // x = Ainv b with Ainv = right half of M
 __global__ void k_dense_apply(const double* __restrict__ M, const double* __restrict__ b,
                               double* __restrict__ x, int N) {
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= N) return;
   const double* row = M + size_t(warp) * 2 * N + N;
@@ -467,12 +477,12 @@ void Amg::smooth(int l, const double* b, double* x, int sweeps, bool zero_guess)
   const int g = (L.n * nb_ + 127) / 128;
   for (int k = 0; k < sweeps; ++k) {
     if (k == 0 && zero_guess) {
-      if (L.n > 0) { C8_NB_SWITCH(nb_, (k_jacobi_update<NB><<<g, 128, 0, s>>>(L.dinv, b, x, opt.omega, 1, L.n))); }
+      if (L.n > 0) { C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_jacobi_update<NB>, L.dinv, b, x, opt.omega, 1, L.n))); }
     } else {
       halo(l, x);
       if (L.n == 0) continue;
-      C8_NB_SWITCH(nb_, (k_bsr_residual<NB, double><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals, x, b, r, L.n)));
-      C8_NB_SWITCH(nb_, (k_jacobi_update<NB><<<g, 128, 0, s>>>(L.dinv, r, x, opt.omega, 0, L.n)));
+      C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_bsr_residual<NB, double>, L.rowptr, L.colind, L.vals, x, b, r, L.n)));
+      C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_jacobi_update<NB>, L.dinv, r, x, opt.omega, 0, L.n)));
     }
   }
 }
@@ -487,16 +497,16 @@ void Amg::sweep(int l, const double* b, const double* xin, double* xout, const d
   const double oc = opt.over_correction, om = opt.omega;
   if (l > 0) {  // coarse levels: a warp per node
     const int gw = (L.n * 32 + 127) / 128;
-    if (xc) { C8_NB_SWITCH(nb_, (k_smooth_warp<NB, true, false><<<gw, 128, 0, s>>>(L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, L.agg, xc, oc, om, L.n))); }
-    else { C8_NB_SWITCH(nb_, (k_smooth_warp<NB, false, false><<<gw, 128, 0, s>>>(L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, nullptr, nullptr, 0.0, om, L.n))); }
+    if (xc) { C8_NB_SWITCH(nb_, (pdl_launch(gw, 128, 0, s)(k_smooth_warp<NB, true, false>, L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, L.agg, xc, oc, om, L.n))); }
+    else { C8_NB_SWITCH(nb_, (pdl_launch(gw, 128, 0, s)(k_smooth_warp<NB, false, false>, L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, nullptr, nullptr, 0.0, om, L.n))); }
     return;
   }
   if (L.vals32) {
-    if (xc) { C8_NB_SWITCH(nb_, (k_smooth<NB, float, true><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals32, L.dinv, b, xin, xout, L.agg, xc, oc, om, L.n, L.npc))); }
-    else { C8_NB_SWITCH(nb_, (k_smooth<NB, float, false><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals32, L.dinv, b, xin, xout, nullptr, nullptr, 0.0, om, L.n, 0))); }
+    if (xc) { C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_smooth<NB, float, true>, L.rowptr, L.colind, L.vals32, L.dinv, b, xin, xout, L.agg, xc, oc, om, L.n, L.npc))); }
+    else { C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_smooth<NB, float, false>, L.rowptr, L.colind, L.vals32, L.dinv, b, xin, xout, nullptr, nullptr, 0.0, om, L.n, 0))); }
   } else {
-    if (xc) { C8_NB_SWITCH(nb_, (k_smooth<NB, double, true><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, L.agg, xc, oc, om, L.n, L.npc))); }
-    else { C8_NB_SWITCH(nb_, (k_smooth<NB, double, false><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, nullptr, nullptr, 0.0, om, L.n, 0))); }
+    if (xc) { C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_smooth<NB, double, true>, L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, L.agg, xc, oc, om, L.n, L.npc))); }
+    else { C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_smooth<NB, double, false>, L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, nullptr, nullptr, 0.0, om, L.n, 0))); }
   }
 }
 
@@ -513,7 +523,7 @@ void Amg::cycle(int l, const double* b, double* xout) {
   const bool coarsest = (l + 1 == int(lv_.size()));
   if (coarsest) {
     if (nd_ > 0 && l > 0) {
-      k_dense_apply<<<(nd_ * 32 + 255) / 256, 256, 0, s>>>(dense_, b, xout, nd_);
+      pdl_launch((nd_ * 32 + 255) / 256, 256, 0, s)(k_dense_apply, dense_, b, xout, nd_);
     } else {
       smooth(l, b, xout, 4 * (opt.nu_pre + opt.nu_post), true);
     }
@@ -526,22 +536,22 @@ void Amg::cycle(int l, const double* b, double* xout) {
   auto buf = [&](int w) { return bufs[(writes - 1 - w) & 1]; };  // the last write goes to xout
   const int g = (L.n * nb_ + 127) / 128;
   amg_dbg(s, "enter", l);
-  if (L.n > 0) { C8_NB_SWITCH(nb_, (k_jacobi_update<NB><<<g, 128, 0, s>>>(L.dinv, b, buf(0), opt.omega, 1, L.n))); }
+  if (L.n > 0) { C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_jacobi_update<NB>, L.dinv, b, buf(0), opt.omega, 1, L.n))); }
   amg_dbg(s, "jacobi zero-guess", l);
   for (int w = 1; w < nu1; ++w) { halo(l, buf(w - 1)); sweep(l, b, buf(w - 1), buf(w), nullptr); amg_dbg(s, "pre sweep", l); }
   const double* cur = buf(nu1 - 1);
   halo(l, cur);
   double* r = (l == 0) ? r0_ : L.r;
   if (L.n > 0) {
-    if (l > 0) { C8_NB_SWITCH(nb_, (k_smooth_warp<NB, false, true><<<(L.n * 32 + 127) / 128, 128, 0, s>>>(L.rowptr, L.colind, L.vals, nullptr, b, cur, r, nullptr, nullptr, 0.0, 0.0, L.n))); }
-    else if (L.vals32) { C8_NB_SWITCH(nb_, (k_bsr_residual<NB, float><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals32, cur, b, r, L.n))); }
-    else { C8_NB_SWITCH(nb_, (k_bsr_residual<NB, double><<<g, 128, 0, s>>>(L.rowptr, L.colind, L.vals, cur, b, r, L.n))); }
+    if (l > 0) { C8_NB_SWITCH(nb_, (pdl_launch((L.n * 32 + 127) / 128, 128, 0, s)(k_smooth_warp<NB, false, true>, L.rowptr, L.colind, L.vals, nullptr, b, cur, r, nullptr, nullptr, 0.0, 0.0, L.n))); }
+    else if (L.vals32) { C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_bsr_residual<NB, float>, L.rowptr, L.colind, L.vals32, cur, b, r, L.n))); }
+    else { C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_bsr_residual<NB, double>, L.rowptr, L.colind, L.vals, cur, b, r, L.n))); }
   }
   amg_dbg(s, "residual", l);
   AmgLevel& C = lv_[l + 1];
   if (C.n > 0) {
     const int gc = (C.n * nb_ + 127) / 128;
-    C8_NB_SWITCH(nb_, (k_restrict<NB><<<gc, 128, 0, s>>>(L.aggptr, L.aggmem, r, C.b, C.n)));
+    C8_NB_SWITCH(nb_, (pdl_launch(gc, 128, 0, s)(k_restrict<NB>, L.aggptr, L.aggmem, r, C.b, C.n)));
     if (L.coarse_replicated) ctx_->allreduce_cb(ctx_->comm_user, C.b, C.n * nb_);
   }
   amg_dbg(s, "restrict", l);

@@ -16,16 +16,23 @@
 
 namespace c8 {
 
-// column j of H from the two Gram-Schmidt passes and the norm, previous rotations applied, new
-// rotation generated, least-squares rhs updated; res[j] = |g[j+1]| (the residual-norm estimate)
+// column j of H from the two Gram-Schmidt passes, previous rotations applied, new rotation
+// generated, least-squares rhs updated; res[j] = |g[j+1]| (the residual-norm estimate).
+// The norm of the new basis vector needs no reduction of its own: the second pass also returned
+// ww = w.w of the vector it corrected (d2[j+1]), and the basis is orthonormal, so
+// |w - V d2|^2 = ww - sum d2^2 (d2 is at rounding level after the first pass: no cancellation).
+// nrm2[0] receives that squared norm for k_normalize.
 __global__ void k_givens(double* __restrict__ H, int ldh, double* __restrict__ cs,
                          double* __restrict__ sn, double* __restrict__ g,
                          const double* __restrict__ d1, const double* __restrict__ d2,
-                         const double* __restrict__ nrm2, int j, double* __restrict__ res) {
+                         double* __restrict__ nrm2, int j, double* __restrict__ res) {
+  pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double* h = H + size_t(j) * ldh;
-  for (int i = 0; i <= j; ++i) h[i] = d1[i] + d2[i];
-  h[j + 1] = sqrt(fmax(nrm2[0], 0.0));
+  double ww = d2[j + 1];
+  for (int i = 0; i <= j; ++i) { h[i] = d1[i] + d2[i]; ww = fma(-d2[i], d2[i], ww); }
+  nrm2[0] = ww;
+  h[j + 1] = sqrt(fmax(ww, 0.0));
   for (int i = 0; i < j; ++i) {
     const double t = cs[i] * h[i] + sn[i] * h[i + 1];
     h[i + 1] = -sn[i] * h[i] + cs[i] * h[i + 1];
@@ -44,6 +51,7 @@ __global__ void k_givens(double* __restrict__ H, int ldh, double* __restrict__ c
 // y = R^-1 g for the leading k columns
 __global__ void k_backsolve(const double* __restrict__ H, int ldh, const double* __restrict__ g,
                             double* __restrict__ y, int k) {
+  pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   for (int i = k - 1; i >= 0; --i) {
     double t = g[i];
@@ -55,6 +63,7 @@ __global__ void k_backsolve(const double* __restrict__ H, int ldh, const double*
 // v *= 1/sqrt(nrm2[0]) (device scalar); g0 (optional) receives the norm
 __global__ void k_normalize(double* __restrict__ v, const double* __restrict__ nrm2, long long n,
                             double* __restrict__ g0) {
+  pdl_wait();
   const double nr = sqrt(fmax(nrm2[0], 0.0));
   const double inv = nr > 0.0 ? 1.0 / nr : 0.0;
   if (g0 && blockIdx.x == 0 && threadIdx.x == 0) g0[0] = nr;
@@ -224,16 +233,16 @@ int c8_gmres(c8_ctx* ctx, const double* A, const double* b, double* x, int resta
     la.spmv(A, ws.z, vj1);
     // classical Gram-Schmidt, two passes: h = V^T w ; w -= V h
     la.multi_dot(ws.V, ld, vj1, j + 1, ws.partial, ws.dots);
-    k_multi_axpy_neg<<<ag, 256, 0, s>>>(ws.V, ld, ws.dots, j + 1, n, vj1);
-    la.multi_dot(ws.V, ld, vj1, j + 1, ws.partial, ws.dots2);
-    k_multi_axpy_neg<<<ag, 256, 0, s>>>(ws.V, ld, ws.dots2, j + 1, n, vj1);
-    la.multi_dot(vj1, 0, vj1, 1, ws.partial, ws.nrm);
-    k_givens<<<1, 32, 0, s>>>(ws.H, ldh, ws.cs, ws.sn, ws.g, ws.dots, ws.dots2, ws.nrm, j, ws.res);
-    k_normalize<<<ag, 256, 0, s>>>(vj1, ws.nrm, n, nullptr);
+    pdl_launch(ag, 256, 0, s)(k_multi_axpy_neg, ws.V, ld, ws.dots, j + 1, n, vj1);
+    la.multi_dot(ws.V, ld, vj1, j + 2, ws.partial, ws.dots2);   // V[j+1] is vj1 itself: dots2[j+1] = w.w
+    pdl_launch(ag, 256, 0, s)(k_multi_axpy_neg, ws.V, ld, ws.dots2, j + 1, n, vj1);
+    pdl_launch(1, 32, 0, s)(k_givens, ws.H, ldh, ws.cs, ws.sn, ws.g, ws.dots, ws.dots2, ws.nrm, j, ws.res);
+    pdl_launch(ag, 256, 0, s)(k_normalize, vj1, ws.nrm, n, nullptr);
   };
   // capture needs a real stream; a partitioned run captures too when its transport only enqueues
   // stream work (NCCL), not when it stages through the host
-  bool graphs = ws.use_graphs && ((!ctx->halo_cb && !ctx->allreduce_cb) || ctx->comm_capturable) &&
+  static const bool graphs_env = [] { const char* e = getenv("C8_GRAPHS"); return !(e && e[0] == '0'); }();
+  bool graphs = graphs_env && ws.use_graphs && ((!ctx->halo_cb && !ctx->allreduce_cb) || ctx->comm_capturable) &&
                 s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
   if (graphs) {
     const int pc_key = use_amg ? 1 : 0;
@@ -251,14 +260,14 @@ int c8_gmres(c8_ctx* ctx, const double* A, const double* b, double* x, int resta
     la.halo(x);
     la.spmv(A, x, ws.w);
     C8_CUDA(ctx, cudaMemcpyAsync(ws.V, b, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    k_axpby<<<ag, 256, 0, s>>>(-1.0, ws.w, 1.0, ws.V, n);
+    pdl_launch(ag, 256, 0, s)(k_axpby, -1.0, ws.w, 1.0, ws.V, n);
     la.multi_dot(ws.V, 0, ws.V, 1, ws.partial, ws.nrm);
     if ((rc = fetch(ws.nrm, 1)) != C8_OK) return rc;
     beta = std::sqrt(ws.h_buf[0]);
     if (beta0 < 0) { beta0 = beta; target = std::max(rel_tol * beta0, abs_tol); }
     if (beta <= target || total >= max_iters || !(beta == beta)) break;
     C8_CUDA(ctx, cudaMemsetAsync(ws.g, 0, size_t(m + 2) * sizeof(double), s));
-    k_normalize<<<ag, 256, 0, s>>>(ws.V, ws.nrm, n, ws.g);   // V0 = r/beta, g[0] = beta
+    pdl_launch(ag, 256, 0, s)(k_normalize, ws.V, ws.nrm, n, ws.g);   // V0 = r/beta, g[0] = beta
     int j = 0, used = 0;
     bool done = false;
     while (j < m && total < max_iters && !done) {
@@ -296,11 +305,11 @@ int c8_gmres(c8_ctx* ctx, const double* A, const double* b, double* x, int resta
     }
     total -= (j - used);  // iterations queued past convergence are not counted
     // x += M^-1 (V y), y from the leading `used` columns
-    k_backsolve<<<1, 32, 0, s>>>(ws.H, ldh, ws.g, ws.coef, used);
+    pdl_launch(1, 32, 0, s)(k_backsolve, ws.H, ldh, ws.g, ws.coef, used);
     C8_CUDA(ctx, cudaMemsetAsync(ws.w, 0, n * sizeof(double), s));
-    k_multi_axpy<<<ag, 256, 0, s>>>(ws.V, ld, ws.coef, used, n, ws.w);
+    pdl_launch(ag, 256, 0, s)(k_multi_axpy, ws.V, ld, ws.coef, used, n, ws.w);
     precond(ws.w, ws.z);
-    k_axpby<<<ag, 256, 0, s>>>(1.0, ws.z, 1.0, x, n);
+    pdl_launch(ag, 256, 0, s)(k_axpby, 1.0, ws.z, 1.0, x, n);
   }
   ws.total_iters += total; ws.total_solves += 1;
   if (info_host) { info_host[0] = total; info_host[1] = beta; info_host[2] = beta0; }

@@ -3,6 +3,7 @@
 #pragma once
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "c8b200.h"
@@ -10,21 +11,84 @@
 
 namespace c8 {
 
+// Programmatic dependent launch (sm_90+): the solver's iteration is a chain of ~50 small dependent
+// kernels; launched with the programmatic-stream-serialization attribute, a kernel's grid is
+// scheduled while its predecessor still runs and parks at griddepcontrol.wait until the
+// predecessor's grid has completed and flushed -- the launch latency leaves the critical path, the
+// data dependency stays.  Every kernel launched through pdl_launch() calls pdl_wait() first.
+// C8_PDL=0 launches the same kernels without the attribute.
+__device__ __forceinline__ void pdl_wait() {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("C8_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+struct PdlLaunch {
+  dim3 grid, block;
+  size_t smem;
+  cudaStream_t stream;
+  template <class... P, class... A>
+  void operator()(void (*kernel)(P...), A&&... args) const {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, P(args)...);
+  }
+};
+inline PdlLaunch pdl_launch(dim3 grid, dim3 block, size_t smem, cudaStream_t stream) {
+  return PdlLaunch{grid, block, smem, stream};
+}
+
+
+// one row of an NB x NB block (or the NB entries of a node) with the widest loads the alignment
+// allows: 16-byte LDG for NB = 4 (float4 / 2 x double2) and NB = 2 doubles; values widened to fp64
+template <int NB, class F>
+__device__ __forceinline__ void ld_row(const F* __restrict__ a, double (&v)[NB]) {
+  if constexpr (NB == 4 && sizeof(F) == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(a));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else if constexpr (NB == 4 && sizeof(F) == 8) {
+    const double2 t0 = __ldg(reinterpret_cast<const double2*>(a));
+    const double2 t1 = __ldg(reinterpret_cast<const double2*>(a) + 1);
+    v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y;
+  } else if constexpr (NB == 2 && sizeof(F) == 8) {
+    const double2 t = __ldg(reinterpret_cast<const double2*>(a));
+    v[0] = t.x; v[1] = t.y;
+  } else if constexpr (NB == 2 && sizeof(F) == 4) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(a));
+    v[0] = t.x; v[1] = t.y;
+  } else {
+#pragma unroll
+    for (int c = 0; c < NB; ++c) v[c] = double(__ldg(&a[c]));
+  }
+}
+
 // y = A x ; one thread per scalar row (node, r); loops over the node's blocks
 template <int NB>
 __global__ void k_bsr_spmv(const int* __restrict__ rowptr, const int* __restrict__ colind,
                            const double* __restrict__ vals, const double* __restrict__ x,
                            double* __restrict__ y, int n_nodes) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_nodes * NB) return;
   const int node = i / NB, r = i % NB;
   double s = 0.0;
   const int b0 = rowptr[node], b1 = rowptr[node + 1];
+#pragma unroll 4
   for (int k = b0; k < b1; ++k) {
-    const double* a = vals + (size_t(k) * NB + r) * NB;
-    const double* xv = x + size_t(__ldg(&colind[k])) * NB;
+    double a[NB], xv[NB];
+    ld_row<NB, double>(vals + (size_t(k) * NB + r) * NB, a);
+    ld_row<NB, double>(x + size_t(__ldg(&colind[k])) * NB, xv);
 #pragma unroll
-    for (int c = 0; c < NB; ++c) s = fma(__ldg(&a[c]), __ldg(&xv[c]), s);
+    for (int c = 0; c < NB; ++c) s = fma(a[c], xv[c], s);
   }
   y[i] = s;
 }
@@ -66,6 +130,7 @@ __global__ void k_block_jacobi_setup(const int* __restrict__ rowptr, const int* 
 template <int NB>
 __global__ void k_block_jacobi_apply(const double* __restrict__ dinv, const double* __restrict__ x,
                                      double* __restrict__ y, int n_nodes) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_nodes * NB) return;
   const int node = i / NB, r = i % NB;
@@ -80,6 +145,7 @@ constexpr int DOT_BLOCK = 256;
 static __global__ void k_multi_dot_partial(const double* __restrict__ V, long long ld,
                                     const double* __restrict__ w, int nv, long long n,
                                     double* __restrict__ partial) {
+  pdl_wait();
   __shared__ double sh[DOT_BLOCK / 32];
   for (int j = blockIdx.y; j < nv; j += gridDim.y) {
     double s = 0.0;
@@ -100,6 +166,7 @@ static __global__ void k_multi_dot_partial(const double* __restrict__ V, long lo
 }
 static __global__ void k_multi_dot_final(const double* __restrict__ partial, int nparts, int nv,
                                   double* __restrict__ out) {
+  pdl_wait();
   const int j = blockIdx.x;
   if (j >= nv) return;
   __shared__ double sh[32];
@@ -118,6 +185,7 @@ static __global__ void k_multi_dot_final(const double* __restrict__ partial, int
 static __global__ void k_multi_axpy_neg(const double* __restrict__ V, long long ld,
                                  const double* __restrict__ h, int nv, long long n,
                                  double* __restrict__ w) {
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     double s = w[i];
@@ -128,6 +196,7 @@ static __global__ void k_multi_axpy_neg(const double* __restrict__ V, long long 
 // y = a*x + b*y
 static __global__ void k_axpby(double a, const double* __restrict__ x, double b, double* __restrict__ y,
                         long long n) {
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     y[i] = a * x[i] + (b == 0.0 ? 0.0 : b * y[i]);
@@ -135,6 +204,7 @@ static __global__ void k_axpby(double a, const double* __restrict__ x, double b,
 // x += sum_j c[j] V[j]  (c on the host -> passed through a device array)
 static __global__ void k_multi_axpy(const double* __restrict__ V, long long ld, const double* __restrict__ c,
                              int nv, long long n, double* __restrict__ x) {
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     double s = x[i];
@@ -192,9 +262,9 @@ struct LinAlg {
   void spmv(const double* A, const double* x, double* y) const {
     const int block = 128, grid = int((n + block - 1) / block);
     switch (nb) {
-      case 2: k_bsr_spmv<2><<<grid, block, 0, s>>>(ctx->d_rowptr, ctx->d_colind, A, x, y, n_nodes); break;
-      case 3: k_bsr_spmv<3><<<grid, block, 0, s>>>(ctx->d_rowptr, ctx->d_colind, A, x, y, n_nodes); break;
-      default: k_bsr_spmv<4><<<grid, block, 0, s>>>(ctx->d_rowptr, ctx->d_colind, A, x, y, n_nodes); break;
+      case 2: pdl_launch(grid, block, 0, s)(k_bsr_spmv<2>, ctx->d_rowptr, ctx->d_colind, A, x, y, n_nodes); break;
+      case 3: pdl_launch(grid, block, 0, s)(k_bsr_spmv<3>, ctx->d_rowptr, ctx->d_colind, A, x, y, n_nodes); break;
+      default: pdl_launch(grid, block, 0, s)(k_bsr_spmv<4>, ctx->d_rowptr, ctx->d_colind, A, x, y, n_nodes); break;
     }
   }
   void jacobi_setup(const double* A, double* dinv) const {
@@ -208,9 +278,9 @@ struct LinAlg {
   void jacobi_apply(const double* dinv, const double* x, double* y) const {
     const int block = 128, grid = int((n + block - 1) / block);
     switch (nb) {
-      case 2: k_block_jacobi_apply<2><<<grid, block, 0, s>>>(dinv, x, y, n_nodes); break;
-      case 3: k_block_jacobi_apply<3><<<grid, block, 0, s>>>(dinv, x, y, n_nodes); break;
-      default: k_block_jacobi_apply<4><<<grid, block, 0, s>>>(dinv, x, y, n_nodes); break;
+      case 2: pdl_launch(grid, block, 0, s)(k_block_jacobi_apply<2>, dinv, x, y, n_nodes); break;
+      case 3: pdl_launch(grid, block, 0, s)(k_block_jacobi_apply<3>, dinv, x, y, n_nodes); break;
+      default: pdl_launch(grid, block, 0, s)(k_block_jacobi_apply<4>, dinv, x, y, n_nodes); break;
     }
   }
   // out_dev[j] = V[j] . w
@@ -218,8 +288,8 @@ struct LinAlg {
                  double* out_dev) const {
     const int gx = grid_for(n, DOT_BLOCK, sms) > 256 ? 256 : grid_for(n, DOT_BLOCK, sms);
     dim3 grid(gx, nv < 64 ? nv : 64);
-    k_multi_dot_partial<<<grid, DOT_BLOCK, 0, s>>>(V, ld, w, nv, n, partial);
-    k_multi_dot_final<<<nv, 256, 0, s>>>(partial, gx, nv, out_dev);
+    pdl_launch(grid, DOT_BLOCK, 0, s)(k_multi_dot_partial, V, ld, w, nv, n, partial);
+    pdl_launch(nv, 256, 0, s)(k_multi_dot_final, partial, gx, nv, out_dev);
     allreduce(out_dev, nv);
   }
 };

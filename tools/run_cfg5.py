@@ -24,6 +24,7 @@ ap.add_argument("--load-steps", type=int, default=2)
 ap.add_argument("--model", default="small_J2")
 ap.add_argument("--local-amg", action="store_true", help="hierarchy on each part's owned block (for comparison)")
 ap.add_argument("--replicate", type=int, default=30000)
+ap.add_argument("--lin-tol", type=float, default=1e-8, help="GMRES relative tolerance (the reference decks use 1e-6)")
 a = ap.parse_args()
 PAR = {"small_J2": dict(E=1000., nu=.25, K=100., Y=2., cte=0., delta_T=0.),   # test/adjoint/notch2D_small_J2_adjoint_check.yaml.in:26-33
        "hyper_J2": dict(E=1000., nu=.25, Y=10., S=0., D=0., A=0., n=0., K=100.)}
@@ -62,7 +63,7 @@ hp.add_dbc(0, 1, node_sets["ymin"], "0.0")
 hp.add_dbc(0, 2, node_sets["zmin"], "0.0")
 hp.add_dbc(0, 1, node_sets["ymax"], "0.001 * t")
 hp.finalize_dbcs()
-hp.set_solver(15, 1e-8, 1e-8, gmres_restart=100, gmres_max_iters=20000, linear_tol=1e-8)
+hp.set_solver(15, 1e-8, 1e-8, gmres_restart=100, gmres_max_iters=20000, linear_tol=a.lin_tol)
 hp.set_qoi_avg_disp()
 setup_s = time.time() - t0
 out = {}
@@ -85,7 +86,7 @@ for rep in range(2):     # the first pass builds the hierarchy and the iteration
                ms_per_load_step=tot / a.load_steps * 1e3, forward_ms=fwd / a.load_steps * 1e3,
                adjoint_ms=adj / a.load_steps * 1e3, krylov_iterations=s1["linear_iters"] - s0["linear_iters"],
                assemblies=s1["assemblies"] - s0["assemblies"], objective=J, gradient=[float(v) for v in g],
-               preconditioner=ctx.preconditioner_info(), amg="owned block" if a.local_amg else "across the parts",
+               preconditioner=ctx.preconditioner_info(), amg="owned block" if a.local_amg else "across the parts", linear_tol=a.lin_tol,
                comm_rank0=ctx.comm_stats(), setup_s=setup_s, pass_index=rep)
     if part is not None:
         out["partition_rank0"] = dict(owned_elems=part.n_owned_elems, halo_elems=part.n_elems - part.n_owned_elems,
