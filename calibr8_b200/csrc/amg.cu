@@ -138,6 +138,84 @@ __global__ void k_smooth_warp(const int* __restrict__ rowptr, const int* __restr
   }
 }
 
+// NB = 4, a warp per node with COALESCED block reads: the values of a node's row are contiguous in
+// memory, so the 32 lanes read 512 consecutive bytes per step -- a lane owns one 16-byte piece of one
+// block (fp64: 8 lanes per block, 4 blocks per step, the piece is half a row; fp32: 4 lanes per
+// block, 8 blocks per step, the piece is a whole row) and multiplies it with the matching entries
+// of x[col].  Lanes holding pieces of the same block row meet in 3 xor-shuffles.  The
+// thread-per-row kernels above touch 8 separate segments per load instruction and the earlier
+// warp-per-node kernel 128-byte-strided scalars (16 LDG.64 per block and lane); this one issues one
+// LDG.128 per 16 bytes of matrix.  RESID_ONLY: xout = b - A x'; else one damped block-Jacobi sweep.
+template <class F, bool PROLONG, bool RESID_ONLY>
+__global__ void k_smooth_cw4(const int* __restrict__ rowptr, const int* __restrict__ colind,
+                             const F* __restrict__ vals, const double* __restrict__ dinv,
+                             const double* __restrict__ b, const double* __restrict__ xin,
+                             double* __restrict__ xout, const int* __restrict__ agg,
+                             const double* __restrict__ xc, double pscale, double omega, int n, int npc) {
+  pdl_wait();
+  constexpr int LPB = sizeof(F) == 8 ? 8 : 4;   // lanes per block
+  constexpr int BPS = 32 / LPB;                 // blocks per step
+  const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (node >= n) return;  // the whole warp leaves together
+  const int j = lane / LPB, p = lane % LPB;
+  double s = 0.0;
+  const int b1 = rowptr[node + 1];
+  for (int k = rowptr[node] + j; k < b1; k += BPS) {
+    const int col = __ldg(&colind[k]);
+    double ps = 0.0;
+    const double* pc = nullptr;
+    if (PROLONG) { ps = col < npc ? pscale : 0.0; pc = xc + size_t(agg[col < npc ? col : 0]) * 4; }
+    if constexpr (sizeof(F) == 8) {
+      const int c0 = (p & 1) * 2;
+      const double2 a = __ldg(reinterpret_cast<const double2*>(vals + size_t(k) * 16) + p);
+      double2 xv = __ldg(reinterpret_cast<const double2*>(xin + size_t(col) * 4 + c0));
+      if (PROLONG) {
+        const double2 q = __ldg(reinterpret_cast<const double2*>(pc + c0));
+        xv.x = fma(ps, q.x, xv.x); xv.y = fma(ps, q.y, xv.y);
+      }
+      s = fma(-double(a.x), xv.x, s); s = fma(-double(a.y), xv.y, s);
+    } else {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(vals + size_t(k) * 16) + p);
+      double2 x0 = __ldg(reinterpret_cast<const double2*>(xin + size_t(col) * 4));
+      double2 x1 = __ldg(reinterpret_cast<const double2*>(xin + size_t(col) * 4) + 1);
+      if (PROLONG) {
+        const double2 q0 = __ldg(reinterpret_cast<const double2*>(pc));
+        const double2 q1 = __ldg(reinterpret_cast<const double2*>(pc) + 1);
+        x0.x = fma(ps, q0.x, x0.x); x0.y = fma(ps, q0.y, x0.y);
+        x1.x = fma(ps, q1.x, x1.x); x1.y = fma(ps, q1.y, x1.y);
+      }
+      s = fma(-double(a.x), x0.x, s); s = fma(-double(a.y), x0.y, s);
+      s = fma(-double(a.z), x1.x, s); s = fma(-double(a.w), x1.y, s);
+    }
+  }
+  // block row of a lane: fp64 p >> 1 (pieces 2r, 2r+1), fp32 p
+  if constexpr (sizeof(F) == 8) {
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 8);
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
+  } else {
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 8);
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
+  }
+  const int row = lane & 3;
+  const int src = sizeof(F) == 8 ? row * 2 : row;   // a lane that holds the sum of block row `row`
+  const double res = __shfl_sync(0xffffffffu, s, src) + b[size_t(node) * 4 + row];
+  if (RESID_ONLY) {
+    if (lane < 4) xout[size_t(node) * 4 + row] = res;
+    return;
+  }
+  double upd = 0.0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    upd = fma(dinv[(size_t(node) * 4 + row) * 4 + c], __shfl_sync(0xffffffffu, res, c), upd);
+  if (lane < 4) {
+    double xo = xin[size_t(node) * 4 + row];
+    if (PROLONG) xo = fma(pscale, xc[size_t(agg[node]) * 4 + row], xo);
+    xout[size_t(node) * 4 + row] = xo + omega * upd;
+  }
+}
+
 __global__ void k_to_float(const double* __restrict__ in, float* __restrict__ out, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -174,6 +252,7 @@ __global__ void k_restrict(const int* __restrict__ aggptr, const int* __restrict
 template <int NB>
 __global__ void k_prolong_add(const int* __restrict__ agg, const double* __restrict__ xc,
                               double* __restrict__ x, double scale, int n) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * NB) return;
   const int node = i / NB, c = i % NB;
@@ -290,6 +369,15 @@ static void amg_dbg(cudaStream_t s, const char* what, int level) {
     abort();
   }
 }
+
+// experiment switches (defaults = the measured best)
+static bool env_flag(const char* name, bool dflt) {
+  const char* e = getenv(name);
+  return e ? e[0] != '0' : dflt;
+}
+static bool cw_coarse() { static const bool v = env_flag("C8_CW_COARSE", true); return v; }   // coalesced warp kernel on levels >= 1
+static bool cw_fine() { static const bool v = env_flag("C8_CW_FINE", false); return v; }      // ... and on the fine level
+static bool fine_prolong_add() { static const bool v = env_flag("C8_FINE_PROLONG_ADD", true); return v; }
 
 #define C8_NB_SWITCH(nb, CALL)  \
   switch (nb) {                 \
@@ -495,8 +583,18 @@ void Amg::sweep(int l, const double* b, const double* xin, double* xout, const d
   cudaStream_t s = ctx_->stream;
   const int g = (L.n * 4 + 127) / 128;
   const double oc = opt.over_correction, om = opt.omega;
+  const int gw = (L.n * 32 + 127) / 128;
+  if (nb_ == 4 && (l > 0 ? cw_coarse() : cw_fine())) {  // a warp per node, coalesced block reads
+    if (l == 0 && L.vals32) {
+      if (xc) pdl_launch(gw, 128, 0, s)(k_smooth_cw4<float, true, false>, L.rowptr, L.colind, L.vals32, L.dinv, b, xin, xout, L.agg, xc, oc, om, L.n, L.npc);
+      else pdl_launch(gw, 128, 0, s)(k_smooth_cw4<float, false, false>, L.rowptr, L.colind, L.vals32, L.dinv, b, xin, xout, nullptr, nullptr, 0.0, om, L.n, 0);
+    } else {
+      if (xc) pdl_launch(gw, 128, 0, s)(k_smooth_cw4<double, true, false>, L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, L.agg, xc, oc, om, L.n, L.npc);
+      else pdl_launch(gw, 128, 0, s)(k_smooth_cw4<double, false, false>, L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, nullptr, nullptr, 0.0, om, L.n, 0);
+    }
+    return;
+  }
   if (l > 0) {  // coarse levels: a warp per node
-    const int gw = (L.n * 32 + 127) / 128;
     if (xc) { C8_NB_SWITCH(nb_, (pdl_launch(gw, 128, 0, s)(k_smooth_warp<NB, true, false>, L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, L.agg, xc, oc, om, L.n))); }
     else { C8_NB_SWITCH(nb_, (pdl_launch(gw, 128, 0, s)(k_smooth_warp<NB, false, false>, L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, nullptr, nullptr, 0.0, om, L.n))); }
     return;
@@ -543,7 +641,12 @@ void Amg::cycle(int l, const double* b, double* xout) {
   halo(l, cur);
   double* r = (l == 0) ? r0_ : L.r;
   if (L.n > 0) {
-    if (l > 0) { C8_NB_SWITCH(nb_, (pdl_launch((L.n * 32 + 127) / 128, 128, 0, s)(k_smooth_warp<NB, false, true>, L.rowptr, L.colind, L.vals, nullptr, b, cur, r, nullptr, nullptr, 0.0, 0.0, L.n))); }
+    if (nb_ == 4 && (l > 0 ? cw_coarse() : cw_fine())) {
+      const int gw = (L.n * 32 + 127) / 128;
+      if (l == 0 && L.vals32) pdl_launch(gw, 128, 0, s)(k_smooth_cw4<float, false, true>, L.rowptr, L.colind, L.vals32, nullptr, b, cur, r, nullptr, nullptr, 0.0, 0.0, L.n, 0);
+      else pdl_launch(gw, 128, 0, s)(k_smooth_cw4<double, false, true>, L.rowptr, L.colind, L.vals, nullptr, b, cur, r, nullptr, nullptr, 0.0, 0.0, L.n, 0);
+    }
+    else if (l > 0) { C8_NB_SWITCH(nb_, (pdl_launch((L.n * 32 + 127) / 128, 128, 0, s)(k_smooth_warp<NB, false, true>, L.rowptr, L.colind, L.vals, nullptr, b, cur, r, nullptr, nullptr, 0.0, 0.0, L.n))); }
     else if (L.vals32) { C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_bsr_residual<NB, float>, L.rowptr, L.colind, L.vals32, cur, b, r, L.n))); }
     else { C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_bsr_residual<NB, double>, L.rowptr, L.colind, L.vals, cur, b, r, L.n))); }
   }
@@ -558,6 +661,12 @@ void Amg::cycle(int l, const double* b, double* xout) {
   cycle(l + 1, C.b, C.x);
   halo(l + 1, C.x);   // the prolongation reads the aggregates of ghost columns
   amg_dbg(s, "coarse cycle", l);
+  if (l == 0 && fine_prolong_add() && L.npc > 0) {
+    // fine level: the correction as an elementwise pass (3 vectors) + a plain sweep, instead of two
+    // more dependent gathers per block inside the sweep
+    C8_NB_SWITCH(nb_, (pdl_launch((L.npc * nb_ + 255) / 256, 256, 0, s)(k_prolong_add<NB>, L.agg, C.x, const_cast<double*>(cur), opt.over_correction, L.npc)));
+    sweep(l, b, cur, buf(nu1), nullptr);
+  } else
   sweep(l, b, cur, buf(nu1), C.x);   // the ghost entries of cur are still current
   amg_dbg(s, "prolong sweep", l);
   for (int w = nu1 + 1; w < writes; ++w) { halo(l, buf(w - 1)); sweep(l, b, buf(w - 1), buf(w), nullptr); amg_dbg(s, "post sweep", l); }

@@ -49,6 +49,7 @@ struct FwdArgs {
   int* n_failed;          // device counter of failed local solves
   double* elem_J;         // optional [n_elems][NX][NX] element Jacobians (reference dof order)
   double* elem_R;         // optional [n_elems][NX]
+  cudaEvent_t elements_done;  // host side only: recorded between the element kernel and the BSR gather (may be null)
 };
 
 }  // namespace c8

@@ -42,6 +42,7 @@ struct Launch {
     const bool fast = a.vals && a.b && !a.elem_J && !a.elem_R;
     if (fast) k_forward_jacobian<C, true><<<grid, block, 0, s>>>(a);
     else k_forward_jacobian<C, false><<<grid, block, 0, s>>>(a);
+    if (a.elements_done) cudaEventRecord(a.elements_done, s);  // xi, b, path and the status are final here
     if (a.vals) gather<false>(a.mesh, a.emat, a.vals, s);
 #ifdef C8_K1_PHASE_CLOCKS
     if (fast) {  // tuning builds: print and reset the per-phase warp-cycle counters

@@ -200,6 +200,8 @@ void c8_destroy(c8_ctx* ctx) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->ev_elements) cudaEventDestroy(ctx->ev_elements);
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -515,6 +517,55 @@ static int forward_impl(c8_ctx* ctx, const double* x, const double* xp, const do
   }
   return C8_OK;
 }
+
+}  // extern "C"
+
+// The reference-facing call with host buffers (Newton iterate in, residual + local-solve status out;
+// the matrix stays resident for the linear solve).  The residual, the local state and the status are
+// final when the element kernel ends, so their way back to the host (de-interleave + D2H on a side
+// stream) overlaps the BSR gather of the matrix.
+int c8::forward_state_host(c8_ctx* ctx, const double* u, const double* p, double* b_u, double* b_p,
+                           int* n_failed) {
+  C8_REQUIRE(ctx, ctx->kt != nullptr, "c8_set_model must be called first");
+  const int nb = ctx->kt->nb, dim = ctx->dim, n = ctx->n_nodes;
+  const size_t nu = size_t(n) * dim, np = (nb > dim) ? size_t(n) : 0;
+  int rc;
+  if ((rc = c8_pack_x(ctx, u, p, ctx->d_x)) != C8_OK) return rc;
+  if (!ctx->side_stream) C8_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+  if (!ctx->ev_elements) C8_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_elements, cudaEventDisableTiming));
+  C8_CUDA(ctx, cudaMemsetAsync(ctx->d_b, 0, size_t(n) * nb * sizeof(double), ctx->stream));
+  C8_CUDA(ctx, cudaMemsetAsync(ctx->d_nfailed, 0, sizeof(int), ctx->stream));
+  FwdArgs a{};
+  a.mesh = ctx->mesh_args();
+  a.model = ctx->model;
+  a.x = ctx->d_x; a.x_prev = ctx->d_xp; a.xi_prev = ctx->d_xip; a.xi = ctx->d_xi; a.xi_ld = ctx->xi_ld;
+  a.vals = ctx->d_A; a.b = ctx->d_b; a.n_failed = ctx->d_nfailed;   // A is overwritten block by block
+  a.emat = element_scratch(ctx);
+  if (!a.emat) return C8_ERR_CUDA;
+  a.elements_done = ctx->ev_elements;
+  ctx->kt->forward_jacobian(a, ctx->stream);
+  C8_CUDA(ctx, cudaGetLastError());
+  cudaStream_t side = ctx->side_stream;
+  C8_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_elements, 0));
+  double* d = stage(ctx, (nu + np) * sizeof(double));
+  C8_REQUIRE(ctx, d != nullptr, "staging allocation failed");
+  k_deinterleave<<<(n * nb + 255) / 256, 256, 0, side>>>(ctx->d_b, d, d + nu, n, dim, nb);
+  C8_CUDA(ctx, cudaMemcpyAsync(b_u, d, nu * sizeof(double), cudaMemcpyDeviceToHost, side));
+  if (np && b_p) C8_CUDA(ctx, cudaMemcpyAsync(b_p, d + nu, np * sizeof(double), cudaMemcpyDeviceToHost, side));
+  int nf = 0;
+  if (ctx->allreduce_cb) {
+    C8_CUDA(ctx, cudaStreamSynchronize(side));
+    if ((rc = fetch_n_failed(ctx, &nf)) != C8_OK) return rc;   // summed over the parts, main stream
+  } else {
+    C8_CUDA(ctx, cudaMemcpyAsync(&nf, ctx->d_nfailed, sizeof(int), cudaMemcpyDeviceToHost, side));
+    C8_CUDA(ctx, cudaStreamSynchronize(side));
+    C8_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the matrix is complete when the call returns
+  }
+  if (n_failed) *n_failed = nf;
+  return nf > 0 ? C8_ERR_LOCAL_SOLVE : C8_OK;
+}
+
+extern "C" {
 
 int c8_forward_jacobian(c8_ctx* ctx, const double* x, const double* xp, const double* xip,
                         double* xi, double* A, double* b, int8_t* path, int* n_failed) {

@@ -11,6 +11,8 @@ struct c8_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t side_stream = nullptr;   // host-buffer calls: result copies that overlap the BSR gather
+  cudaEvent_t ev_elements = nullptr;
   std::string err;
 
   // mesh
@@ -75,6 +77,8 @@ double* stage(c8_ctx* ctx, size_t bytes);
 double* pinned(c8_ctx* ctx, size_t bytes);
 int fetch_n_failed(c8_ctx* ctx, int* out);
 double* element_scratch(c8_ctx* ctx);
+// eval_forward_jacobian on the resident state with HOST nodal buffers (c8_state_forward_jacobian)
+int forward_state_host(c8_ctx* ctx, const double* u, const double* p, double* b_u, double* b_p, int* n_failed);
 }  // namespace c8
 
 #define C8_CUDA(ctx, call)                                        \

@@ -52,20 +52,7 @@ int c8_state_set_prev(c8_ctx* ctx, const double* u_prev, const double* p_prev,
 
 int c8_state_forward_jacobian(c8_ctx* ctx, const double* u, const double* p, double* b_u,
                               double* b_p, int* n_failed) {
-  C8_REQUIRE(ctx, ctx->kt != nullptr, "c8_set_model must be called first");
-  const KernelTable* k = ctx->kt;
-  int rc;
-  if ((rc = c8_pack_x(ctx, u, p, ctx->d_x)) != C8_OK) return rc;
-  C8_CUDA(ctx, cudaMemsetAsync(ctx->d_A, 0, size_t(ctx->nnzb) * k->nb * k->nb * sizeof(double),
-                               ctx->stream));
-  C8_CUDA(ctx, cudaMemsetAsync(ctx->d_b, 0, size_t(ctx->n_nodes) * k->nb * sizeof(double),
-                               ctx->stream));
-  int nf = 0;
-  rc = c8_forward_jacobian(ctx, ctx->d_x, ctx->d_xp, ctx->d_xip, ctx->d_xi, ctx->d_A, ctx->d_b,
-                           nullptr, &nf);
-  if (n_failed) *n_failed = nf;
-  if (rc != C8_OK) return rc;
-  return c8_unpack_x(ctx, ctx->d_b, b_u, b_p);
+  return forward_state_host(ctx, u, p, b_u, b_p, n_failed);
 }
 
 int c8_state_get_xi(c8_ctx* ctx, double* xi_host) { return c8_unpack_xi(ctx, ctx->d_xi, xi_host); }

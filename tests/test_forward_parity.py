@@ -124,6 +124,35 @@ def test_host_buffer_entry_point():
     ctx.close()
 
 
+@pytest.mark.parametrize("name", ["3d_hyper_J2", "2d_small_hill_plane_stress"])
+def test_resident_state_host_call(name):
+    """c8_state_forward_jacobian (bench.py's e2e call: host nodal iterate in, host residual + status
+    out, matrix resident; the copies back overlap the BSR gather) against the oracle, twice in a row."""
+    r = run_pair(name)
+    orc, ctx, rB = r["orc"], r["ctx"], r["rB"]
+    (u1, p1), (u2, p2) = r["fields"]
+    ctx.state_set_prev(u1, p1, r["xi1"])
+    nr = orc.num_resid
+    for rep in range(2):
+        bu = np.zeros(ctx.n_nodes * ctx.dim)
+        bp = np.zeros(ctx.n_nodes) if nr > 1 else None
+        nf = ctx.state_forward_jacobian(np.ascontiguousarray(u2), None if p2 is None else np.ascontiguousarray(p2),
+                                        bu, bp)
+        assert nf == 0
+        bs = [bu] if nr == 1 else [bu, bp]
+        for i in range(nr):
+            assert np.abs(bs[i] - rB["b"][i]).max() < TOL * np.abs(rB["b"][i]).max()
+        assert rel_err_blockwise(ctx.state_get_xi(), rB["xi"], 0) < TOL
+        # the resident matrix is complete when the call returns
+        A = int(ctx.state_ptrs()["A"])   # device pointer of the resident BSR values
+        for i in range(nr):
+            for j in range(nr):
+                rp_o, _ = orc.graph(i, j)
+                vals = ctx.csr_block_values(i, j, A)
+                assert rel_err_rows(vals, rB["A"][i * nr + j], rp_o) < TOL
+    ctx.close()
+
+
 def test_local_solve_failure_is_reported():
     """max_iters too small for a plastic step -> status -1 like the reference (evaluations.cpp:95-97)."""
     import torch

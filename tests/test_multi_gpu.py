@@ -71,6 +71,8 @@ def _solve(case, mesh, part, ctx_setup, measured=None, area=None, params=None):
     g = hp.adjoint_gradient()
     u_last = hp.get_step(d["num_steps"])[0][0]
     stats = ctx.comm_stats()
+    stats["krylov_iterations"] = hp.stats()["linear_iters"]
+    stats["amg_levels"] = ctx.preconditioner_info()["levels"]
     hp.close(); ctx.close()
     return J, g, u_last, stats
 
@@ -160,13 +162,16 @@ def _check(world, transport, case):
     d, mesh_name, _ = _deck(case)
     mesh = load_mesh(mesh_name)
     measured, area = _measured(case, mesh)
-    J1, g1, u1, _ = _solve(case, mesh, None, None, measured, area)
+    J1, g1, u1, st1 = _solve(case, mesh, None, None, measured, area)
     res = _run_parts(world, transport, case)
     u = np.zeros((mesh.n_nodes, mesh.dim))
     for rank, J, g, gid, u_owned, stats in res:
         assert abs(J - J1) <= 1e-8 * abs(J1), (rank, J, J1)                       # objective, 1e-8 relative
         assert np.abs(g - g1).max() <= 1e-8 * np.abs(g1).max(), (rank, g, g1)     # adjoint gradient
         assert stats["halo_calls"] > 0 and stats["allreduce_calls"] > 0
+        # the multigrid hierarchy spans the parts: the Krylov iteration count stays that of one part
+        # (a hierarchy on each part's owned block needs 1.4x (2 parts) to 2x (8 parts) as many)
+        assert stats["krylov_iterations"] <= 1.25 * st1["krylov_iterations"] + 10, (stats, st1)
         u[gid] = u_owned
     assert np.abs(u - u1.reshape(-1, mesh.dim)).max() <= 1e-8 * np.abs(u1).max()
 
