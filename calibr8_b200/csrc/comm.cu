@@ -13,9 +13,17 @@
 //               that the library already loaded in the process (e.g. torch's) is the one used.
 //   host-staged pack -> pinned host -> caller's exchange function (MPI / gloo) -> ghost range.
 //               This is what a calibr8 MPI rank without NCCL binds (PCU/MPI callbacks).
+//   NVLink push EXPERIMENTAL, off unless C8_P2P=1 (written at the end of round 1, not yet run on a
+//               multi-GPU box): the halo copy as two small kernels over CUDA-IPC peer memory -- pack
+//               and store straight into the neighbour's staging buffer + release a flag; wait for the
+//               neighbours' flags and unpack -- in place of the pack kernel + ncclSend/Recv group
+//               (~20 us per halo copy, 9 per Arnoldi iteration of a partitioned run).  Sequence
+//               numbers live on the device, so the kernels replay inside the iteration graphs.
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <vector>
@@ -90,6 +98,7 @@ struct Comm {
   struct Level { HaloPlanHost plan; int* d_send_nodes = nullptr; };
   std::vector<Level> levels;
   bool library_transport = false;   // NCCL or host-staged (not the caller's own c8_set_comm hooks)
+  struct P2P* p2p = nullptr;        // NVLink push halo (experimental, C8_P2P=1)
   // statistics
   long long n_halo = 0, n_allreduce = 0, halo_bytes = 0;
 };
@@ -104,12 +113,109 @@ __global__ void k_halo_pack(const double* __restrict__ v, const int* __restrict_
   out[i] = v[size_t(__ldg(&nodes[k])) * nb + c];
 }
 
+
+// ---- NVLink push halo (experimental, C8_P2P=1) --------------------------------------------------
+constexpr int P2P_MAXN = 16;          // neighbours per part
+constexpr size_t P2P_HEADER = 1024;   // bytes before the staging area: flags[16] | seq @256 | done[2] @264
+struct P2PPlan { int n; int send_ptr[P2P_MAXN + 1]; int recv_ptr[P2P_MAXN + 1]; };
+struct P2PPeers {
+  double* stage[P2P_MAXN];              // neighbour's staging area (peer mapping)
+  unsigned long long* flag[P2P_MAXN];   // this part's flag inside the neighbour's header
+  long long stride[P2P_MAXN];           // doubles per parity slot of the neighbour's staging area
+  int dst_off[P2P_MAXN];                // node offset of this part's message there (the neighbour's level-0 recv_ptr)
+  int recv_off[P2P_MAXN];               // own level-0 recv_ptr
+};
+struct P2P {
+  bool ready = false;
+  char* base = nullptr;                 // own header + staging (2 parity slots x n_recv0 x NBMAX doubles)
+  long long stride = 0;
+  std::vector<void*> peer_base;
+  P2PPeers peers{};
+};
+
+// pack the send nodes of every neighbour straight into its staging slot (parity = seq & 1); the last
+// CTA to finish releases this part's flag at every neighbour with the value seq + 1
+__global__ void k_halo_push(const double* __restrict__ vec, const int* __restrict__ send_nodes, P2PPlan pl,
+                            P2PPeers pe, int nb, int maxnb, const unsigned long long* seq,
+                            unsigned int* done) {
+  const unsigned long long s = *reinterpret_cast<const volatile unsigned long long*>(seq);
+  const int total = pl.send_ptr[pl.n] * nb;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int node_i = i / nb, c = i - node_i * nb;
+    int k = 0;
+    while (node_i >= pl.send_ptr[k + 1]) ++k;
+    const int j = node_i - pl.send_ptr[k];
+    pe.stage[k][(s & 1ull) * pe.stride[k] + size_t(pe.dst_off[k]) * maxnb + size_t(j) * nb + c] =
+        vec[size_t(__ldg(&send_nodes[node_i])) * nb + c];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(done, 1u);
+    if (prev == gridDim.x - 1) {
+      *done = 0;
+      __threadfence_system();
+      for (int k = 0; k < pl.n; ++k) *reinterpret_cast<volatile unsigned long long*>(pe.flag[k]) = s + 1;
+    }
+  }
+}
+
+// wait until every neighbour has released seq + 1, copy the staging slot into the ghost range, and
+// let the last CTA advance the sequence number
+__global__ void k_halo_pull(double* __restrict__ ghost, const double* stage, const unsigned long long* flags,
+                            P2PPlan pl, P2PPeers pe, long long stride, int nb, int maxnb,
+                            unsigned long long* seq, unsigned int* done) {
+  const unsigned long long s = *reinterpret_cast<volatile unsigned long long*>(seq);
+  if (threadIdx.x < pl.n) {
+    const volatile unsigned long long* f = flags + threadIdx.x;
+    while (*f < s + 1) { }
+  }
+  __syncthreads();
+  __threadfence_system();
+  const int total = pl.recv_ptr[pl.n] * nb;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int node_i = i / nb, c = i - node_i * nb;
+    int k = 0;
+    while (node_i >= pl.recv_ptr[k + 1]) ++k;
+    const int j = node_i - pl.recv_ptr[k];
+    // the slot was written by a peer through NVLink: read it from L2, not from a stale L1 line
+    ghost[size_t(node_i) * nb + c] =
+        __ldcg(&stage[(s & 1ull) * stride + size_t(pe.recv_off[k]) * maxnb + size_t(j) * nb + c]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(done, 1u);
+    if (prev == gridDim.x - 1) {
+      *done = 0;
+      __threadfence();
+      *reinterpret_cast<volatile unsigned long long*>(seq) = s + 1;
+    }
+  }
+}
+
 // one halo copy over NCCL for any level's plan: pack -> grouped send/recv straight into the ghost range
 static void halo_nccl_plan(Comm& c, const int* d_send_nodes, const std::vector<int>& send_ptr,
                            const std::vector<int>& recv_ptr, int n_owned, double* vec, int nb) {
   if (c.n_nbr == 0) return;
   cudaStream_t s = c.ctx->stream;
   const int n_send = send_ptr[c.n_nbr], n_recv = recv_ptr[c.n_nbr];
+  if (c.p2p && c.p2p->ready) {
+    P2P& q = *c.p2p;
+    P2PPlan pl;
+    pl.n = c.n_nbr;
+    for (int k = 0; k <= c.n_nbr; ++k) { pl.send_ptr[k] = send_ptr[k]; pl.recv_ptr[k] = recv_ptr[k]; }
+    unsigned long long* flags = reinterpret_cast<unsigned long long*>(q.base);
+    unsigned long long* seq = reinterpret_cast<unsigned long long*>(q.base + 256);
+    unsigned int* done = reinterpret_cast<unsigned int*>(q.base + 264);
+    const double* stage = reinterpret_cast<const double*>(q.base + P2P_HEADER);
+    auto grid = [](int work) { const int g = (work + 255) / 256; return g < 1 ? 1 : (g > 148 ? 148 : g); };
+    k_halo_push<<<grid(n_send * nb), 256, 0, s>>>(vec, d_send_nodes, pl, q.peers, nb, NBMAX, seq, done);
+    k_halo_pull<<<grid(n_recv * nb), 256, 0, s>>>(vec + size_t(n_owned) * nb, stage, flags, pl, q.peers, q.stride,
+                                                  nb, NBMAX, seq, done + 1);
+    ++c.n_halo;
+    c.halo_bytes += (long long)(n_send + n_recv) * nb * 8;
+    return;
+  }
   if (n_send)
     k_halo_pack<<<(n_send * nb + 255) / 256, 256, 0, s>>>(vec, d_send_nodes, c.d_sendbuf, n_send, nb);
   g_nccl.GroupStart();
@@ -123,6 +229,89 @@ static void halo_nccl_plan(Comm& c, const int* d_send_nodes, const std::vector<i
   if (r != ncclSuccess) c.last = g_nccl.GetErrorString(r);
   ++c.n_halo;
   c.halo_bytes += (long long)(n_send + n_recv) * nb * 8;
+}
+
+static void p2p_release(Comm& c) {
+  if (!c.p2p) return;
+  for (void* p : c.p2p->peer_base)
+    if (p) cudaIpcCloseMemHandle(p);
+  if (c.p2p->base) cudaFree(c.p2p->base);
+  delete c.p2p;
+  c.p2p = nullptr;
+}
+
+// Maps every neighbour's staging buffer into this process (CUDA IPC, one box) and learns where this
+// part's messages go there.  The 64-byte handles and the per-rank tables travel by one ncclAllReduce
+// of zero-padded doubles (every rank fills its own segment).  Any failure leaves NCCL send/recv in use.
+static void p2p_setup(Comm& c) {
+  if (c.n_nbr == 0 || c.n_nbr > P2P_MAXN || c.nranks < 2) return;
+  cudaStream_t s = c.ctx->stream;
+  P2P* q = new P2P();
+  c.p2p = q;
+  q->stride = (long long)(c.n_recv > 0 ? c.n_recv : 1) * NBMAX;
+  const size_t bytes = P2P_HEADER + size_t(2) * q->stride * sizeof(double);
+  if (cudaMalloc(&q->base, bytes) != cudaSuccess) { p2p_release(c); return; }
+  cudaMemsetAsync(q->base, 0, bytes, s);
+  cudaIpcMemHandle_t mine;
+  if (cudaIpcGetMemHandle(&mine, q->base) != cudaSuccess) { cudaGetLastError(); p2p_release(c); return; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  // per rank: 64 handle bytes | stride | for every sender: recv offset + 1 | flag slot + 1
+  const int W = 64 + 1 + 2 * c.nranks;
+  std::vector<double> tab(size_t(W) * c.nranks, 0.0);
+  double* me = tab.data() + size_t(W) * c.rank;
+  const unsigned char* hb = reinterpret_cast<const unsigned char*>(&mine);
+  for (int i = 0; i < 64; ++i) me[i] = double(hb[i]);
+  me[64] = double(q->stride);
+  for (int k = 0; k < c.n_nbr; ++k) {
+    me[65 + c.nbr_rank[k]] = double(c.recv_ptr[k] + 1);
+    me[65 + c.nranks + c.nbr_rank[k]] = double(k + 1);
+  }
+  double* d_tab = nullptr;
+  if (cudaMalloc(&d_tab, tab.size() * sizeof(double)) != cudaSuccess) { p2p_release(c); return; }
+  cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, s);
+  g_nccl.AllReduce(d_tab, d_tab, tab.size(), ncclDouble, ncclSum, c.nccl, s);
+  cudaMemcpyAsync(tab.data(), d_tab, tab.size() * sizeof(double), cudaMemcpyDeviceToHost, s);
+  const bool ok = cudaStreamSynchronize(s) == cudaSuccess;
+  cudaFree(d_tab);
+  if (!ok) { p2p_release(c); return; }
+  q->peer_base.assign(c.n_nbr, nullptr);
+  bool all = true;
+  for (int k = 0; k < c.n_nbr && all; ++k) {
+    const double* row = tab.data() + size_t(W) * c.nbr_rank[k];
+    cudaIpcMemHandle_t h;
+    unsigned char* b = reinterpret_cast<unsigned char*>(&h);
+    for (int i = 0; i < 64; ++i) b[i] = (unsigned char)(row[i] + 0.5);
+    const int dst_off = int(row[65 + c.rank] + 0.5) - 1, slot = int(row[65 + c.nranks + c.rank] + 0.5) - 1;
+    if (dst_off < 0 || slot < 0 ||
+        cudaIpcOpenMemHandle(&q->peer_base[k], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      all = false;
+      break;
+    }
+    char* pb = static_cast<char*>(q->peer_base[k]);
+    q->peers.stage[k] = reinterpret_cast<double*>(pb + P2P_HEADER);
+    q->peers.flag[k] = reinterpret_cast<unsigned long long*>(pb) + slot;
+    q->peers.stride[k] = (long long)(row[64] + 0.5);
+    q->peers.dst_off[k] = dst_off;
+    q->peers.recv_off[k] = c.recv_ptr[k];
+  }
+  // every rank must agree before anyone pushes: a part that failed would never release its flags
+  double flag_ok = all ? 0.0 : 1.0, *d_ok = nullptr;
+  if (cudaMalloc(&d_ok, sizeof(double)) == cudaSuccess) {
+    cudaMemcpyAsync(d_ok, &flag_ok, sizeof(double), cudaMemcpyHostToDevice, s);
+    g_nccl.AllReduce(d_ok, d_ok, 1, ncclDouble, ncclSum, c.nccl, s);
+    cudaMemcpyAsync(&flag_ok, d_ok, sizeof(double), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    cudaFree(d_ok);
+  } else {
+    flag_ok = 1.0;
+  }
+  if (flag_ok != 0.0) {
+    fprintf(stderr, "[c8b200] C8_P2P=1: peer mapping not available on every part, using NCCL send/recv\n");
+    p2p_release(c);
+    return;
+  }
+  q->ready = true;
 }
 
 static void halo_nccl(void* user, double* vec, int nb) {
@@ -242,6 +431,7 @@ void comm_release(c8_ctx* ctx) {
   if (it == g_comm.end()) return;
   Comm& c = it->second;
   drop_levels(c);
+  p2p_release(c);
   if (c.nccl && g_nccl.lib) g_nccl.CommDestroy(c.nccl);
   if (c.d_send_nodes) cudaFree(c.d_send_nodes);
   if (c.d_sendbuf) cudaFree(c.d_sendbuf);
@@ -346,6 +536,9 @@ int c8_nccl_init(c8_ctx* ctx, const char* id128, int rank, int nranks) {
   const int rc = c8_set_comm(ctx, &halo_nccl, &allreduce_nccl, &c);
   ctx->comm_capturable = true;
   c.library_transport = true;
+  p2p_release(c);
+  const char* e = getenv("C8_P2P");
+  if (e && e[0] == '1') p2p_setup(c);   // experimental NVLink push halo, see the header of this file
   return rc;
 }
 

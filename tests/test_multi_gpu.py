@@ -107,6 +107,9 @@ def _measured(case, mesh):
 
 def _worker(rank, world, port, transport, case, q):
     import sys
+    if transport == "nccl_p2p":     # experimental NVLink push halo (csrc/comm.cu), same checks
+        os.environ["C8_P2P"] = "1"
+        transport = "nccl"
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
     import torch.distributed as dist
@@ -191,3 +194,12 @@ def test_two_parts_nccl(case):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     _check(2, "nccl", case)
+
+
+@pytest.mark.skipif(os.environ.get("C8_TEST_P2P") != "1",
+                    reason="experimental NVLink push halo: set C8_TEST_P2P=1 on a box with >= 2 GPUs")
+def test_two_parts_nccl_p2p_push_halo():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    _check(2, "nccl_p2p", "notch_small_J2")
