@@ -17,8 +17,10 @@
 //               multi-GPU box): the halo copy as two small kernels over CUDA-IPC peer memory -- pack
 //               and store straight into the neighbour's staging buffer + release a flag; wait for the
 //               neighbours' flags and unpack -- in place of the pack kernel + ncclSend/Recv group
-//               (~20 us per halo copy, 9 per Arnoldi iteration of a partitioned run).  Sequence
-//               numbers live on the device, so the kernels replay inside the iteration graphs.
+//               (~20 us per halo copy, 9 per Arnoldi iteration of a partitioned run), and the small
+//               allreduces (<= 128 doubles: Gram-Schmidt dots, norms, scalars) as one single-CTA
+//               push / wait / sum-in-rank-order kernel (C8_P2P_ALLREDUCE=0 keeps NCCL for those).
+//               Sequence numbers live on the device, so the kernels replay inside the iteration graphs.
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -116,7 +118,8 @@ __global__ void k_halo_pack(const double* __restrict__ v, const int* __restrict_
 
 // ---- NVLink push halo (experimental, C8_P2P=1) --------------------------------------------------
 constexpr int P2P_MAXN = 16;          // neighbours per part
-constexpr size_t P2P_HEADER = 1024;   // bytes before the staging area: flags[16] | seq @256 | done[2] @264
+constexpr size_t P2P_HEADER = 1024;   // bytes before the staging area: halo flags[16] | seq @256 | done[2] @264 |
+                                      // allreduce flags[16] @512 | allreduce seq @640
 struct P2PPlan { int n; int send_ptr[P2P_MAXN + 1]; int recv_ptr[P2P_MAXN + 1]; };
 struct P2PPeers {
   double* stage[P2P_MAXN];              // neighbour's staging area (peer mapping)
@@ -125,12 +128,20 @@ struct P2PPeers {
   int dst_off[P2P_MAXN];                // node offset of this part's message there (the neighbour's level-0 recv_ptr)
   int recv_off[P2P_MAXN];               // own level-0 recv_ptr
 };
+constexpr int P2P_AR_MAX = 128;       // doubles per small allreduce (Gram-Schmidt dots, scalars)
+struct P2PAll {                       // every rank (not only the halo neighbours), for the small allreduce
+  int nranks, rank;
+  double* area[P2P_MAXN];             // rank r's allreduce area [2 parities][nranks senders][P2P_AR_MAX]
+  unsigned long long* flag[P2P_MAXN]; // this rank's flag in rank r's header (offset 512)
+};
 struct P2P {
   bool ready = false;
-  char* base = nullptr;                 // own header + staging (2 parity slots x n_recv0 x NBMAX doubles)
+  bool ar_ready = false;
+  char* base = nullptr;                 // own header | halo staging (2 parity slots x n_recv0 x NBMAX doubles) | allreduce area
   long long stride = 0;
-  std::vector<void*> peer_base;
+  std::vector<void*> peer_base;         // opened IPC mappings, one per rank (nullptr: not opened / self)
   P2PPeers peers{};
+  P2PAll all{};
 };
 
 // pack the send nodes of every neighbour straight into its staging slot (parity = seq & 1); the last
@@ -193,6 +204,36 @@ __global__ void k_halo_pull(double* __restrict__ ghost, const double* stage, con
   }
 }
 
+// Small allreduce (n <= P2P_AR_MAX) in ONE launch of one CTA: push this part's values into every
+// rank's area (parity = seq & 1), release the flags, wait for every rank's flag, sum in rank order
+// (the same order everywhere, so every part gets the same bits) and advance the sequence number.
+__global__ void k_allreduce_push(double* __restrict__ buf, int n, P2PAll pa, const double* my_area,
+                                 const unsigned long long* my_flags, unsigned long long* seq) {
+  const unsigned long long s = *reinterpret_cast<volatile unsigned long long*>(seq);
+  const int t = threadIdx.x;
+  const size_t slot = (s & 1ull) * size_t(pa.nranks) * P2P_AR_MAX;
+  if (t < n) {
+    const double v = buf[t];
+    for (int r = 0; r < pa.nranks; ++r) pa.area[r][slot + size_t(pa.rank) * P2P_AR_MAX + t] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < pa.nranks) {
+    *reinterpret_cast<volatile unsigned long long*>(pa.flag[t]) = s + 1;
+    const volatile unsigned long long* f = my_flags + t;
+    while (*f < s + 1) { }
+  }
+  __syncthreads();
+  __threadfence_system();
+  if (t < n) {
+    double acc = 0.0;
+    for (int r = 0; r < pa.nranks; ++r) acc += __ldcg(&my_area[slot + size_t(r) * P2P_AR_MAX + t]);
+    buf[t] = acc;
+  }
+  __syncthreads();
+  if (t == 0) *reinterpret_cast<volatile unsigned long long*>(seq) = s + 1;
+}
+
 // one halo copy over NCCL for any level's plan: pack -> grouped send/recv straight into the ghost range
 static void halo_nccl_plan(Comm& c, const int* d_send_nodes, const std::vector<int>& send_ptr,
                            const std::vector<int>& recv_ptr, int n_owned, double* vec, int nb) {
@@ -244,12 +285,13 @@ static void p2p_release(Comm& c) {
 // part's messages go there.  The 64-byte handles and the per-rank tables travel by one ncclAllReduce
 // of zero-padded doubles (every rank fills its own segment).  Any failure leaves NCCL send/recv in use.
 static void p2p_setup(Comm& c) {
-  if (c.n_nbr == 0 || c.n_nbr > P2P_MAXN || c.nranks < 2) return;
+  if (c.n_nbr == 0 || c.n_nbr > P2P_MAXN || c.nranks < 2 || c.nranks > P2P_MAXN) return;
   cudaStream_t s = c.ctx->stream;
   P2P* q = new P2P();
   c.p2p = q;
   q->stride = (long long)(c.n_recv > 0 ? c.n_recv : 1) * NBMAX;
-  const size_t bytes = P2P_HEADER + size_t(2) * q->stride * sizeof(double);
+  const size_t ar_bytes = size_t(2) * c.nranks * P2P_AR_MAX * sizeof(double);
+  const size_t bytes = P2P_HEADER + size_t(2) * q->stride * sizeof(double) + ar_bytes;
   if (cudaMalloc(&q->base, bytes) != cudaSuccess) { p2p_release(c); return; }
   cudaMemsetAsync(q->base, 0, bytes, s);
   cudaIpcMemHandle_t mine;
@@ -274,26 +316,41 @@ static void p2p_setup(Comm& c) {
   const bool ok = cudaStreamSynchronize(s) == cudaSuccess;
   cudaFree(d_tab);
   if (!ok) { p2p_release(c); return; }
-  q->peer_base.assign(c.n_nbr, nullptr);
+  // map every rank's buffer (the small allreduce talks to all of them, the halo to the neighbours)
+  q->peer_base.assign(c.nranks, nullptr);
+  std::vector<char*> base_of(c.nranks, nullptr);
   bool all = true;
-  for (int k = 0; k < c.n_nbr && all; ++k) {
-    const double* row = tab.data() + size_t(W) * c.nbr_rank[k];
+  for (int r = 0; r < c.nranks && all; ++r) {
+    if (r == c.rank) { base_of[r] = q->base; continue; }
+    const double* row = tab.data() + size_t(W) * r;
     cudaIpcMemHandle_t h;
     unsigned char* b = reinterpret_cast<unsigned char*>(&h);
     for (int i = 0; i < 64; ++i) b[i] = (unsigned char)(row[i] + 0.5);
-    const int dst_off = int(row[65 + c.rank] + 0.5) - 1, slot = int(row[65 + c.nranks + c.rank] + 0.5) - 1;
-    if (dst_off < 0 || slot < 0 ||
-        cudaIpcOpenMemHandle(&q->peer_base[k], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+    if (cudaIpcOpenMemHandle(&q->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
       cudaGetLastError();
+      q->peer_base[r] = nullptr;
       all = false;
       break;
     }
-    char* pb = static_cast<char*>(q->peer_base[k]);
-    q->peers.stage[k] = reinterpret_cast<double*>(pb + P2P_HEADER);
-    q->peers.flag[k] = reinterpret_cast<unsigned long long*>(pb) + slot;
+    base_of[r] = static_cast<char*>(q->peer_base[r]);
+  }
+  for (int k = 0; k < c.n_nbr && all; ++k) {
+    const int r = c.nbr_rank[k];
+    const double* row = tab.data() + size_t(W) * r;
+    const int dst_off = int(row[65 + c.rank] + 0.5) - 1, slot = int(row[65 + c.nranks + c.rank] + 0.5) - 1;
+    if (dst_off < 0 || slot < 0) { all = false; break; }   // the neighbour relation is not symmetric
+    q->peers.stage[k] = reinterpret_cast<double*>(base_of[r] + P2P_HEADER);
+    q->peers.flag[k] = reinterpret_cast<unsigned long long*>(base_of[r]) + slot;
     q->peers.stride[k] = (long long)(row[64] + 0.5);
     q->peers.dst_off[k] = dst_off;
     q->peers.recv_off[k] = c.recv_ptr[k];
+  }
+  q->all.nranks = c.nranks;
+  q->all.rank = c.rank;
+  for (int r = 0; r < c.nranks && all; ++r) {
+    const long long stride_r = (long long)(tab[size_t(W) * r + 64] + 0.5);
+    q->all.area[r] = reinterpret_cast<double*>(base_of[r] + P2P_HEADER + size_t(2) * stride_r * sizeof(double));
+    q->all.flag[r] = reinterpret_cast<unsigned long long*>(base_of[r] + 512) + c.rank;
   }
   // every rank must agree before anyone pushes: a part that failed would never release its flags
   double flag_ok = all ? 0.0 : 1.0, *d_ok = nullptr;
@@ -312,6 +369,8 @@ static void p2p_setup(Comm& c) {
     return;
   }
   q->ready = true;
+  const char* e = getenv("C8_P2P_ALLREDUCE");
+  q->ar_ready = !(e && e[0] == '0');
 }
 
 static void halo_nccl(void* user, double* vec, int nb) {
@@ -321,6 +380,15 @@ static void halo_nccl(void* user, double* vec, int nb) {
 
 static void allreduce_nccl(void* user, double* buf, int n) {
   Comm& c = *static_cast<Comm*>(user);
+  if (c.p2p && c.p2p->ar_ready && n <= P2P_AR_MAX) {
+    P2P& q = *c.p2p;
+    const double* my_area = reinterpret_cast<const double*>(q.base + P2P_HEADER + size_t(2) * q.stride * sizeof(double));
+    k_allreduce_push<<<1, P2P_AR_MAX, 0, c.ctx->stream>>>(
+        buf, n, q.all, my_area, reinterpret_cast<const unsigned long long*>(q.base + 512),
+        reinterpret_cast<unsigned long long*>(q.base + 640));
+    ++c.n_allreduce;
+    return;
+  }
   ncclResult_t r = g_nccl.AllReduce(buf, buf, size_t(n), ncclDouble, ncclSum, c.nccl, c.ctx->stream);
   if (r != ncclSuccess) c.last = g_nccl.GetErrorString(r);
   ++c.n_allreduce;
