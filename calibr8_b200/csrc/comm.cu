@@ -554,6 +554,12 @@ int c8_set_halo_plan(c8_ctx* ctx, int n_nbr, const int32_t* nbr_rank, const int3
   c.n_recv = n_nbr ? recv_ptr[n_nbr] : 0;
   c.send_ptr.resize(n_nbr + 1, 0);   // n_nbr == 0: one zero entry
   c.recv_ptr.resize(n_nbr + 1, 0);
+  C8_REQUIRE(ctx, c.n_recv == ctx->n_nodes - ctx->n_owned_nodes,
+             "halo plan: received node count differs from the ghost count (c8_set_partition first)");
+  for (int i = 0; i < c.n_send; ++i)
+    C8_REQUIRE(ctx, send_nodes[i] >= 0 && send_nodes[i] < ctx->n_owned_nodes,
+               "halo plan: a send node is not owned");
+  // host copy for the multigrid's per-level plans; a new plan invalidates the hierarchy
   drop_levels(c);
   c.plan0.n_owned = ctx->n_owned_nodes;
   c.plan0.nbr_rank = c.nbr_rank;
@@ -561,11 +567,6 @@ int c8_set_halo_plan(c8_ctx* ctx, int n_nbr, const int32_t* nbr_rank, const int3
   c.plan0.recv_ptr = c.recv_ptr;
   c.plan0.send_nodes.assign(send_nodes, send_nodes + c.n_send);
   c8_linalg_invalidate(ctx);
-  C8_REQUIRE(ctx, c.n_recv == ctx->n_nodes - ctx->n_owned_nodes,
-             "halo plan: received node count differs from the ghost count (c8_set_partition first)");
-  for (int i = 0; i < c.n_send; ++i)
-    C8_REQUIRE(ctx, send_nodes[i] >= 0 && send_nodes[i] < ctx->n_owned_nodes,
-               "halo plan: a send node is not owned");
   if (c.d_send_nodes) cudaFree(c.d_send_nodes);
   if (c.d_sendbuf) cudaFree(c.d_sendbuf);
   if (c.h_send) cudaFreeHost(c.h_send);
