@@ -498,7 +498,7 @@ class HostProblem:
 SYMBOLS += [
     "c8_set_partition", "c8_get_partition", "c8_set_comm", "c8_set_halo_plan", "c8_nccl_unique_id",
     "c8_nccl_init", "c8_set_comm_host", "c8_set_comm_rank", "c8_halo", "c8_halo_nb", "c8_allreduce", "c8_comm_stats",
-    "c8_comm_release",
+    "c8_comm_release", "c8_comm_p2p_active",
 ]
 _EXCHANGE_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int)
 _HOST_ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_double), C.c_int)
@@ -564,6 +564,12 @@ def _ctx_comm_stats(self):
     return dict(halo_calls=int(out[0]), allreduce_calls=int(out[1]), halo_bytes=int(out[2]))
 
 
+def _ctx_p2p_active(self):
+    v = int(self.lib.c8_comm_p2p_active(self.h))
+    return dict(halo=bool(v & 1), allreduce=bool(v & 2))
+
+
+Context.p2p_active = _ctx_p2p_active
 Context.set_partition = _ctx_set_partition
 Context.nccl_init = _ctx_nccl_init
 Context.set_comm_host = _ctx_set_comm_host

@@ -283,62 +283,89 @@ static void p2p_release(Comm& c) {
 
 // Maps every neighbour's staging buffer into this process (CUDA IPC, one box) and learns where this
 // part's messages go there.  The 64-byte handles and the per-rank tables travel by one ncclAllReduce
-// of zero-padded doubles (every rank fills its own segment).  Any failure leaves NCCL send/recv in use.
+// of zero-padded doubles (every rank fills its own segment).  Any failure on any rank leaves NCCL
+// send/recv in use on every rank.
 static void p2p_setup(Comm& c) {
-  if (c.n_nbr == 0 || c.n_nbr > P2P_MAXN || c.nranks < 2 || c.nranks > P2P_MAXN) return;
+  // Every rank of the communicator takes part in BOTH collectives below, whatever happened locally: a
+  // rank that cannot set up (no neighbours, too many, an allocation or IPC failure) contributes a zero
+  // segment to the table and a fail flag to the agreement, and P2P is released everywhere.
+  if (c.nranks < 2) return;
   cudaStream_t s = c.ctx->stream;
+  bool ok = c.n_nbr >= 1 && c.n_nbr <= P2P_MAXN && c.nranks <= P2P_MAXN;
   P2P* q = new P2P();
   c.p2p = q;
   q->stride = (long long)(c.n_recv > 0 ? c.n_recv : 1) * NBMAX;
   const size_t ar_bytes = size_t(2) * c.nranks * P2P_AR_MAX * sizeof(double);
   const size_t bytes = P2P_HEADER + size_t(2) * q->stride * sizeof(double) + ar_bytes;
-  if (cudaMalloc(&q->base, bytes) != cudaSuccess) { p2p_release(c); return; }
-  cudaMemsetAsync(q->base, 0, bytes, s);
   cudaIpcMemHandle_t mine;
-  if (cudaIpcGetMemHandle(&mine, q->base) != cudaSuccess) { cudaGetLastError(); p2p_release(c); return; }
+  std::memset(&mine, 0, sizeof(mine));
+  if (ok && cudaMalloc(&q->base, bytes) != cudaSuccess) { cudaGetLastError(); q->base = nullptr; ok = false; }
+  if (ok) cudaMemsetAsync(q->base, 0, bytes, s);
+  if (ok && cudaIpcGetMemHandle(&mine, q->base) != cudaSuccess) { cudaGetLastError(); ok = false; }
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
   // per rank: 64 handle bytes | stride | for every sender: recv offset + 1 | flag slot + 1
   const int W = 64 + 1 + 2 * c.nranks;
   std::vector<double> tab(size_t(W) * c.nranks, 0.0);
-  double* me = tab.data() + size_t(W) * c.rank;
-  const unsigned char* hb = reinterpret_cast<const unsigned char*>(&mine);
-  for (int i = 0; i < 64; ++i) me[i] = double(hb[i]);
-  me[64] = double(q->stride);
-  for (int k = 0; k < c.n_nbr; ++k) {
-    me[65 + c.nbr_rank[k]] = double(c.recv_ptr[k] + 1);
-    me[65 + c.nranks + c.nbr_rank[k]] = double(k + 1);
+  if (ok) {
+    double* me = tab.data() + size_t(W) * c.rank;
+    const unsigned char* hb = reinterpret_cast<const unsigned char*>(&mine);
+    for (int i = 0; i < 64; ++i) me[i] = double(hb[i]);
+    me[64] = double(q->stride);
+    for (int k = 0; k < c.n_nbr; ++k) {
+      me[65 + c.nbr_rank[k]] = double(c.recv_ptr[k] + 1);
+      me[65 + c.nranks + c.nbr_rank[k]] = double(k + 1);
+    }
   }
+  // collective 0: can every rank hold the table?  (an allreduce needs the same count everywhere, so a
+  // rank without the buffer cannot enter collective 1; agree on skipping it instead)
   double* d_tab = nullptr;
-  if (cudaMalloc(&d_tab, tab.size() * sizeof(double)) != cudaSuccess) { p2p_release(c); return; }
+  const bool have_tab = cudaMalloc(&d_tab, tab.size() * sizeof(double)) == cudaSuccess;
+  if (!have_tab) { cudaGetLastError(); ok = false; }
+  double pre = have_tab ? 0.0 : 1.0, *d_pre = nullptr;
+  if (cudaMalloc(&d_pre, sizeof(double)) != cudaSuccess) {
+    // not even one double: no collective is possible; end the job loudly rather than hang the others
+    fprintf(stderr, "[c8b200] C8_P2P=1: out of device memory during set-up\n");
+    std::abort();
+  }
+  cudaMemcpyAsync(d_pre, &pre, sizeof(double), cudaMemcpyHostToDevice, s);
+  g_nccl.AllReduce(d_pre, d_pre, 1, ncclDouble, ncclSum, c.nccl, s);
+  cudaMemcpyAsync(&pre, d_pre, sizeof(double), cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  if (pre != 0.0) {   // agreed everywhere: nobody enters collective 1, nobody uses P2P
+    if (d_tab) cudaFree(d_tab);
+    cudaFree(d_pre);
+    p2p_release(c);
+    return;
+  }
+  // collective 1: the table (a rank that failed locally contributes a zero segment)
   cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, s);
   g_nccl.AllReduce(d_tab, d_tab, tab.size(), ncclDouble, ncclSum, c.nccl, s);
   cudaMemcpyAsync(tab.data(), d_tab, tab.size() * sizeof(double), cudaMemcpyDeviceToHost, s);
-  const bool ok = cudaStreamSynchronize(s) == cudaSuccess;
+  if (cudaStreamSynchronize(s) != cudaSuccess) ok = false;
   cudaFree(d_tab);
-  if (!ok) { p2p_release(c); return; }
   // map every rank's buffer (the small allreduce talks to all of them, the halo to the neighbours)
   q->peer_base.assign(c.nranks, nullptr);
   std::vector<char*> base_of(c.nranks, nullptr);
-  bool all = true;
-  for (int r = 0; r < c.nranks && all; ++r) {
+  for (int r = 0; r < c.nranks && ok; ++r) {
     if (r == c.rank) { base_of[r] = q->base; continue; }
     const double* row = tab.data() + size_t(W) * r;
+    if (row[64] == 0.0) { ok = false; break; }   // that rank contributed nothing: it failed locally
     cudaIpcMemHandle_t h;
     unsigned char* b = reinterpret_cast<unsigned char*>(&h);
     for (int i = 0; i < 64; ++i) b[i] = (unsigned char)(row[i] + 0.5);
     if (cudaIpcOpenMemHandle(&q->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
       cudaGetLastError();
       q->peer_base[r] = nullptr;
-      all = false;
+      ok = false;
       break;
     }
     base_of[r] = static_cast<char*>(q->peer_base[r]);
   }
-  for (int k = 0; k < c.n_nbr && all; ++k) {
+  for (int k = 0; k < c.n_nbr && ok; ++k) {
     const int r = c.nbr_rank[k];
     const double* row = tab.data() + size_t(W) * r;
     const int dst_off = int(row[65 + c.rank] + 0.5) - 1, slot = int(row[65 + c.nranks + c.rank] + 0.5) - 1;
-    if (dst_off < 0 || slot < 0) { all = false; break; }   // the neighbour relation is not symmetric
+    if (dst_off < 0 || slot < 0) { ok = false; break; }   // the neighbour relation is not symmetric
     q->peers.stage[k] = reinterpret_cast<double*>(base_of[r] + P2P_HEADER);
     q->peers.flag[k] = reinterpret_cast<unsigned long long*>(base_of[r]) + slot;
     q->peers.stride[k] = (long long)(row[64] + 0.5);
@@ -347,24 +374,22 @@ static void p2p_setup(Comm& c) {
   }
   q->all.nranks = c.nranks;
   q->all.rank = c.rank;
-  for (int r = 0; r < c.nranks && all; ++r) {
+  for (int r = 0; r < c.nranks && ok; ++r) {
     const long long stride_r = (long long)(tab[size_t(W) * r + 64] + 0.5);
     q->all.area[r] = reinterpret_cast<double*>(base_of[r] + P2P_HEADER + size_t(2) * stride_r * sizeof(double));
     q->all.flag[r] = reinterpret_cast<unsigned long long*>(base_of[r] + 512) + c.rank;
   }
-  // every rank must agree before anyone pushes: a part that failed would never release its flags
-  double flag_ok = all ? 0.0 : 1.0, *d_ok = nullptr;
-  if (cudaMalloc(&d_ok, sizeof(double)) == cudaSuccess) {
-    cudaMemcpyAsync(d_ok, &flag_ok, sizeof(double), cudaMemcpyHostToDevice, s);
-    g_nccl.AllReduce(d_ok, d_ok, 1, ncclDouble, ncclSum, c.nccl, s);
-    cudaMemcpyAsync(&flag_ok, d_ok, sizeof(double), cudaMemcpyDeviceToHost, s);
-    cudaStreamSynchronize(s);
-    cudaFree(d_ok);
-  } else {
-    flag_ok = 1.0;
-  }
+  // collective 2: every rank must agree before anyone pushes (a part that failed would never release
+  // its flags)
+  double flag_ok = ok ? 0.0 : 1.0;
+  cudaMemcpyAsync(d_pre, &flag_ok, sizeof(double), cudaMemcpyHostToDevice, s);
+  g_nccl.AllReduce(d_pre, d_pre, 1, ncclDouble, ncclSum, c.nccl, s);
+  cudaMemcpyAsync(&flag_ok, d_pre, sizeof(double), cudaMemcpyDeviceToHost, s);
+  if (cudaStreamSynchronize(s) != cudaSuccess) flag_ok = 1.0;
+  cudaFree(d_pre);
   if (flag_ok != 0.0) {
-    fprintf(stderr, "[c8b200] C8_P2P=1: peer mapping not available on every part, using NCCL send/recv\n");
+    if (c.rank == 0)
+      fprintf(stderr, "[c8b200] C8_P2P=1: peer mapping not available on every part, using NCCL send/recv\n");
     p2p_release(c);
     return;
   }
@@ -542,43 +567,76 @@ int c8_set_comm(c8_ctx* ctx, c8_halo_fn halo, c8_allreduce_fn allreduce, void* u
 
 int c8_set_halo_plan(c8_ctx* ctx, int n_nbr, const int32_t* nbr_rank, const int32_t* send_ptr,
                      const int32_t* send_nodes, const int32_t* recv_ptr) {
+  // validate against the arguments first; the stored plan is only touched once everything passed
   C8_REQUIRE(ctx, n_nbr >= 0, "negative neighbour count");
-  C8_CUDA(ctx, cudaSetDevice(ctx->device));
-  Comm& c = g_comm[ctx];
-  c.ctx = ctx;
-  c.n_nbr = n_nbr;
-  c.nbr_rank.assign(nbr_rank, nbr_rank + n_nbr);
-  c.send_ptr.assign(send_ptr, send_ptr + n_nbr + 1);
-  c.recv_ptr.assign(recv_ptr, recv_ptr + n_nbr + 1);
-  c.n_send = n_nbr ? send_ptr[n_nbr] : 0;
-  c.n_recv = n_nbr ? recv_ptr[n_nbr] : 0;
-  c.send_ptr.resize(n_nbr + 1, 0);   // n_nbr == 0: one zero entry
-  c.recv_ptr.resize(n_nbr + 1, 0);
-  C8_REQUIRE(ctx, c.n_recv == ctx->n_nodes - ctx->n_owned_nodes,
+  C8_REQUIRE(ctx, n_nbr == 0 || (nbr_rank && send_ptr && recv_ptr), "halo plan: null array");
+  int n_send = 0, n_recv = 0;
+  if (n_nbr) {
+    C8_REQUIRE(ctx, send_ptr[0] == 0 && recv_ptr[0] == 0, "halo plan: prefix arrays must start at 0");
+    for (int k = 0; k < n_nbr; ++k) {
+      C8_REQUIRE(ctx, send_ptr[k + 1] >= send_ptr[k] && recv_ptr[k + 1] >= recv_ptr[k],
+                 "halo plan: prefix arrays must be non-decreasing");
+      C8_REQUIRE(ctx, nbr_rank[k] >= 0, "halo plan: negative neighbour rank");
+    }
+    n_send = send_ptr[n_nbr];
+    n_recv = recv_ptr[n_nbr];
+  }
+  C8_REQUIRE(ctx, n_recv == ctx->n_nodes - ctx->n_owned_nodes,
              "halo plan: received node count differs from the ghost count (c8_set_partition first)");
-  for (int i = 0; i < c.n_send; ++i)
+  C8_REQUIRE(ctx, n_send == 0 || send_nodes != nullptr, "halo plan: null send list");
+  for (int i = 0; i < n_send; ++i)
     C8_REQUIRE(ctx, send_nodes[i] >= 0 && send_nodes[i] < ctx->n_owned_nodes,
                "halo plan: a send node is not owned");
-  // host copy for the multigrid's per-level plans; a new plan invalidates the hierarchy
-  drop_levels(c);
-  c.plan0.n_owned = ctx->n_owned_nodes;
-  c.plan0.nbr_rank = c.nbr_rank;
-  c.plan0.send_ptr = c.send_ptr;
-  c.plan0.recv_ptr = c.recv_ptr;
-  c.plan0.send_nodes.assign(send_nodes, send_nodes + c.n_send);
-  c8_linalg_invalidate(ctx);
+  C8_CUDA(ctx, cudaSetDevice(ctx->device));
+  // allocate the new buffers before dropping the old ones
+  int* d_send_nodes = nullptr;
+  double *d_sendbuf = nullptr, *h_send = nullptr, *h_recv = nullptr;
+  auto drop_new = [&]() {
+    if (d_send_nodes) cudaFree(d_send_nodes);
+    if (d_sendbuf) cudaFree(d_sendbuf);
+    if (h_send) cudaFreeHost(h_send);
+    if (h_recv) cudaFreeHost(h_recv);
+  };
+  bool ok = true;
+  if (n_send) {
+    ok = ok && cuda_ok(ctx, cudaMalloc(&d_send_nodes, n_send * sizeof(int)), "cudaMalloc(send nodes)");
+    ok = ok && cuda_ok(ctx, cudaMemcpy(d_send_nodes, send_nodes, n_send * sizeof(int), cudaMemcpyHostToDevice),
+                       "cudaMemcpy(send nodes)");
+    ok = ok && cuda_ok(ctx, cudaMalloc(&d_sendbuf, size_t(n_send) * NBMAX * sizeof(double)), "cudaMalloc(send buffer)");
+  }
+  ok = ok && cuda_ok(ctx, cudaMallocHost(&h_send, size_t(n_send + 1) * NBMAX * sizeof(double)), "cudaMallocHost");
+  ok = ok && cuda_ok(ctx, cudaMallocHost(&h_recv, size_t(n_recv + 1) * NBMAX * sizeof(double)), "cudaMallocHost");
+  if (!ok) { drop_new(); return C8_ERR_CUDA; }
+  // commit
+  Comm& c = g_comm[ctx];
+  c.ctx = ctx;
+  p2p_release(c);   // its staging buffer was sized from the old plan (re-created by the next c8_nccl_init)
+  drop_levels(c);   // a new plan invalidates the multigrid's per-level plans
   if (c.d_send_nodes) cudaFree(c.d_send_nodes);
   if (c.d_sendbuf) cudaFree(c.d_sendbuf);
   if (c.h_send) cudaFreeHost(c.h_send);
   if (c.h_recv) cudaFreeHost(c.h_recv);
-  c.d_send_nodes = nullptr; c.d_sendbuf = nullptr; c.h_send = c.h_recv = nullptr;
-  if (c.n_send) {
-    C8_CUDA(ctx, cudaMalloc(&c.d_send_nodes, c.n_send * sizeof(int)));
-    C8_CUDA(ctx, cudaMemcpy(c.d_send_nodes, send_nodes, c.n_send * sizeof(int), cudaMemcpyHostToDevice));
-    C8_CUDA(ctx, cudaMalloc(&c.d_sendbuf, size_t(c.n_send) * NBMAX * sizeof(double)));
+  c.d_send_nodes = d_send_nodes; c.d_sendbuf = d_sendbuf; c.h_send = h_send; c.h_recv = h_recv;
+  c.n_nbr = n_nbr;
+  c.nbr_rank.assign(nbr_rank, nbr_rank + n_nbr);
+  c.send_ptr.assign(send_ptr, send_ptr + (n_nbr ? n_nbr + 1 : 0));
+  c.recv_ptr.assign(recv_ptr, recv_ptr + (n_nbr ? n_nbr + 1 : 0));
+  c.send_ptr.resize(n_nbr + 1, 0);   // n_nbr == 0: one zero entry
+  c.recv_ptr.resize(n_nbr + 1, 0);
+  c.n_send = n_send;
+  c.n_recv = n_recv;
+  c.plan0.n_owned = ctx->n_owned_nodes;
+  c.plan0.nbr_rank = c.nbr_rank;
+  c.plan0.send_ptr = c.send_ptr;
+  c.plan0.recv_ptr = c.recv_ptr;
+  c.plan0.send_nodes.assign(send_nodes, send_nodes + n_send);
+  c8_linalg_invalidate(ctx);
+  if (c.nccl) {   // re-plan on a live communicator: ranks are known now, and the push halo is rebuilt
+    for (int k = 0; k < n_nbr; ++k)
+      if (nbr_rank[k] >= c.nranks) return fail(ctx, C8_ERR_USAGE, "halo plan: neighbour rank out of range");
+    const char* e = getenv("C8_P2P");
+    if (e && e[0] == '1') p2p_setup(c);
   }
-  C8_CUDA(ctx, cudaMallocHost(&c.h_send, size_t(c.n_send + 1) * NBMAX * sizeof(double)));
-  C8_CUDA(ctx, cudaMallocHost(&c.h_recv, size_t(c.n_recv + 1) * NBMAX * sizeof(double)));
   return C8_OK;
 }
 
@@ -597,6 +655,10 @@ int c8_nccl_init(c8_ctx* ctx, const char* id128, int rank, int nranks) {
   C8_REQUIRE(ctx, it != g_comm.end(), "c8_set_halo_plan must be called before c8_nccl_init");
   Comm& c = it->second;
   C8_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (int k = 0; k < c.n_nbr; ++k)
+    C8_REQUIRE(ctx, c.nbr_rank[k] < nranks && c.nbr_rank[k] != rank, "halo plan: neighbour rank out of range");
+  p2p_release(c);
+  if (c.nccl) { g_nccl.CommDestroy(c.nccl); c.nccl = nullptr; }   // a second init replaces the communicator
   ncclUniqueId id;
   std::memcpy(&id, id128, 128);
   ncclResult_t r = g_nccl.CommInitRank(&c.nccl, nranks, id, rank);
@@ -656,6 +718,12 @@ int c8_comm_stats(c8_ctx* ctx, int64_t* out3) {
   if (it == g_comm.end()) { out3[0] = out3[1] = out3[2] = 0; return C8_OK; }
   out3[0] = it->second.n_halo; out3[1] = it->second.n_allreduce; out3[2] = it->second.halo_bytes;
   return C8_OK;
+}
+
+int c8_comm_p2p_active(c8_ctx* ctx) {
+  auto it = g_comm.find(ctx);
+  if (it == g_comm.end() || !it->second.p2p) return 0;
+  return (it->second.p2p->ready ? 1 : 0) | (it->second.p2p->ar_ready ? 2 : 0);
 }
 
 void c8_comm_release(c8_ctx* ctx) { comm_release(ctx); }

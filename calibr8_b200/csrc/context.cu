@@ -184,7 +184,11 @@ c8_ctx* c8_create(int device) {
     return nullptr;
   }
   ctx->own_stream = true;
-  cudaMalloc(&ctx->d_nfailed, sizeof(int));
+  if (cudaMalloc(&ctx->d_nfailed, sizeof(int)) != cudaSuccess) {
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return nullptr;
+  }
   return ctx;
 }
 
@@ -292,6 +296,7 @@ int c8_set_mesh(c8_ctx* ctx, int dim, int n_elems, int n_nodes, const int32_t* c
   if (!upload(ctx, &ctx->d_eoff, eoff)) return C8_ERR_CUDA;
   if (elem_set && ctx->n_es > 1) {
     std::vector<int> es(elem_set, elem_set + n_elems);
+    for (int v : es) C8_REQUIRE(ctx, v >= 0 && v < ctx->n_es, "element set id out of range");
     if (!upload(ctx, &ctx->d_elem_es, es)) return C8_ERR_CUDA;
   } else {
     if (ctx->d_elem_es) cudaFree(ctx->d_elem_es);
@@ -299,6 +304,11 @@ int c8_set_mesh(c8_ctx* ctx, int dim, int n_elems, int n_nodes, const int32_t* c
   }
   ctx->n_owned_nodes = n_nodes;
   ctx->n_owned_elems = n_elems;
+  // a new mesh is a one-part mesh until c8_set_partition / c8_set_halo_plan say otherwise: the old
+  // halo plan, transport and hooks describe another node numbering
+  c8_comm_release(ctx);
+  ctx->halo_cb = nullptr; ctx->allreduce_cb = nullptr; ctx->comm_user = nullptr;
+  ctx->comm_capturable = false;
   c8_linalg_invalidate(ctx);
   ctx->xi_ld = (long long)((n_elems + 31) / 32) * 32;  // 256-byte aligned component rows
   return C8_OK;
@@ -339,7 +349,12 @@ int c8_set_model(c8_ctx* ctx, int global_type, int local_type, const double* par
 int c8_set_params(c8_ctx* ctx, const double* params) {
   C8_REQUIRE(ctx, ctx->kt != nullptr, "c8_set_model must be called first");
   const size_t n = size_t(ctx->n_es) * ctx->kt->npar;
-  if (!ctx->d_params) C8_CUDA(ctx, cudaMalloc(&ctx->d_params, n * sizeof(double)));
+  if (n > ctx->params_cap) {   // another model / more element sets than the first call sized it for
+    if (ctx->d_params) cudaFree(ctx->d_params);
+    ctx->d_params = nullptr; ctx->params_cap = 0; ctx->model.params = nullptr;
+    C8_CUDA(ctx, cudaMalloc(&ctx->d_params, n * sizeof(double)));
+    ctx->params_cap = n;
+  }
   C8_CUDA(ctx, cudaMemcpyAsync(ctx->d_params, params, n * sizeof(double), cudaMemcpyHostToDevice,
                                ctx->stream));
   C8_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

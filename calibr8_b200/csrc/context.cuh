@@ -46,6 +46,7 @@ struct c8_ctx {
   int global_type = -1, local_type = -1;
   c8::ModelArgs model{};
   double* d_params = nullptr;
+  size_t params_cap = 0;          // doubles allocated at d_params
   std::vector<double> h_params;   // [n_es][npar] host copy
 
   // scratch / resident system

@@ -82,10 +82,21 @@ C8_DI int local_newton(const Kin<C::D, double, double>& k0, const Elem<C>& E, co
     for (int q = 0; q < NXI; ++q) Cd[q] = make_dual<LXI>(0.0);
     return 0;
   } else {
-    Model::guess(k0, E.xip, E.par, md.abs_tol, xi);
     int path = 0, iter = 1;
     double R_norm_0 = 1.0;
     bool converged = false;
+    // R_norm_0 of the relative test is the residual norm at the REFERENCE's starting point
+    // (src/small_J2.cpp:147-151).  Where the Newton starts at a closed-form predictor instead, the
+    // model returns that norm with the guess (it is |f| of the trial state, which the predictor
+    // needs anyway), so a deck converges by rel_tol exactly when it does in the reference.
+    bool have_r0 = false;
+    if constexpr (has_predictor<Model>::value) {
+      const double r0 = Model::guess_r0(k0, E.xip, E.par, md.abs_tol, xi);
+      have_r0 = r0 >= 0.0;
+      R_norm_0 = have_r0 ? r0 : 1.0;
+    } else {
+      Model::guess(k0, E.xip, E.par, md.abs_tol, xi);
+    }
     // WARP-UNIFORM body: every lane evaluates the residual and takes part in the solve (full-mask
     // shuffles); lanes that are done re-evaluate at their unchanged xi, which reproduces the same
     // Cd / path, and simply do not apply the update.
@@ -106,7 +117,7 @@ C8_DI int local_newton(const Kin<C::D, double, double>& k0, const Elem<C>& E, co
 #pragma unroll
       for (int q = 0; q < NXI; ++q) nrm += Cd[q].v * Cd[q].v;
       const double R_norm = sqrt(nrm);
-      if (work && iter == 1) R_norm_0 = R_norm;
+      if (work && iter == 1 && !have_r0) R_norm_0 = R_norm;
       const double R_norm_rel = R_norm / R_norm_0;
       const bool conv_now = (R_norm_rel < md.rel_tol) || (R_norm < md.abs_tol);
       const bool update = work && !conv_now;
@@ -386,6 +397,14 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian(co
     // the reference aborts the assembly (src/evaluations.cpp:95-97): report, scatter nothing
     if (t == 0) atomicAdd(a.n_failed, 1);
     if (a.path && t == 0) a.path[e] = -1;
+    // the element contributes nothing: clear its scratch slot, so that the gather does not sum stale
+    // data of an earlier call into A when the caller ignores the status
+    if (a.vals != nullptr) {
+      double* em = a.emat + size_t(e) * C::NX * C::NX + t * LX;
+      for (int r = 0; r < C::NX; ++r)
+        for (int s = 0; s < LX; ++s)
+          if (t * LX + s < C::NX) em[r * C::NX + s] = 0.0;
+    }
   }
   if (ok) {
 #pragma unroll

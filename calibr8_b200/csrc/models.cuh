@@ -36,6 +36,12 @@ struct Kin {
 template <class A, class B, class C, class D, class E>
 using prom5_t = prom_t<prom4_t<A, B, C, D>, E>;
 
+// models whose local Newton starts at a closed-form predictor declare HAS_PREDICTOR and guess_r0()
+template <class M, class = void> struct has_predictor { static constexpr bool value = false; };
+template <class M> struct has_predictor<M, decltype(void(M::HAS_PREDICTOR))> {
+  static constexpr bool value = M::HAS_PREDICTOR;
+};
+
 C8_DI bool is_plastic(double f, double abs_tol) { return (f > abs_tol) || (fabs(f) < abs_tol); }
 
 // material_params.hpp:12-30
@@ -169,8 +175,17 @@ struct SmallJ2 {
   // point starts AT the solution of the same residual (the Newton then only confirms |C| < tol):
   //   dgam = (|s_tr| - sqrt(2/3) sigma_y(alpha_old)) / (2 mu + 2/3 K),  n = s_tr / |s_tr|,
   //   pstrain = pstrain_old + dgam n,  alpha = alpha_old + sqrt(2/3) dgam.
+  // HAS_PREDICTOR: guess_r0() also returns the residual norm at the REFERENCE's starting point
+  // (xi_prev), which is the R_norm_0 of its relative convergence test (src/small_J2.cpp:147-151):
+  // there R_pstrain = 0 (dgam = 0) and R_alpha = f, so the norm is |f|; -1 where no predictor was
+  // applied (the Newton then starts at the reference's own point and measures R_norm_0 itself).
+  static constexpr bool HAS_PREDICTOR = true;
   template <class K> static C8_DI void guess(const K& k, const double* xip, const double* par, double abs_tol,
                                              double* xi) {
+    (void)guess_r0(k, xip, par, abs_tol, xi);
+  }
+  template <class K> static C8_DI double guess_r0(const K& k, const double* xip, const double* par,
+                                                  double abs_tol, double* xi) {
 #pragma unroll
     for (int i = 0; i < NXI; ++i) xi[i] = xip[i];
     const double sqrt_23 = 0.81649658092772603;
@@ -178,7 +193,9 @@ struct SmallJ2 {
     const Mat<double, DIM> s = small_dev_stress<DIM>(k.gu, xip, par[0], par[1]);
     const double s_mag = norm(s);
     const double f = (s_mag - sqrt_23 * (par[3] + par[2] * xip[NS])) / mu;
+    double r0 = -1.0;
     if (is_plastic(f, abs_tol) && s_mag > 0.0) {
+      r0 = fabs(f);
       const double dgam = mu * f / (2.0 * mu + (2.0 / 3.0) * par[2]);
       const double g = dgam / s_mag;
 #pragma unroll
@@ -187,6 +204,7 @@ struct SmallJ2 {
         for (int j = i; j < DIM; ++j) xi[SymIdx<DIM>::idx(i, j)] = xip[SymIdx<DIM>::idx(i, j)] + g * s.a[i][j];
       xi[NS] = xip[NS] + sqrt_23 * dgam;
     }
+    return r0;
   }
   template <class TK, class TKP, class TX, class TXP, class TP>
   static C8_DI int residual(const Kin<DIM, TK, TKP>& k, const TX* xi, const TXP* xip,
@@ -472,8 +490,17 @@ struct HyperJ2 {
   //   dgam = mu f_tr / (2 mu Ie + 2/3 K),  |zeta| = |dev bt| - 2 Ie dgam,  alpha = alpha_old + sqrt(2/3) dgam
   // and Ie follows from det(zeta + Ie I) = 1 by a scalar Newton: the full local Newton then starts at
   // the solution (1 evaluation to confirm |C| < tol instead of 4-5 iterations).
+  // HAS_PREDICTOR / guess_r0: as in SmallJ2.  At the reference's starting point (the trial state,
+  // alpha = alpha_old) R_zeta = 0, R_Ie = det(be_bar_trial) - 1 = 0 up to rounding (be_bar_trial is a
+  // unimodular transform of zeta_old + Ie_old I) and R_alpha = f, so R_norm_0 = |f_trial|.
+  static constexpr bool HAS_PREDICTOR = true;
   template <class K> static C8_DI void guess(const K& k, const double* xip, const double* par, double abs_tol,
                                              double* xi) {
+    (void)guess_r0(k, xip, par, abs_tol, xi);
+  }
+  template <class K> static C8_DI double guess_r0(const K& k, const double* xip, const double* par,
+                                                  double abs_tol, double* xi) {
+    double r0 = -1.0;
     const Mat<double, DIM> zo = unpack_sym<double, DIM>(xip);
     const Mat<double, DIM> bt = be_bar_trial<DIM>(k, zo, xip[NS]);
     Mat<double, DIM> z = dev(bt);
@@ -485,6 +512,7 @@ struct HyperJ2 {
       const double z_mag = norm(z);
       const double f = (mu * z_mag - sqrt_23 * (par[2] + par[7] * alpha)) / mu;
       if (is_plastic(f, abs_tol) && z_mag > 0.0) {
+        r0 = fabs(f);
         // zeta = nhat m(Ie), m = |dev bt| - 2 Ie dgam(Ie); Ie from the isochoric constraint
         // det(zeta + Ie I) = 1 by a scalar Newton in plain doubles (a few dozen flops per step,
         // against ~10^3 for one AD evaluation + 8x8 solve of the full local Newton)
@@ -520,6 +548,7 @@ struct HyperJ2 {
     pack_sym<double, DIM>(z, xi);
     xi[NS] = Ie;
     xi[NS + 1] = alpha;
+    return r0;
   }
   template <class TK, class TKP, class TX, class TXP, class TP>
   static C8_DI int residual(const Kin<DIM, TK, TKP>& k, const TX* xi, const TXP* xip,

@@ -244,6 +244,8 @@ int c8_halo(c8_ctx* ctx, double* vec_dev);              /* nodal vector [n_nodes
 int c8_halo_nb(c8_ctx* ctx, double* vec_dev, int nb);   /* nodal vector [n_nodes][nb], nb <= 4 */
 int c8_allreduce(c8_ctx* ctx, double* buf_dev, int n);
 int c8_comm_stats(c8_ctx* ctx, int64_t* out3 /* halo calls, allreduce calls, halo bytes */);
+/* bit 0: the NVLink push halo (C8_P2P=1) is active on this part, bit 1: the one-CTA small allreduce */
+int c8_comm_p2p_active(c8_ctx* ctx);
 void c8_comm_release(c8_ctx* ctx);
 
 int c8_get_coords(c8_ctx* ctx, double* coords_host /* [n_nodes][3] */);

@@ -11,6 +11,7 @@
 // Also a dense full-pivoting LU solve standing in for Eigen's
 // `fullPivLu().solve()` (src/evaluations.cpp:112, src/small_J2.cpp:157).
 #pragma once
+#include <limits>
 #include <vector>
 #include <cassert>
 #include "fad.hpp"
@@ -190,9 +191,15 @@ inline EVector matvec(EMatrix const& A, EVector const& x) {
 // Full-pivoting LU solve of A X = B (A n x n, B n x m) -- the role of
 // Eigen::FullPivLU::solve at src/evaluations.cpp:112.
 inline EMatrix full_piv_lu_solve(EMatrix A, EMatrix B) {
+  // Eigen::FullPivLU semantics (Eigen/src/LU/FullPivLU.h, computeInPlace + _solve_impl): the
+  // elimination stops at an exactly zero corner; the solve uses the `rank` leading pivots (those above
+  // maxpivot * epsilon * n) and sets the remaining unknowns to zero -- so a zero matrix (the elastic
+  // model's dC/dxi, src/elastic.cpp) solves to zero instead of NaN.
   int const n = A.r, m = B.c;
   std::vector<int> colperm(n);
   for (int i = 0; i < n; ++i) colperm[i] = i;
+  int nonzero_pivots = n;
+  double maxpivot = 0.;
   for (int k = 0; k < n; ++k) {
     int pr = k, pc = k;
     double best = -1.;
@@ -201,6 +208,8 @@ inline EMatrix full_piv_lu_solve(EMatrix A, EMatrix B) {
         double const v = std::abs(A(i, j));
         if (v > best) { best = v; pr = i; pc = j; }
       }
+    if (best == 0.) { nonzero_pivots = k; break; }
+    if (best > maxpivot) maxpivot = best;
     if (pr != k) {
       for (int j = 0; j < n; ++j) std::swap(A(k, j), A(pr, j));
       for (int j = 0; j < m; ++j) std::swap(B(k, j), B(pr, j));
@@ -218,13 +227,18 @@ inline EMatrix full_piv_lu_solve(EMatrix A, EMatrix B) {
     }
     C8_FLOPS((long long)(n - k - 1) * (1 + 2 * (n - k - 1) + 2 * m));
   }
+  int rank = 0;
+  double const thresh = maxpivot * (std::numeric_limits<double>::epsilon() * n);
+  for (int i = 0; i < nonzero_pivots; ++i) rank += (std::abs(A(i, i)) > thresh);
   EMatrix Y(n, m);
-  for (int j = 0; j < m; ++j)
-    for (int i = n - 1; i >= 0; --i) {
+  for (int j = 0; j < m; ++j) {
+    for (int i = rank; i < n; ++i) Y(i, j) = 0.;
+    for (int i = rank - 1; i >= 0; --i) {
       double s = B(i, j);
-      for (int k = i + 1; k < n; ++k) s -= A(i, k) * Y(k, j);
+      for (int k = i + 1; k < rank; ++k) s -= A(i, k) * Y(k, j);
       Y(i, j) = s / A(i, i);
     }
+  }
   C8_FLOPS((long long)m * n * (n + 1));
   EMatrix X(n, m);
   for (int i = 0; i < n; ++i)

@@ -73,6 +73,7 @@ def _solve(case, mesh, part, ctx_setup, measured=None, area=None, params=None):
     stats = ctx.comm_stats()
     stats["krylov_iterations"] = hp.stats()["linear_iters"]
     stats["amg_levels"] = ctx.preconditioner_info()["levels"]
+    stats["p2p"] = ctx.p2p_active()
     hp.close(); ctx.close()
     return J, g, u_last, stats
 
@@ -172,6 +173,8 @@ def _check(world, transport, case):
         assert abs(J - J1) <= 1e-8 * abs(J1), (rank, J, J1)                       # objective, 1e-8 relative
         assert np.abs(g - g1).max() <= 1e-8 * np.abs(g1).max(), (rank, g, g1)     # adjoint gradient
         assert stats["halo_calls"] > 0 and stats["allreduce_calls"] > 0
+        if transport == "nccl_p2p":   # a silent fall-back to ncclSend/Recv must not pass as the push halo
+            assert stats["p2p"]["halo"], stats
         # the multigrid hierarchy spans the parts: the Krylov iteration count stays that of one part
         # (a hierarchy on each part's owned block needs 1.4x (2 parts) to 2x (8 parts) as many)
         assert stats["krylov_iterations"] <= 1.25 * st1["krylov_iterations"] + 10, (stats, st1)

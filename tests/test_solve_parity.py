@@ -162,3 +162,59 @@ def test_calibration_objective_and_gradient(golden):
     assert abs(J - J_o) / abs(J_o) < J_TOL, (J, J_o)
     assert np.abs(g - g_o).max() < G_TOL * np.abs(g_o).max(), (g, g_o)
     hp.close(); ctx.close()
+
+
+def test_calibration_3d_hill_objective_and_gradient():
+    """BASELINE configs[2] in miniature: 3-D Hill anisotropic plasticity, `calibration` QoI with the
+    displacement mismatch on the zmax face (Calibration::compute_surface_mismatch,
+    src/calibration.cpp:225-303) and the reaction on the ymax plane, adjoint gradient w.r.t. the 8
+    active parameters Y, S, D, R00, R11, R01, R02, R12 -- GPU vs oracle."""
+    from calibr8_b200 import meshgen
+    from oracle.driver import Adjoint
+    from oracle.pyoracle import PARAM_NAMES
+    from test_adjoint_parity import facets_on_plane
+    from parity_common import HILL3D
+    mesh = meshgen.box_tets(4, notch_radius=0.3)
+    truth = dict(HILL3D)
+    start = dict(truth, Y=2.2, S=8., D=2.5, R00=1.05, R11=0.95, R01=1.05, R02=1.0, R12=1.0)
+    N = 4
+    deck = dict(global_type="mechanics", local_type="small_hill", params=truth,
+                dbcs=[[0, 0, "xmin", "0.0"], [0, 1, "ymin", "0.0"], [0, 2, "zmin", "0.0"],
+                      [0, 1, "ymax", "0.0012 * t"]],
+                num_steps=N, global_max_iters=30, global_tol=1e-11, local_max_iters=60, local_tol=1e-12)
+    names = PARAM_NAMES["small_hill"]
+    act = [names.index(a) for a in ("Y", "S", "D", "R00", "R11", "R01", "R02", "R12")]
+    fac = facets_on_plane(mesh, 2, 1.0)
+    qoi = dict(balance_factor=1e2, coord_idx=1, coord_value=1.0, reaction_force_comp=1,
+               weights=(1e8, 1e8, 1e8))
+    # synthetic data at the true parameters (oracle)
+    o, p = oracle_problem(deck, mesh)
+    o.set_qoi_calibration(facet=fac, **qoi)
+    zero_meas = np.zeros((mesh.n_nodes, 3))
+    p.solve(lambda step: o.qoi_set_step(1.0, float(N), 0.0, zero_meas))
+    assert p.xi[N][:, 6].max() > 1e-4, "the truth run must yield"
+    loads, measured = [], []
+    for step in range(1, N + 1):
+        o.qoi_set_step(1.0, float(N), 0.0, zero_meas)
+        o.qoi(p.x[step], p.x[step - 1], p.xi[step], p.xi[step - 1], step)
+        loads.append(o.calibration_state()["total_load"])
+        measured.append(p.x[step][0].reshape(-1, 3).copy())
+    area = o.calibration_state()["area"]
+    # oracle objective + gradient at the starting parameters
+    d2 = dict(deck, params=start)
+    o2, p2 = oracle_problem(d2, mesh, active=[act])
+    o2.set_qoi_calibration(facet=fac, **qoi)
+
+    def setup(step):
+        o2.qoi_set_step(1.0, float(N), loads[step - 1], measured[step - 1])
+    J_o = p2.solve(setup)
+    g_o = Adjoint(p2, max_iters=30, abs_tol=1e-14, rel_tol=1e-12).gradient([list(range(len(act)))], len(act), setup)
+    assert J_o > 0 and (np.abs(g_o) > 0).all()
+    # GPU
+    ctx, hp = gpu_problem(d2, mesh, qoi=None)
+    hp.set_qoi_calibration(measured=np.stack(measured), load_data=loads, area=area, facet=fac, **qoi)
+    J = hp.primal_solve()
+    g = hp.adjoint_gradient()[act]
+    assert abs(J - J_o) / abs(J_o) < J_TOL, (J, J_o)
+    assert np.abs(g - g_o).max() < G_TOL * np.abs(g_o).max(), (g, g_o)
+    hp.close(); ctx.close()
