@@ -14,8 +14,11 @@ metric  = QP residual+Jacobian evals/s (fp64)  [= elements / second; one coupled
 value   = kernel-path throughput with inputs resident in HBM (memset A,b + K1 per step)
 e2e     = the same through c8_state_forward_jacobian with HOST nodal buffers
           (H2D of the Newton iterate, assembly, D2H of the residual + status every step)
-N > 1   = the mesh is split into N element slabs (one rank per GPU, weak scaling: every rank
-          assembles its own ~1M-tet part; no data-path collective in this kernel-level bench).
+N > 1   = STRONG scaling: the same mesh is split into N parts (recursive coordinate bisection, one rank
+          per GPU); a part evaluates its owned + halo elements and only OWNED points are counted.
+          K1 itself has no data-path collective; the forward+adjoint leg (same mesh, partitioned) uses
+          NCCL halo copies and allreduces.  parity_vs_n1 compares every N > 1 run with the one-GPU
+          values of tests/golden/bench_n1.json.
 """
 import argparse
 import json
@@ -35,6 +38,14 @@ UNIT = "QP evals/s"
 PARAMS = dict(E=1000., nu=.25, Y=10., S=0., D=0., A=0., n=0., K=100.)   # test/primal/notch_hyper_J2.yaml.in:25-34
 LOCAL = dict(max_iters=500, abs_tol=1e-12, rel_tol=1e-12)             # same deck :20-24
 LINEAR_TOL = 1e-6   # Belos "Convergence Tolerance" of the same deck (:59); Newton tolerances 1e-8 (:16-18)
+# general-path rows: the iterated local Newton with exp / pow in the yield law, i.e. what a
+# Voce / power-law calibration runs, and the Hill model of BASELINE configs[2] (no closed-form predictor);
+# name -> (local residual, parameters, displacement scale of the synthetic state)
+GENERAL_PATHS = {
+    "hyper_J2_general": ("hyper_J2", dict(E=1000., nu=.25, Y=10., S=10., D=2., A=1., n=.5, K=100.), 1.0),
+    "small_hill": ("small_hill", dict(E=1000., nu=.25, Y=2., R00=1., R11=.9, R22=1.1, R01=1., R02=.95, R12=1.05,
+                                      S=10., D=2.), 0.2),
+}
 AMP = 2.2e-3
 N_CELLS = 56
 NOTCH = 0.2
@@ -149,109 +160,193 @@ def flops_per_qp_reference():
         return float(json.load(f)["K1"])
 
 
-def calibration_step(ctx, mesh, load_steps):
+def calibration_step(ctx, mesh, part, load_steps, world, dev):
     """forward + adjoint gradient wall time per load step (BASELINE.json metric, second half) for
-    BASELINE configs[1]: u_y(ymax) = 0.001 t, symmetry planes, average-displacement objective."""
+    BASELINE configs[1]: 3-D hyper-J2 notched specimen, u_y(ymax) = 0.001 t over `load_steps` steps
+    (20 in the config: 2 % stretch, the notch yields from about step 8 on), symmetry planes,
+    average-displacement objective, adjoint gradient w.r.t. every model parameter.
+    part is None on one GPU; otherwise this rank's part of the SAME mesh (strong scaling): NCCL halo
+    copies of Krylov vectors / Newton iterates and fp64 allreduces, issued by the library."""
     import torch
+    import torch.distributed as dist
     from calibr8_b200.capi import HostProblem
+    ns = mesh.node_sets if part is None else part.node_sets
     hp = HostProblem(ctx)
-    hp.set_time(load_steps, 1.0)
-    hp.add_dbc(0, 0, mesh.node_sets["xmin"], "0.0")
-    hp.add_dbc(0, 1, mesh.node_sets["ymin"], "0.0")
-    hp.add_dbc(0, 2, mesh.node_sets["zmin"], "0.0")
-    hp.add_dbc(0, 1, mesh.node_sets["ymax"], "0.001 * t")
+    hp.add_dbc(0, 0, ns["xmin"], "0.0")
+    hp.add_dbc(0, 1, ns["ymin"], "0.0")
+    hp.add_dbc(0, 2, ns["zmin"], "0.0")
+    hp.add_dbc(0, 1, ns["ymax"], "0.001 * t")
     hp.finalize_dbcs()
     hp.set_solver(15, 1e-8, 1e-8, gmres_restart=100, gmres_max_iters=20000, linear_tol=LINEAR_TOL)
     hp.set_qoi_avg_disp()
-    if os.environ.get("C8_BENCH_PROFILE"):
-        hp.profile(True)
-    out = {}
-    for rep in range(2):   # the first pass builds the multigrid hierarchy and loads the kernels
-        s0 = hp.stats()
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        J = hp.primal_solve()
-        torch.cuda.synchronize(); t1 = time.perf_counter()
-        g = hp.adjoint_gradient()
-        torch.cuda.synchronize(); t2 = time.perf_counter()
-        s1 = hp.stats()
-        out = {"metric": "forward+adjoint gradient wall-time/load step", "unit": "ms",
-               "value": (t2 - t0) / load_steps * 1e3,
-               "forward_ms_per_load_step": (t1 - t0) / load_steps * 1e3,
-               "adjoint_ms_per_load_step": (t2 - t1) / load_steps * 1e3,
-               "load_steps": load_steps, "assemblies": s1["assemblies"] - s0["assemblies"],
-               "krylov_iterations": s1["linear_iters"] - s0["linear_iters"],
-               "objective": J, "gradient": [float(v) for v in g],
-               "preconditioner": ctx.preconditioner_info(),
-               "phase_seconds_cumulative": hp.profile(bool(os.environ.get("C8_BENCH_PROFILE"))),
-               "note": "Newton tol 1e-8 and GMRES rel tol 1e-6 as in the reference deck (test/primal/notch_hyper_J2.yaml.in), "
-                       "GMRES(100), aggregation-AMG right preconditioner; "
-                       "second of two passes (the first builds the hierarchy)"}
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # untimed: one load step forward + adjoint builds the multigrid hierarchy and loads every kernel
+    hp.set_time(1, 1.0)
+    hp.primal_solve(); hp.adjoint_gradient()
+    hp.set_time(load_steps, 1.0)
+    hp.profile(True)                      # phase timers (stream-synchronised around each phase)
+    p0 = hp.profile(True)
+    s0 = hp.stats()
+    sync(); t0 = time.perf_counter()
+    J = hp.primal_solve()
+    sync(); t1 = time.perf_counter()
+    g = hp.adjoint_gradient()
+    sync(); t2 = time.perf_counter()
+    s1 = hp.stats()
+    p1 = hp.profile(True)
+    tt = torch.tensor([t2 - t0, t1 - t0, t2 - t1], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    tot, fwd, adj = [float(v) for v in tt.tolist()]
+    xi_last = hp.get_step(load_steps)[1]
+    n_own = ctx.n_elems if part is None else part.n_owned_elems
+    yielded = torch.tensor([float((xi_last[:n_own, -1] > 0).sum()), float(n_own)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(yielded)
+    its = s1["linear_iters"] - s0["linear_iters"]
+    asm = s1["assemblies"] - s0["assemblies"]
+    out = {"metric": "forward+adjoint gradient wall-time/load step", "unit": "ms",
+           "value": tot / load_steps * 1e3, "forward_ms_per_load_step": fwd / load_steps * 1e3,
+           "adjoint_ms_per_load_step": adj / load_steps * 1e3, "load_steps": load_steps,
+           "assemblies": asm, "krylov_iterations": its,
+           "krylov_iterations_per_assembly": its / max(asm, 1),
+           "objective": J, "gradient": [float(v) for v in g],
+           "gradient_parameters": list(ctx.param_names),
+           "yielded_fraction_last_step": float(yielded[0] / yielded[1]),
+           "phase_seconds": {k: p1[k] - p0[k] for k in p1},
+           "preconditioner": ctx.preconditioner_info(),
+           "note": "BASELINE configs[1] at spec: Newton tol 1e-8 and GMRES rel tol 1e-6 as in the reference deck "
+                   "(test/primal/notch_hyper_J2.yaml.in), GMRES(100), aggregation-AMG right preconditioner (fine-level "
+                   "operator kept in fp32 inside the preconditioner only; the Krylov iteration, its residuals and the "
+                   "converged solution are fp64); one untimed load step first (hierarchy + kernel load); phase timers "
+                   "on (they add stream synchronisations)"}
+    if part is not None:
+        out["scaling"] = "strong"
+        out["partition"] = {"parts": world, "owned_elems_rank0": part.n_owned_elems,
+                            "halo_elems_rank0": part.n_elems - part.n_owned_elems,
+                            "ghost_nodes_rank0": part.n_nodes - part.n_owned_nodes,
+                            "neighbours_rank0": int(part.nbr_rank.size)}
+        out["comm_rank0"] = ctx.comm_stats()
+        out["p2p_rank0"] = ctx.p2p_active()
     hp.close()
     return out
 
 
-def calibration_step_partitioned(mesh, load_steps, rank, world, local_rank):
-    """The same forward + adjoint gradient with the mesh partitioned over the ranks (strong
-    scaling): RCB element partition, owned/ghost halo plan, NCCL halo copies + allreduces issued by
-    the library (c8_nccl_init); the objective and gradient are identical on every rank."""
+def kernel_rows(ctx, st, dfma_peak, hbm_peak):
+    """Every other kernel of the path on the bench state (1 GPU): K2..K6 with their own roofline.
+    K3/K4/K6 are fp64-bound AD sweeps (reference flop count from the op-counting oracle, golden fixture);
+    K2/K5 evaluate in plain doubles and are gather-bound (algorithmic bytes: conn + nodal + state)."""
     import torch
-    import torch.distributed as dist
-    from calibr8_b200 import partition
-    from calibr8_b200.capi import Context, HostProblem
-    elem_part, part = partition.partition_mesh(mesh, world, rank=rank)
-    ctx = Context(local_rank)
-    ctx.set_mesh(mesh.dim, part.conn, part.coords)
-    ctx.set_model("mechanics", "hyper_J2", PARAMS, **LOCAL)
-    ctx.set_partition(part)
+    from calibr8_b200.capi import make_qoi
+    fl = json.load(open(os.path.join(ROOT, "tests", "golden", "flop_counts.json")))
+    x, xp, xi, xip, A, b = st["x"], st["xp"], st["xi"], st["xip"], st["A"], st["b"]
+    n, nn = ctx.n_elems, ctx.n_nodes
 
-    def bcast(raw):
-        t = torch.zeros(128, dtype=torch.uint8, device=torch.device("cuda", local_rank))
-        if raw is not None:
-            t.copy_(torch.tensor(list(raw), dtype=torch.uint8))
-        dist.broadcast(t, 0)
-        return bytes(t.cpu().tolist())
-    ctx.nccl_init(rank, world, bcast)
-    hp = HostProblem(ctx)
-    hp.set_time(load_steps, 1.0)
-    hp.add_dbc(0, 0, part.node_sets["xmin"], "0.0")
-    hp.add_dbc(0, 1, part.node_sets["ymin"], "0.0")
-    hp.add_dbc(0, 2, part.node_sets["zmin"], "0.0")
-    hp.add_dbc(0, 1, part.node_sets["ymax"], "0.001 * t")
-    hp.finalize_dbcs()
-    hp.set_solver(15, 1e-8, 1e-8, gmres_restart=100, gmres_max_iters=20000, linear_tol=LINEAR_TOL)
-    hp.set_qoi_avg_disp()
-    if os.environ.get("C8_BENCH_PROFILE"):
-        hp.profile(True)
-    out = {}
-    for rep in range(2):
-        s0 = hp.stats()
-        dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
-        J = hp.primal_solve()
-        torch.cuda.synchronize(); t1 = time.perf_counter()
-        g = hp.adjoint_gradient()
-        torch.cuda.synchronize(); dist.barrier(); t2 = time.perf_counter()
-        s1 = hp.stats()
-        tt = torch.tensor([t2 - t0, t1 - t0, t2 - t1], dtype=torch.float64, device=torch.device("cuda", local_rank))
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        tot, fwd, adj = [float(v) for v in tt.tolist()]
-        cs = ctx.comm_stats()
-        out = {"metric": "forward+adjoint gradient wall-time/load step", "unit": "ms", "scaling": "strong",
-               "value": tot / load_steps * 1e3, "forward_ms_per_load_step": fwd / load_steps * 1e3,
-               "adjoint_ms_per_load_step": adj / load_steps * 1e3, "load_steps": load_steps,
-               "assemblies": s1["assemblies"] - s0["assemblies"],
-               "krylov_iterations": s1["linear_iters"] - s0["linear_iters"],
-               "objective": J, "gradient": [float(v) for v in g],
-               "partition": {"parts": world, "owned_elems_rank0": part.n_owned_elems,
-                             "halo_elems_rank0": part.n_elems - part.n_owned_elems,
-                             "ghost_nodes_rank0": part.n_nodes - part.n_owned_nodes,
-                             "neighbours_rank0": int(part.nbr_rank.size)},
-               "comm_rank0": cs, "phase_seconds_cumulative": hp.profile(bool(os.environ.get("C8_BENCH_PROFILE"))),
-               "note": "1M-tet mesh split over the ranks; NCCL halo copy of Krylov vectors / Newton iterate and "
-                       "fp64 allreduce of dots, objective, gradient; the multigrid hierarchy spans the parts "
-                       "(halo copy per sweep on the partitioned levels, coarse levels replicated)",
-               "preconditioner": ctx.preconditioner_info()}
-    hp.close(); ctx.close()
-    return out
+    def timeit(fn, pre=lambda: None, reps=5):
+        ts = []
+        for k in range(reps + 2):
+            pre()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            if k >= 2:
+                ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
+
+    dev = x.device
+    g = ctx.alloc("xi"); f = torch.zeros(ctx.xi_ld * ctx.nx, dtype=torch.float64, device=dev)
+    rhs = ctx.alloc("b"); z = ctx.alloc("x"); z.copy_(torch.randn(z.shape, dtype=z.dtype, device=dev, generator=torch.Generator(device=dev).manual_seed(1)))
+    phi = ctx.alloc("xi")
+    sc = torch.zeros(8, dtype=torch.float64, device=dev)
+    grad = torch.zeros(64, dtype=torch.float64, device=dev)
+    q = make_qoi("avg_disp")
+    t = {}
+    t["K2"] = timeit(lambda: ctx.global_residual(x, xp, xi, xip, b), lambda: b.zero_())
+    t["K3"] = timeit(lambda: ctx.adjoint_jacobian(q, x, xp, xi, xip, g, f, A, rhs), lambda: (rhs.zero_(), g.zero_()))
+    t["K4"] = timeit(lambda: ctx.adjoint_local(x, xp, xi, xip, z, phi, g, f))
+    t["K5"] = timeit(lambda: ctx.qoi_value(q, x, xp, xi, xip, 0, sc), lambda: sc.zero_())
+    t["K6"] = timeit(lambda: ctx.qoi_gradient(q, x, xp, xi, xip, z, phi, grad), lambda: grad.zero_())
+    names = {"K2": "eval_global_residual", "K3": "eval_adjoint_jacobian (element kernel + transposed BSR gather)",
+             "K4": "solve_adjoint_local", "K5": "eval_qoi", "K6": "eval_qoi_gradient"}
+    nxi, nx = ctx.nxi, ctx.nx
+    # algorithmic bytes per launch: connectivity + xi streams + nodal fields once (+ outputs)
+    nodal = nn * (24 + 32 + 32)
+    bytes_ = {"K2": n * (16 + 2 * nxi * 8) + nodal + nn * 32,
+              "K5": n * 16 + nn * (24 + 32)}
+    rows = {}
+    for k in ("K2", "K3", "K4", "K5", "K6"):
+        r = {"reference_fn": names[k], "ms": t[k], "M_qp_per_s": n / t[k] / 1e3}
+        if k in bytes_:
+            gbs = bytes_[k] / (t[k] * 1e-3) * 1e-9
+            r["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                             "algorithmic_bytes_per_launch": bytes_[k],
+                             "note": "plain-double evaluation (no AD in the reference either), bound by the nodal gather"}
+        else:
+            tf = fl[k] * n / (t[k] * 1e-3) * 1e-12
+            r["roofline"] = {"bound": "fp64", "achieved": tf, "peak": dfma_peak, "unit": "TFLOP/s", "frac": tf / dfma_peak,
+                             "algorithmic_flops_per_qp": fl[k], "flops_definition": "reference algorithm's count"}
+        rows[k] = r
+    return rows
+
+
+def general_path_rows(mesh, fields, dev_index, stream, dfma_peak):
+    """K1 on the states that take the GENERAL path of the local solve (no closed-form predictor, exp / pow
+    in the yield law): hyper-J2 with Voce + power-law hardening, and the Hill model of BASELINE configs[2]."""
+    import torch
+    from calibr8_b200.capi import Context
+    fl = json.load(open(os.path.join(ROOT, "tests", "golden", "flop_counts.json")))
+    (u1, p1), (u2, p2) = fields
+    rows = {}
+    for key, (ltype, params, amp_scale) in GENERAL_PATHS.items():
+        c = Context(dev_index)
+        c.set_mesh(mesh.dim, mesh.conn, mesh.coords)
+        c.set_model("mechanics", ltype, params, **LOCAL)
+        c.set_stream(stream.cuda_stream)
+        x, xp, x0 = c.alloc("x"), c.alloc("x"), c.alloc("x")
+        xi0, xip, xi = c.alloc("xi"), c.alloc("xi"), c.alloc("xi")
+        A, b, path = c.alloc("A"), c.alloc("b"), c.alloc("path")
+        c.pack_x(u2 * amp_scale, p2, x); c.pack_x(u1 * amp_scale, p1, xp)
+        c.init_xi(xi0); c.init_xi(xip)
+        assert c.forward_jacobian(xp, x0, xi0, xip, None, b) == 0
+        ts = []
+        for k in range(8):
+            b.zero_(); xi.copy_(xip)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); c.forward_jacobian(x, xp, xip, xi, A, b, path, check=False); e1.record()
+            torch.cuda.synchronize()
+            if k >= 3:
+                ts.append(e0.elapsed_time(e1))
+        assert c.forward_jacobian(x, xp, xip, xi, None, None, path) == 0
+        ms = float(np.median(ts))
+        tf = fl["K1_" + key] * c.n_elems / (ms * 1e-3) * 1e-12
+        rows[key] = {"local_residual": ltype, "params": params, "ms": ms, "M_qp_per_s": c.n_elems / ms / 1e3,
+                     "plastic_fraction": float(path.to(torch.float32).mean().item()),
+                     "reference_newton_iterations_per_plastic_point": fl["newton_iters_plastic_" + key],
+                     "roofline": {"bound": "fp64", "achieved": tf, "peak": dfma_peak, "unit": "TFLOP/s",
+                                  "frac": tf / dfma_peak, "algorithmic_flops_per_qp": fl["K1_" + key],
+                                  "flops_definition": "reference algorithm's count"}}
+        c.close()
+        del x, xp, x0, xi0, xip, xi, A, b, path
+        torch.cuda.empty_cache()
+    return rows
+
+
+def measured_traffic():
+    """DRAM bytes per launch of the K1 kernels from the committed ncu --set full summary of this round
+    (profiles/r02_ncu_summary.json, written by tools/ncu_extract.py); None when the file is absent."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_summary.json")))
+        ks = d["kernels"]
+        el = next(v for k, v in ks.items() if k.startswith("k_forward_jacobian"))
+        ga = next(v for k, v in ks.items() if k.startswith("k_bsr_gather"))
+        return {"traffic": el["dram_bytes"] + ga["dram_bytes"], "element_kernel": el, "gather": ga,
+                "source": "profiles/r02_ncu_summary.json (" + d.get("command", "") + ")"}
+    except Exception:
+        return None
 
 
 def run_reference(args):
@@ -273,7 +368,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * float(np.mean([r["seconds"] for r in vals])),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "3D finite-strain hyper_J2 mixed u-p, notched box tets (bounded sample)",
                    "note": "CPU restatement of the reference algorithm (oracle/), not the Trilinos binary: "
@@ -289,6 +384,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
+    from calibr8_b200 import partition
     from calibr8_b200.capi import Context
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -299,17 +395,40 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
+    # ---- the SAME ~1M-tet mesh at every N (strong scaling): N > 1 splits it into N parts (recursive
+    # coordinate bisection); a part assembles the complete rows of its owned nodes, so it evaluates its
+    # owned elements plus the halo elements touching an owned node.  Only OWNED quadrature points count.
     mesh = workload_mesh()
-    (u1, p1), (u2, p2) = workload_fields(mesh, seed=0)   # identical per-GPU work on every rank (weak scaling)
+    fields = workload_fields(mesh, seed=0)
+    (u1, p1), (u2, p2) = fields
+    part = None
     ctx = Context(local_rank)
-    ctx.set_mesh(mesh.dim, mesh.conn, mesh.coords)
+    if world > 1:
+        _, part = partition.partition_mesh(mesh, world, rank=rank)
+        ctx.set_mesh(mesh.dim, part.conn, part.coords)
+    else:
+        ctx.set_mesh(mesh.dim, mesh.conn, mesh.coords)
     ctx.set_model("mechanics", "hyper_J2", PARAMS, **LOCAL)
     # one explicit (non-default) stream for torch's fills/copies, the CUDA-event timers and every
     # kernel of the library (CUDA-graph capture in the Krylov solver needs a real stream)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    n = ctx.n_elems
+    if part is not None:
+        ctx.set_partition(part)
+
+        def bcast(raw):
+            t = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if raw is not None:
+                t.copy_(torch.tensor(list(raw), dtype=torch.uint8))
+            dist.broadcast(t, 0)
+            return bytes(t.cpu().tolist())
+        ctx.nccl_init(rank, world, bcast)
+        loc = lambda a, nc: part.localize_nodal(a, nc)
+        u1, p1, u2, p2 = loc(u1, 3), loc(p1, 1), loc(u2, 3), loc(p2, 1)
+    n_local = ctx.n_elems                                  # owned + halo elements of this rank
+    n_owned = part.n_owned_elems if part is not None else ctx.n_elems
+    n_total = mesh.n_elems                                 # = sum of the owned counts
 
     # --- untimed set-up: history state xi_prev from one assembly at the previous synthetic state
     x, xp, x0 = ctx.alloc("x"), ctx.alloc("x"), ctx.alloc("x")
@@ -335,7 +454,10 @@ def run_ours(args):
     torch.cuda.synchronize()
     nf = ctx.forward_jacobian(x, xp, xip, xi, None, None, path)   # status check outside the timing
     assert nf == 0
-    plastic = float(path.to(torch.float32).mean().item())
+    pl = torch.tensor([float(path[:n_owned].to(torch.float32).sum().item()), float(n_owned)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(pl)
+    plastic = float(pl[0] / pl[1])
 
     if world > 1:
         dist.barrier()
@@ -359,6 +481,17 @@ def run_ours(args):
     total_ms = ev[0].elapsed_time(ev[-1])
     k_ms = float(np.mean([a.elapsed_time(c) for a, c in kev]))
 
+    # --- checksums of the assembled system over the OWNED rows (N > 1: compared with the one-GPU values
+    # of tests/golden/bench_n1.json -> parity of the partitioned assembly, measured by the driver's own run)
+    y = ctx.alloc("x")
+    ctx.spmv(A, x, y)
+    torch.cuda.synchronize()
+    nrow = (part.n_owned_nodes if part is not None else ctx.n_nodes) * ctx.nb
+    chk = torch.stack([(b[:nrow] * b[:nrow]).sum(), (y[:nrow] * y[:nrow]).sum()])
+    if world > 1:
+        dist.all_reduce(chk)
+    checks = {"b_dot_b": float(chk[0]), "Ax_dot_Ax": float(chk[1])}
+
     # --- e2e: host nodal buffers through the resident-state entry point
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     hu, hp_ = pin(u2), pin(p2)
@@ -376,6 +509,8 @@ def run_ours(args):
     for _ in range(2):
         e2e_step()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
@@ -385,7 +520,6 @@ def run_ours(args):
     d2h = (ctx.n_nodes * 4) * 8 + 4
 
     # --- K9 BSR SpMV on the matrix just assembled (HBM-bound): y = A x, 20 launches
-    y = ctx.alloc("x")
     for _ in range(3):
         ctx.spmv(A, x, y)
     sev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -397,62 +531,105 @@ def run_ours(args):
     spmv_ms = sev[0].elapsed_time(sev[1]) / 20
     spmv_bytes = ctx.nnzb * (ctx.nb * ctx.nb * 8 + 4) + ctx.n_nodes * (4 + 2 * ctx.nb * 8)
 
-    # --- the second half of BASELINE.json's metric: forward load-step solve + adjoint objective
-    # gradient through the C++ host solvers (Newton + line search, AMG-GMRES, reverse sweep), on the
-    # same mesh and model, a bounded number of load steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+
+    # --- the other kernels of the path and the general-path rows (one GPU only; secondary legs must
+    # not lose the headline line)
+    kernels = general = None
+    if world == 1 and not args.no_kernels:
+        try:
+            kernels = kernel_rows(ctx, dict(x=x, xp=xp, xi=xi, xip=xip, A=A, b=b), dfma_peak, hbm_peak)
+        except Exception as ex:   # noqa: BLE001
+            kernels = {"error": repr(ex)[:300]}
+
+    # --- the second half of BASELINE.json's metric: forward load-step solves + adjoint objective
+    # gradient through the C++ host solvers (Newton + line search, AMG-GMRES, reverse sweep) on the
+    # same mesh and model, BASELINE configs[1]'s 20 load steps
     cal = None
     if not args.no_solve:
-        # secondary leg: a failure here must not lose the headline line
         try:
-            if world == 1:
-                cal = calibration_step(ctx, mesh, args.load_steps)
-            else:
-                cal = calibration_step_partitioned(mesh, args.load_steps, rank, world, local_rank)
+            cal = calibration_step(ctx, mesh, part, args.load_steps, world, dev)
         except Exception as ex:   # noqa: BLE001
+            # (every rank sees the same allreduced norms, so a solver failure is raised on all ranks at
+            # the same point of the collective sequence)
             cal = {"metric": "forward+adjoint gradient wall-time/load step", "error": repr(ex)[:300]}
 
     # max over ranks
     t = torch.tensor([total_ms, k_ms, e2e_s], dtype=torch.float64, device=dev)
+    halo = torch.tensor([float(n_local - n_owned)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(halo)
     total_ms, k_ms, e2e_s = [float(v) for v in t.tolist()]
     ms_per_step = total_ms / args.steps
-    value = n * world / (ms_per_step * 1e-3)
-    e2e_value = n * world / e2e_s
+    value = n_total / (ms_per_step * 1e-3)
+    e2e_value = n_total / e2e_s
+    n_dev = ctx.n_nodes
+    nnzb = ctx.nnzb
+    del x, xp, x0, xi0, xip, xi, A, b, path, y
+    ctx.close()
+    torch.cuda.empty_cache()
+    if world == 1 and not args.no_kernels:
+        try:
+            general = general_path_rows(mesh, fields, local_rank, stream, dfma_peak)
+        except Exception as ex:   # noqa: BLE001
+            general = {"error": repr(ex)[:300]}
 
     if rank == 0:
         flops_qp = flops_per_qp_reference()
-        achieved_tf = flops_qp * n / (k_ms * 1e-3) * 1e-12
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        nnzb = ctx.nnzb
-        bytes_per_launch = (n * (16 + 64 + 64 + 64 + 64 + 1) + ctx.n_nodes * (24 + 32 + 32 + 32)
-                            + nnzb * 16 * 8)
+        # per-launch figures are those of the slowest rank's kernels: its local elements, owned + halo
+        achieved_tf = flops_qp * n_local / (k_ms * 1e-3) * 1e-12
+        bytes_per_launch = (n_local * (16 + 64 + 64 + 64 + 64 + 1) + n_dev * (24 + 32 + 32 + 32) + nnzb * 16 * 8)
+        traffic = measured_traffic() if world == 1 else None
+        golden_path = os.path.join(ROOT, "tests", "golden", "bench_n1.json")
+        parity = None
+        if args.write_golden and world == 1 and cal and "objective" in cal:
+            json.dump({"command": "python bench.py --write-golden (one B200)", "n_elems": n_total, "checks": checks,
+                       "load_steps": cal["load_steps"], "objective": cal["objective"], "gradient": cal["gradient"]},
+                      open(golden_path, "w"), indent=1)
+        elif os.path.exists(golden_path):
+            gold = json.load(open(golden_path))
+            rel = lambda a, c: abs(a - c) / abs(c) if c != 0 else abs(a)
+            parity = {"reference": "tests/golden/bench_n1.json (one-GPU run of this bench)",
+                      "rel_b": rel(checks["b_dot_b"], gold["checks"]["b_dot_b"]) / 2,
+                      "rel_Ax": rel(checks["Ax_dot_Ax"], gold["checks"]["Ax_dot_Ax"]) / 2}
+            ok = parity["rel_b"] < 1e-10 and parity["rel_Ax"] < 1e-10
+            if cal and "objective" in cal and cal["load_steps"] == gold["load_steps"]:
+                g0, g1 = np.array(gold["gradient"]), np.array(cal["gradient"])
+                parity["rel_J"] = rel(cal["objective"], gold["objective"])
+                parity["rel_grad"] = float(np.abs(g1 - g0).max() / np.abs(g0).max())
+                ok = ok and parity["rel_J"] < 1e-8 and parity["rel_grad"] < 1e-8
+            parity["ok"] = bool(ok)
+            parity["tolerances"] = "assembled residual / matrix action 1e-10, objective and adjoint gradient 1e-8 (north_star)"
         cpu = None
-        if args.gpus == 1 and not args.no_cpu:
-            c1 = cpu_sample(1, 28)
-            cpu = {"value": c1["evals_per_s"], "unit": UNIT, "cores": 1, "kind": "port",
-                   "host_cores_available": os.cpu_count(),
-                   "sample": f"one {c1['n_elems']}-tet notched box (28 cells/side) of the same hyper-J2 "
-                             f"state, full eval_forward_jacobian incl. CSR scatter, 1 thread, "
-                             f"{c1['seconds']:.1f} s"}
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            ca = min([cpu_sample(cores, 12) for _ in range(2)], key=lambda r: r["seconds"])
+            c1 = cpu_sample(1, 20)
+            cpu = {"value": ca["evals_per_s"], "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{cores} threads x one {ca['n_elems']}-tet notched box (12 cells/side) of the same hyper-J2 "
+                             f"state, full eval_forward_jacobian incl. CSR scatter, {ca['seconds']:.2f} s",
+                   "single_core": {"value": c1["evals_per_s"], "sample": f"one {c1['n_elems']}-tet box, {c1['seconds']:.1f} s"}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": f"3D finite-strain hyper_J2 + mixed u-p mechanics, notched unit box, "
-                            f"{N_CELLS} cells/side Kuhn tets",
-                "n_elems_per_gpu": n, "n_nodes_per_gpu": ctx.n_nodes, "nnz_blocks_4x4": nnzb,
+                            f"{N_CELLS} cells/side Kuhn tets (BASELINE configs[1]); the same mesh at every N",
+                "n_elems": n_total, "n_elems_slowest_rank_incl_halo": n_local,
+                "halo_elems_total": int(halo.item()), "n_nodes_rank0": n_dev, "nnz_blocks_4x4_rank0": nnzb,
                 "plastic_fraction": plastic, "local_newton": LOCAL,
                 "timed_region": "memset(b) + xi<-xi_prev copy + K1 (eval_forward_jacobian: element kernel + BSR gather) per step",
-                "l2_policy": "inputs larger than L2 (A 4x4-BSR values %.0f MB + state %.0f MB per step)"
-                             % (nnzb * 128 / 1e6, n * 8 * 8 * 3 / 1e6),
-                "parallelism": "1 rank/GPU, element slabs, no data-path collective" if world > 1 else "1 GPU",
+                "l2_policy": "inputs larger than L2 at N<=2 (A 4x4-BSR values %.0f MB + state + element scratch %.0f MB per rank)"
+                             % (nnzb * 128 / 1e6, n_local * 2048 / 1e6),
+                "parallelism": ("%d ranks, RCB element partition, owned QPs counted, halo elements evaluated redundantly, "
+                                "no data-path collective in K1" % world) if world > 1 else "1 GPU",
             },
             "kernel_ms": k_ms,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": dfma_peak, "unit": "TFLOP/s",
@@ -460,24 +637,24 @@ def run_ours(args):
                          "peak_source": "DFMA micro-benchmark measured in this run (c8_bench_dfma); "
                                         "MEASURED_PEAKS.json has no fp64 entry",
                          "algorithmic_flops_per_qp": flops_qp,
-                         "flops_definition": "reference algorithm's count (16-wide AD on every op, "
-                                             "op-counting oracle); the kernel executes fewer",
+                         "flops_definition": "reference algorithm's count (16-wide AD on every op, 4-5 local Newton "
+                                             "iterations per plastic point; op-counting oracle); the kernel executes fewer "
+                                             "-- executed DFMA TFLOP/s: profiles/README.md",
                          "kernels": "k_forward_jacobian<Cfg<3,0,HyperJ2<3>,4>,true> + k_bsr_gather<4,4,false>",
-                         "traffic": 4.72e9,
-                         "traffic_source": "ncu --set full, dram read+write per launch: element kernel 0.10+2.12 GB, "
-                                           "gather 2.17+0.33 GB (profiles/r01c_*; the scratch is written once, read once)"},
+                         "traffic": traffic["traffic"] if traffic else None,
+                         "traffic_source": traffic["source"] if traffic else None},
             "roofline_hbm": {"bound": "hbm", "achieved": bytes_per_launch / (k_ms * 1e-3) * 1e-9,
                              "peak": hbm_peak, "unit": "GB/s",
                              "frac": bytes_per_launch / (k_ms * 1e-3) * 1e-9 / hbm_peak,
                              "algorithmic_bytes_per_launch": bytes_per_launch,
-                             "copy_gbs_measured_this_run": copy_peak, "traffic": 4.72e9,
-                             "note": "K1 is fp64-bound; the two-phase assembly moves 7.4x the compulsory bytes "
-                                     "(2 KB scratch per tet written and read once) to avoid 256 fp64 atomics per tet"},
+                             "copy_gbs_measured_this_run": copy_peak,
+                             "traffic": traffic["traffic"] if traffic else None},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
                     "api": "c8_state_forward_jacobian (host nodal iterate in, host residual + status out)"},
-            "gpu_launches": 2 * args.steps,   # element kernel + BSR gather per step
+            "gpu_launches": 2 * args.steps * world,   # element kernel + BSR gather per step and rank
             "clocks": clocks,
+            "checksums": checks,
         }
         line["roofline_spmv"] = {"bound": "hbm", "achieved": spmv_bytes / (spmv_ms * 1e-3) * 1e-9,
                                  "peak": hbm_peak, "unit": "GB/s",
@@ -485,12 +662,17 @@ def run_ours(args):
                                  "kernel": "k_bsr_spmv<4>", "ms_per_launch": spmv_ms,
                                  "algorithmic_bytes_per_launch": spmv_bytes,
                                  "bytes_definition": "8 B/value + 4 B/block index + rowptr + x read + y write"}
+        if parity:
+            line["parity_vs_n1"] = parity
         if cal:
             line["forward_adjoint"] = cal
+        if kernels:
+            line["kernels"] = kernels
+        if general:
+            line["general_path"] = general
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -503,7 +685,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-solve", action="store_true", help="skip the forward+adjoint load-step leg")
-    ap.add_argument("--load-steps", type=int, default=2)
+    ap.add_argument("--no-kernels", action="store_true", help="skip the K2..K6 and general-path rows")
+    ap.add_argument("--load-steps", type=int, default=20, help="BASELINE configs[1]: 20 load steps")
+    ap.add_argument("--write-golden", action="store_true",
+                    help="one GPU: store the checksums / objective / gradient as tests/golden/bench_n1.json")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

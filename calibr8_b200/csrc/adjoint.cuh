@@ -332,7 +332,14 @@ __global__ void __launch_bounds__(128) k_adjoint_local(const AdjArgs a) {
 #pragma unroll
       for (int s = 0; s < LXI; ++s) JT[i][s] = pick(t * LXI + s == r, v, JT[i][s]);
     }
-  group_gauss_jordan<NXI, LXI, 0, G, true>(JT, dummy, rhs, mask);  // rhs := phi
+  if constexpr (Model::HAS_NEWTON) {
+    group_gauss_jordan<NXI, LXI, 0, G, true>(JT, dummy, rhs, mask);  // rhs := phi
+  } else {
+    // Elastic: C == 0 identically, dC/dxi is the zero matrix and the reference's rank-revealing LU
+    // (Eigen::FullPivLU, src/evaluations.cpp:624) returns phi = 0 -- as in local_sensitivity()
+#pragma unroll
+    for (int q = 0; q < NXI; ++q) rhs[q] = 0.0;
+  }
   if (!in_range) return;  // no shuffles below
 #pragma unroll
   for (int q = 0; q < NXI; ++q)

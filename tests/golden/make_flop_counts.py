@@ -39,6 +39,17 @@ def main(n_cells=6):
     o.flops_reset(); o.qoi([u2, p2], [u1, p1], rB["xi"], rA["xi"], 1); out["K5"] = o.flops_reset() / n
     o.flops_reset(); o.qoi_gradient([u2, p2], [u1, p1], rB["xi"], rA["xi"], z, phi, [[0, 1, 2, 3]], 4, 1)
     out["K6"] = o.flops_reset() / n
+    # K1 on the general-path states of bench.py (iterated local Newton, exp / pow in the yield law)
+    for key, (ltype, params, amp_scale) in bench.GENERAL_PATHS.items():
+        og = Oracle(3, mesh.conn, mesh.coords, global_type="mechanics", local_type=ltype, params=[params],
+                    count_flops=True, **bench.LOCAL)
+        x0g = og.init_xi()
+        a1, a2 = [u1 * amp_scale, p1], [u2 * amp_scale, p2]
+        rAg = og.forward_jacobian(a1, og.zeros_x(), x0g, x0g, assemble=False)
+        og.flops_reset(); rBg = og.forward_jacobian(a2, a1, rAg["xi"], rAg["xi"])
+        out["K1_" + key] = og.flops_reset() / n
+        out["plastic_fraction_" + key] = float(rBg["path"].mean())
+        out["newton_iters_plastic_" + key] = float(rBg["iters"][rBg["path"] == 1].mean())
     json.dump(out, open(os.path.join(HERE, "flop_counts.json"), "w"), indent=1)
     print(json.dumps(out, indent=1))
 
