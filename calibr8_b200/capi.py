@@ -296,11 +296,11 @@ class Context:
 # adjoint / QoI / linear-algebra entry points and the C++ host step solvers (c8h_*)
 SYMBOLS += [
     "c8_adjoint_jacobian", "c8_adjoint_local", "c8_qoi_value", "c8_qoi_gradient", "c8_spmv",
-    "c8_dot", "c8_axpby", "c8_apply_dbc", "c8_gmres", "c8_linalg_release", "c8_get_coords",
+    "c8_dot", "c8_axpby", "c8_apply_dbc", "c8_apply_tbc", "c8_gmres", "c8_linalg_release", "c8_get_coords",
     "c8_get_conn", "c8_get_stream",
 ]
 HOST_SYMBOLS = [
-    "c8h_create", "c8h_destroy", "c8h_last_error", "c8h_set_time", "c8h_add_dbc",
+    "c8h_create", "c8h_destroy", "c8h_last_error", "c8h_set_time", "c8h_add_dbc", "c8h_add_tbc",
     "c8h_finalize_dbcs", "c8h_set_solver", "c8h_set_qoi_avg_disp", "c8h_set_qoi_calibration",
     "c8h_primal_solve", "c8h_adjoint_gradient", "c8h_get_step", "c8h_get_adjoint_step", "c8h_stats",
     "c8h_profile", "c8h_eval_expr", "c8h_describe_residuals",
@@ -374,6 +374,12 @@ def _ctx_apply_dbc(self, A, R, x, nodes, eqs, vals, is_adjoint=False):
                                       _dp(vals), int(nodes.numel()), int(is_adjoint)))
 
 
+def _ctx_apply_tbc(self, R, side_nodes, traction):
+    """side_nodes int32 device [n_sides][dim], traction float64 device [n_sides][dim]"""
+    self._check(self.lib.c8_apply_tbc(self.h, _dp(R), _dp(side_nodes), _dp(traction),
+                                      int(side_nodes.numel()) // self.dim))
+
+
 def _ctx_gmres(self, A, b, x, restart=100, max_iters=5000, rel_tol=1e-10, abs_tol=0.0):
     info = (C.c_double * 3)()
     rc = self.lib.c8_gmres(self.h, _dp(A), _dp(b), _dp(x), restart, max_iters, C.c_double(rel_tol),
@@ -390,6 +396,7 @@ Context.qoi_gradient = _ctx_qoi_gradient
 Context.spmv = _ctx_spmv
 Context.dot = _ctx_dot
 Context.apply_dbc = _ctx_apply_dbc
+Context.apply_tbc = _ctx_apply_tbc
 Context.gmres = _ctx_gmres
 
 
@@ -433,6 +440,12 @@ class HostProblem:
 
     def finalize_dbcs(self):
         self._check(self.lib.c8h_finalize_dbcs(self.h))
+
+    def add_tbc(self, resid, side_nodes, exprs):
+        """traction bc [resid, side set, x-val, y-val(, z-val)]: side_nodes [n_sides][dim] node ids"""
+        sn = np.ascontiguousarray(side_nodes, dtype=np.int32).reshape(-1, self.ctx.dim)
+        ex = ";".join(str(e) for e in list(exprs)[: self.ctx.dim])
+        self._check(self.lib.c8h_add_tbc(self.h, resid, _hp(sn), int(sn.shape[0]), ex.encode()))
 
     def set_solver(self, newton_max_iters=15, abs_tol=1e-8, rel_tol=1e-8, gmres_restart=100,
                    gmres_max_iters=4000, linear_tol=1e-10, verbose=False):

@@ -37,4 +37,19 @@ int c8_apply_dbc(c8_ctx* ctx, double* A_vals_dev, double* R_dev, const double* x
   return C8_OK;
 }
 
+int c8_apply_tbc(c8_ctx* ctx, double* R_dev, const int32_t* side_nodes_dev, const double* traction_dev,
+                 int n_sides) {
+  C8_REQUIRE(ctx, ctx->kt != nullptr, "c8_set_model must be called first");
+  if (n_sides == 0) return C8_OK;
+  const int block = 128, grid = (n_sides + block - 1) / block;
+  if (ctx->dim == 3)
+    k_apply_tbc<3><<<grid, block, 0, ctx->stream>>>(ctx->d_coords, side_nodes_dev, traction_dev, R_dev, n_sides,
+                                                    ctx->kt->nb, ctx->n_owned_nodes);
+  else
+    k_apply_tbc<2><<<grid, block, 0, ctx->stream>>>(ctx->d_coords, side_nodes_dev, traction_dev, R_dev, n_sides,
+                                                    ctx->kt->nb, ctx->n_owned_nodes);
+  C8_CUDA(ctx, cudaGetLastError());
+  return C8_OK;
+}
+
 }  // extern "C"

@@ -238,6 +238,45 @@ __global__ void k_apply_dbc(const int* __restrict__ rowptr, const int* __restric
   R[row] = is_adjoint ? 0.0 : diag * (x[row] - dbc_val[i]);
 }
 
+// Traction boundary conditions, apply_primal_tbc of the reference (src/tbcs.cpp:17-86):
+//   R[n, d] -= T_d(x_q, t) N_n(x_q) w dv   over the side quadrature of the local variables' order
+// (getIPFitShape(dim, 1): ONE point at the side centroid, where every linear side basis function is
+// 1/DIM and w dv is the side's area (3-D) or length (2-D)).  One thread per side; trac holds the
+// traction vector at the side's quadrature point (the host evaluates the deck's expression strings
+// there).  Rows of ghost nodes belong to another part and are skipped.
+template <int DIM>
+__global__ void k_apply_tbc(const double* __restrict__ coords, const int* __restrict__ side_nodes,
+                            const double* __restrict__ trac, double* __restrict__ R, int n_sides,
+                            int nb, int n_row_nodes) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_sides) return;
+  int nd[DIM];
+  double X[DIM][DIM];
+#pragma unroll
+  for (int a = 0; a < DIM; ++a) {
+    nd[a] = side_nodes[s * DIM + a];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) X[a][k] = coords[size_t(nd[a]) * DIM + k];
+  }
+  double wdv;
+  if constexpr (DIM == 3) {
+    const double ax = X[1][0] - X[0][0], ay = X[1][1] - X[0][1], az = X[1][2] - X[0][2];
+    const double bx = X[2][0] - X[0][0], by = X[2][1] - X[0][1], bz = X[2][2] - X[0][2];
+    const double cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+    wdv = 0.5 * sqrt(cx * cx + cy * cy + cz * cz);
+  } else {
+    const double ax = X[1][0] - X[0][0], ay = X[1][1] - X[0][1];
+    wdv = sqrt(ax * ax + ay * ay);
+  }
+#pragma unroll
+  for (int a = 0; a < DIM; ++a) {
+    if (nd[a] >= n_row_nodes) continue;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+      atomicAdd(&R[size_t(nd[a]) * nb + d], -trac[s * DIM + d] * (1.0 / DIM) * wdv);
+  }
+}
+
 static inline int grid_for(long long n, int block, int sms) {
   long long g = (n + block - 1) / block;
   const long long cap = (long long)sms * 8;

@@ -29,6 +29,15 @@ struct Dbc {  // "bc name: [resid_idx, eq, node_set_name, value]", src/dbcs.cpp:
   Expr expr;
 };
 
+struct Tbc {  // "bc name: [resid_idx, side_set_name, x-val, y-val(, z-val)]", src/tbcs.cpp:28-35
+  int resid;
+  std::vector<int> side_nodes;     // [n_sides][dim] local node ids
+  std::vector<Expr> exprs;         // one per dimension
+  int n_sides = 0;
+  int* d_side_nodes = nullptr;
+  double* d_traction = nullptr;    // [n_sides][dim] at the side quadrature points, current step
+};
+
 struct SolverParams {
   int newton_max_iters = 15;           // "nonlinear max iters"
   double newton_abs_tol = 1e-8;        // "nonlinear absolute tol"
@@ -92,6 +101,7 @@ class Problem {
   int num_steps = 0;
   double step_size = 1.;
   std::vector<Dbc> dbcs;
+  std::vector<Tbc> tbcs;
   SolverParams sp;
   int qoi_type = 0;  // 0 average displacement, 1 calibration
   CalibrationQoi cal;
@@ -119,6 +129,9 @@ class Problem {
   void add_dbc(int resid, int eq, const int* nodes, int n, const std::string& expr);
   void finalize_dbcs();
   void eval_dbc_values(double t);
+  void add_tbc(int resid, const int* side_nodes, int n_sides, const std::vector<std::string>& exprs);
+  void eval_tbc_values(double t);    // traction vectors at the side quadrature points for time t
+  void apply_tbcs(double* R) const;  // apply_primal_tbcs, src/tbcs.cpp:88-98
   void allocate_history();
   double norm(const double* v) const;
   double dot(const double* a, const double* c) const;

@@ -35,6 +35,10 @@ Problem::~Problem() {
   if (d_dbc_val) cudaFree(d_dbc_val);
   for (double* p : cal.d_measured) if (p) cudaFree(p);
   if (cal.d_facet) cudaFree(cal.d_facet);
+  for (Tbc& t : tbcs) {
+    if (t.d_side_nodes) cudaFree(t.d_side_nodes);
+    if (t.d_traction) cudaFree(t.d_traction);
+  }
 }
 
 void Problem::check(int rc, const char* what) const {
@@ -89,6 +93,53 @@ void Problem::eval_dbc_values(double t) {
     }
   if (n_dbc)
     C8H_CUDA(cudaMemcpy(d_dbc_val, h_dbc_val.data(), n_dbc * sizeof(double), cudaMemcpyHostToDevice));
+}
+
+void Problem::add_tbc(int resid, const int* side_nodes, int n_sides, const std::vector<std::string>& exprs) {
+  if (resid != 0) throw std::runtime_error("traction bcs act on the displacement residual (index 0)");
+  if (int(exprs.size()) < dim) throw std::runtime_error("traction bc: one expression per dimension");
+  Tbc t;
+  t.resid = resid;
+  for (int d = 0; d < dim; ++d) t.exprs.emplace_back(exprs[d]);
+  // keep the sides that touch an owned node (their other nodes are local: the part holds every
+  // element touching an owned node); rows of ghost nodes are skipped by the kernel
+  for (int s = 0; s < n_sides; ++s) {
+    bool any_owned = false, all_local = true;
+    for (int a = 0; a < dim; ++a) {
+      const int nd = side_nodes[s * dim + a];
+      all_local = all_local && nd >= 0 && nd < n_nodes;
+      any_owned = any_owned || (nd >= 0 && nd < n_owned_nodes);
+    }
+    if (!any_owned) continue;
+    if (!all_local) throw std::runtime_error("traction bc: a side of an owned node has a non-local node");
+    for (int a = 0; a < dim; ++a) t.side_nodes.push_back(side_nodes[s * dim + a]);
+  }
+  t.n_sides = int(t.side_nodes.size()) / dim;
+  if (t.n_sides) {
+    C8H_CUDA(cudaMalloc(&t.d_side_nodes, t.side_nodes.size() * sizeof(int)));
+    C8H_CUDA(cudaMemcpy(t.d_side_nodes, t.side_nodes.data(), t.side_nodes.size() * sizeof(int), cudaMemcpyHostToDevice));
+    C8H_CUDA(cudaMalloc(&t.d_traction, t.side_nodes.size() * sizeof(double)));
+  }
+  tbcs.push_back(std::move(t));
+}
+
+void Problem::eval_tbc_values(double t) {
+  for (Tbc& bc : tbcs) {
+    if (!bc.n_sides) continue;
+    std::vector<double> T(size_t(bc.n_sides) * dim);
+    for (int s = 0; s < bc.n_sides; ++s) {
+      double xq[3] = {0., 0., 0.};   // mapLocalToGlobal of the one-point rule = the side centroid
+      for (int a = 0; a < dim; ++a)
+        for (int k = 0; k < 3; ++k) xq[k] += coords[size_t(bc.side_nodes[s * dim + a]) * 3 + k] / dim;
+      for (int d = 0; d < dim; ++d) T[size_t(s) * dim + d] = bc.exprs[d](xq[0], xq[1], xq[2], t);
+    }
+    C8H_CUDA(cudaMemcpy(bc.d_traction, T.data(), T.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+}
+
+void Problem::apply_tbcs(double* R) const {
+  for (const Tbc& bc : tbcs)
+    check(c8_apply_tbc(ctx, R, bc.d_side_nodes, bc.d_traction, bc.n_sides), "c8_apply_tbc");
 }
 
 // (re)size a per-step history to [0..num_steps] arrays of n doubles, zero-filled; arrays of the
@@ -174,6 +225,7 @@ bool Primal::assemble(int step, double* R_norm) {
   ++P.n_assemblies;
   if (rc == C8_ERR_LOCAL_SOLVE) return false;
   P.check(rc, "c8_forward_jacobian");
+  P.apply_tbcs(P.b.get());   // apply_primal_tbcs(tbcs, disc, R_ghost, t), src/primal.cpp:107
   P.check(c8_apply_dbc(P.ctx, P.A.get(), P.b.get(), P.x[step].get(), P.d_dbc_node, P.d_dbc_eq,
                        P.d_dbc_val, P.n_dbc, 0), "c8_apply_dbc");
   *R_norm = P.norm(P.b.get());
@@ -197,6 +249,7 @@ void Primal::solve_at_step(int step) {
   C8H_CUDA(cudaMemcpyAsync(P.x[step].get(), P.x[step - 1].get(), xb, cudaMemcpyDeviceToDevice, s));
   C8H_CUDA(cudaMemcpyAsync(P.xi[step].get(), P.xi[step - 1].get(), xib, cudaMemcpyDeviceToDevice, s));
   P.eval_dbc_values(P.time(step));
+  P.eval_tbc_values(P.time(step));
   int iter = 1;
   bool converged = false;
   double resid_norm_0 = 1.;
@@ -407,6 +460,18 @@ int c8h_add_dbc(c8h_problem* h, int resid, int eq, const int32_t* nodes, int n, 
   C8H_TRY(h, h->P.add_dbc(resid, eq, nodes, n, expr));
 }
 int c8h_finalize_dbcs(c8h_problem* h) { C8H_TRY(h, h->P.finalize_dbcs()); }
+// side_nodes [n_sides][dim] local node ids; exprs: dim expressions in x, y, z, t separated by ';'
+int c8h_add_tbc(c8h_problem* h, int resid, const int32_t* side_nodes, int n_sides, const char* exprs) {
+  C8H_TRY(h, {
+    std::vector<std::string> ex;
+    std::string cur;
+    for (const char* c = exprs; ; ++c) {
+      if (*c == ';' || *c == 0) { ex.push_back(cur); cur.clear(); if (*c == 0) break; }
+      else cur += *c;
+    }
+    h->P.add_tbc(resid, side_nodes, n_sides, ex);
+  });
+}
 int c8h_set_solver(c8h_problem* h, int newton_max_iters, double abs_tol, double rel_tol,
                    int gmres_restart, int gmres_max_iters, double linear_tol, int print) {
   SolverParams& s = h->P.sp;

@@ -188,6 +188,12 @@ int c8_axpby(c8_ctx* ctx, double a, const double* x_dev, double b, double* y_dev
 int c8_apply_dbc(c8_ctx* ctx, double* A_vals_dev, double* R_dev, const double* x_dev,
                  const int32_t* dbc_node_dev, const int32_t* dbc_eq_dev, const double* dbc_val_dev,
                  int n_dbc, int is_adjoint);
+/* apply_primal_tbcs, tbcs.cpp:17-98 (called from Primal::solve_at_step, primal.cpp:107, between the
+ * assembly and the Dirichlet rows): R[n, d] -= T_d N_n w dv over the one-point side quadrature.
+ * side_nodes_dev [n_sides][dim] local node ids of every side of the set, traction_dev [n_sides][dim]
+ * the traction vector at each side's quadrature point (= centroid), residual 0 (displacement) rows */
+int c8_apply_tbc(c8_ctx* ctx, double* R_dev, const int32_t* side_nodes_dev, const double* traction_dev,
+                 int n_sides);
 /* restarted GMRES(m), device-resident Arnoldi, right preconditioned (c8_set_preconditioner);
  * info_host[3] = iterations, final |r|, initial |r| */
 int c8_gmres(c8_ctx* ctx, const double* A_vals_dev, const double* b_dev, double* x_dev,

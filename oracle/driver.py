@@ -3,6 +3,7 @@
 Restates, with scipy's sparse direct solver in place of Belos/Teko/MueLu:
   Primal::solve_at_step     src/primal.cpp:31-208  (+ src/line_search.hpp:56-135)
   apply_expression_primal_dbcs  src/dbcs.cpp:28-121
+  apply_primal_tbcs         src/tbcs.cpp:17-98
   Adjoint::solve_at_step    src/adjoint.cpp:76-189
   Adjoint_Objective value/gradient  src/adjoint_objective.cpp:22-118
   VirtualPower / VFM objectives     src/virtual_power.cpp:109-203,
@@ -59,6 +60,35 @@ def apply_primal_dbcs(orc, dbcs, A, R, x, t, is_adjoint=False):
                     vals[lo:hi] = 0.0
 
 
+class Tbc:
+    """"bc name: [resid_idx, side_set_name, x-val, y-val(, z-val)]" (src/tbcs.cpp:28-35):
+    sides = [n_sides][dim] node ids of each side of the set, exprs = one expression per dimension"""
+
+    def __init__(self, resid, sides, exprs):
+        self.resid, self.sides, self.exprs = resid, np.asarray(sides), list(exprs)
+
+
+def apply_primal_tbcs(orc, tbcs, R, t):
+    """src/tbcs.cpp:17-86: R[n,d] -= T_d(x_q, t) N_n(x_q) w dv over the side quadrature of the local
+    variables' order (getIPFitShape(dim, 1): one point at the side centroid, where every linear side
+    basis function is 1/dim and w dv = the side's area (3-D, w = 1/2, dv = |a x b|) or length (2-D,
+    w = 2 on [-1, 1], dv = length / 2)."""
+    dim = orc.dim
+    for bc in tbcs:
+        neq = orc.neq[bc.resid]
+        for side in bc.sides:
+            X = orc.coords[side]
+            xq = X.mean(axis=0)
+            if dim == 3:
+                wdv = 0.5 * float(np.linalg.norm(np.cross(X[1] - X[0], X[2] - X[0])))
+            else:
+                wdv = float(np.linalg.norm(X[1] - X[0]))
+            T = [eval_expr(e, xq[0], xq[1], xq[2], t) for e in bc.exprs[:dim]]
+            for node in side:
+                for d in range(dim):
+                    R[bc.resid][node * neq + d] -= T[d] * (1.0 / dim) * wdv
+
+
 def norm_b(R):
     return math.sqrt(sum(float(r @ r) for r in R))
 
@@ -110,7 +140,7 @@ class Primal:
         self.num_steps, self.step_size = num_steps, step_size
         self.max_iters, self.abs_tol, self.rel_tol = max_iters, abs_tol, rel_tol
         self.verbose = verbose
-        self.tbc = tbc  # optional callable(R, t) adding traction terms
+        self.tbc = tbc  # optional callable(R, t) adding traction terms, or a list of Tbc
         self.reset()
 
     def reset(self):
@@ -131,7 +161,10 @@ class Primal:
             return None
         A, R = r["A"], r["b"]
         if self.tbc:
-            self.tbc(R, t)
+            if callable(self.tbc):
+                self.tbc(R, t)
+            else:
+                apply_primal_tbcs(o, self.tbc, R, t)
         apply_primal_dbcs(o, self.dbcs, A, R, x, t)
         return A, R, r["xi"]
 

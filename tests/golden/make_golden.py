@@ -78,6 +78,14 @@ DECKS = {
         dbcs=B2 + [[0, 1, "ymax", "0.001 * t"]],
         num_steps=8, global_max_iters=15, global_tol=1e-8, local_max_iters=500, local_tol=1e-12,
         J=6.5626182813091150e-03, rel_tol=1e-4),
+    # traction boundary condition (src/tbcs.cpp:17-98): [resid, side set, x-val, y-val, z-val]
+    "cube_hyperelasticity_traction": dict(
+        src="test/primal/cube_hyperelasticity_traction.yaml.in:5-51", mesh="cube", global_type="mechanics",
+        local_type="hyper_J2", params=dict(E=1000., nu=.25, K=100., Y=100000., S=0., D=0., A=0., n=0.),
+        dbcs=[[0, 0, "ymin", "0.0"], [0, 1, "ymin", "0.0"], [0, 2, "ymin", "0.0"]],
+        tbcs=[[0, "ymax", "0.", "0.1 * t", "0."]],
+        num_steps=4, global_max_iters=10, global_tol=1e-8, local_max_iters=30, local_tol=1e-12,
+        J=1.61757374785081228e-04, rel_tol=1e-4),
 }
 
 FD_DROPS = {

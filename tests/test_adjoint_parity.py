@@ -368,3 +368,41 @@ def test_local_newton_relative_tolerance():
         # both sides stop at rel_tol = 1e-8 of their first residual: the states agree to that level
         assert rel_err_blockwise(c.unpack_xi(xi2), rB["xi"], 0) < 1e-7
         c.close()
+
+
+@pytest.mark.parametrize("name", ["3d_hyper_J2", "2d_small_hill_plane_stress", "2d_small_J2"])
+def test_traction_bc_kernel(name):
+    """c8_apply_tbc <-> apply_primal_tbc (src/tbcs.cpp:17-86): R[n, d] -= T_d N_n w dv over the one-point
+    side quadrature, against the oracle's restatement (oracle/driver.py) on every boundary side of the
+    mesh with a position- and time-dependent traction, entry-wise at 1e-10."""
+    import torch
+    from calibr8_b200 import capi
+    from oracle.driver import Tbc, apply_primal_tbcs
+    P = Pair(name)
+    o, c, mesh = P.orc, P.ctx, P.mesh
+    dim = mesh.dim
+    # every boundary side: faces (3-D) / edges (2-D) that belong to exactly one element
+    import itertools
+    cnt = {}
+    for e in range(mesh.n_elems):
+        for f in itertools.combinations(sorted(int(v) for v in mesh.conn[e]), dim):
+            cnt[f] = cnt.get(f, 0) + 1
+    sides = np.array([f for f, k in cnt.items() if k == 1], dtype=np.int32)
+    assert sides.shape[0] > 10
+    exprs = ["0.3 * t + x * y", "sin(3.0 * x) - 0.5 * t * z", "0.1 + y * y"][:dim]
+    t = 1.7
+    R_o = o.zeros_b()
+    apply_primal_tbcs(o, [Tbc(0, sides, exprs)], R_o, t)
+    cent = mesh.coords[sides].mean(axis=1)
+    trac = np.stack([capi.eval_expr(ex, cent, t) for ex in exprs], axis=1)
+    R = c.alloc("b")
+    sn = torch.from_numpy(sides).cuda()
+    tr = torch.from_numpy(np.ascontiguousarray(trac)).cuda()
+    torch.cuda.synchronize()
+    c.apply_tbc(R, sn, tr)
+    c.synchronize()
+    Rh = c.unpack_x(R)
+    assert np.abs(Rh[0] - R_o[0]).max() < TOL * np.abs(R_o[0]).max()
+    if len(Rh) > 1:
+        assert np.abs(Rh[1]).max() == 0.0     # the pressure rows see no traction
+    c.close()

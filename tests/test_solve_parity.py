@@ -26,6 +26,8 @@ def gpu_problem(d, mesh, params=None, qoi="avg_disp", lin_tol=1e-12):
     for r, e, s, v in d["dbcs"]:
         hp.add_dbc(r, e, mesh.node_sets[s], v)
     hp.finalize_dbcs()
+    for tb in d.get("tbcs", []):
+        hp.add_tbc(tb[0], mesh.side_sets[tb[1]], tb[2:])
     hp.set_solver(d["global_max_iters"], d["global_tol"], d["global_tol"], gmres_restart=200,
                   gmres_max_iters=20000, linear_tol=lin_tol)
     if qoi == "avg_disp":
@@ -34,21 +36,23 @@ def gpu_problem(d, mesh, params=None, qoi="avg_disp", lin_tol=1e-12):
 
 
 def oracle_problem(d, mesh, params=None, active=None):
-    from oracle.driver import Dbc, Primal
+    from oracle.driver import Dbc, Primal, Tbc
     from oracle.pyoracle import Oracle
     o = Oracle(mesh.dim, mesh.conn, mesh.coords, global_type=d["global_type"],
                local_type=d["local_type"], params=[params or d["params"]],
                max_iters=d["local_max_iters"], abs_tol=d["local_tol"], rel_tol=d["local_tol"],
                active=active)
     bcs = [Dbc(r, e, mesh.node_sets[s], v) for r, e, s, v in d["dbcs"]]
+    tbcs = [Tbc(t[0], mesh.side_sets[t[1]], t[2:]) for t in d.get("tbcs", [])]
     p = Primal(o, bcs, d["num_steps"], 1.0, max_iters=d["global_max_iters"],
-               abs_tol=d["global_tol"], rel_tol=d["global_tol"])
+               abs_tol=d["global_tol"], rel_tol=d["global_tol"], tbc=tbcs or None)
     return o, p
 
 
 DECKS = ["cube_elastic", "cube_hyper_J2", "notch_small_J2", "notch_hyper_J2", "notch2D_small_J2",
          "notch2D_small_J2_plane_strain", "notch2D_small_J2_plane_stress",
-         "notch2D_hyper_J2_plane_stress", "notch2D_hyper_J2_plane_strain"]
+         "notch2D_hyper_J2_plane_stress", "notch2D_hyper_J2_plane_strain",
+         "cube_hyperelasticity_traction"]       # traction bcs (src/tbcs.cpp:17-98)
 
 
 @pytest.mark.parametrize("name", DECKS)
