@@ -46,6 +46,13 @@ C8_DI void load_measured(const QoiArgs& q, const Elem<C>& E, double (&um)[C::NN]
 
 // ---------------------------------------------------------------------------------------
 // K3
+// Register diet (round 2; the first version kept 255 registers and a 2.2 KB spill frame, 7.5 GB of
+// local-memory traffic per launch at 1 M tets):
+//   * the element record (connectivity, geometry, nodal x / x_prev, parameters, xi_prev: ~65 doubles
+//     that every thread of the group held redundantly) lives in shared memory, one copy per group;
+//   * the passes are ordered so that each one's temporaries die before the next starts: QoI
+//     xi-derivatives (needs the xi-seeded state) -> sensitivity solve -> (dxi/dx)^T g and the
+//     right-hand side -> element matrix rows last.
 template <class C>
 __global__ void __launch_bounds__(128) k_adjoint_jacobian(const AdjArgs a) {
   using Model = typename C::Model;
@@ -59,28 +66,61 @@ __global__ void __launch_bounds__(128) k_adjoint_jacobian(const AdjArgs a) {
   const int e = in_range ? gid / G : a.mesh.n_elems - 1;
   const unsigned mask = group_mask<C>();
 
-  Elem<C> E;
-  load_elem<C>(a.mesh, a.model, a.x, a.x_prev, a.xi_prev, a.xi_ld, e, E);
+  __shared__ Elem<C> sE[128 / G];
+  load_elem_shared<C>(a.mesh, a.model, a.x, a.x_prev, a.xi_prev, a.xi_ld, e, t, sE[threadIdx.x / G]);
+  __syncwarp();   // a group never spans two warps
+  const Elem<C>& E = sE[threadIdx.x / G];
   double xi[NXI];
 #pragma unroll
   for (int q = 0; q < NXI; ++q) xi[q] = __ldg(&a.xi[size_t(q) * a.xi_ld + e]);
   Kin<D, double, double> k0;
   k0.gu = grad_u_val<D, NB>(E.xn, E.g);
   k0.gup = grad_u_val<D, NB>(E.xpn, E.g);
+  const double wdv = quad1_weight<D>() * E.g.dv;
+  const bool calib = a.qoi.type != QOI_AVG_DISP;
+  const int nmask = calib ? load_node_mask<D>(a.qoi, a.mesh.coords, E.nodes) : 0;
+  const double coef = a.qoi.balance_factor * a.qoi.dt_over_T * a.qoi.load_mismatch;
 
-  // dC/dxi at the stored state (no Newton, src/evaluations.cpp:442-446)
-  Dual<LXI> xs[NXI], Cd[NXI];
+  // ---- xi seeded: dC/dxi at the stored state (no Newton, src/evaluations.cpp:442-446) and the QoI's
+  // dJ/dxi (:474-478): g -= dJ/dxi
+  double gq[NXI];
 #pragma unroll
-  for (int q = 0; q < NXI; ++q) xs[q] = seeded<LXI>(xi[q], q, t * LXI);
-  const int path = Model::residual(k0, xs, E.xip, E.par, a.model.abs_tol, Cd);
+  for (int q = 0; q < NXI; ++q) gq[q] = a.g[size_t(q) * a.xi_ld + e];
+  Dual<LXI> Cd[NXI];
+  int path;
+  {
+    Dual<LXI> xs[NXI];
+#pragma unroll
+    for (int q = 0; q < NXI; ++q) xs[q] = seeded<LXI>(xi[q], q, t * LXI);
+    path = Model::residual(k0, xs, E.xip, E.par, a.model.abs_tol, Cd);
+    if (nmask) {   // calibration load term (group-uniform branch)
+      double p0 = 0.0;
+      if constexpr (C::M == MECH_MIXED) {
+#pragma unroll
+        for (int n = 0; n < NN; ++n) p0 += E.xn[n][D] * (1.0 / NN);
+      }
+      const Mat<Dual<LXI>, D> Pxi = first_pk<D, C::M, Model>(k0, p0, xs, E.par, a.model.thickness);
+      const Dual<LXI> load = calibration_load<D>(a.qoi, Pxi, E.g, wdv, nmask);
+#pragma unroll
+      for (int q = 0; q < NXI; ++q) {
+        const double v = group_bcast<G>(mask, load.d[q % LXI], q / LXI);
+        gq[q] -= coef * v;
+      }
+    }
+  }
+  if (in_range) {
+#pragma unroll
+    for (int q = 0; q < NXI; ++q)
+      if (q % G == t) a.g[size_t(q) * a.xi_ld + e] = gq[q];
+  }
 
+  // ---- x seeded: dC/dx, dxi/dx = -(dC/dxi)^-1 dC/dx
   SeededX<C> sx;
   sx.init(E, k0.gu, t);
   Kin<D, Dual<LX>, double> k2;
   k2.gu = sx.gu;
   k2.gup = k0.gup;
   Dual<LX> xid[NXI];
-  double dxi_dx[NXI][LX];
   {
     // as in K1 (forward.cuh): the pressure lane carries no constitutive derivative, and an
     // all-elastic warp needs no solve
@@ -108,20 +148,60 @@ __global__ void __launch_bounds__(128) k_adjoint_jacobian(const AdjArgs a) {
     for (int q = 0; q < NXI; ++q) {
       xid[q].v = xi[q];
 #pragma unroll
+      for (int s = 0; s < LX; ++s) xid[q].d[s] = s < L2 ? Bc[q][s < L2 ? s : 0] : 0.0;
+    }
+  }
+
+  // ---- rhs = -dJ/dx + f + dxi/dx^T g (:481-488); dJ/dx with x seeded and xi NOT seeded (:468-472)
+  {
+    double r[LX];
+#pragma unroll
+    for (int s = 0; s < LX; ++s) {
+      double v = 0.0;
+#pragma unroll
+      for (int q = 0; q < NXI; ++q) v = fma(xid[q].d[s], gq[q], v);
+      r[s] = v;
+    }
+    if (!calib) {
+#pragma unroll
+      for (int s = 0; s < LX; ++s) r[s] -= (sx.xl.eq[s] < D) ? (1.0 / NN) * wdv / D : 0.0;
+    } else {
+      const bool in_obj = (D == 2) || (a.qoi.facet && a.qoi.facet[size_t(e) * 3] >= 0);
+      if (in_obj) {
+        Dual<LX> un[NN][D];
+        seeded_nodal_u<C, LX>(E, sx.xl, un);
+        double um[NN][D], X[NN][D];
+        load_measured<C>(a.qoi, E, um, X, a.mesh.coords);
+        const signed char* fv = (D == 3) ? &a.qoi.facet[size_t(e) * 3] : nullptr;
+        const Dual<LX> mm = calibration_disp_mismatch<D, Dual<LX>>(a.qoi, un, um, X, E.g.dv, fv);
+#pragma unroll
+        for (int s = 0; s < LX; ++s) r[s] -= mm.d[s];
+      }
+      if (nmask) {
+        const Mat<Dual<LX>, D> Px = first_pk<D, C::M, Model>(k2, sx.p, xi, E.par, a.model.thickness);
+        const Dual<LX> load = calibration_load<D>(a.qoi, Px, E.g, wdv, nmask);
+#pragma unroll
+        for (int s = 0; s < LX; ++s) r[s] -= coef * load.d[s];
+      }
+    }
+    if (in_range) {
+#pragma unroll
       for (int s = 0; s < LX; ++s) {
-        dxi_dx[q][s] = s < L2 ? Bc[q][s < L2 ? s : 0] : 0.0;
-        xid[q].d[s] = dxi_dx[q][s];
+        if (sx.xl.nsel[s] == 0.0) continue;
+        const int c = t * LX + s;
+        const double v = r[s] + __ldg(&a.f[size_t(c) * a.xi_ld + e]);
+        if (E.nodes[sx.xl.node[s]] < a.mesh.n_row_nodes)
+          atomicAdd(&a.b[size_t(E.nodes[sx.xl.node[s]]) * NB + sx.xl.eq[s]], v);
       }
     }
   }
 
-  // total Jacobian -> element-matrix scratch; the gather pass transposes (matrix only)
-  const double wdv = quad1_weight<D>() * E.g.dv;
+  // ---- total Jacobian -> element-matrix scratch; the gather pass transposes (matrix only)
   FwdArgs fa{};
   fa.mesh = a.mesh;
   fa.vals = a.vals;
   fa.emat = a.emat;
-  Scatter<C, false> sc{fa, E, sx.xl, e, t, in_range};  // element matrix only; rhs is added below
+  Scatter<C, false> sc{fa, E, sx.xl, e, t, in_range};  // element matrix only; the rhs was added above
   sc.init();
   {
     const Mat<Dual<LX>, D> P = first_pk<D, C::M, Model>(k2, sx.p, xid, E.par, a.model.thickness);
@@ -171,70 +251,6 @@ __global__ void __launch_bounds__(128) k_adjoint_jacobian(const AdjArgs a) {
     }
 #pragma unroll
     for (int n = 0; n < NN; ++n) sc.row(n, D, Rp[n]);
-  }
-
-  // QoI derivatives: dJ/dx (x seeded, xi NOT seeded) and dJ/dxi (xi seeded), :468-478
-  double dJ_dx[LX];
-#pragma unroll
-  for (int s = 0; s < LX; ++s) dJ_dx[s] = 0.0;
-  double gq[NXI];
-#pragma unroll
-  for (int q = 0; q < NXI; ++q) gq[q] = a.g[size_t(q) * a.xi_ld + e];
-  if (a.qoi.type == QOI_AVG_DISP) {
-#pragma unroll
-    for (int s = 0; s < LX; ++s)
-      dJ_dx[s] = (sx.xl.eq[s] < D) ? (1.0 / NN) * wdv / D : 0.0;
-  } else {
-    const bool in_obj = (D == 2) || (a.qoi.facet && a.qoi.facet[size_t(e) * 3] >= 0);
-    if (in_obj) {
-      Dual<LX> un[NN][D];
-      seeded_nodal_u<C, LX>(E, sx.xl, un);
-      double um[NN][D], X[NN][D];
-      load_measured<C>(a.qoi, E, um, X, a.mesh.coords);
-      const signed char* fv = (D == 3) ? &a.qoi.facet[size_t(e) * 3] : nullptr;
-      const Dual<LX> mm = calibration_disp_mismatch<D, Dual<LX>>(a.qoi, un, um, X, E.g.dv, fv);
-#pragma unroll
-      for (int s = 0; s < LX; ++s) dJ_dx[s] += mm.d[s];
-    }
-    const int nmask = load_node_mask<D>(a.qoi, a.mesh.coords, E.nodes);
-    if (nmask) {
-      const double coef = a.qoi.balance_factor * a.qoi.dt_over_T * a.qoi.load_mismatch;
-      {
-        const Mat<Dual<LX>, D> Px = first_pk<D, C::M, Model>(k2, sx.p, xi, E.par, a.model.thickness);
-        const Dual<LX> load = calibration_load<D>(a.qoi, Px, E.g, wdv, nmask);
-#pragma unroll
-        for (int s = 0; s < LX; ++s) dJ_dx[s] += coef * load.d[s];
-      }
-      {
-        double p0 = 0.0;
-        if constexpr (C::M == MECH_MIXED) {
-#pragma unroll
-          for (int n = 0; n < NN; ++n) p0 += E.xn[n][D] * (1.0 / NN);
-        }
-        const Mat<Dual<LXI>, D> Pxi = first_pk<D, C::M, Model>(k0, p0, xs, E.par, a.model.thickness);
-        const Dual<LXI> load = calibration_load<D>(a.qoi, Pxi, E.g, wdv, nmask);
-#pragma unroll
-        for (int q = 0; q < NXI; ++q) {
-          const double v = group_bcast<G>(mask, load.d[q % LXI], q / LXI);
-          gq[q] -= coef * v;
-        }
-      }
-    }
-  }
-  // g -= dJ/dxi (stored) ; rhs = -dJ/dx + f + dxi/dx^T g, :481-488
-  if (!in_range) return;  // no shuffles below
-#pragma unroll
-  for (int q = 0; q < NXI; ++q)
-    if (q % G == t) a.g[size_t(q) * a.xi_ld + e] = gq[q];
-#pragma unroll
-  for (int s = 0; s < LX; ++s) {
-    if (sx.xl.nsel[s] == 0.0) continue;
-    const int c = t * LX + s;
-    double r = -dJ_dx[s] + __ldg(&a.f[size_t(c) * a.xi_ld + e]);
-#pragma unroll
-    for (int q = 0; q < NXI; ++q) r = fma(dxi_dx[q][s], gq[q], r);
-    if (E.nodes[sx.xl.node[s]] < a.mesh.n_row_nodes)
-      atomicAdd(&a.b[size_t(E.nodes[sx.xl.node[s]]) * NB + sx.xl.eq[s]], r);
   }
 }
 

@@ -62,6 +62,36 @@ C8_DI void load_elem(const MeshArgs& m, const ModelArgs& md, const double* __res
   for (int q = 0; q < C::NXI; ++q) E.xip[q] = __ldg(&xi_prev[size_t(q) * xi_ld + e]);
 }
 
+// The same record written ONCE per thread group into shared memory (E lives in __shared__): the G
+// threads split the loads -- thread n < NN fetches node n's id and nodal rows, the parameters and
+// xi_prev are strided over the group, the last thread computes the geometry -- instead of every
+// thread holding a private copy (~65 doubles in 3-D) in registers.  Callers __syncwarp() afterwards
+// (a group never spans two warps).
+template <class C>
+C8_DI void load_elem_shared(const MeshArgs& m, const ModelArgs& md, const double* __restrict__ x,
+                            const double* __restrict__ x_prev, const double* __restrict__ xi_prev,
+                            long long xi_ld, int e, int t, Elem<C>& E) {
+  static_assert(C::G >= 2, "needs at least two threads per group");
+  for (int n = t; n < C::NN; n += C::G) {
+    const int nd = __ldg(&m.conn[size_t(e) * C::NN + n]);
+    E.nodes[n] = nd;
+#pragma unroll
+    for (int q = 0; q < C::NB; ++q) {
+      E.xn[n][q] = __ldg(&x[size_t(nd) * C::NB + q]);
+      E.xpn[n][q] = x_prev ? __ldg(&x_prev[size_t(nd) * C::NB + q]) : 0.0;
+    }
+  }
+  const int es = m.elem_es ? __ldg(&m.elem_es[e]) : 0;
+  for (int q = t; q < C::NPAR; q += C::G) E.par[q] = __ldg(&md.params[es * md.npar + q]);
+  for (int q = t; q < C::NXI; q += C::G) E.xip[q] = __ldg(&xi_prev[size_t(q) * xi_ld + e]);
+  if (t == C::G - 1) {
+    int nodes[C::NN];
+#pragma unroll
+    for (int n = 0; n < C::NN; ++n) nodes[n] = __ldg(&m.conn[size_t(e) * C::NN + n]);
+    load_geom<C::D>(m.coords, nodes, E.g);
+  }
+}
+
 // The local Newton of LocalResidual::solve_nonlinear (e.g. src/small_J2.cpp:121-173).
 // xi: in = values gathered from the current xi field, out = converged state.
 // Cd: the last residual evaluation with xi seeded (value + this thread's dC/dxi columns).
@@ -378,8 +408,16 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian(co
   const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane / G * G));
 
   C8_PHASE_START();
+#ifdef C8_K1_SMEM_ELEM
+  // element record in shared memory, one copy per group (see load_elem_shared)
+  __shared__ Elem<C> sE[C8_K1_BLOCK / G];
+  load_elem_shared<C>(a.mesh, a.model, a.x, a.x_prev, a.xi_prev, a.xi_ld, e, t, sE[threadIdx.x / G]);
+  __syncwarp();
+  const Elem<C>& E = sE[threadIdx.x / G];
+#else
   Elem<C> E;
   load_elem<C>(a.mesh, a.model, a.x, a.x_prev, a.xi_prev, a.xi_ld, e, E);
+#endif
   double xi[NXI];
 #pragma unroll
   for (int q = 0; q < NXI; ++q) xi[q] = a.xi[size_t(q) * a.xi_ld + e];

@@ -87,7 +87,7 @@ for rep in range(2):     # the first pass builds the hierarchy and the iteration
                adjoint_ms=adj / a.load_steps * 1e3, krylov_iterations=s1["linear_iters"] - s0["linear_iters"],
                assemblies=s1["assemblies"] - s0["assemblies"], objective=J, gradient=[float(v) for v in g],
                preconditioner=ctx.preconditioner_info(), amg="owned block" if a.local_amg else "across the parts", linear_tol=a.lin_tol,
-               comm_rank0=ctx.comm_stats(), setup_s=setup_s, pass_index=rep)
+               comm_rank0=ctx.comm_stats(), p2p_rank0=ctx.p2p_active(), setup_s=setup_s, pass_index=rep)
     if part is not None:
         out["partition_rank0"] = dict(owned_elems=part.n_owned_elems, halo_elems=part.n_elems - part.n_owned_elems,
                                       ghost_nodes=part.n_nodes - part.n_owned_nodes, neighbours=int(part.nbr_rank.size))
