@@ -302,7 +302,7 @@ SYMBOLS += [
 HOST_SYMBOLS = [
     "c8h_create", "c8h_destroy", "c8h_last_error", "c8h_set_time", "c8h_add_dbc", "c8h_add_tbc",
     "c8h_finalize_dbcs", "c8h_set_solver", "c8h_set_qoi_avg_disp", "c8h_set_qoi_calibration",
-    "c8h_primal_solve", "c8h_adjoint_gradient", "c8h_get_step", "c8h_get_adjoint_step", "c8h_stats",
+    "c8h_set_qoi_mismatch", "c8h_get_loads", "c8h_primal_solve", "c8h_adjoint_gradient", "c8h_get_step", "c8h_get_adjoint_step", "c8h_stats",
     "c8h_profile", "c8h_eval_expr", "c8h_describe_residuals",
 ]
 
@@ -313,12 +313,15 @@ class C8Qoi(C.Structure):
                 ("dt_over_T", C.c_double), ("inv_area", C.c_double), ("load_mismatch", C.c_double),
                 ("coord_idx", C.c_int), ("coord_value", C.c_double), ("coord_tol", C.c_double),
                 ("reaction_force_comp", C.c_int), ("measured_dev", C.c_void_p),
-                ("facet_dev", C.c_void_p)]
+                ("facet_dev", C.c_void_p), ("compute_torque", C.c_int), ("normal_2d", C.c_double * 2)]
+
+
+QOI_TYPES = {"avg_disp": 0, "calibration": 1, "reaction_mismatch": 2, "load_mismatch": 3, "surface_mismatch": 4}
 
 
 def make_qoi(kind="avg_disp", **kw):
     q = C8Qoi()
-    q.type = 0 if kind == "avg_disp" else 1
+    q.type = QOI_TYPES[kind]
     w = kw.get("weights", (1., 1., 1.))
     for k in range(3):
         q.weights[k] = w[k] if k < len(w) else 1.0
@@ -334,6 +337,9 @@ def make_qoi(kind="avg_disp", **kw):
     q.measured_dev = None if m is None else m.data_ptr()
     f = kw.get("facet")
     q.facet_dev = None if f is None else f.data_ptr()
+    q.compute_torque = int(bool(kw.get("compute_torque", False)))
+    n2 = kw.get("normal_2d", (0., 0.))
+    q.normal_2d[0], q.normal_2d[1] = float(n2[0]), float(n2[1])
     return q
 
 
@@ -466,6 +472,24 @@ class HostProblem:
             self.h, C.c_double(balance_factor), coord_idx, C.c_double(coord_value),
             C.c_double(coord_tol), reaction_force_comp, _hp(w), _hp(measured), _hp(load_data),
             _hp(fct), C.c_double(area)))
+
+    def set_qoi_mismatch(self, kind, *, coord_idx=0, coord_value=0.0, coord_tol=1e-12, reaction_force_comp=0,
+                         compute_torque=False, facet=None, normal_2d=None, measured=None, load_data=None):
+        """'reaction mismatch' / 'load mismatch' / 'surface mismatch' (src/qoi.cpp:272-287).  load_data None =
+        the reference's "load out file" mode (mismatch against zero; loads() returns the file's lines)."""
+        k = QOI_TYPES[kind.replace(" ", "_")]
+        fct = None if facet is None else np.ascontiguousarray(facet, dtype=np.int8)
+        n2 = None if normal_2d is None else np.ascontiguousarray(normal_2d, dtype=np.float64)
+        m = None if measured is None else np.ascontiguousarray(measured, dtype=np.float64)
+        ld = None if load_data is None else np.ascontiguousarray(load_data, dtype=np.float64)
+        self._check(self.lib.c8h_set_qoi_mismatch(self.h, k, coord_idx, C.c_double(coord_value), C.c_double(coord_tol),
+                                                  reaction_force_comp, int(compute_torque), _hp(fct), _hp(n2),
+                                                  _hp(m), _hp(ld)))
+
+    def loads(self):
+        out = np.zeros(self.num_steps)
+        self._check(self.lib.c8h_get_loads(self.h, _hp(out)))
+        return out
 
     def primal_solve(self):
         J = C.c_double(0)

@@ -4,7 +4,10 @@
 
 namespace c8 {
 
-enum QoiType { QOI_AVG_DISP = 0, QOI_CALIBRATION = 1 };
+// QoI<T> classes of the reference: avg_disp.cpp, calibration.cpp, reaction_mismatch.cpp,
+// load_mismatch.cpp, surface_mismatch.cpp
+enum QoiType { QOI_AVG_DISP = 0, QOI_CALIBRATION = 1, QOI_REACTION_MISMATCH = 2, QOI_LOAD_MISMATCH = 3,
+               QOI_SURFACE_MISMATCH = 4 };
 
 struct QoiArgs {
   int type;
@@ -18,7 +21,13 @@ struct QoiArgs {
   double coord_value, coord_tol;
   int reaction_force_comp;
   const double* measured;      // [n_nodes][DIM] measured displacement of the step
-  const signed char* facet;    // 3-D: [n_elems][3] local vertex ids of the facet on the side set, -1 none
+  const signed char* facet;    // [n_elems][3] local vertex ids of the facet on the side set, -1 none (2-D: 2 ids)
+  int compute_torque;          // reaction mismatch "compute torque": moment about axis reaction_force_comp
+  double normal_2d[2];         // load mismatch "2D surface normal"
+  // which integrands the type carries
+  __host__ __device__ bool has_disp() const { return type == QOI_CALIBRATION || type == QOI_SURFACE_MISMATCH; }
+  __host__ __device__ bool has_node_load() const { return type == QOI_CALIBRATION || type == QOI_REACTION_MISMATCH; }
+  __host__ __device__ bool has_face_load() const { return type == QOI_LOAD_MISMATCH; }
 };
 
 struct AdjArgs {

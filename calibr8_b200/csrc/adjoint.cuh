@@ -78,8 +78,14 @@ __global__ void __launch_bounds__(128) k_adjoint_jacobian(const AdjArgs a) {
   k0.gup = grad_u_val<D, NB>(E.xpn, E.g);
   const double wdv = quad1_weight<D>() * E.g.dv;
   const bool calib = a.qoi.type != QOI_AVG_DISP;
-  const int nmask = calib ? load_node_mask<D>(a.qoi, a.mesh.coords, E.nodes) : 0;
+  const int nmask = a.qoi.has_node_load() ? load_node_mask<D>(a.qoi, a.mesh.coords, E.nodes) : 0;
+  const signed char* fv = a.qoi.facet ? &a.qoi.facet[size_t(e) * 3] : nullptr;
+  const bool fload = a.qoi.has_face_load() && fv && fv[0] >= 0;   // load mismatch: facet on the side set
   const double coef = a.qoi.balance_factor * a.qoi.dt_over_T * a.qoi.load_mismatch;
+  double fN[D], fwdv = 0.0;
+#pragma unroll
+  for (int k = 0; k < D; ++k) fN[k] = 0.0;
+  if (fload) facet_normal<D>(a.qoi, a.mesh.coords, E.nodes, fv, fN, fwdv);
 
   // ---- xi seeded: dC/dxi at the stored state (no Newton, src/evaluations.cpp:442-446) and the QoI's
   // dJ/dxi (:474-478): g -= dJ/dxi
@@ -93,14 +99,19 @@ __global__ void __launch_bounds__(128) k_adjoint_jacobian(const AdjArgs a) {
 #pragma unroll
     for (int q = 0; q < NXI; ++q) xs[q] = seeded<LXI>(xi[q], q, t * LXI);
     path = Model::residual(k0, xs, E.xip, E.par, a.model.abs_tol, Cd);
-    if (nmask) {   // calibration load term (group-uniform branch)
+    if (nmask || fload) {   // load term: coordinate-plane nodes or side-set facet (group-uniform branch)
       double p0 = 0.0;
       if constexpr (C::M == MECH_MIXED) {
+        if (nmask) {
 #pragma unroll
-        for (int n = 0; n < NN; ++n) p0 += E.xn[n][D] * (1.0 / NN);
+          for (int n = 0; n < NN; ++n) p0 += E.xn[n][D] * (1.0 / NN);
+        } else {
+          p0 = facet_pressure<D, NB>(E.xn, fv);
+        }
       }
-      const Mat<Dual<LXI>, D> Pxi = first_pk<D, C::M, Model>(k0, p0, xs, E.par, a.model.thickness);
-      const Dual<LXI> load = calibration_load<D>(a.qoi, Pxi, E.g, wdv, nmask);
+      const Mat<Dual<LXI>, D> Pxi = first_pk<D, C::M, Model>(k0, p0, xs, E.par, nmask ? a.model.thickness : 1.0);
+      const Dual<LXI> load = nmask ? calibration_load<D>(a.qoi, Pxi, E.g, wdv, nmask, a.mesh.coords, E.nodes)
+                                   : face_normal_load<D>(Pxi, fN, fwdv);
 #pragma unroll
       for (int q = 0; q < NXI; ++q) {
         const double v = group_bcast<G>(mask, load.d[q % LXI], q / LXI);
@@ -166,20 +177,33 @@ __global__ void __launch_bounds__(128) k_adjoint_jacobian(const AdjArgs a) {
 #pragma unroll
       for (int s = 0; s < LX; ++s) r[s] -= (sx.xl.eq[s] < D) ? (1.0 / NN) * wdv / D : 0.0;
     } else {
-      const bool in_obj = (D == 2) || (a.qoi.facet && a.qoi.facet[size_t(e) * 3] >= 0);
+      const bool in_obj = a.qoi.has_disp() && (D == 2 ? a.qoi.type == QOI_CALIBRATION : (fv && fv[0] >= 0));
       if (in_obj) {
         Dual<LX> un[NN][D];
         seeded_nodal_u<C, LX>(E, sx.xl, un);
         double um[NN][D], X[NN][D];
         load_measured<C>(a.qoi, E, um, X, a.mesh.coords);
-        const signed char* fv = (D == 3) ? &a.qoi.facet[size_t(e) * 3] : nullptr;
-        const Dual<LX> mm = calibration_disp_mismatch<D, Dual<LX>>(a.qoi, un, um, X, E.g.dv, fv);
+        const Dual<LX> mm = calibration_disp_mismatch<D, Dual<LX>>(a.qoi, un, um, X, E.g.dv, (D == 3) ? fv : nullptr);
 #pragma unroll
         for (int s = 0; s < LX; ++s) r[s] -= mm.d[s];
       }
       if (nmask) {
         const Mat<Dual<LX>, D> Px = first_pk<D, C::M, Model>(k2, sx.p, xi, E.par, a.model.thickness);
-        const Dual<LX> load = calibration_load<D>(a.qoi, Px, E.g, wdv, nmask);
+        const Dual<LX> load = calibration_load<D>(a.qoi, Px, E.g, wdv, nmask, a.mesh.coords, E.nodes);
+#pragma unroll
+        for (int s = 0; s < LX; ++s) r[s] -= coef * load.d[s];
+      }
+      if (fload) {
+        // the pressure at the facet centroid, seeded w.r.t. the pressure dofs of the facet's nodes
+        Dual<LX> pf = make_dual<LX>(facet_pressure<D, NB>(E.xn, fv));
+#pragma unroll
+        for (int s = 0; s < LX; ++s) {
+          const int nd = sx.xl.node[s];
+          const bool in_f = fv[0] == nd || fv[1] == nd || (D == 3 && fv[2] == nd);
+          pf.d[s] = (sx.xl.eq[s] == D && in_f) ? 1.0 / D : 0.0;
+        }
+        const Mat<Dual<LX>, D> Px = first_pk<D, C::M, Model>(k2, pf, xi, E.par, 1.0);
+        const Dual<LX> load = face_normal_load<D>(Px, fN, fwdv);
 #pragma unroll
         for (int s = 0; s < LX; ++s) r[s] -= coef * load.d[s];
       }
@@ -470,14 +494,23 @@ __global__ void __launch_bounds__(128) k_qoi_gradient(const AdjArgs a) {
 #pragma unroll
           for (int s = 0; s < LP; ++s) acc[s] = fma(r.d[s], z[n][i], acc[s]);
         }
-      if (a.qoi.type == QOI_CALIBRATION) {
+      const double coef = a.qoi.balance_factor * a.qoi.dt_over_T * a.qoi.load_mismatch;
+      if (a.qoi.has_node_load()) {
         const int nmask = load_node_mask<D>(a.qoi, a.mesh.coords, E.nodes);
         if (nmask) {
-          const double coef = a.qoi.balance_factor * a.qoi.dt_over_T * a.qoi.load_mismatch;
-          const TP load = calibration_load<D>(a.qoi, P, E.g, wdv, nmask);
+          const TP load = calibration_load<D>(a.qoi, P, E.g, wdv, nmask, a.mesh.coords, E.nodes);
 #pragma unroll
           for (int s = 0; s < LP; ++s) acc[s] += coef * load.d[s];
         }
+      }
+      if (a.qoi.has_face_load() && a.qoi.facet && a.qoi.facet[size_t(e) * 3] >= 0) {
+        const signed char* fv = &a.qoi.facet[size_t(e) * 3];
+        double fN[D], fwdv;
+        facet_normal<D>(a.qoi, a.mesh.coords, E.nodes, fv, fN, fwdv);
+        const Mat<TP, D> Pf = first_pk<D, C::M, Model>(k0, facet_pressure<D, NB>(E.xn, fv), xi, par, 1.0);
+        const TP load = face_normal_load<D>(Pf, fN, fwdv);
+#pragma unroll
+        for (int s = 0; s < LP; ++s) acc[s] += coef * load.d[s];
       }
     }
     if constexpr (C::M == MECH_MIXED) {
@@ -559,7 +592,8 @@ __global__ void __launch_bounds__(128) k_qoi_value(const AdjArgs a, int mode) {
       }
       v = s / D;
     } else if (mode == 0) {
-      const bool in_obj = (D == 2) || (a.qoi.facet && a.qoi.facet[size_t(e) * 3] >= 0);
+      const signed char* fv0 = a.qoi.facet ? &a.qoi.facet[size_t(e) * 3] : nullptr;
+      const bool in_obj = a.qoi.has_disp() && (D == 2 ? a.qoi.type == QOI_CALIBRATION : (fv0 && fv0[0] >= 0));
       if (in_obj) {
         double un[NN][D], um[NN][D], X[NN][D];
 #pragma unroll
@@ -567,25 +601,33 @@ __global__ void __launch_bounds__(128) k_qoi_value(const AdjArgs a, int mode) {
 #pragma unroll
           for (int i = 0; i < D; ++i) un[n][i] = E.xn[n][i];
         load_measured<C>(a.qoi, E, um, X, a.mesh.coords);
-        const signed char* fv = (D == 3) ? &a.qoi.facet[size_t(e) * 3] : nullptr;
-        v = calibration_disp_mismatch<D, double>(a.qoi, un, um, X, E.g.dv, fv);
+        v = calibration_disp_mismatch<D, double>(a.qoi, un, um, X, E.g.dv, (D == 3) ? fv0 : nullptr);
       }
     } else {
-      const int nmask = load_node_mask<D>(a.qoi, a.mesh.coords, E.nodes);
-      if (nmask) {
+      const int nmask = a.qoi.has_node_load() ? load_node_mask<D>(a.qoi, a.mesh.coords, E.nodes) : 0;
+      const signed char* fv = a.qoi.facet ? &a.qoi.facet[size_t(e) * 3] : nullptr;
+      const bool fload = a.qoi.has_face_load() && fv && fv[0] >= 0;
+      if (nmask || fload) {
         double xi[NXI];
 #pragma unroll
         for (int q = 0; q < NXI; ++q) xi[q] = __ldg(&a.xi[size_t(q) * a.xi_ld + e]);
         Kin<D, double, double> k0;
         k0.gu = grad_u_val<D, NB>(E.xn, E.g);
         k0.gup = grad_u_val<D, NB>(E.xpn, E.g);
-        double p0 = 0.0;
-        if constexpr (C::M == MECH_MIXED) {
+        if (nmask) {
+          double p0 = 0.0;
+          if constexpr (C::M == MECH_MIXED) {
 #pragma unroll
-          for (int n = 0; n < NN; ++n) p0 += E.xn[n][D] * (1.0 / NN);
+            for (int n = 0; n < NN; ++n) p0 += E.xn[n][D] * (1.0 / NN);
+          }
+          const Mat<double, D> P = first_pk<D, C::M, Model>(k0, p0, xi, E.par, a.model.thickness);
+          v = calibration_load<D>(a.qoi, P, E.g, wdv, nmask, a.mesh.coords, E.nodes);
+        } else {
+          double fN[D], fwdv;
+          facet_normal<D>(a.qoi, a.mesh.coords, E.nodes, fv, fN, fwdv);
+          const Mat<double, D> P = first_pk<D, C::M, Model>(k0, facet_pressure<D, NB>(E.xn, fv), xi, E.par, 1.0);
+          v = face_normal_load<D>(P, fN, fwdv);
         }
-        const Mat<double, D> P = first_pk<D, C::M, Model>(k0, p0, xi, E.par, a.model.thickness);
-        v = calibration_load<D>(a.qoi, P, E.g, wdv, nmask);
       }
     }
   }

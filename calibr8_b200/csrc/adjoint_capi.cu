@@ -28,6 +28,8 @@ static QoiArgs to_args(const c8_qoi* q) {
   a.reaction_force_comp = q->reaction_force_comp;
   a.measured = q->measured_dev;
   a.facet = (const signed char*)q->facet_dev;
+  a.compute_torque = q->compute_torque;
+  a.normal_2d[0] = q->normal_2d[0]; a.normal_2d[1] = q->normal_2d[1];
   return a;
 }
 

@@ -59,8 +59,11 @@ struct CalibrationQoi {
   double weights[3] = {1., 1., 1.};
   std::vector<double> load_data;           // measured load per step ("load input file")
   std::vector<double*> d_measured;         // per step (1..N) device [n_nodes][dim]
-  signed char* d_facet = nullptr;          // 3-D side-set facets
+  signed char* d_facet = nullptr;          // side-set facets [n_elems][3] local vertex ids
   double area = 1.;
+  bool compute_torque = false;             // reaction mismatch "compute torque"
+  double normal_2d[2] = {0., 0.};          // load mismatch "2D surface normal"
+  std::vector<double> total_load;          // per step: what "load out file" holds (load.dat)
 };
 
 class DevVec {  // RAII device array
@@ -103,7 +106,7 @@ class Problem {
   std::vector<Dbc> dbcs;
   std::vector<Tbc> tbcs;
   SolverParams sp;
-  int qoi_type = 0;  // 0 average displacement, 1 calibration
+  int qoi_type = 0;  // c8_qoi.type: 0 average displacement, 1 calibration, 2 reaction / 3 load / 4 surface mismatch
   CalibrationQoi cal;
 
   // history (device)

@@ -179,7 +179,7 @@ void Problem::axpy(double a, const double* xs, double* y) const {
 static c8_qoi make_qoi(const Problem& P, int step, double load_mismatch) {
   c8_qoi q{};
   q.type = P.qoi_type;
-  if (P.qoi_type == 1) {
+  if (P.qoi_type >= 1) {
     for (int k = 0; k < 3; ++k) q.weights[k] = P.cal.weights[k];
     q.balance_factor = P.cal.balance_factor;
     q.dt_over_T = P.step_size / (P.num_steps * P.step_size);
@@ -191,13 +191,28 @@ static c8_qoi make_qoi(const Problem& P, int step, double load_mismatch) {
     q.reaction_force_comp = P.cal.reaction_force_comp;
     q.measured_dev = (step >= 1 && step <= int(P.cal.d_measured.size())) ? P.cal.d_measured[step - 1] : nullptr;
     q.facet_dev = (const int8_t*)P.cal.d_facet;
+    q.compute_torque = P.cal.compute_torque ? 1 : 0;
+    q.normal_2d[0] = P.cal.normal_2d[0]; q.normal_2d[1] = P.cal.normal_2d[1];
+  }
+  if (P.qoi_type == 2 || P.qoi_type == 3) {
+    // reaction / load mismatch: the integrand is mismatch * load and J += 1/2 mismatch^2
+    // (src/reaction_mismatch.cpp:150-153,208-211): the calibration load term with unit factors
+    q.balance_factor = 1.0; q.dt_over_T = 1.0;
+  }
+  if (P.qoi_type == 4) {
+    // surface mismatch: sum |u - u_meas|^2 w dv over the facets (src/surface_mismatch.cpp:98-105) = the
+    // calibration surface integrand 1/2 sum_d w_d (.)^2 / area * dt/T with w_d = 2, area = dt/T = 1
+    for (int k = 0; k < 3; ++k) q.weights[k] = 2.0;
+    q.inv_area = 1.0; q.dt_over_T = 1.0; q.balance_factor = 0.0;
   }
   return q;
 }
 
+static bool qoi_has_load(int type) { return type == 1 || type == 2 || type == 3; }
+
 // preprocess_qoi + preprocess_finalize: total load on the plane -> load mismatch of the step
 static double preprocess_load_mismatch(Problem& P, int step, double* total_load_out = nullptr) {
-  if (P.qoi_type != 1) return 0.0;
+  if (!qoi_has_load(P.qoi_type)) return 0.0;
   c8_qoi q = make_qoi(P, step, 0.0);
   cudaStream_t s = (cudaStream_t)c8_get_stream(P.ctx);
   C8H_CUDA(cudaMemsetAsync(P.work.get(), 0, 2 * sizeof(double), s));
@@ -331,7 +346,10 @@ void Primal::solve_at_step(int step) {
 
 double Primal::eval_qoi(int step) {
   cudaStream_t s = (cudaStream_t)c8_get_stream(P.ctx);
-  const double mismatch = preprocess_load_mismatch(P, step);
+  double total_load = 0.0;
+  const double mismatch = preprocess_load_mismatch(P, step, &total_load);
+  if (int(P.cal.total_load.size()) < P.num_steps) P.cal.total_load.assign(P.num_steps, 0.0);
+  P.cal.total_load[step - 1] = total_load;   // the "load out file" line of the step
   c8_qoi q = make_qoi(P, step, mismatch);
   C8H_CUDA(cudaMemsetAsync(P.work.get(), 0, 2 * sizeof(double), s));
   P.check(c8_qoi_value(P.ctx, &q, P.x[step].get(), P.x[step - 1].get(), P.xi[step].get(),
@@ -341,8 +359,8 @@ double Primal::eval_qoi(int step) {
   C8H_CUDA(cudaMemcpyAsync(h, P.work.get(), 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   C8H_CUDA(cudaStreamSynchronize(s));
   double J = h[0];
-  if (P.qoi_type == 1)  // Calibration::postprocess, src/calibration.cpp:373-393 (single rank)
-    J += 0.5 * P.cal.balance_factor * q.dt_over_T * mismatch * mismatch;
+  // Calibration::postprocess, src/calibration.cpp:373-393; Reaction/LoadMismatch::postprocess (unit factors)
+  if (qoi_has_load(P.qoi_type)) J += 0.5 * q.balance_factor * q.dt_over_T * mismatch * mismatch;
   return J;
 }
 
@@ -508,6 +526,52 @@ int c8h_set_qoi_calibration(c8h_problem* h, double balance_factor, int coord_idx
       C8H_CUDA(cudaMalloc(&c.d_facet, size_t(P.n_elems) * 3));
       C8H_CUDA(cudaMemcpy(c.d_facet, facet_host, size_t(P.n_elems) * 3, cudaMemcpyHostToDevice));
     }
+  });
+}
+
+// "reaction mismatch" (kind 2), "load mismatch" (3), "surface mismatch" (4) of src/qoi.cpp:272-287.
+// facet_host [n_elems][3] local vertex ids of the side-set facet (-1: none; 2-D: two ids), kinds 3, 4;
+// measured_host [num_steps][n_nodes][dim], kind 4; load_data [num_steps] = "load input file" or NULL
+// (= "load out file" mode: mismatch against zero, the loads are read back with c8h_get_loads)
+int c8h_set_qoi_mismatch(c8h_problem* h, int kind, int coord_idx, double coord_value, double coord_tol,
+                         int reaction_force_comp, int compute_torque, const int8_t* facet_host,
+                         const double* normal_2d, const double* measured_host, const double* load_data) {
+  C8H_TRY(h, {
+    Problem& P = h->P;
+    if (kind < 2 || kind > 4) throw std::runtime_error("mismatch QoI kind must be 2, 3 or 4");
+    if (kind == 4 && P.dim != 3) throw std::runtime_error("surface mismatch is a 3-D QoI (src/surface_mismatch.cpp:98-101)");
+    if (kind >= 3 && !facet_host) throw std::runtime_error("load / surface mismatch need the side-set facets");
+    P.qoi_type = kind;
+    CalibrationQoi& c = P.cal;
+    c.enabled = true;
+    c.balance_factor = 1.; c.area = 1.;
+    c.coord_idx = coord_idx; c.coord_value = coord_value; c.coord_tol = coord_tol;
+    c.reaction_force_comp = reaction_force_comp; c.compute_torque = compute_torque != 0;
+    c.normal_2d[0] = normal_2d ? normal_2d[0] : 0.; c.normal_2d[1] = normal_2d ? normal_2d[1] : 0.;
+    c.load_data.clear();
+    if (load_data) c.load_data.assign(load_data, load_data + P.num_steps);
+    for (double* p : c.d_measured) if (p) cudaFree(p);
+    c.d_measured.clear();
+    if (measured_host) {
+      c.d_measured.assign(P.num_steps, nullptr);
+      const size_t nm = size_t(P.n_nodes) * P.dim;
+      for (int s = 0; s < P.num_steps; ++s) {
+        C8H_CUDA(cudaMalloc(&c.d_measured[s], nm * sizeof(double)));
+        C8H_CUDA(cudaMemcpy(c.d_measured[s], measured_host + size_t(s) * nm, nm * sizeof(double), cudaMemcpyHostToDevice));
+      }
+    }
+    if (c.d_facet) { cudaFree(c.d_facet); c.d_facet = nullptr; }
+    if (facet_host) {
+      C8H_CUDA(cudaMalloc(&c.d_facet, size_t(P.n_elems) * 3));
+      C8H_CUDA(cudaMemcpy(c.d_facet, facet_host, size_t(P.n_elems) * 3, cudaMemcpyHostToDevice));
+    }
+  });
+}
+// total load of every step of the last primal solve (ReactionMismatch "load out file", load.dat)
+int c8h_get_loads(c8h_problem* h, double* loads_out /* [num_steps] */) {
+  C8H_TRY(h, {
+    for (int s = 0; s < h->P.num_steps; ++s)
+      loads_out[s] = s < int(h->P.cal.total_load.size()) ? h->P.cal.total_load[s] : 0.0;
   });
 }
 

@@ -129,8 +129,14 @@ int c8_state_ptrs(c8_ctx* ctx, double** x_dev, double** x_prev_dev, double** xi_
                   double** xi_prev_dev, double** A_vals_dev, double** b_dev);
 
 /* ---- adjoint pass and objective integrands ----
- * QoI description (QoI<T> of the reference; type 0 = "average displacement" avg_disp.cpp:15-33,
- * type 1 = "calibration" calibration.cpp:414-478).  NULL = average displacement. */
+ * QoI description (QoI<T> of the reference).  NULL = average displacement.
+ *   type 0 "average displacement"  avg_disp.cpp:15-33
+ *   type 1 "calibration"           calibration.cpp:414-478 (displacement mismatch + plane load)
+ *   type 2 "reaction mismatch"     reaction_mismatch.cpp:58-212 (plane load or torque; the caller
+ *                                  passes balance_factor = dt_over_T = 1)
+ *   type 3 "load mismatch"         load_mismatch.cpp:79-259 (normal load over the side-set facets)
+ *   type 4 "surface mismatch"      surface_mismatch.cpp:32-117 (the caller passes weights = 2,
+ *                                  inv_area = dt_over_T = 1: sum |u - u_meas|^2 w dv over the facets) */
 typedef struct c8_qoi {
   int type;
   double weights[3];        /* "displacement weights" */
@@ -142,7 +148,9 @@ typedef struct c8_qoi {
   double coord_value, coord_tol;
   int reaction_force_comp;  /* "reaction force component" */
   const double* measured_dev;  /* [n_nodes][dim] measured displacement of the step */
-  const int8_t* facet_dev;     /* 3-D: [n_elems][3] local vertex ids of the side-set facet or -1 */
+  const int8_t* facet_dev;     /* [n_elems][3] local vertex ids of the side-set facet or -1 (2-D: 2 ids) */
+  int compute_torque;          /* type 2 "compute torque": moment about axis reaction_force_comp */
+  double normal_2d[2];         /* type 3 in 2-D: "2D surface normal" */
 } c8_qoi;
 
 /* History arrays: g [nxi][xi_ld], f [nx][xi_ld] (element dofs node-interleaved), phi [nxi][xi_ld]. */

@@ -51,7 +51,7 @@ struct Problem {
   CsrGraph ngraph;
   CsrGraph bgraph[2][2];
   std::vector<int> offsets[2][2];  // scatter offsets, src/disc.cpp:414-459
-  int qoi_type = 0;                // 0 avg disp, 1 calibration
+  int qoi_type = 0;                // 0 avg disp, 1 calibration, 2 reaction / 3 load / 4 surface mismatch
   CalibrationData cal;
   std::unique_ptr<QoI<double>> q_d;
   std::unique_ptr<QoI<Fad>> q_f;
@@ -823,6 +823,30 @@ void orc_set_qoi_calibration(void* p, double balance_factor, int coord_idx, doub
   if (facet) P.cal.facet.assign(facet, facet + size_t(P.disc.n_elems) * 3);
   P.q_d = std::make_unique<Calibration<double>>(&P.cal);
   P.q_f = std::make_unique<Calibration<Fad>>(&P.cal);
+}
+// kind 2 reaction mismatch (plane + component [+ torque]), 3 load mismatch (facet [+ 2-D normal]),
+// 4 surface mismatch (facet); facet [n_elems*3] local vertex ids of the side-set facet, -1 none
+void orc_set_qoi_mismatch(void* p, int kind, int coord_idx, double coord_value, double coord_tol,
+                          int reaction_force_comp, int compute_torque, int const* facet,
+                          double const* normal_2d) {
+  Problem& P = *static_cast<Problem*>(p);
+  P.qoi_type = kind;
+  P.cal = CalibrationData();
+  P.cal.coord_idx = coord_idx; P.cal.coord_value = coord_value; P.cal.coord_tol = coord_tol;
+  P.cal.reaction_force_comp = reaction_force_comp;
+  P.cal.compute_torque = compute_torque != 0;
+  if (facet) P.cal.facet.assign(facet, facet + size_t(P.disc.n_elems) * 3);
+  if (normal_2d) { P.cal.normal_2d[0] = normal_2d[0]; P.cal.normal_2d[1] = normal_2d[1]; }
+  if (kind == 2) {
+    P.q_d = std::make_unique<ReactionMismatch<double>>(&P.cal);
+    P.q_f = std::make_unique<ReactionMismatch<Fad>>(&P.cal);
+  } else if (kind == 3) {
+    P.q_d = std::make_unique<LoadMismatch<double>>(&P.cal);
+    P.q_f = std::make_unique<LoadMismatch<Fad>>(&P.cal);
+  } else {
+    P.q_d = std::make_unique<SurfaceMismatch<double>>(&P.cal);
+    P.q_f = std::make_unique<SurfaceMismatch<Fad>>(&P.cal);
+  }
 }
 void orc_qoi_set_step(void* p, double dt, double total_time, double load_meas,
                       double const* measured) {

@@ -220,6 +220,16 @@ class Oracle:
                                          C.c_double(coord_value), C.c_double(coord_tol),
                                          reaction_force_comp, _p(w), _p(self._facet))
 
+    def set_qoi_mismatch(self, kind, *, coord_idx=0, coord_value=0.0, coord_tol=1e-12, reaction_force_comp=0,
+                         compute_torque=False, facet=None, normal_2d=None):
+        """kind: 'reaction' (coordinate plane, component / torque), 'load' (facet [n_elems][3] local vertex
+        ids of the side-set facet, 2-D: normal_2d), 'surface' (facet; measured field per step)"""
+        k = {"reaction": 2, "load": 3, "surface": 4}[kind]
+        self._facet = None if facet is None else np.ascontiguousarray(facet, dtype=np.int32)
+        n2 = None if normal_2d is None else np.ascontiguousarray(normal_2d, dtype=np.float64)
+        self.lib.orc_set_qoi_mismatch(self.h, k, coord_idx, C.c_double(coord_value), C.c_double(coord_tol),
+                                      reaction_force_comp, int(compute_torque), _p(self._facet), _p(n2))
+
     def qoi_set_step(self, dt, total_time, load_meas, measured):
         self._measured = None if measured is None else np.ascontiguousarray(measured, dtype=np.float64)
         self.lib.orc_qoi_set_step(self.h, C.c_double(dt), C.c_double(total_time),

@@ -107,6 +107,8 @@ class Pair:
         if kind == "avg_disp":
             o.set_qoi_avg_disp()
             return make_qoi("avg_disp")
+        if kind != "calibration":
+            return self._set_mismatch_qoi(kind)
         rng = np.random.RandomState(11)
         # "measured" displacement: the current one perturbed, so that the mismatch is non-zero
         u = self.x[0].reshape(-1, mesh.dim)
@@ -146,10 +148,69 @@ class Pair:
         return q
 
 
+    def _set_mismatch_qoi(self, kind):
+        """reaction mismatch (plane load / torque), load mismatch (normal load over the ymax facets),
+        surface mismatch (zmax facets) -- src/reaction_mismatch.cpp, load_mismatch.cpp, surface_mismatch.cpp"""
+        import torch
+        from calibr8_b200.capi import make_qoi
+        o, c, mesh = self.orc, self.ctx, self.mesh
+        dim = mesh.dim
+        rng = np.random.RandomState(12)
+        u = self.x[0].reshape(-1, dim)
+        meas = u * (1.0 + 0.05 * rng.uniform(-1., 1., size=u.shape))
+        m3 = np.zeros((mesh.n_nodes, 3)); m3[:, :dim] = meas
+        load_meas = 0.01
+        fac = None
+        if kind in ("load", "surface"):
+            plane = 1 if kind == "load" else 2
+            on = np.abs(mesh.coords[mesh.conn][:, :, plane] - 1.0) < 1e-12
+            fac = np.full((mesh.n_elems, 3), -1, dtype=np.int32)
+            for e in np.nonzero(on.sum(axis=1) == dim)[0]:
+                fac[e, :dim] = np.nonzero(on[e])[0]
+            assert (fac[:, 0] >= 0).sum() > 0
+        torque = kind == "reaction_torque"
+        comp = 2 if torque else 1
+        okind = {"reaction": "reaction", "reaction_torque": "reaction", "load": "load", "surface": "surface"}[kind]
+        o.set_qoi_mismatch(okind, coord_idx=1, coord_value=1.0, reaction_force_comp=comp, compute_torque=torque,
+                           facet=fac, normal_2d=(0., 1.))
+        o.qoi_set_step(1.0, 4.0, load_meas, m3)
+        self.J_orc = o.qoi(self.x, self.xp, self.xi, self.xip, 1)
+        st = o.calibration_state()
+        self._keep = (torch.from_numpy(np.ascontiguousarray(meas)).cuda(),
+                      None if fac is None else torch.from_numpy(fac.astype(np.int8)).cuda())
+        ctype = {"reaction": "reaction_mismatch", "reaction_torque": "reaction_mismatch", "load": "load_mismatch",
+                 "surface": "surface_mismatch"}[kind]
+        if kind == "surface":     # the host's mapping of the surface integrand (host.cu make_qoi)
+            q = make_qoi(ctype, weights=(2., 2., 2.), balance_factor=0.0, dt_over_T=1.0, inv_area=1.0,
+                         measured=self._keep[0], facet=self._keep[1])
+        else:
+            q = make_qoi(ctype, balance_factor=1.0, dt_over_T=1.0, inv_area=1.0, coord_idx=1, coord_value=1.0,
+                         coord_tol=1e-12, reaction_force_comp=comp, compute_torque=torque, facet=self._keep[1],
+                         normal_2d=(0., 1.))
+        sc = torch.zeros(8, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        if kind != "surface":
+            c.qoi_value(q, self.dx, self.dxp, self.dxi, self.dxip, 1, sc)
+            c.synchronize()
+            total = float(sc[1].item())
+            assert abs(st["total_load"]) > 0
+            assert abs(total - st["total_load"]) <= TOL * abs(st["total_load"]), (total, st)
+            q.load_mismatch = total - load_meas
+        c.qoi_value(q, self.dx, self.dxp, self.dxi, self.dxip, 0, sc)
+        c.synchronize()
+        J = float(sc[0].item()) + (0.5 * q.load_mismatch ** 2 if kind != "surface" else 0.0)
+        assert self.J_orc > 0 and abs(J - self.J_orc) <= TOL * abs(self.J_orc), (J, self.J_orc)
+        return q
+
+
 ADJ_CASES = [("3d_small_J2", "avg_disp"), ("3d_small_hill", "calibration"), ("3d_hyper_J2", "avg_disp"),
              ("3d_hyper_J2", "calibration"), ("3d_elastic", "avg_disp"),
              ("2d_small_hill_plane_stress", "calibration"), ("2d_hyper_J2_plane_stress", "avg_disp"),
-             ("2d_small_J2", "avg_disp"), ("2d_hyper_J2_plane_strain", "calibration")]
+             ("2d_small_J2", "avg_disp"), ("2d_hyper_J2_plane_strain", "calibration"),
+             # reaction / load / surface mismatch QoIs
+             ("3d_small_hill", "reaction"), ("3d_hyper_J2", "reaction_torque"), ("3d_hyper_J2", "load"),
+             ("3d_small_J2", "load"), ("2d_hyper_J2_plane_stress", "load"), ("2d_small_hill_plane_strain", "load"),
+             ("3d_small_J2", "surface"), ("2d_small_hill_plane_stress", "reaction")]
 
 
 @pytest.mark.parametrize("name,qoi", ADJ_CASES)
@@ -177,7 +238,7 @@ def test_adjoint_entry_points(name, qoi):
     for i in range(nr):
         assert np.abs(rhs_h[i] - rhs_o[i]).max() < TOL * np.abs(rhs_o[i]).max(), i
     assert rel_err_blockwise(c.unpack_xi(g_d), g_o, 0) < TOL
-    if qoi == "calibration":
+    if qoi not in ("avg_disp", "surface"):
         assert np.abs(g_o - P.g).max() > 0 or o.n_xi == 1   # the load term did reach g
 
     # ---- K4: phi, f, g of the previous step -----------------------------------------------------

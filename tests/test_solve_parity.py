@@ -222,3 +222,54 @@ def test_calibration_3d_hill_objective_and_gradient():
     assert abs(J - J_o) / abs(J_o) < J_TOL, (J, J_o)
     assert np.abs(g - g_o).max() < G_TOL * np.abs(g_o).max(), (g, g_o)
     hp.close(); ctx.close()
+
+
+@pytest.mark.parametrize("kind", ["reaction mismatch", "load mismatch", "surface mismatch"])
+def test_mismatch_qoi_objective_and_gradient(kind):
+    """The reaction / load / surface mismatch objectives end to end (forward solves, two-pass total
+    load, adjoint gradient) on the GPU vs the oracle: src/reaction_mismatch.cpp, load_mismatch.cpp,
+    surface_mismatch.cpp; "load out file" lines (load.dat) included."""
+    from calibr8_b200 import meshgen
+    from oracle.driver import Adjoint
+    from oracle.pyoracle import PARAM_NAMES
+    mesh = meshgen.box_tets(3, notch_radius=0.3)
+    params = dict(E=1000., nu=.25, K=100., Y=2., cte=0., delta_T=0.)
+    N = 3
+    deck = dict(global_type="mechanics", local_type="small_J2", params=params,
+                dbcs=[[0, 0, "xmin", "0.0"], [0, 1, "ymin", "0.0"], [0, 2, "zmin", "0.0"], [0, 1, "ymax", "0.0015 * t"]],
+                num_steps=N, global_max_iters=30, global_tol=1e-11, local_max_iters=60, local_tol=1e-13)
+    names = PARAM_NAMES["small_J2"]
+    act = [names.index(a) for a in ("E", "nu", "K", "Y")]
+    rng = np.random.RandomState(4)
+    meas = [1e-3 * rng.uniform(-1, 1, size=(mesh.n_nodes, 3)) for _ in range(N)]
+    load_meas = [0.3, 0.5, 0.6]
+
+    def facets(plane):
+        on = np.abs(mesh.coords[mesh.conn][:, :, plane] - 1.0) < 1e-12
+        fac = np.full((mesh.n_elems, 3), -1, dtype=np.int32)
+        for e in np.nonzero(on.sum(axis=1) == 3)[0]:
+            fac[e] = np.nonzero(on[e])[0]
+        return fac
+    okw = {"reaction mismatch": dict(coord_idx=1, coord_value=1.0, reaction_force_comp=1),
+           "load mismatch": dict(facet=facets(1)), "surface mismatch": dict(facet=facets(2))}[kind]
+    o, p = oracle_problem(deck, mesh, active=[act])
+    o.set_qoi_mismatch(kind.split()[0], **okw)
+    setup = lambda step: o.qoi_set_step(1.0, float(N), load_meas[step - 1], meas[step - 1])
+    J_o = p.solve(setup)
+    g_o = Adjoint(p, max_iters=30, abs_tol=1e-14, rel_tol=1e-12).gradient([list(range(4))], 4, setup)
+    loads_o = []
+    for step in range(1, N + 1):
+        setup(step)
+        o.qoi(p.x[step], p.x[step - 1], p.xi[step], p.xi[step - 1], step)
+        loads_o.append(o.calibration_state()["total_load"])
+    assert J_o > 0 and p.xi[-1][:, -1].max() > 0
+    ctx, hp = gpu_problem(deck, mesh, qoi=None)
+    hp.set_qoi_mismatch(kind, measured=np.stack(meas) if kind == "surface mismatch" else None,
+                        load_data=None if kind == "surface mismatch" else load_meas, **okw)
+    J = hp.primal_solve()
+    g = hp.adjoint_gradient()[act]
+    assert abs(J - J_o) / abs(J_o) < J_TOL, (J, J_o)
+    assert np.abs(g - g_o).max() < G_TOL * np.abs(g_o).max(), (g, g_o)
+    if kind != "surface mismatch":
+        assert np.abs(hp.loads() - np.array(loads_o)).max() < 1e-9 * np.abs(loads_o).max()
+    hp.close(); ctx.close()

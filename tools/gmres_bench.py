@@ -24,4 +24,5 @@ for pc, kw in CASES:
             sol.zero_(); torch.cuda.synchronize(); t0 = time.perf_counter()
             info = ctx.gmres(A, rhs, sol, restart=restart, max_iters=int(os.environ.get("ITS", "200")), rel_tol=1e-30)
             ctx.synchronize(); t1 = time.perf_counter()
-        print(f"{pc:13s} {kw} restart {restart:3d}: {1e3*(t1-t0)/info['iters']:.3f} ms/it ({info['iters']} its, resid {info['resid']:.2e})", flush=True)
+        print(f"{pc:13s} {kw} restart {restart:3d}: {1e3*(t1-t0)/info['iters']:.3f} ms/it ({info['iters']} its, resid {info['resid']:.6e}, "
+              f"|sol| {float(sol.norm()):.12e})", flush=True)
