@@ -7,7 +7,8 @@
 
 Same YAML deck schema as the reference (src/main_primal.cpp, src/main_objective.cpp:512-560):
 `problem`, `discretization`, `residuals`, `dirichlet bcs: expression`, `quantity of interest`,
-`inverse`, `virtual fields`.  Same text outputs, one `%.17e` per line:
+`traction bcs`, `inverse`, `virtual fields`; QoI types `average displacement`, `calibration`,
+`reaction mismatch`, `load mismatch`, `surface mismatch`.  Same text outputs, one `%.17e` per line:
 `objective_value[_label].txt`, `objective_gradient[_label].txt` (src/main_objective.cpp:199-219),
 the QoI side file `load out file` (src/reaction_mismatch.cpp:137-147).  The unmodified Python
 drivers of the reference (py/calibr8/util/driver_support.py) only need the executable names mapped.
@@ -25,7 +26,7 @@ import sys
 import numpy as np
 
 from . import meshio
-from .capi import PARAM_NAMES, Context, HostProblem, eval_expr, make_qoi
+from .capi import PARAM_NAMES, Context, HostProblem, eval_expr
 
 
 def load_deck(path):
@@ -83,6 +84,9 @@ def build(deck, base, override=None, device=0):
     for _, bc in (deck.get("dirichlet bcs", {}).get("expression", {}) or {}).items():
         hp.add_dbc(int(bc[0]), int(bc[1]), mesh.node_sets[str(bc[2])], str(bc[3]))
     hp.finalize_dbcs()
+    # traction bcs, "bc name: [resid_idx, side_set_name, x-val, y-val(, z-val)]" (src/tbcs.cpp:28-35)
+    for _, bc in (deck.get("traction bcs") or {}).items():
+        hp.add_tbc(int(bc[0]), mesh.side_sets[str(bc[1])], [str(v) for v in bc[2:2 + mesh.dim]])
     lin_tol = 1e-10
     try:
         la = deck["linear algebra"]
@@ -102,26 +106,46 @@ def _area(mesh):
                               (X[:, 1, 1] - X[:, 0, 1]) * (X[:, 2, 0] - X[:, 0, 0])).sum())
 
 
-def _loads_on_plane(ctx, hp, qoi_deck, nsteps):
-    """total reaction on the coordinate plane per step (QoI preprocess pass, reaction_mismatch.cpp:58-103)"""
-    import torch
-    q = make_qoi("calibration", coord_idx=int(qoi_deck["coordinate index"]),
-                 coord_value=float(qoi_deck["coordinate value"]),
-                 reaction_force_comp=int(qoi_deck["reaction force component"]))
-    out = []
-    xs = [hp.get_step(s) for s in range(nsteps + 1)]
-    dev = lambda: (ctx.alloc("x"), ctx.alloc("xi"))
-    (x0, xi0), (x1, xi1) = dev(), dev()
-    sc = torch.zeros(2, dtype=torch.float64, device=x0.device)
-    for s in range(1, nsteps + 1):
-        (xa, xia), (xb, xib) = xs[s], xs[s - 1]
-        ctx.pack_x(xa[0], xa[1] if len(xa) > 1 else None, x1); ctx.pack_xi(xia, xi1)
-        ctx.pack_x(xb[0], xb[1] if len(xb) > 1 else None, x0); ctx.pack_xi(xib, xi0)
-        sc.zero_(); torch.cuda.synchronize()
-        ctx.qoi_value(q, x1, x0, xi1, xi0, 1, sc)
-        ctx.synchronize()
-        out.append(float(sc[1].item()))
-    return out
+def set_qoi(hp, mesh, q, base, nsteps, measured):
+    """create_qoi (src/qoi.cpp:261-289) for the QoIs on the path.  A QoI with a `load out file` runs in
+    write mode (mismatch against zero); the file's lines come back through hp.loads()."""
+    t = q["type"]
+    loads = None
+    if q.get("load input file"):
+        loads = np.loadtxt(_resolve(base, q["load input file"])).reshape(-1)[:nsteps]
+    if t == "average displacement":
+        hp.set_qoi_avg_disp()
+    elif t == "calibration":
+        assert measured is not None, "the calibration objective needs a *_synthetic/ mesh directory"
+        w = [float(v) for v in q.get("displacement weights", [1.0] * mesh.dim)]
+        facet = meshio.side_set_facets(mesh, str(q["side set"])) if mesh.dim == 3 else None
+        if mesh.dim == 3:
+            X = mesh.coords[mesh.conn]
+            on = facet[:, 0] >= 0
+            idx = np.nonzero(on)[0]
+            a_, b_, c_ = (X[idx, facet[idx, k]] for k in range(3))
+            area = float(0.5 * np.linalg.norm(np.cross(b_ - a_, c_ - a_), axis=1).sum())
+        else:
+            area = _area(mesh)
+        hp.set_qoi_calibration(balance_factor=float(q.get("balance factor", 1.0)),
+                               coord_idx=int(q["coordinate index"]), coord_value=float(q["coordinate value"]),
+                               coord_tol=float(q.get("coordinate tolerance", 1e-12)),
+                               reaction_force_comp=int(q["reaction force component"]), weights=w,
+                               measured=measured, load_data=loads if loads is not None else np.zeros(nsteps),
+                               area=area, facet=facet)
+    elif t == "reaction mismatch":
+        hp.set_qoi_mismatch(t, coord_idx=int(q["coordinate index"]), coord_value=float(q["coordinate value"]),
+                            coord_tol=float(q.get("coordinate tolerance", 1e-12)),
+                            reaction_force_comp=int(q["reaction force component"]),
+                            compute_torque=bool(q.get("compute torque", False)), load_data=loads)
+    elif t == "load mismatch":
+        hp.set_qoi_mismatch(t, facet=meshio.side_set_facets(mesh, str(q["side set"])),
+                            normal_2d=q.get("2D surface normal"), load_data=loads)
+    elif t == "surface mismatch":
+        assert measured is not None, "the surface mismatch objective needs a *_synthetic/ mesh directory"
+        hp.set_qoi_mismatch(t, facet=meshio.side_set_facets(mesh, str(q["side set"])), measured=measured)
+    else:
+        raise SystemExit(f"quantity of interest '{t}' is not on this path")
 
 
 def _write_lines(path, values):
@@ -136,13 +160,11 @@ def run_primal(deck_path):
     ctx, hp, mesh, _ = build(deck, base)
     q = deck.get("quantity of interest", {"type": "average displacement"})
     nsteps = int(deck["discretization"]["num steps"])
-    hp.set_qoi_avg_disp()
+    set_qoi(hp, mesh, q, base, nsteps, None)
     J = hp.primal_solve()
-    if q["type"] == "average displacement":
-        print("QoI (average displacement): %.17e" % J)
-    if q["type"] in ("reaction mismatch", "calibration") and q.get("load out file"):
-        loads = _loads_on_plane(ctx, hp, q, nsteps)
-        _write_lines(_resolve(os.getcwd(), q["load out file"]), loads)
+    print("QoI (%s): %.17e" % (q["type"], J))
+    if q.get("load out file"):      # written by the QoI's preprocess pass (src/reaction_mismatch.cpp:137-147)
+        _write_lines(_resolve(os.getcwd(), q["load out file"]), hp.loads())
     if deck.get("problem", {}).get("write synthetic", False):
         out = os.path.join(os.getcwd(), deck["problem"]["name"] + "_synthetic")
         os.makedirs(out, exist_ok=True)
@@ -176,17 +198,7 @@ def run_objective(deck_path, gradient, label=""):
     act = _active(deck, mesh, ltype)
     assert all(e == 0 for e, _ in act) or ctx.n_es > 1
     if otype in ("adjoint", "pdeco", "femu"):
-        q = deck["quantity of interest"]
-        if q["type"] == "calibration":
-            assert measured is not None, "the calibration objective needs a *_synthetic/ mesh directory"
-            loads = np.loadtxt(_resolve(base, q["load input file"])).reshape(-1)
-            w = [float(v) for v in q.get("displacement weights", [1.0] * mesh.dim)]
-            hp.set_qoi_calibration(balance_factor=float(q.get("balance factor", 1.0)),
-                                   coord_idx=int(q["coordinate index"]), coord_value=float(q["coordinate value"]),
-                                   reaction_force_comp=int(q["reaction force component"]), weights=w,
-                                   measured=measured, load_data=loads[:nsteps], area=_area(mesh))
-        else:
-            hp.set_qoi_avg_disp()
+        set_qoi(hp, mesh, deck["quantity of interest"], base, nsteps, measured)
         J = hp.primal_solve()
         g = hp.adjoint_gradient() if gradient else None
     elif otype in ("vfm", "fs_vfm", "adjoint_vfm"):
@@ -228,16 +240,7 @@ def _setup_objective(deck, base):
     hi = [float(bounds[n][1]) for n in names]
     kw = {}
     if otype in ("adjoint", "pdeco", "femu"):
-        q = deck["quantity of interest"]
-        if q["type"] == "calibration":
-            loads = np.loadtxt(_resolve(base, q["load input file"])).reshape(-1)
-            w = [float(v) for v in q.get("displacement weights", [1.0] * mesh.dim)]
-            hp.set_qoi_calibration(balance_factor=float(q.get("balance factor", 1.0)),
-                                   coord_idx=int(q["coordinate index"]), coord_value=float(q["coordinate value"]),
-                                   reaction_force_comp=int(q["reaction force component"]), weights=w,
-                                   measured=measured, load_data=loads[:nsteps], area=_area(mesh))
-        else:
-            hp.set_qoi_avg_disp()
+        set_qoi(hp, mesh, deck["quantity of interest"], base, nsteps, measured)
         kind = "adjoint"
     else:
         vf = deck["virtual fields"]

@@ -46,8 +46,8 @@ def read_smb(path):
     """Return dict(dim, coords, edges, tris, tets (vertex lists), class_{vtx,edge,tri,tet})."""
     buf = open(path, "rb").read()
     magic, version, dim, nparts = struct.unpack(">4I", buf[:16])
-    if magic != 0 or nparts != 1:
-        raise ValueError(f"{path}: unsupported smb header magic={magic} nparts={nparts}")
+    if magic != 0:
+        raise ValueError(f"{path}: unsupported smb header magic={magic}")
     counts = dict(zip(_TYPES, struct.unpack(">8I", buf[16:48])))
     off = 48
     down = {}
@@ -60,10 +60,18 @@ def read_smb(path):
     xyz = np.frombuffer(buf, dtype=">f8", count=nv * 3, offset=off).astype(np.float64).reshape(nv, 3)
     off += 8 * nv * 3
     off += 8 * nv * 2  # parametric coordinates
-    (n_remote,) = struct.unpack(">I", buf[off:off + 4])
+    # remote-copy links of a part of a partitioned mesh (<name>_<n>p<part>.smb): number of peer parts,
+    # then per peer (peer id, count, `count` local vertex ids in the order both sides share)
+    (n_peers,) = struct.unpack(">I", buf[off:off + 4])
     off += 4
-    if n_remote != 0:
-        raise ValueError("remote copies present: not a serial mesh")
+    remotes = {}
+    for _ in range(n_peers):
+        peer, cnt = struct.unpack(">2I", buf[off:off + 8])
+        off += 8
+        remotes[int(peer)] = np.frombuffer(buf, dtype=">u4", count=cnt, offset=off).astype(np.int64)
+        off += 4 * cnt
+    if n_peers and nparts == 1:
+        raise ValueError("remote copies present in a serial mesh")
     cls = {}
     for t in _TYPES:
         n = counts[t]
@@ -90,7 +98,7 @@ def read_smb(path):
         vol = np.einsum("ij,ij->i", a, np.cross(b, c))
         neg = vol < 0
         tets[neg] = tets[neg][:, [0, 2, 1, 3]]
-    return dict(dim=int(dim), coords=xyz, edges=edges, tris=tris, tets=tets,
+    return dict(dim=int(dim), nparts=int(nparts), remotes=remotes, coords=xyz, edges=edges, tris=tris, tets=tets,
                 tris_e=tris_e, tets_f=tets_f,
                 cls_vtx=cls["vtx"], cls_edge=cls["edge"], cls_tri=cls["tri"], cls_tet=cls["tet"])
 
@@ -161,6 +169,25 @@ def read_assoc(path):
     return out
 
 
+def reference_partition(mesh: Mesh, part_paths) -> np.ndarray:
+    """Element ownership of a mesh the reference partitioned offline (SCOREC `split`: Zoltan ->
+    ParMETIS, test/mesh/*/Makefile): part_paths = the `<name>_<n>p<k>.smb` files in part order.
+    Elements are matched to the serial mesh through their vertex coordinates.  -> elem_part [n_elems]"""
+    dim = mesh.dim
+    key = lambda X: tuple(sorted(tuple(np.round(x, 12)) for x in X))
+    where = {key(mesh.coords[mesh.conn[e]]): e for e in range(mesh.n_elems)}
+    elem_part = np.full(mesh.n_elems, -1, dtype=np.int32)
+    for k, path in enumerate(part_paths):
+        smb = read_smb(path)
+        conn = smb["tets"] if dim == 3 else smb["tris"]
+        for c in conn:
+            e = where[key(smb["coords"][c])]
+            assert elem_part[e] < 0, "an element belongs to exactly one part"
+            elem_part[e] = k
+    assert (elem_part >= 0).all(), "every element of the serial mesh is in a part"
+    return elem_part
+
+
 def load_calibr8_mesh(smb_path, dmg_path, assoc_path) -> Mesh:
     smb = read_smb(smb_path)
     closure = read_dmg(dmg_path)
@@ -196,6 +223,26 @@ def load_calibr8_mesh(smb_path, dmg_path, assoc_path) -> Mesh:
     return Mesh(dim=dim, coords=np.ascontiguousarray(smb["coords"]),
                 conn=np.ascontiguousarray(conn.astype(np.int32)), elem_set=elem_set,
                 elem_set_names=elem_set_names, node_sets=node_sets, side_sets=side_sets)
+
+
+def side_set_facets(mesh: Mesh, name: str) -> np.ndarray:
+    """[n_elems][3] int8: local vertex ids of the element facet that lies on side set `name`, -1 where
+    none (2-D: two ids).  The mapping QoI::setup_side_set_mapping builds (src/qoi.cpp, load_mismatch.cpp:48-76)."""
+    dim = mesh.dim
+    sides = {tuple(sorted(int(v) for v in s)) for s in np.asarray(mesh.side_sets[name])}
+    fac = np.full((mesh.n_elems, 3), -1, dtype=np.int8)
+    import itertools
+    combos = list(itertools.combinations(range(dim + 1), dim))
+    conn = np.asarray(mesh.conn)
+    node_on = np.zeros(mesh.n_nodes, dtype=bool)
+    for s in sides:
+        node_on[list(s)] = True
+    cand = np.nonzero(node_on[conn].sum(axis=1) >= dim)[0]
+    for e in cand:
+        for c in combos:
+            if tuple(sorted(int(conn[e, k]) for k in c)) in sides:
+                fac[e, :dim] = c
+    return fac
 
 
 def save_npz(mesh: Mesh, path):

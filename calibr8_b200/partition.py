@@ -140,11 +140,19 @@ def build_part(mesh, elem_part: np.ndarray, rank: int, n_parts: int, owner=None)
                 recv_ptr=np.asarray(recv_ptr, dtype=np.int32), node_sets=node_sets)
 
 
-def partition_mesh(mesh, n_parts: int, rank: int | None = None):
-    """RCB element partition; returns (elem_part, [Part...]) or (elem_part, Part) for one rank."""
+def partition_mesh(mesh, n_parts: int, rank: int | None = None, elem_part=None):
+    """Element partition; returns (elem_part, [Part...]) or (elem_part, Part) for one rank.
+    elem_part: the caller's own element -> part map (the hook for METIS / ParMETIS output or for the
+    reference's offline SCOREC `split`, see meshio.reference_partition); None: recursive coordinate
+    bisection of the element centroids (works on unstructured meshes too, exact on structured boxes)."""
     conn, coords = np.asarray(mesh.conn), np.asarray(mesh.coords)
-    cent = coords[conn].mean(axis=1)[:, : mesh.dim]
-    elem_part = rcb(cent, n_parts)
+    if elem_part is None:
+        cent = coords[conn].mean(axis=1)[:, : mesh.dim]
+        elem_part = rcb(cent, n_parts)
+    else:
+        elem_part = np.ascontiguousarray(elem_part, dtype=np.int32)
+        if elem_part.shape != (conn.shape[0],) or elem_part.min() < 0 or elem_part.max() >= n_parts:
+            raise ValueError("elem_part must map every element to a part in [0, n_parts)")
     owner = node_owners(conn, elem_part, coords.shape[0])
     if rank is not None:
         return elem_part, build_part(mesh, elem_part, rank, n_parts, owner)

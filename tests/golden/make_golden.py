@@ -101,7 +101,12 @@ def main():
         m = meshio.load_calibr8_mesh(f"{REF}/mesh/{name}/{name}0.smb", f"{REF}/mesh/{name}/{name}.dmg",
                                      f"{REF}/mesh/{name}/{name}.txt")
         meshio.save_npz(m, os.path.join(HERE, f"mesh_{name}.npz"))
-        print(name, m.n_nodes, m.n_elems)
+        # the reference's OWN two-part partition of the mesh (SCOREC split -> ParMETIS, test/mesh/*/Makefile):
+        # element ownership as a fixture, for the partition / halo-plan / partitioned-solve tests
+        ep = meshio.reference_partition(m, [f"{REF}/mesh/{name}/{name}_2p{k}.smb" for k in range(2)])
+        import numpy as np
+        np.save(os.path.join(HERE, f"partition_{name}_2p.npy"), ep.astype(np.int8))
+        print(name, m.n_nodes, m.n_elems, "reference 2-part split:", np.bincount(ep).tolist())
     json.dump(dict(decks=DECKS, fd_drops=FD_DROPS), open(os.path.join(HERE, "golden.json"), "w"), indent=1)
 
 

@@ -106,7 +106,14 @@ def _measured(case, mesh):
     return meas, float(area)
 
 
-def _worker(rank, world, port, transport, case, q):
+def _elem_part(mesh_name, how):
+    """None (recursive coordinate bisection) or the reference's own two-part SCOREC split of the mesh"""
+    if how != "reference":
+        return None
+    return np.load(os.path.join(ROOT, "tests", "golden", f"partition_{mesh_name}_2p.npy")).astype(np.int32)
+
+
+def _worker(rank, world, port, transport, case, q, how="rcb"):
     import sys
     if transport == "nccl_p2p":     # experimental NVLink push halo (csrc/comm.cu), same checks
         os.environ["C8_P2P"] = "1"
@@ -124,7 +131,7 @@ def _worker(rank, world, port, transport, case, q):
         _, mesh_name, _ = _deck(case)
         mesh = load_mesh(mesh_name)
         measured, area = _measured(case, mesh)
-        _, part = partition.partition_mesh(mesh, world, rank=rank)
+        _, part = partition.partition_mesh(mesh, world, rank=rank, elem_part=_elem_part(mesh_name, how))
 
         def setup(ctx):
             if transport == "host":
@@ -144,12 +151,12 @@ def _worker(rank, world, port, transport, case, q):
         dist.destroy_process_group()
 
 
-def _run_parts(world, transport, case):
+def _run_parts(world, transport, case, how="rcb"):
     import torch.multiprocessing as mp
     mpc = mp.get_context("spawn")
     q = mpc.Queue()
     port = _free_port()
-    procs = [mpc.Process(target=_worker, args=(r, world, port, transport, case, q)) for r in range(world)]
+    procs = [mpc.Process(target=_worker, args=(r, world, port, transport, case, q, how)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in range(world)]
@@ -159,7 +166,7 @@ def _run_parts(world, transport, case):
     return sorted(res, key=lambda r: r[0])
 
 
-def _check(world, transport, case):
+def _check(world, transport, case, how="rcb"):
     import torch
     from conftest import load_mesh
     torch.cuda.set_device(0)
@@ -167,7 +174,7 @@ def _check(world, transport, case):
     mesh = load_mesh(mesh_name)
     measured, area = _measured(case, mesh)
     J1, g1, u1, st1 = _solve(case, mesh, None, None, measured, area)
-    res = _run_parts(world, transport, case)
+    res = _run_parts(world, transport, case, how)
     u = np.zeros((mesh.n_nodes, mesh.dim))
     for rank, J, g, gid, u_owned, stats in res:
         assert abs(J - J1) <= 1e-8 * abs(J1), (rank, J, J1)                       # objective, 1e-8 relative
@@ -185,6 +192,13 @@ def _check(world, transport, case):
 @pytest.mark.parametrize("case", ["notch_small_J2", "calibration2D"])
 def test_two_parts_host_staged_one_gpu(case):
     _check(2, "host", case)
+
+
+@pytest.mark.parametrize("case", ["notch_small_J2", "calibration2D"])
+def test_reference_partition_host_staged_one_gpu(case):
+    """element ownership = the reference's own offline two-part split of its regression meshes
+    (test/mesh/notch/notch_2p{0,1}.smb, SCOREC split -> ParMETIS), fixtures tests/golden/partition_*_2p.npy"""
+    _check(2, "host", case, how="reference")
 
 
 def test_three_parts_host_staged_one_gpu():

@@ -22,12 +22,31 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("dim,n_parts", [(3, 2), (3, 3), (3, 8), (2, 2), (2, 4)])
-def test_partition_invariants(dim, n_parts):
-    mesh = meshgen.box_tets(6, notch_radius=0.3) if dim == 3 else meshgen.square_tris(12, notch_radius=0.3)
-    elem_part, parts = partition.partition_mesh(mesh, n_parts)
+def _mesh_and_partition(kind, n_parts):
+    """structured synthetic boxes, or the reference's own UNSTRUCTURED regression meshes (gmsh) with
+    RCB or with the reference's own two-part SCOREC split (ParMETIS) as the element ownership"""
+    import os
+    from conftest import GOLDEN, load_mesh
+    if kind == "box3d":
+        return meshgen.box_tets(6, notch_radius=0.3), None
+    if kind == "box2d":
+        return meshgen.square_tris(12, notch_radius=0.3), None
+    name, how = kind.split(":")
+    mesh = load_mesh(name)
+    ep = np.load(os.path.join(GOLDEN, f"partition_{name}_2p.npy")).astype(np.int32) if how == "reference" else None
+    return mesh, ep
+
+
+@pytest.mark.parametrize("kind,n_parts", [("box3d", 2), ("box3d", 3), ("box3d", 8), ("box2d", 2), ("box2d", 4),
+                                          ("notch:rcb", 2), ("notch:rcb", 4), ("notch2D:rcb", 4),
+                                          ("notch:reference", 2), ("notch2D:reference", 2), ("cube:reference", 2)])
+def test_partition_invariants(kind, n_parts):
+    mesh, ep = _mesh_and_partition(kind, n_parts)
+    elem_part, parts = partition.partition_mesh(mesh, n_parts, elem_part=ep)
     counts = np.bincount(elem_part, minlength=n_parts)
     assert counts.sum() == mesh.n_elems and counts.max() - counts.min() <= n_parts
+    if ep is not None:
+        assert np.array_equal(elem_part, ep)      # the reference's ownership is used as given
     owned_nodes = np.concatenate([p.node_gid[: p.n_owned_nodes] for p in parts])
     assert np.array_equal(np.sort(owned_nodes), np.arange(mesh.n_nodes))      # each node owned once
     owned_elems = np.concatenate([p.elem_gid[: p.n_owned_elems] for p in parts])
