@@ -301,7 +301,7 @@ SYMBOLS += [
 ]
 HOST_SYMBOLS = [
     "c8h_create", "c8h_destroy", "c8h_last_error", "c8h_set_time", "c8h_add_dbc", "c8h_add_tbc",
-    "c8h_finalize_dbcs", "c8h_set_solver", "c8h_set_qoi_avg_disp", "c8h_set_qoi_calibration",
+    "c8h_finalize_dbcs", "c8h_set_solver", "c8h_set_line_search", "c8h_set_qoi_avg_disp", "c8h_set_qoi_calibration",
     "c8h_set_qoi_mismatch", "c8h_get_loads", "c8h_primal_solve", "c8h_adjoint_gradient", "c8h_get_step", "c8h_get_adjoint_step", "c8h_stats",
     "c8h_profile", "c8h_eval_expr", "c8h_describe_residuals",
 ]
@@ -458,6 +458,11 @@ class HostProblem:
         self._check(self.lib.c8h_set_solver(self.h, newton_max_iters, C.c_double(abs_tol),
                                             C.c_double(rel_tol), gmres_restart, gmres_max_iters,
                                             C.c_double(linear_tol), int(verbose)))
+
+    def set_line_search(self, sufficient_decrease=1e-4, min_backtrack=0.5, max_backtrack=0.9, max_evals=4):
+        """the deck's `line search` sublist of the global residual (src/line_search.hpp:33-49)"""
+        self._check(self.lib.c8h_set_line_search(self.h, C.c_double(sufficient_decrease), C.c_double(min_backtrack),
+                                                 C.c_double(max_backtrack), int(max_evals)))
 
     def set_qoi_avg_disp(self):
         self._check(self.lib.c8h_set_qoi_avg_disp(self.h))

@@ -97,6 +97,9 @@ def build(deck, base, override=None, device=0):
     hp.set_solver(int(g.get("nonlinear max iters", 15)), float(g.get("nonlinear absolute tol", 1e-8)),
                   float(g.get("nonlinear relative tol", 1e-8)), gmres_restart=200, gmres_max_iters=20000,
                   linear_tol=max(lin_tol, 1e-13), verbose=bool(g.get("print convergence", False)))
+    ls = g.get("line search") or {}
+    hp.set_line_search(float(ls.get("sufficient decrease", 1e-4)), float(ls.get("min backtrack factor", 0.5)),
+                       float(ls.get("max backtrack factor", 0.9)), int(ls.get("max evals", 4)))
     return ctx, hp, mesh, measured
 
 

@@ -333,6 +333,10 @@ void Primal::solve_at_step(int step) {
     }
     if (!assembled_any) throw std::runtime_error("primal: line search could not assemble");
     const double a_final = accepted ? alpha : best_alpha;
+    if (sp.print && (!accepted || a_final != 1.0))
+      std::printf("    line search: alpha = %.3e%s\n", a_final,
+                  accepted ? "" : (best_phi >= psi_0 ? " (max evals reached, ||R|| not reduced: increase 'max evals' "
+                                                       "or reduce the load increment)" : " (max evals reached)"));
     if (sp.reuse_accepted_assembly && last_eval_ok && a_final == alpha_applied) {
       have_assembly = true;       // x, xi, A, R are exactly the state of the last trial
       rn_kept = last_eval_rn;
@@ -497,6 +501,16 @@ int c8h_set_solver(c8h_problem* h, int newton_max_iters, double abs_tol, double 
   s.gmres_restart = gmres_restart; s.gmres_max_iters = gmres_max_iters; s.linear_tol = linear_tol;
   s.print = print != 0;
   return 0;
+}
+// the deck's "line search" sublist of the global residual (src/line_search.hpp:33-49): "sufficient
+// decrease", "min backtrack factor", "max backtrack factor", "max evals"
+int c8h_set_line_search(c8h_problem* h, double c1, double backtrack_min, double backtrack_max, int max_evals) {
+  C8H_TRY(h, {
+    if (!(c1 > 0.) || !(backtrack_min > 0. && backtrack_min <= backtrack_max && backtrack_max < 1.) || max_evals < 1)
+      throw std::runtime_error("line search: need c1 > 0, 0 < min <= max backtrack factor < 1, max evals >= 1");
+    SolverParams& s = h->P.sp;
+    s.ls_c1 = c1; s.ls_bmin = backtrack_min; s.ls_bmax = backtrack_max; s.ls_max_evals = max_evals;
+  });
 }
 int c8h_set_qoi_avg_disp(c8h_problem* h) { h->P.qoi_type = 0; return 0; }
 // measured_host: [num_steps][n_nodes][dim]; load_data [num_steps]; facet_host [n_elems][3] or NULL

@@ -24,10 +24,12 @@ if which in ("cfg3", "both"):
                        (0, 1, "ymax", "0.004 * (2/3.14159265358979) * asin(sin(2*3.14159265358979*t/12.5))" )]:
         hp.add_dbc(r, e, mesh.node_sets[s], v)
     hp.finalize_dbcs()
-    hp.set_solver(40, 1e-8, 1e-8, gmres_restart=100, gmres_max_iters=20000, linear_tol=1e-8,
+    hp.set_solver(int(os.environ.get("NEWTON", "40")), 1e-8, 1e-8, gmres_restart=100, gmres_max_iters=20000, linear_tol=float(os.environ.get("LINTOL", "1e-8")),
                   verbose=bool(os.environ.get("VERBOSE")))
     hp.set_qoi_avg_disp()
-    for rep in range(2):
+    if os.environ.get("LS_EVALS"):      # the deck's "line search: max evals" (src/line_search.hpp:33-49)
+        hp.set_line_search(max_evals=int(os.environ["LS_EVALS"]), min_backtrack=float(os.environ.get("LS_BMIN", "0.5")))
+    for rep in range(1 if os.environ.get("ONCE") else 2):
         torch.cuda.synchronize(); t0 = time.perf_counter(); J = hp.primal_solve()
         torch.cuda.synchronize(); t1 = time.perf_counter(); g = hp.adjoint_gradient()
         torch.cuda.synchronize(); t2 = time.perf_counter()
