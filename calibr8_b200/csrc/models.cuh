@@ -544,6 +544,71 @@ struct HyperJ2 {
         z = scale(m, nhat);
         alpha += sqrt_23 * dgam;
       }
+    } else if constexpr (DIM == 3) {
+      // Non-linear isotropic hardening (Voce and / or power law): the same radial-return structure,
+      // zeta = nhat m with m = |dev bt| - 2 Ie dgam, leaves TWO scalar unknowns (dgam, Ie) and the two
+      // scalar equations  g1 = mu m - sqrt(2/3) sigma_y(alpha_old + sqrt(2/3) dgam) = 0  (yield) and
+      // g2 = det(m nhat + Ie I) - 1 = 0  (isochoric): a 2 x 2 Newton in plain doubles (one exp / pow
+      // pair per step) instead of 4-5 iterations of the AD Newton with its 8 x 8 solve.  It starts
+      // right of the root in dgam (linear hardening with the smallest slope K), where the convex g1
+      // cannot stall on the infinite slope of the power law at alpha = 0.  Only an initial guess:
+      // whatever it leaves, the local Newton of the reference finishes.
+      const double sqrt_23 = 0.81649658092772603;
+      const double mu = mu_of(par[0], par[1]);
+      const double Y = par[2], S = par[3], D = par[4], A = par[5], n = par[6], K = par[7];
+      auto sigma_y = [&](double a, double& dsy) {
+        double v = Y + K * a;
+        dsy = K;
+        if (S != 0.0) { const double ex = exp(-D * a); v += S * (1.0 - ex); dsy += S * D * ex; }
+        if (A != 0.0) { const double pw = pow(a + 1e-12, n); v += A * pw; dsy += A * n * pw / (a + 1e-12); }
+        return v;
+      };
+      const double z_mag = norm(z);
+      double dsy0;
+      const double f = (mu * z_mag - sqrt_23 * sigma_y(alpha, dsy0)) / mu;
+      if (is_plastic(f, abs_tol) && z_mag > 0.0) {
+        r0 = fabs(f);
+        const Mat<double, DIM> nhat = scale(1.0 / z_mag, z);
+        const double kmin = K > 0.0 ? K : 0.0;
+        double dgam = mu * f / (2.0 * mu * Ie + (2.0 / 3.0) * kmin);
+        double m = z_mag - 2.0 * Ie * dgam;
+        bool polish = false;   // one more (quadratically convergent) step after the test first passes:
+                               // the state then sits at rounding level like the reference's last iterate
+#pragma unroll 1
+        for (int it = 0; it < 24; ++it) {
+          double dsy;
+          const double sy = sigma_y(alpha + sqrt_23 * dgam, dsy);
+          m = z_mag - 2.0 * Ie * dgam;
+          const Mat<double, DIM> Amat = add_diag(scale(m, nhat), Ie);
+          const double g1 = mu * m - sqrt_23 * sy;
+          const double g2 = det(Amat) - 1.0;
+          if (fabs(g1) < 1e-12 * mu && fabs(g2) < 1e-12) {
+            if (polish) break;
+            polish = true;
+          }
+          const Mat<double, DIM> adj = cofactor_T(Amat);
+          double dg2_dm = 0.0, tr_adj = 0.0;
+#pragma unroll
+          for (int i = 0; i < DIM; ++i) {
+            tr_adj += adj(i, i);
+#pragma unroll
+            for (int j = 0; j < DIM; ++j) dg2_dm += adj(j, i) * nhat(i, j);
+          }
+          // Jacobian of (g1, g2) w.r.t. (dgam, Ie); dm/ddgam = -2 Ie, dm/dIe = -2 dgam
+          const double a11 = -2.0 * mu * Ie - (2.0 / 3.0) * dsy, a12 = -2.0 * mu * dgam;
+          const double a21 = -2.0 * Ie * dg2_dm, a22 = -2.0 * dgam * dg2_dm + tr_adj;
+          const double dt = a11 * a22 - a12 * a21;
+          if (dt == 0.0) break;
+          double d_dgam = (-g1 * a22 + g2 * a12) / dt;
+          const double d_Ie = (-a11 * g2 + a21 * g1) / dt;
+          if (dgam + d_dgam < 0.0) d_dgam = -0.5 * dgam;   // stay on the loading side
+          dgam += d_dgam;
+          Ie += d_Ie;
+        }
+        m = z_mag - 2.0 * Ie * dgam;
+        z = scale(m, nhat);
+        alpha += sqrt_23 * dgam;
+      }
     }
     pack_sym<double, DIM>(z, xi);
     xi[NS] = Ie;

@@ -23,7 +23,12 @@ COMBOS = {
     "2d_hyper_J2_plane_stress": (2, "mechanics_plane_stress", "hyper_J2_plane_stress",
                                  dict(E=1000., nu=.25, Y=2., S=10., D=2., A=1., n=.5, K=20.), 0.45e-3),
 }
-LOCAL_TOL = dict(max_iters=60, abs_tol=1e-12, rel_tol=1e-12)
+# Local Newton tolerance of the parity runs.  1e-14 rather than the decks' 1e-12: an iterate accepted at
+# |C| < 1e-12 carries a state error that the Jacobian amplifies (hyper-J2 with power-law hardening:
+# the oracle at 1e-12 and at 1e-15 differ by 1.2e-10 in the element Jacobian, see
+# profiles/README.md), so entry-level parity at 1e-10 is only meaningful between CONVERGED local
+# states -- whichever iteration path (reference start, or the kernels' return-map predictors) led there.
+LOCAL_TOL = dict(max_iters=60, abs_tol=1e-14, rel_tol=1e-14)
 
 
 def make_mesh(dim, size="small"):
