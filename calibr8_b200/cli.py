@@ -72,7 +72,16 @@ def build(deck, base, override=None, device=0):
     g, l = res["global residual"], res["local residual"]
     ctx = Context(device)
     ctx.set_mesh(mesh.dim, mesh.conn, mesh.coords, mesh.elem_set, len(mesh.elem_set_names))
-    ctx.set_model(g["type"], l["type"], _materials(l, mesh, override),
+    gtype = g["type"]
+    if gtype == "mechanics" and not bool(g.get("mixed formulation", True)):
+        # displacement-only mechanics (src/mechanics.cpp:18-54): usable with a local residual whose cauchy()
+        # is the full stress -- small_hill_plane_stress -- where it IS mechanics_plane_stress with unit
+        # thickness (host/residuals.hpp: create_global_residual(..., mixed = false))
+        if l["type"] != "small_hill_plane_stress":
+            raise SystemExit("mixed formulation: false needs a local residual whose cauchy() does not read the "
+                             "pressure field (small_hill_plane_stress)")
+        gtype, g = "mechanics_plane_stress", dict(g, thickness=1.0)
+    ctx.set_model(gtype, l["type"], _materials(l, mesh, override),
                   max_iters=int(l.get("nonlinear max iters", 0)),
                   abs_tol=float(l.get("nonlinear absolute tol", 0.0)),
                   rel_tol=float(l.get("nonlinear relative tol", 0.0)),

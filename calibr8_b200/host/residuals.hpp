@@ -96,7 +96,20 @@ inline GlobalResidual create_global_residual(const std::string& type, int ndims,
   GlobalResidual g;
   g.type = type; g.ndims = ndims;
   if (type == "mechanics") {
-    if (!mixed) throw std::runtime_error("create_global_residual: only the mixed u-p formulation is in scope");
+    if (!mixed) {
+      // "mixed formulation: false" (src/mechanics.cpp:18-54): ONE residual u, one ip set, the momentum
+      // balance with local->cauchy().  The cauchy() of the mixed-type models of this path reads the
+      // pressure residual (src/small_J2.cpp:252-263 ...), which does not exist in this mode, so the only
+      // in-scope local residuals it can drive are the plane-stress ones, whose cauchy() is the full
+      // stress: sum_j sigma_ij dN/dX_j w dv == mechanics_plane_stress with unit thickness (small strain;
+      // the finite-strain plane-stress model differs by the z stretch and is rejected by the caller).
+      if (ndims != 2)
+        throw std::runtime_error("create_global_residual: displacement-only mechanics needs a local residual whose "
+                                 "cauchy() does not read the pressure (the plane-stress models, 2-D)");
+      g.c8_type = C8_MECHANICS_PLANE_STRESS;
+      g.resid_names = {"u"}; g.var_types = {VECTOR}; g.num_eqs = {2};
+      return g;
+    }
     g.c8_type = C8_MECHANICS;
     g.resid_names = {"u", "p"}; g.var_types = {VECTOR, SCALAR};
     g.num_eqs = {get_num_eqs(VECTOR, ndims), 1};
