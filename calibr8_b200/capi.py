@@ -41,7 +41,7 @@ SYMBOLS = [
     "c8_unpack_xi", "c8_init_xi", "c8_forward_jacobian", "c8_forward_jacobian_elem",
     "c8_global_residual", "c8_forward_jacobian_host", "c8_resident_matrix", "c8_set_stream",
     "c8_synchronize", "c8_state_set_prev", "c8_state_forward_jacobian", "c8_state_get_xi",
-    "c8_state_ptrs", "c8_bench_dfma", "c8_bench_copy",
+    "c8_state_ptrs", "c8_bench_dfma", "c8_bench_copy", "c8_set_assembly_chunk",
 ]
 
 _lib = None
@@ -111,6 +111,10 @@ class Context:
         raise C8Error(f"c8 error {rc}: {self.lib.c8_last_error(self.h).decode()}")
 
     # ---- set-up ------------------------------------------------------------------
+    def set_assembly_chunk(self, chunk_elems):
+        """before set_mesh: elements per chunk of the two-phase assembly (0 one pass, -1 default)"""
+        self._check(self.lib.c8_set_assembly_chunk(self.h, int(chunk_elems)))
+
     def set_mesh(self, dim, conn, coords, elem_set=None, n_elem_sets=1):
         conn = np.ascontiguousarray(conn, dtype=np.int32)
         coords = np.ascontiguousarray(coords, dtype=np.float64)

@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(128) k_adjoint_jacobian(const AdjArgs a) {
   fa.mesh = a.mesh;
   fa.vals = a.vals;
   fa.emat = a.emat;
+  fa.elem_begin = 0; fa.elem_end = a.mesh.n_elems;   // one pass over the whole mesh (full scratch)
   Scatter<C, false> sc{fa, E, sx.xl, e, t, in_range};  // element matrix only; the rhs was added above
   sc.init();
   {

@@ -33,13 +33,37 @@ struct Launch {
     k_bsr_gather<C::NB, C::NN, TRANSPOSE><<<(unsigned)((work + 255) / 256), 256, 0, s>>>(
         m.gptr, m.gsrc, emat, vals, m.n_row_blocks);
   }
-  static void forward_jacobian(const FwdArgs& a, cudaStream_t s) {
-    if (a.mesh.n_elems == 0) return;
-    const long long threads = (long long)a.mesh.n_elems * C::G;
+  static void forward_jacobian(const FwdArgs& a0, cudaStream_t s) {
+    if (a0.mesh.n_elems == 0) return;
+    FwdArgs a = a0;
     const int block = C8_K1_BLOCK;
-    const unsigned grid = (unsigned)((threads + block - 1) / block);
     // FAST: the production call (matrix + residual, no element-level output) is branch-free
     const bool fast = a.vals && a.b && !a.elem_J && !a.elem_R;
+    if constexpr (C::NB % 2 == 0) {
+      if (a.vals && a.mesh.chunk_elems > 0 && a.mesh.n_chunks > 1 && a.cg_ptr_host) {
+        // chunked two-phase assembly: element kernel of chunk c, then its gather while the chunk's
+        // element matrices are still in L2 (args.h)
+        for (int c = 0; c < a.mesh.n_chunks; ++c) {
+          a.elem_begin = c * a.mesh.chunk_elems;
+          a.elem_end = a.elem_begin + a.mesh.chunk_elems < a.mesh.n_elems ? a.elem_begin + a.mesh.chunk_elems : a.mesh.n_elems;
+          const long long threads = (long long)(a.elem_end - a.elem_begin) * C::G;
+          const unsigned grid = (unsigned)((threads + block - 1) / block);
+          if (fast) k_forward_jacobian<C, true><<<grid, block, 0, s>>>(a);
+          else k_forward_jacobian<C, false><<<grid, block, 0, s>>>(a);
+          if (c + 1 == a.mesh.n_chunks && a.elements_done) cudaEventRecord(a.elements_done, s);
+          const int en0 = a.cg_ptr_host[c], nen = a.cg_end_host[c] - en0;
+          if (nen > 0) {
+            const long long work = (long long)nen * (C::NB * C::NB / 2);
+            k_bsr_gather_chunk<C::NB, C::NN><<<(unsigned)((work + 255) / 256), 256, 0, s>>>(
+                a.mesh.cg_blk, a.mesh.cg_k, a.mesh.gsrc, a.emat, a.vals, en0, nen, a.elem_begin);
+          }
+        }
+        return;
+      }
+    }
+    a.elem_begin = 0; a.elem_end = a.mesh.n_elems;
+    const long long threads = (long long)a.mesh.n_elems * C::G;
+    const unsigned grid = (unsigned)((threads + block - 1) / block);
     if (fast) k_forward_jacobian<C, true><<<grid, block, 0, s>>>(a);
     else k_forward_jacobian<C, false><<<grid, block, 0, s>>>(a);
     if (a.elements_done) cudaEventRecord(a.elements_done, s);  // xi, b, path and the status are final here

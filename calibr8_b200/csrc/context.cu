@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace c8 {
@@ -145,6 +146,36 @@ double* element_scratch(c8_ctx* ctx) {
   return ctx->d_emat;
 }
 
+bool chunked_assembly(c8_ctx* ctx, FwdArgs& a) {
+  a.cg_ptr_host = nullptr;
+  if (ctx->n_chunks < 2 || !a.vals || a.elem_J || a.elem_R) return false;
+  // a partition keeps the rows of its owned nodes only: those are the leading blocks, and inside a chunk
+  // the entries are sorted by block, so the owned rows are a prefix of every chunk's entries
+  const int n_row_blocks = ctx->h_rowptr[ctx->n_owned_nodes];
+  if (ctx->cg_end_rows != n_row_blocks) {
+    ctx->h_cg_end.assign(ctx->n_chunks, 0);
+    for (int c = 0; c < ctx->n_chunks; ++c) {
+      const unsigned* b0 = ctx->h_cg_blk.data() + ctx->h_cg_ptr[c];
+      const unsigned* b1 = ctx->h_cg_blk.data() + ctx->h_cg_ptr[c + 1];
+      const unsigned* it = std::partition_point(b0, b1, [&](unsigned w) { return int(w & 0x7fffffffu) < n_row_blocks; });
+      ctx->h_cg_end[c] = int(it - ctx->h_cg_blk.data());
+    }
+    ctx->cg_end_rows = n_row_blocks;
+  }
+  const int nx = ctx->kt->nx;
+  if (!ctx->d_emat_chunk || ctx->emat_chunk_nx != nx) {
+    if (ctx->d_emat_chunk) cudaFree(ctx->d_emat_chunk);
+    ctx->d_emat_chunk = nullptr;
+    const size_t bytes = (size_t(ctx->chunk_elems) + 1) * nx * nx * sizeof(double);
+    if (cudaMalloc(&ctx->d_emat_chunk, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
+    ctx->emat_chunk_nx = nx;
+  }
+  a.emat = ctx->d_emat_chunk;
+  a.cg_ptr_host = ctx->h_cg_ptr.data();
+  a.cg_end_host = ctx->h_cg_end.data();
+  return true;
+}
+
 __global__ void k_int_to_double(const int* i, double* d) { *d = double(*i); }
 
 // number of failed local solves over ALL parts (PCU_Add_Int of the status, src/primal.cpp:96)
@@ -200,7 +231,7 @@ void c8_destroy(c8_ctx* ctx) {
   void* ptrs[] = {ctx->d_conn, ctx->d_coords, ctx->d_elem_es, ctx->d_rowptr, ctx->d_colind,
                   ctx->d_eoff, ctx->d_params, ctx->d_nfailed, ctx->d_A, ctx->d_b, ctx->d_x,
                   ctx->d_xp, ctx->d_xi, ctx->d_xip, ctx->d_stage, ctx->d_scalar, ctx->d_gptr,
-                  ctx->d_gsrc, ctx->d_emat};
+                  ctx->d_gsrc, ctx->d_emat, ctx->d_cg_ptr, ctx->d_cg_blk, ctx->d_cg_k, ctx->d_emat_chunk};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -287,6 +318,53 @@ int c8_set_mesh(c8_ctx* ctx, int dim, int n_elems, int n_nodes, const int32_t* c
     for (size_t q = 0; q < eoff.size(); ++q) gsrc[pos[eoff[q]]++] = int(q);
     if (!upload(ctx, &ctx->d_gptr, gptr)) return C8_ERR_CUDA;
     if (!upload(ctx, &ctx->d_gsrc, gsrc)) return C8_ERR_CUDA;
+    // chunked forward assembly (args.h): split every block's contribution list at the chunk
+    // boundaries of the element index; entries sorted by chunk, then block.  OFF by default (one pass):
+    // measured on B200 at 1 M tets it is slower at every chunk size (2.15 ms one pass; 2.62 / 2.81 / 2.90 /
+    // 3.26 ms at 75 776 / 37 888 / 18 944 / 9 472 elements per chunk) -- every element-kernel launch pays
+    // a fixed ~10-15 us (cold instruction cache of the 140 KB program on every SM + the tail of its last
+    // wave), which outweighs reading the scratch from L2.  c8_set_assembly_chunk / C8_ASM_CHUNK enable it.
+    static const int chunk_default = [] { const char* e = getenv("C8_ASM_CHUNK"); return e ? atoi(e) : 0; }();
+    const int chunk_env = ctx->chunk_request >= 0 ? ctx->chunk_request : chunk_default;
+    ctx->chunk_elems = 0; ctx->n_chunks = 0; ctx->h_cg_ptr.clear();
+    if (ctx->d_emat_chunk) { cudaFree(ctx->d_emat_chunk); ctx->d_emat_chunk = nullptr; }
+    if (chunk_env > 0 && n_elems > 2 * chunk_env) {
+      const int CE = chunk_env, nch = (n_elems + CE - 1) / CE;
+      const int npair = nn * nn;
+      std::vector<std::vector<unsigned>> blk(nch);
+      std::vector<std::vector<int>> kk(nch);
+      for (int b = 0; b < ctx->nnzb; ++b) {
+        int k = gptr[b];
+        const int k1 = gptr[b + 1];
+        bool first = true;
+        if (k == k1) {   // a block without contributions (isolated node): cleared by chunk 0
+          blk[0].push_back(unsigned(b) | 0x80000000u);
+          kk[0].push_back(k); kk[0].push_back(k);
+        }
+        while (k < k1) {
+          const int c = (gsrc[k] / npair) / CE;
+          int k2 = k + 1;
+          while (k2 < k1 && (gsrc[k2] / npair) / CE == c) ++k2;
+          blk[c].push_back(unsigned(b) | (first ? 0x80000000u : 0u));
+          kk[c].push_back(k); kk[c].push_back(k2);
+          first = false;
+          k = k2;
+        }
+      }
+      std::vector<unsigned> cblk;
+      std::vector<int> ck;
+      ctx->h_cg_ptr.assign(nch + 1, 0);
+      for (int c = 0; c < nch; ++c) {
+        cblk.insert(cblk.end(), blk[c].begin(), blk[c].end());
+        ck.insert(ck.end(), kk[c].begin(), kk[c].end());
+        ctx->h_cg_ptr[c + 1] = int(cblk.size());
+      }
+      ctx->h_cg_blk = cblk; ctx->cg_end_rows = -1;
+      if (!upload(ctx, &ctx->d_cg_blk, cblk)) return C8_ERR_CUDA;
+      if (!upload(ctx, &ctx->d_cg_k, ck)) return C8_ERR_CUDA;
+      if (!upload(ctx, &ctx->d_cg_ptr, ctx->h_cg_ptr)) return C8_ERR_CUDA;
+      ctx->chunk_elems = CE; ctx->n_chunks = nch;
+    }
   }
   if (ctx->d_emat) { cudaFree(ctx->d_emat); ctx->d_emat = nullptr; ctx->emat_elems = 0; }
   if (!upload(ctx, &ctx->d_conn, ctx->h_conn)) return C8_ERR_CUDA;
@@ -311,6 +389,12 @@ int c8_set_mesh(c8_ctx* ctx, int dim, int n_elems, int n_nodes, const int32_t* c
   ctx->comm_capturable = false;
   c8_linalg_invalidate(ctx);
   ctx->xi_ld = (long long)((n_elems + 31) / 32) * 32;  // 256-byte aligned component rows
+  return C8_OK;
+}
+
+int c8_set_assembly_chunk(c8_ctx* ctx, int chunk_elems) {
+  C8_REQUIRE(ctx, chunk_elems >= -1, "chunk size must be >= 0 (0: one pass), or -1 for the default");
+  ctx->chunk_request = chunk_elems;
   return C8_OK;
 }
 
@@ -515,11 +599,11 @@ static int forward_impl(c8_ctx* ctx, const double* x, const double* xp, const do
   a.model = ctx->model;
   a.x = x; a.x_prev = xp; a.xi_prev = xip; a.xi = xi; a.xi_ld = ctx->xi_ld;
   a.vals = A; a.b = b; a.path = (signed char*)path; a.n_failed = ctx->d_nfailed;
-  if (A) {
+  a.elem_J = eJ; a.elem_R = eR;
+  if (A && !c8::chunked_assembly(ctx, a)) {
     a.emat = element_scratch(ctx);
     if (!a.emat) return C8_ERR_CUDA;
   }
-  a.elem_J = eJ; a.elem_R = eR;
   (void)transpose;
   C8_CUDA(ctx, cudaMemsetAsync(ctx->d_nfailed, 0, sizeof(int), ctx->stream));
   ctx->kt->forward_jacobian(a, ctx->stream);
@@ -555,8 +639,10 @@ int c8::forward_state_host(c8_ctx* ctx, const double* u, const double* p, double
   a.model = ctx->model;
   a.x = ctx->d_x; a.x_prev = ctx->d_xp; a.xi_prev = ctx->d_xip; a.xi = ctx->d_xi; a.xi_ld = ctx->xi_ld;
   a.vals = ctx->d_A; a.b = ctx->d_b; a.n_failed = ctx->d_nfailed;   // A is overwritten block by block
-  a.emat = element_scratch(ctx);
-  if (!a.emat) return C8_ERR_CUDA;
+  if (!chunked_assembly(ctx, a)) {
+    a.emat = element_scratch(ctx);
+    if (!a.emat) return C8_ERR_CUDA;
+  }
   a.elements_done = ctx->ev_elements;
   ctx->kt->forward_jacobian(a, ctx->stream);
   C8_CUDA(ctx, cudaGetLastError());

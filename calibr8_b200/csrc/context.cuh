@@ -32,6 +32,17 @@ struct c8_ctx {
   double* d_emat = nullptr;    // element-matrix scratch [n_elems + 1][nx][nx]
   size_t emat_elems = 0;
   int emat_nx = 0;
+  // chunked forward assembly (args.h): plan + a scratch of one chunk
+  int chunk_elems = 0, n_chunks = 0;
+  int chunk_request = -1;     // c8_set_assembly_chunk: elements per chunk, 0 one pass, -1 default / C8_ASM_CHUNK
+  std::vector<int> h_cg_ptr, h_cg_end;   // entry range per chunk; end of the owned-row prefix
+  std::vector<unsigned> h_cg_blk;
+  int cg_end_rows = -1;                  // n_row_blocks the ends were computed for
+  int* d_cg_ptr = nullptr;
+  unsigned* d_cg_blk = nullptr;
+  int* d_cg_k = nullptr;
+  double* d_emat_chunk = nullptr;
+  int emat_chunk_nx = 0;
   long long xi_ld = 0;
   // partition (multi-GPU): local nodes [0, n_owned_nodes) are owned, the rest are ghosts; local
   // elements [0, n_owned_elems) are owned, the rest are halo elements computed redundantly
@@ -67,6 +78,8 @@ struct c8_ctx {
     m.n_row_nodes = n_owned_nodes;
     m.elem_es = d_elem_es; m.eoff = d_eoff; m.gptr = d_gptr; m.gsrc = d_gsrc; m.nnzb = nnzb;
     m.n_row_blocks = h_rowptr.empty() ? 0 : h_rowptr[n_owned_nodes];
+    m.chunk_elems = chunk_elems; m.n_chunks = n_chunks;
+    m.cg_ptr = d_cg_ptr; m.cg_blk = d_cg_blk; m.cg_k = d_cg_k;
     return m;
   }
 };
@@ -78,6 +91,8 @@ double* stage(c8_ctx* ctx, size_t bytes);
 double* pinned(c8_ctx* ctx, size_t bytes);
 int fetch_n_failed(c8_ctx* ctx, int* out);
 double* element_scratch(c8_ctx* ctx);
+// scratch + plan of the chunked forward assembly into a (fills emat, cg_ptr_host); false: not active
+bool chunked_assembly(c8_ctx* ctx, c8::FwdArgs& a);
 // eval_forward_jacobian on the resident state with HOST nodal buffers (c8_state_forward_jacobian)
 int forward_state_host(c8_ctx* ctx, const double* u, const double* p, double* b_u, double* b_p, int* n_failed);
 }  // namespace c8

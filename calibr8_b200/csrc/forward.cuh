@@ -267,8 +267,8 @@ struct Scatter {
   double bacc[NBACC];
   C8_DI void init() {
     constexpr int NX = C::NX;
-    if (a.vals != nullptr)
-      em = a.emat + size_t(on ? e : a.mesh.n_elems) * NX * NX + t * C::LX;
+    if (a.vals != nullptr)   // slot of the element in the scratch; the slot after the last one is the sink
+      em = a.emat + size_t(on ? e - a.elem_begin : a.elem_end - a.elem_begin) * NX * NX + t * C::LX;
 #pragma unroll
     for (int j = 0; j < NBACC; ++j) bacc[j] = 0.0;
   }
@@ -366,6 +366,37 @@ __global__ void k_bsr_gather(const int* __restrict__ gptr, const int* __restrict
   }
 }
 
+// Phase 2 for ONE CHUNK of elements [e0, e0 + chunk): every plan entry is a (block, contribution
+// range) pair of the chunk; the first chunk that touches a block overwrites it, later ones accumulate
+// (chunks run in element order and the contributions inside an entry are in element order, so the sum
+// has the same order as the one-pass gather: bit-identical values).  emat holds the chunk only.
+template <int NB, int NN>
+__global__ void k_bsr_gather_chunk(const unsigned* __restrict__ cblk, const int* __restrict__ ck,
+                                   const int* __restrict__ gsrc, const double* __restrict__ emat,
+                                   double* __restrict__ vals, int entry0, int n_entries, int e0) {
+  constexpr int BB = NB * NB, NX = NB * NN;
+  static_assert(NB % 2 == 0, "chunked gather: even block size");
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)n_entries * (BB / 2)) return;
+  const int en = entry0 + int(i / (BB / 2)), ent = int(i % (BB / 2)) * 2;
+  const int r = ent / NB, c = ent % NB;
+  const unsigned bw = __ldg(&cblk[en]);
+  const int blk = int(bw & 0x7fffffffu);
+  const bool first = (bw >> 31) != 0u;
+  double2* dst = reinterpret_cast<double2*>(vals + size_t(blk) * BB + ent);
+  double s0 = 0.0, s1 = 0.0;
+  if (!first) { const double2 v = *dst; s0 = v.x; s1 = v.y; }
+  const int k1 = __ldg(&ck[2 * en + 1]);
+  for (int k = __ldg(&ck[2 * en]); k < k1; ++k) {
+    const int q = __ldg(&gsrc[k]);
+    const int e = q / (NN * NN), rem = q - e * (NN * NN);
+    const int na = rem / NN, nb = rem - na * NN;
+    const double2 v = *reinterpret_cast<const double2*>(emat + size_t(e - e0) * NX * NX + (na * NB + r) * NX + nb * NB + c);
+    s0 += v.x; s1 += v.y;
+  }
+  *dst = make_double2(s0, s1);
+}
+
 // Optional per-phase cycle counters (tuning builds only: -DC8_K1_PHASE_CLOCKS)
 #ifdef C8_K1_PHASE_CLOCKS
 static __device__ unsigned long long g_k1_phase_clocks[8];
@@ -400,10 +431,10 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian(co
   constexpr int D = C::D, NN = C::NN, NB = C::NB, NXI = C::NXI, LX = C::LX, G = C::G;
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int t = gid % G;
-  const bool in_range = (gid / G) < a.mesh.n_elems;
+  const bool in_range = a.elem_begin + (gid / G) < a.elem_end;
   // out-of-range groups recompute the last element (no stores) so that every thread of the CTA
   // reaches the phase barriers below
-  const int e = in_range ? gid / G : a.mesh.n_elems - 1;
+  const int e = in_range ? a.elem_begin + gid / G : a.elem_end - 1;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane / G * G));
 
@@ -438,7 +469,7 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian(co
     // the element contributes nothing: clear its scratch slot, so that the gather does not sum stale
     // data of an earlier call into A when the caller ignores the status
     if (a.vals != nullptr) {
-      double* em = a.emat + size_t(e) * C::NX * C::NX + t * LX;
+      double* em = a.emat + size_t(e - a.elem_begin) * C::NX * C::NX + t * LX;
       for (int r = 0; r < C::NX; ++r)
         for (int s = 0; s < LX; ++s)
           if (t * LX + s < C::NX) em[r * C::NX + s] = 0.0;

@@ -55,6 +55,12 @@ const char* c8_version(void);
 int c8_set_mesh(c8_ctx* ctx, int dim, int n_elems, int n_nodes, const int32_t* conn_host,
                 const double* coords_host, const int32_t* elem_set_host, int n_elem_sets);
 
+/* Two-phase assembly of eval_forward_jacobian (scatter_lhs, global_residual.cpp:556-586): the element
+ * matrices of a CHUNK of elements go to a scratch that stays in L2 and are summed into the BSR blocks by
+ * the chunk's gather pass, chunk after chunk (bit-identical to one pass over the whole mesh).  Call before
+ * c8_set_mesh: elements per chunk (0 = one pass with a full-size scratch, -1 = default: $C8_ASM_CHUNK, else
+ * one pass -- measured faster on B200, profiles/README.md).  Meshes below two chunks use one pass. */
+int c8_set_assembly_chunk(c8_ctx* ctx, int chunk_elems);
 /* replaces create_global_residual / create_local_residual + LocalResidual::init_params;
  * params_host [n_elem_sets][npar] in the model's parameter order */
 int c8_set_model(c8_ctx* ctx, int global_type, int local_type, const double* params_host,

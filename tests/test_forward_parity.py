@@ -253,3 +253,53 @@ def test_tiny_and_ragged_meshes(n_elems):
             ref = rB["A"][i * 2 + j]
             assert np.abs(v - ref).max() < TOL * max(np.abs(ref).max(), 1e-300)
     ctx.close()
+
+
+@pytest.mark.parametrize("name,owned_frac", [("3d_hyper_J2", 1.0), ("3d_small_hill", 1.0), ("2d_small_hill_plane_stress", 1.0),
+                                             ("3d_small_J2", 0.6)])
+def test_chunked_assembly_is_bit_identical(name, owned_frac):
+    """The chunked two-phase assembly (element kernel + gather per chunk of elements, the chunk's element
+    matrices staying in L2) gives the SAME BITS as one pass over the whole mesh: chunks run in element
+    order and every block keeps its summation order.  Also with a partition's row filter (only the rows
+    of the leading `owned` nodes are assembled)."""
+    import torch
+    from calibr8_b200.capi import Context
+    from parity_common import LOCAL_TOL
+    dim, gtype, ltype, params, amp = COMBOS[name]
+    mesh = make_mesh(dim, "large")
+    (u1, p1), (u2, p2) = synthetic_fields(mesh, amp, gtype == "mechanics")
+    out = {}
+    for chunk in (0, 96, 400):
+        ctx = Context(0)
+        ctx.set_assembly_chunk(chunk)
+        ctx.set_mesh(mesh.dim, mesh.conn, mesh.coords)
+        ctx.set_model(gtype, ltype, params, **LOCAL_TOL)
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        if owned_frac < 1.0:   # a row filter as a partition sets it (no halo plan needed for the assembly)
+            n_own = int(mesh.n_nodes * owned_frac)
+            assert ctx.lib.c8_set_partition(ctx.h, n_own, mesh.n_elems) == 0
+        x, xp, x0 = ctx.alloc("x"), ctx.alloc("x"), ctx.alloc("x")
+        xi0, xip, xi = ctx.alloc("xi"), ctx.alloc("xi"), ctx.alloc("xi")
+        ctx.pack_x(u2, p2, x); ctx.pack_x(u1, p1, xp); ctx.init_xi(xi0); ctx.init_xi(xip)
+        assert ctx.forward_jacobian(xp, x0, xi0, xip, None, ctx.alloc("b")) == 0
+        res = []
+        for rep in range(2):      # twice: the second pass overwrites the first one's matrix
+            A, b = ctx.alloc("A"), ctx.alloc("b")
+            A.fill_(float("nan")); torch.cuda.synchronize()
+            xi.copy_(xip)
+            assert ctx.forward_jacobian(x, xp, xip, xi, A, b) == 0
+            torch.cuda.synchronize()
+            res.append((A.clone(), b.clone()))
+        n_rows = ctx.n_nodes if owned_frac == 1.0 else int(mesh.n_nodes * owned_frac)
+        rowptr, _ = ctx.bsr_pattern()
+        nvals = int(rowptr[n_rows]) * ctx.nb * ctx.nb
+        assert torch.equal(res[0][0][:nvals], res[1][0][:nvals])
+        assert not torch.isnan(res[0][0][:nvals]).any()
+        if owned_frac < 1.0:      # rows of the other nodes are left untouched
+            assert torch.isnan(res[0][0][nvals:]).all()
+        out[chunk] = (res[0][0][:nvals].clone(), res[0][1].clone())
+        ctx.close()
+    assert mesh.n_elems > 2 * 400
+    for chunk in (96, 400):
+        assert torch.equal(out[chunk][0], out[0][0]), chunk     # bit-identical matrix
+        assert torch.allclose(out[chunk][1], out[0][1], rtol=1e-13, atol=1e-16)   # residual: atomics order
