@@ -19,7 +19,7 @@ GLOBAL_TYPES = {"mechanics": 0, "mechanics_plane_stress": 1}
 LOCAL_TYPES = {
     "elastic": 0, "small_J2": 1, "small_hill": 2, "small_hill_plane_stress": 3,
     "hyper_J2": 4, "hyper_J2_plane_stress": 5, "small_hill_plane_strain": 6,
-    "hyper_J2_plane_strain": 7,
+    "hyper_J2_plane_strain": 7, "hypo_hill": 8, "hypo_hill_plane_strain": 9, "hypo_hill_plane_stress": 10,
 }
 # parameter order per model = LocalResidual::init_params of each reference model file
 PARAM_NAMES = {
@@ -31,6 +31,9 @@ PARAM_NAMES = {
     "hyper_J2": ["E", "nu", "Y", "S", "D", "A", "n", "K"],
     "hyper_J2_plane_stress": ["E", "nu", "Y", "S", "D", "A", "n", "K"],
     "hyper_J2_plane_strain": ["E", "nu", "K", "Y", "Y_inf", "delta"],
+    "hypo_hill": ["E", "nu", "Y", "R00", "R11", "R22", "R01", "R02", "R12", "S", "D"],
+    "hypo_hill_plane_strain": ["E", "nu", "Y", "S", "D", "R00", "R11", "R22", "R01"],
+    "hypo_hill_plane_stress": ["E", "nu", "Y", "S", "D", "R00", "R11", "R22", "R01", "Q00", "Q01", "Q10", "Q11"],
 }
 
 # every symbol include/c8b200.h declares (checked by tests/test_capi_symbols.py)

@@ -21,13 +21,17 @@ const KernelTable* table_2d_mixed_small_hill_pe();
 const KernelTable* table_2d_mixed_hyper_j2_pe();
 const KernelTable* table_2d_ps_small_hill();
 const KernelTable* table_2d_ps_hyper_j2();
+const KernelTable* table_3d_mixed_hypo_hill();
+const KernelTable* table_2d_mixed_hypo_hill_pe();
+const KernelTable* table_2d_ps_hypo_hill();
 
 const KernelTable* find_kernel_table(int dim, int mech, int local_type) {
   const KernelTable* all[] = {
       table_3d_mixed_elastic(),  table_3d_mixed_small_j2(),     table_3d_mixed_small_hill(),
       table_3d_mixed_hyper_j2(), table_2d_mixed_elastic(),      table_2d_mixed_small_j2(),
       table_2d_mixed_small_hill_pe(), table_2d_mixed_hyper_j2_pe(), table_2d_ps_small_hill(),
-      table_2d_ps_hyper_j2()};
+      table_2d_ps_hyper_j2(),    table_3d_mixed_hypo_hill(),    table_2d_mixed_hypo_hill_pe(),
+      table_2d_ps_hypo_hill()};
   for (const KernelTable* t : all)
     if (t->dim == dim && t->mech == mech && t->local_type == local_type) return t;
   return nullptr;

@@ -14,6 +14,9 @@
 //   HyperJ2               src/hyper_J2.cpp:136-360
 //   HyperJ2PlaneStress    src/hyper_J2_plane_stress.cpp:140-411
 //   HyperJ2PlaneStrain    src/hyper_J2_plane_strain.cpp:129-372
+//   HypoHill              src/hypo_hill.cpp:141-346, src/hypo_kinematics.hpp:10-17
+//   HypoHillPlaneStrain   src/hypo_hill_plane_strain.cpp:137-379
+//   HypoHillPlaneStress   src/hypo_hill_plane_stress.cpp:155-403
 // Packed xi order = the reference's residual order (sym tensor first, then scalars).
 #pragma once
 #include "tensor.cuh"
@@ -23,7 +26,7 @@ namespace c8 {
 enum LocalType {
   L_ELASTIC = 0, L_SMALL_J2 = 1, L_SMALL_HILL = 2, L_SMALL_HILL_PLANE_STRESS = 3,
   L_HYPER_J2 = 4, L_HYPER_J2_PLANE_STRESS = 5, L_SMALL_HILL_PLANE_STRAIN = 6,
-  L_HYPER_J2_PLANE_STRAIN = 7
+  L_HYPER_J2_PLANE_STRAIN = 7, L_HYPO_HILL = 8, L_HYPO_HILL_PLANE_STRAIN = 9, L_HYPO_HILL_PLANE_STRESS = 10
 };
 enum { PATH_ELASTIC = 0, PATH_PLASTIC = 1 };
 
@@ -863,6 +866,249 @@ struct HyperJ2PlaneStress {
     const R h = kappa / 2.0 * (J - 1.0 / J);
     sig(0, 0) += h; sig(1, 1) += h;
     return sig;
+  }
+  template <class TP> static C8_DI TP pscale(const TP*) { return conv<TP>(0.0); }
+};
+
+// =============================================================================
+// Hypoelastic Hill plasticity in the unrotated configuration: the local state is the unrotated Cauchy
+// stress TC (+ alpha), driven by the unrotated rate of deformation
+//   d = R^T sym((F - F_prev) F^-1) R,   R = polar_rotation(F)          src/hypo_kinematics.hpp:10-17
+// and the Cauchy stress handed to the mechanics residual is R TC R^T.
+template <int DIM, class TK, class TKP>
+C8_DI Mat<prom_t<TK, TKP>, DIM> unrotated_rate(const Kin<DIM, TK, TKP>& k) {
+  const Mat<TK, DIM> F = add_diag(k.gu, 1.0);
+  const Mat<TKP, DIM> Fp = add_diag(k.gup, 1.0);
+  const Mat<TK, DIM> Fi = inverse(F);
+  const Mat<TK, DIM> R = polar_rotation(F);
+  const auto Lv = (F - Fp) * Fi;
+  const auto Dm = scale(0.5, Lv + transpose(Lv));
+  return transpose(R) * Dm * R;
+}
+template <int DIM, class TK, class TX>
+C8_DI Mat<prom_t<TK, TX>, DIM> rotate_forward(const Mat<TK, DIM>& gu, const Mat<TX, DIM>& TC) {
+  const Mat<TK, DIM> R = polar_rotation(add_diag(gu, 1.0));
+  return R * TC * transpose(R);
+}
+
+template <int DIM>
+struct HypoHill {
+  static_assert(DIM == 3, "hypo_hill is a 3-D model");
+  static constexpr int NS = 6, NXI = 7, NPAR = 11, TYPE = L_HYPO_HILL;
+  static constexpr bool FINITE = true, HAS_NEWTON = true, PLANE_STRESS = false;
+  static constexpr bool ELASTIC_J_IDENTITY = false;   // the TC rows are scaled by 1 / mu
+  static constexpr int Z_STRETCH = -1;
+  static C8_DI void init(double* xi) {
+#pragma unroll
+    for (int i = 0; i < NXI; ++i) xi[i] = 0.0;
+  }
+  // elastic predictor, src/hypo_hill.cpp:163-177
+  template <class K> static C8_DI void guess(const K& k, const double* xip, const double* par, double, double* xi) {
+    const double lambda = lambda_of(par[0], par[1]), mu = mu_of(par[0], par[1]);
+    const Mat<double, 3> d = unrotated_rate<3>(k);
+    const double ltd = lambda * trace(d);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = i; j < 3; ++j)
+        xi[SymIdx<3>::idx(i, j)] = xip[SymIdx<3>::idx(i, j)] + (i == j ? ltd : 0.0) + 2.0 * mu * d.a[i][j];
+    xi[NS] = xip[NS];
+  }
+  template <class TK, class TKP, class TX, class TXP, class TP>
+  static C8_DI int residual(const Kin<3, TK, TKP>& k, const TX* xi, const TXP* xip, const TP* par,
+                            double abs_tol, prom5_t<TK, TKP, TX, TXP, TP>* C) {
+    using R = prom5_t<TK, TKP, TX, TXP, TP>;
+    const TP mu = mu_of(par[0], par[1]), lambda = lambda_of(par[0], par[1]);
+    const double imu = 1.0 / val(mu);
+    const Hill<TP> hp = hill_params(par[3], par[4], par[5], par[6], par[7], par[8]);
+    const Mat<TX, 3> TC = unpack_sym<TX, 3>(xi);
+    const auto hill = hill_value(TC, hp);
+    const auto sigma_yield = par[2] + par[9] * (1.0 - dexp(-par[10] * xi[NS]));
+    const auto f = (hill - sigma_yield) * imu;
+    const auto d = unrotated_rate<3>(k);
+    const auto ltd = lambda * trace(d);
+    const bool plastic = is_plastic(val(f), abs_tol);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = i; j < 3; ++j) {
+        const int q = SymIdx<3>::idx(i, j);
+        R r = conv<R>(xi[q] - xip[q] - 2.0 * mu * d.a[i][j]);
+        if (i == j) r -= ltd;
+        C[q] = r * imu;
+      }
+    if (plastic) {
+      const auto n = hill_normal(TC, hp, hill);
+      const auto dgam = xi[NS] - xip[NS];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = i; j < 3; ++j) {
+          const int q = SymIdx<3>::idx(i, j);
+          C[q] += conv<R>((2.0 * mu * dgam * n.a[i][j]) * imu);
+        }
+      C[NS] = conv<R>(f);
+      return PATH_PLASTIC;
+    }
+    C[NS] = conv<R>(xi[NS] - xip[NS]);
+    return PATH_ELASTIC;
+  }
+  template <class TK, class TKP, class TX, class TP>
+  static C8_DI Mat<prom3_t<TK, TX, TP>, 3> dev_cauchy(const Kin<3, TK, TKP>& k, const TX* xi, const TP*) {
+    return mat_conv<prom3_t<TK, TX, TP>>(dev(rotate_forward<3>(k.gu, unpack_sym<TX, 3>(xi))));
+  }
+  template <class TK, class TKP, class TX, class TP>
+  static C8_DI prom3_t<TK, TX, TP> hydro(const Kin<3, TK, TKP>& k, const TX* xi, const TP*) {
+    return conv<prom3_t<TK, TX, TP>>(trace(rotate_forward<3>(k.gu, unpack_sym<TX, 3>(xi))) / 3.0);
+  }
+  template <class TP> static C8_DI TP pscale(const TP* par) { return kappa_of(par[0], par[1]); }
+};
+
+// xi = TC(00,01,11), alpha, TC_zz ; params E, nu, Y, S, D, R00, R11, R22, R01 (R02 = R12 = 1)
+template <int DIM>
+struct HypoHillPlaneStrain {
+  static_assert(DIM == 2, "plane strain is 2-D");
+  static constexpr int NS = 3, NXI = 5, NPAR = 9, TYPE = L_HYPO_HILL_PLANE_STRAIN;
+  static constexpr bool FINITE = true, HAS_NEWTON = true, PLANE_STRESS = false;
+  static constexpr bool ELASTIC_J_IDENTITY = true;    // no 1 / mu scaling in this variant
+  static constexpr int Z_STRETCH = -1;
+  static C8_DI void init(double* xi) {
+#pragma unroll
+    for (int i = 0; i < NXI; ++i) xi[i] = 0.0;
+  }
+  template <class K> static C8_DI void guess(const K& k, const double* xip, const double* par, double, double* xi) {
+    const double lambda = lambda_of(par[0], par[1]), mu = mu_of(par[0], par[1]);
+    const Mat<double, 2> d = unrotated_rate<2>(k);
+    const double ltd = lambda * trace(d);
+    xi[0] = xip[0] + ltd + 2.0 * mu * d(0, 0);
+    xi[1] = xip[1] + 2.0 * mu * d(0, 1);
+    xi[2] = xip[2] + ltd + 2.0 * mu * d(1, 1);
+    xi[3] = xip[3];
+    xi[4] = xip[4] + ltd;
+  }
+  template <class TK, class TKP, class TX, class TXP, class TP>
+  static C8_DI int residual(const Kin<2, TK, TKP>& k, const TX* xi, const TXP* xip, const TP* par,
+                            double abs_tol, prom5_t<TK, TKP, TX, TXP, TP>* C) {
+    using R = prom5_t<TK, TKP, TX, TXP, TP>;
+    const TP mu = mu_of(par[0], par[1]), lambda = lambda_of(par[0], par[1]);
+    const TP one = conv<TP>(1.0);
+    const Hill<TP> hp = hill_params(par[5], par[6], par[7], par[8], one, one);
+    Mat<TX, 3> TC3 = embed3(unpack_sym<TX, 2>(xi));
+    TC3(2, 2) = xi[4];
+    const auto phi = hill_value(TC3, hp);
+    const auto sigma_yield = par[2] + par[3] * (1.0 - dexp(-par[4] * xi[3]));
+    const auto f = (phi - sigma_yield) / val(mu);
+    const auto d = unrotated_rate<2>(k);
+    const auto ltd = lambda * trace(d);
+    C[0] = conv<R>(xi[0] - xip[0] - ltd - 2.0 * mu * d(0, 0));
+    C[1] = conv<R>(xi[1] - xip[1] - 2.0 * mu * d(0, 1));
+    C[2] = conv<R>(xi[2] - xip[2] - ltd - 2.0 * mu * d(1, 1));
+    C[4] = conv<R>(xi[4] - xip[4] - ltd);
+    if (is_plastic(val(f), abs_tol)) {
+      const auto n = hill_normal(TC3, hp, phi);
+      const auto dgam = xi[3] - xip[3];
+      const auto tm = 2.0 * mu * dgam;
+      C[0] += conv<R>(tm * n(0, 0));
+      C[1] += conv<R>(tm * n(0, 1));
+      C[2] += conv<R>(tm * n(1, 1));
+      C[4] += conv<R>(tm * (-(n(0, 0) + n(1, 1))));
+      C[3] = conv<R>(f);
+      return PATH_PLASTIC;
+    }
+    C[3] = conv<R>(xi[3] - xip[3]);
+    return PATH_ELASTIC;
+  }
+  // hydro = (tr(R TC R^T) + TC_zz) / 3 ; dev = R TC R^T - hydro I, src/hypo_hill_plane_strain.cpp:351-371
+  template <class TK, class TKP, class TX, class TP>
+  static C8_DI Mat<prom3_t<TK, TX, TP>, 2> dev_cauchy(const Kin<2, TK, TKP>& k, const TX* xi, const TP*) {
+    using R = prom3_t<TK, TX, TP>;
+    Mat<R, 2> rc = mat_conv<R>(rotate_forward<2>(k.gu, unpack_sym<TX, 2>(xi)));
+    const R h = (trace(rc) + xi[4]) / 3.0;
+    rc(0, 0) -= h; rc(1, 1) -= h;
+    return rc;
+  }
+  template <class TK, class TKP, class TX, class TP>
+  static C8_DI prom3_t<TK, TX, TP> hydro(const Kin<2, TK, TKP>& k, const TX* xi, const TP*) {
+    using R = prom3_t<TK, TX, TP>;
+    const Mat<R, 2> rc = mat_conv<R>(rotate_forward<2>(k.gu, unpack_sym<TX, 2>(xi)));
+    return (trace(rc) + xi[4]) / 3.0;
+  }
+  template <class TP> static C8_DI TP pscale(const TP* par) { return kappa_of(par[0], par[1]); }
+};
+
+// xi = TC(00,01,11), alpha, lambda_z ; params E, nu, Y, S, D, R00, R11, R22, R01, Q00, Q01, Q10, Q11
+template <int DIM>
+struct HypoHillPlaneStress {
+  static_assert(DIM == 2, "plane stress is 2-D");
+  static constexpr int NS = 3, NXI = 5, NPAR = 13, TYPE = L_HYPO_HILL_PLANE_STRESS;
+  static constexpr bool FINITE = true, HAS_NEWTON = true, PLANE_STRESS = true;
+  static constexpr bool ELASTIC_J_IDENTITY = true;    // elastic branch: unscaled rows, C = xi - g(xi_prev, F)
+  static constexpr int Z_STRETCH = 4;
+  static C8_DI void init(double* xi) { xi[0] = xi[1] = xi[2] = xi[3] = 0.0; xi[4] = 1.0; }
+  template <class TP> static C8_DI Mat<TP, 2> frame(const TP* par) {
+    Mat<TP, 2> Q;
+    Q(0, 0) = par[9]; Q(0, 1) = par[10]; Q(1, 0) = par[11]; Q(1, 1) = par[12];
+    return Q;
+  }
+  // d = Q^T R^T D R Q, src/hypo_hill_plane_stress.cpp:165-179
+  template <class TK, class TKP, class TP>
+  static C8_DI Mat<prom3_t<TK, TKP, TP>, 2> eval_d(const Kin<2, TK, TKP>& k, const TP* par) {
+    const Mat<TP, 2> Q = frame(par);
+    return mat_conv<prom3_t<TK, TKP, TP>>(transpose(Q) * unrotated_rate<2>(k) * Q);
+  }
+  template <class K> static C8_DI void guess(const K& k, const double* xip, const double* par, double, double* xi) {
+    const double lambda = lambda_of(par[0], par[1]), mu = mu_of(par[0], par[1]);
+    const Mat<double, 2> d = eval_d(k, par);
+    const double d_zz = -lambda * trace(d) / (lambda + 2.0 * mu);
+    const double l = lambda * (trace(d) + d_zz);
+    xi[0] = xip[0] + l + 2.0 * mu * d(0, 0);
+    xi[1] = xip[1] + 2.0 * mu * d(0, 1);
+    xi[2] = xip[2] + l + 2.0 * mu * d(1, 1);
+    xi[3] = xip[3];
+    xi[4] = xip[4] / (1.0 - d_zz);
+  }
+  template <class TK, class TKP, class TX, class TXP, class TP>
+  static C8_DI int residual(const Kin<2, TK, TKP>& k, const TX* xi, const TXP* xip, const TP* par,
+                            double abs_tol, prom5_t<TK, TKP, TX, TXP, TP>* C) {
+    using R = prom5_t<TK, TKP, TX, TXP, TP>;
+    const TP mu = mu_of(par[0], par[1]), lambda = lambda_of(par[0], par[1]);
+    const TP one = conv<TP>(1.0);
+    const Hill<TP> hp = hill_params(par[5], par[6], par[7], par[8], one, one);
+    const Mat<TX, 3> TC3 = embed3(unpack_sym<TX, 2>(xi));
+    const auto phi = hill_value(TC3, hp);
+    const auto sigma_yield = par[2] + par[3] * (1.0 - dexp(-par[4] * xi[3]));
+    const auto f = (phi - sigma_yield) / val(mu);
+    const auto d = eval_d(k, par);
+    const auto d_zz = -lambda * trace(d) / (lambda + 2.0 * mu);
+    const auto l = lambda * (trace(d) + d_zz);
+    C[0] = conv<R>(xi[0] - xip[0] - l - 2.0 * mu * d(0, 0));
+    C[1] = conv<R>(xi[1] - xip[1] - 2.0 * mu * d(0, 1));
+    C[2] = conv<R>(xi[2] - xip[2] - l - 2.0 * mu * d(1, 1));
+    if (is_plastic(val(f), abs_tol)) {
+      const auto n = hill_normal(TC3, hp, phi);
+      const auto dgam = xi[3] - xip[3];
+      const auto dp_zz = -(dgam * n(0, 0) + dgam * n(1, 1));
+      const auto corr = 2.0 * mu * dp_zz / (2.0 * mu + lambda);   // return-map correction of d_zz
+      const double imu = 1.0 / val(mu);
+      // the (unforced) plastic branch alone scales the TC rows by 1 / val(mu), :321
+      C[0] = conv<R>((C[0] + 2.0 * mu * (dgam * n(0, 0)) - lambda * corr) * imu);
+      C[1] = conv<R>((C[1] + 2.0 * mu * (dgam * n(0, 1))) * imu);
+      C[2] = conv<R>((C[2] + 2.0 * mu * (dgam * n(1, 1)) - lambda * corr) * imu);
+      C[3] = conv<R>(f);
+      C[4] = conv<R>(xi[4] - xip[4] / (1.0 - (d_zz + corr)));
+      return PATH_PLASTIC;
+    }
+    C[3] = conv<R>(xi[3] - xip[3]);
+    C[4] = conv<R>(xi[4] - xip[4] / (1.0 - d_zz));
+    return PATH_ELASTIC;
+  }
+  // sigma = R Q TC Q^T R^T, :366-382
+  template <class TK, class TKP, class TX, class TP>
+  static C8_DI Mat<prom3_t<TK, TX, TP>, 2> cauchy(const Kin<2, TK, TKP>& k, const TX* xi, const TP* par) {
+    using R = prom3_t<TK, TX, TP>;
+    const Mat<TP, 2> Q = frame(par);
+    const auto core = Q * unpack_sym<TX, 2>(xi) * transpose(Q);
+    return mat_conv<R>(rotate_forward<2>(k.gu, core));
   }
   template <class TP> static C8_DI TP pscale(const TP*) { return conv<TP>(0.0); }
 };

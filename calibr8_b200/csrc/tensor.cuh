@@ -160,6 +160,86 @@ template <class T, int N, class S> C8_DI Mat<T, N> add_diag(const Mat<T, N>& A, 
   return r;
 }
 
+// ---- minitensor::polar_rotation (Trilinos MiniTensor, not vendored in the reference tree) ----------
+// |x| and max(a, b) on the value part, derivatives of the selected operand (Sacado's semantics)
+C8_DI double dabs(double a) { return fabs(a); }
+template <int L> C8_DI Dual<L> dabs(const Dual<L>& a) { return a.v >= 0.0 ? a : -a; }
+template <class T> C8_DI T tmax(const T& a, const T& b) { return val(a) >= val(b) ? a : b; }
+// max absolute column sum / max absolute row sum
+template <class T, int N> C8_DI T norm_1(const Mat<T, N>& A) {
+  T best = dabs(A.a[0][0]);
+#pragma unroll
+  for (int i = 1; i < N; ++i) best += dabs(A.a[i][0]);
+#pragma unroll
+  for (int j = 1; j < N; ++j) {
+    T s = dabs(A.a[0][j]);
+#pragma unroll
+    for (int i = 1; i < N; ++i) s += dabs(A.a[i][j]);
+    best = tmax(best, s);
+  }
+  return best;
+}
+template <class T, int N> C8_DI T norm_infinity(const Mat<T, N>& A) {
+  T best = dabs(A.a[0][0]);
+#pragma unroll
+  for (int j = 1; j < N; ++j) best += dabs(A.a[0][j]);
+#pragma unroll
+  for (int i = 1; i < N; ++i) {
+    T s = dabs(A.a[i][0]);
+#pragma unroll
+    for (int j = 1; j < N; ++j) s += dabs(A.a[i][j]);
+    best = tmax(best, s);
+  }
+  return best;
+}
+template <class T, int N> C8_DI double frob_val(const Mat<T, N>& A) {
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) s += val(A.a[i][j]) * val(A.a[i][j]);
+  return sqrt(s);
+}
+// Rotation R of the polar decomposition A = R U by Higham's scaled Newton iteration
+//   X <- 1/2 (mu X + X^-T / mu),  mu = ((|Y|_1 |Y|_inf) / (|X|_1 |X|_inf))^(1/4),  Y = X^-1,
+// scaling switched off once the relative change drops below 0.01, left when |Z - X|_F <= sqrt(sqrt(N) eps)
+// or the change stops decreasing.  The reference evaluates it in its AD scalar (src/global_residual.hpp:
+// 302-305, src/hypo_hill_plane_stress.cpp:174), so dR/dF is the derivative OF THE TRUNCATED ITERATION; the
+// same iteration is therefore run here in Dual<L> (control flow on the value part, identical in every
+// thread of a group), not replaced by the closed-form derivative of the exact rotation.
+template <class T, int N> C8_DI Mat<T, N> polar_rotation(const Mat<T, N>& A) {
+  bool scale = true;
+  const double tol_scale = 0.01;
+  const double sqrt_tol_conv = sqrt(sqrt(double(N)) * 2.220446049250313e-16);
+  Mat<T, N> X = A;
+  double gamma = 2.0;
+#pragma unroll 1
+  for (int it = 0; it < 128; ++it) {
+    const Mat<T, N> Y = inverse(X);
+    T mu = conv<T>(1.0);
+    if (scale) mu = dsqrt(dsqrt((norm_1(Y) * norm_infinity(Y)) / (norm_1(X) * norm_infinity(X))));
+    const T imu = 1.0 / mu;
+    Mat<T, N> Z;
+    double nD2 = 0.0, nZ2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        Z.a[i][j] = 0.5 * (mu * X.a[i][j] + Y.a[j][i] * imu);
+        const double dz = val(Z.a[i][j]) - val(X.a[i][j]);
+        nD2 += dz * dz;
+        nZ2 += val(Z.a[i][j]) * val(Z.a[i][j]);
+      }
+    const double nD = sqrt(nD2), delta = nD / sqrt(nZ2);
+    if (scale && delta < tol_scale) scale = false;
+    const bool end_iter = nD <= sqrt_tol_conv || (delta > 0.5 * gamma && !scale);
+    X = Z;
+    gamma = delta;
+    if (end_iter) break;
+  }
+  return X;
+}
+
 // packed symmetric storage order of the reference (src/local_residual.cpp:196-218):
 // 3-D (00,01,02,11,12,22), 2-D (00,01,11)
 template <int DIM> struct SymIdx;

@@ -73,9 +73,24 @@ inline LocalResidual create_local_residual(const std::string& type, int ndims) {
     r.c8_type = C8_HYPER_J2_PLANE_STRAIN; r.finite_deformation = true;
     add("zeta", SYM_TENSOR); add("Ie", SCALAR); add("alpha", SCALAR);
     r.param_names = {"E", "nu", "K", "Y", "Y_inf", "delta"};
+  } else if (type == "hypo_hill") {                      // src/hypo_hill.cpp:43-70
+    r.c8_type = C8_HYPO_HILL; r.finite_deformation = true;
+    add("TC", SYM_TENSOR); add("alpha", SCALAR);
+    r.param_names = {"E", "nu", "Y", "R00", "R11", "R22", "R01", "R02", "R12", "S", "D"};
+  } else if (type == "hypo_hill_plane_strain") {         // src/hypo_hill_plane_strain.cpp:40-73
+    r.c8_type = C8_HYPO_HILL_PLANE_STRAIN; r.finite_deformation = true;
+    add("TC", SYM_TENSOR); add("alpha", SCALAR); add("TC_zz", SCALAR);
+    r.param_names = {"E", "nu", "Y", "S", "D", "R00", "R11", "R22", "R01"};
+  } else if (type == "hypo_hill_plane_stress") {         // src/hypo_hill_plane_stress.cpp:44-77
+    r.c8_type = C8_HYPO_HILL_PLANE_STRESS; r.finite_deformation = true;
+    add("TC", SYM_TENSOR); add("alpha", SCALAR); add("lambda_z", SCALAR);
+    r.z_stretch_idx = 2;
+    r.param_names = {"E", "nu", "Y", "S", "D", "R00", "R11", "R22", "R01", "Q00", "Q01", "Q10", "Q11"};
   } else {
     throw std::runtime_error("create_local_residual: type '" + type + "' is not in the hot-path scope");
   }
+  if ((type == "small_hill" || type == "hypo_hill") && ndims != 3)
+    throw std::runtime_error("create_local_residual: " + type + " needs a 3-D mesh");
   if ((type.find("plane") != std::string::npos) && ndims != 2)
     throw std::runtime_error("create_local_residual: " + type + " needs a 2-D mesh");
   return r;

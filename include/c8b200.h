@@ -44,6 +44,9 @@ typedef struct c8_ctx c8_ctx;
 #define C8_HYPER_J2_PLANE_STRESS 5
 #define C8_SMALL_HILL_PLANE_STRAIN 6
 #define C8_HYPER_J2_PLANE_STRAIN 7
+#define C8_HYPO_HILL 8              /* hypo_hill.cpp, 3-D */
+#define C8_HYPO_HILL_PLANE_STRAIN 9 /* hypo_hill_plane_strain.cpp */
+#define C8_HYPO_HILL_PLANE_STRESS 10 /* hypo_hill_plane_stress.cpp */
 
 /* ---- context / discretisation (replaces Disc::build_data, disc.cpp:563-583) ---- */
 c8_ctx* c8_create(int device);

@@ -837,11 +837,346 @@ class HyperJ2PlaneStrain : public LocalResidual<T> {
   }
 };
 
+// ---------------------------------------------------------------------------
+// src/hypo_kinematics.hpp:10-17
+template <class T>
+Tensor<T> compute_unrotated_rate_of_deformation(Tensor<T> const& F, Tensor<T> const& F_prev,
+                                                Tensor<T> const& R) {
+  Tensor<T> const Finv = inverse(F);
+  Tensor<T> const L = (F - F_prev) * Finv;
+  Tensor<T> const D = 0.5 * (L + transpose(L));
+  return transpose(R) * D * R;
+}
+
+// src/hypo_hill.cpp (3-D): unrotated Cauchy stress TC (sym) + alpha; Hill-48 yield on TC
+template <class T>
+class HypoHill : public LocalResidual<T> {
+ public:
+  explicit HypoHill(int ndims) {
+    this->m_num_residuals = 2;
+    this->m_num_eqs = {get_num_eqs(SYM_TENSOR, ndims), 1};
+    this->m_var_types = {SYM_TENSOR, SCALAR};
+  }
+  void init_variables_impl() override {   // :127-139
+    this->set_sym_tensor_xi(0, zero<T>(this->m_num_dims));
+    this->set_scalar_xi(1, T(0.));
+  }
+  Tensor<T> eval_d(GlobalResidual<T>& g) {   // :141-147
+    if (m_kinematics_cached) return m_d;
+    return compute_unrotated_rate_of_deformation(g.F(), g.F_prev(), g.R());
+  }
+  int solve_nonlinear(GlobalResidual<T>& g) override {   // :155-226
+    m_d = eval_d(g);
+    m_kinematics_cached = true;
+    {
+      double const E = val(this->m_params[0]), nu = val(this->m_params[1]);
+      double const lambda = compute_lambda(E, nu), mu = compute_mu(E, nu);
+      Tensor<T> const I = eye<T>(this->m_num_dims);
+      Tensor<T> const TC_old = this->sym_tensor_xi_prev(0);
+      T const alpha_old = this->scalar_xi_prev(1);
+      Tensor<T> const d = eval_d(g);
+      Tensor<T> const TC = TC_old + (lambda * trace(d)) * I + (2. * mu) * d;
+      this->set_sym_tensor_xi(0, TC);
+      this->set_scalar_xi(1, alpha_old);
+    }
+    int const path = this->newton(g);
+    m_kinematics_cached = false;
+    return path;
+  }
+  int evaluate(GlobalResidual<T>& g, bool force_path, int path_in) override {   // :233-310
+    int path = this->ELASTIC;
+    T const E = this->m_params[0], nu = this->m_params[1], Y = this->m_params[2];
+    T const R00 = this->m_params[3], R11 = this->m_params[4], R22 = this->m_params[5];
+    T const R01 = this->m_params[6], R02 = this->m_params[7], R12 = this->m_params[8];
+    T const S = this->m_params[9], D = this->m_params[10];
+    T const lambda = compute_lambda(E, nu), mu = compute_mu(E, nu);
+    HillParams<T> const hp = compute_hill_params(R00, R11, R22, R01, R02, R12);
+    Tensor<T> const TC_old = this->sym_tensor_xi_prev(0);
+    T const alpha_old = this->scalar_xi_prev(1);
+    Tensor<T> const TC = this->sym_tensor_xi(0);
+    T const alpha = this->scalar_xi(1);
+    T const hill = compute_hill_value(TC, hp);
+    T const sigma_yield = Y + S * (1. - exp(-D * alpha));
+    T const f = (hill - sigma_yield) / val(mu);
+    Tensor<T> const I = eye<T>(this->m_num_dims);
+    Tensor<T> const d = eval_d(g);
+    Tensor<T> R_TC = TC - TC_old - (lambda * trace(d)) * I - (2. * mu) * d;
+    R_TC = R_TC / val(mu);
+    T R_alpha;
+    bool plastic;
+    if (!force_path) plastic = (f > this->m_abs_tol || std::abs(val(f)) < this->m_abs_tol);
+    else plastic = (path_in == this->PLASTIC);
+    if (plastic) {
+      T const dgam = alpha - alpha_old;
+      Tensor<T> const n = compute_hill_normal(TC, hp, hill);
+      R_TC = R_TC + ((2. * mu * dgam) * n) / val(mu);
+      R_alpha = f;
+      path = this->PLASTIC;
+    } else {
+      R_alpha = alpha - alpha_old;
+      path = this->ELASTIC;
+    }
+    this->set_sym_tensor_R(0, R_TC);
+    this->set_scalar_R(1, R_alpha);
+    return path;
+  }
+  bool is_finite_deformation() override { return true; }
+  Tensor<T> rotated_cauchy(GlobalResidual<T>& g) {   // :312-318
+    Tensor<T> const TC = this->sym_tensor_xi(0);
+    Tensor<T> const R = g.R();
+    return R * TC * transpose(R);
+  }
+  Tensor<T> cauchy(GlobalResidual<T>& g) override {   // :320-329
+    T const p = g.scalar_x(1);
+    Tensor<T> const I = eye<T>(this->m_num_dims);
+    return this->dev_cauchy(g) - p * I;
+  }
+  Tensor<T> dev_cauchy(GlobalResidual<T>& g) override { return dev(rotated_cauchy(g)); }   // :331-335
+  T hydro_cauchy(GlobalResidual<T>& g) override { return trace(rotated_cauchy(g)) / 3.; }  // :337-340
+  T pressure_scale_factor() override { return compute_kappa(this->m_params[0], this->m_params[1]); }
+
+ private:
+  Tensor<T> m_d;
+  bool m_kinematics_cached = false;
+};
+
+// src/hypo_hill_plane_strain.cpp:135-384: xi = TC (2-D sym), alpha, TC_zz; mixed u-p mechanics
+template <class T>
+Tensor<T> hypo_eval_d_2D(GlobalResidual<T>& g) {   // src/hypo_hill_plane_strain.cpp:137-151
+  Tensor<T> const I = eye<T>(g.num_dims());
+  Tensor<T> const F = g.grad_vector_x(0) + I;
+  Tensor<T> const F_prev = g.grad_vector_x_prev(0) + I;
+  Tensor<T> const Finv = inverse(F);
+  Tensor<T> const R = polar_rotation(F);
+  Tensor<T> const L = (F - F_prev) * Finv;
+  Tensor<T> const D = 0.5 * (L + transpose(L));
+  return transpose(R) * D * R;
+}
+
+template <class T>
+class HypoHillPlaneStrain : public LocalResidual<T> {
+ public:
+  explicit HypoHillPlaneStrain(int ndims) {
+    this->m_num_residuals = 3;
+    this->m_num_eqs = {get_num_eqs(SYM_TENSOR, ndims), 1, 1};
+    this->m_var_types = {SYM_TENSOR, SCALAR, SCALAR};
+  }
+  void init_variables_impl() override {
+    this->set_sym_tensor_xi(0, zero<T>(this->m_num_dims));
+    this->set_scalar_xi(1, T(0.));
+    this->set_scalar_xi(2, T(0.));
+  }
+  int solve_nonlinear(GlobalResidual<T>& g) override {   // :158-218
+    double const E = val(this->m_params[0]), nu = val(this->m_params[1]);
+    double const lambda = compute_lambda(E, nu), mu = compute_mu(E, nu);
+    Tensor<T> const I = eye<T>(this->m_num_dims);
+    Tensor<T> const TC_old = this->sym_tensor_xi_prev(0);
+    T const alpha_old = this->scalar_xi_prev(1);
+    T const TC_zz_old = this->scalar_xi_prev(2);
+    Tensor<T> const d = hypo_eval_d_2D(g);
+    Tensor<T> const TC = TC_old + (lambda * trace(d)) * I + (2. * mu) * d;
+    T const TC_zz = TC_zz_old + lambda * trace(d);
+    this->set_sym_tensor_xi(0, TC);
+    this->set_scalar_xi(1, alpha_old);
+    this->set_scalar_xi(2, TC_zz);
+    return this->newton(g);
+  }
+  int evaluate(GlobalResidual<T>& g, bool force_path, int path_in) override {   // :225-325
+    int path = this->ELASTIC;
+    T const E = this->m_params[0], nu = this->m_params[1], Y = this->m_params[2];
+    T const S = this->m_params[3], D = this->m_params[4];
+    T const R00 = this->m_params[5], R11 = this->m_params[6], R22 = this->m_params[7], R01 = this->m_params[8];
+    T const lambda = compute_lambda(E, nu), mu = compute_mu(E, nu);
+    Tensor<T> const TC_old = this->sym_tensor_xi_prev(0);
+    T const alpha_old = this->scalar_xi_prev(1);
+    T const TC_zz_old = this->scalar_xi_prev(2);
+    Tensor<T> const TC = this->sym_tensor_xi(0);
+    T const alpha = this->scalar_xi(1);
+    T const TC_zz = this->scalar_xi(2);
+    Tensor<T> TC_3D = insert_2D_tensor_into_3D(TC);
+    TC_3D(2, 2) = TC_zz;
+    T const R02 = T(1.), R12 = T(1.);
+    HillParams<T> const hp = compute_hill_params(R00, R11, R22, R01, R02, R12);
+    T const phi = compute_hill_value(TC_3D, hp);
+    T const sigma_yield = Y + S * (1. - exp(-D * alpha));
+    T const f = (phi - sigma_yield) / val(mu);
+    Tensor<T> const I = eye<T>(this->m_num_dims);
+    Tensor<T> const d = hypo_eval_d_2D(g);
+    Tensor<T> R_TC = TC - TC_old - (lambda * trace(d)) * I - (2. * mu) * d;
+    T R_TC_zz = TC_zz - TC_zz_old - lambda * trace(d);
+    T R_alpha;
+    bool plastic;
+    if (!force_path) plastic = (f > this->m_abs_tol || std::abs(val(f)) < this->m_abs_tol);
+    else plastic = (path_in == this->PLASTIC);
+    if (plastic) {
+      Tensor<T> const n_3D = compute_hill_normal(TC_3D, hp, phi);
+      Tensor<T> const n_2D = extract_2D_tensor_from_3D(n_3D);
+      T const dgam = alpha - alpha_old;
+      Tensor<T> const dp_2D = dgam * n_2D;
+      T const dp_zz = -trace(dp_2D);
+      R_TC = R_TC + (2. * mu) * dp_2D;
+      R_alpha = f;
+      R_TC_zz = R_TC_zz + 2. * mu * dp_zz;
+      path = this->PLASTIC;
+    } else {
+      R_alpha = alpha - alpha_old;
+      path = this->ELASTIC;
+    }
+    this->set_sym_tensor_R(0, R_TC);
+    this->set_scalar_R(1, R_alpha);
+    this->set_scalar_R(2, R_TC_zz);
+    return path;
+  }
+  bool is_finite_deformation() override { return true; }
+  Tensor<T> rotated_cauchy(GlobalResidual<T>& g) {   // :327-337
+    Tensor<T> const I = eye<T>(this->m_num_dims);
+    Tensor<T> const F = g.grad_vector_x(0) + I;
+    Tensor<T> const TC = this->sym_tensor_xi(0);
+    Tensor<T> const R = polar_rotation(F);
+    return R * TC * transpose(R);
+  }
+  Tensor<T> cauchy(GlobalResidual<T>& g) override {   // :339-349
+    T const p = g.scalar_x(1);
+    Tensor<T> const I = eye<T>(this->m_num_dims);
+    return this->dev_cauchy(g) - p * I;
+  }
+  Tensor<T> dev_cauchy(GlobalResidual<T>& g) override {   // :351-359
+    Tensor<T> const RC = rotated_cauchy(g);
+    Tensor<T> const I = eye<T>(this->m_num_dims);
+    return RC - this->hydro_cauchy(g) * I;
+  }
+  T hydro_cauchy(GlobalResidual<T>& g) override {   // :361-366
+    Tensor<T> const RC = rotated_cauchy(g);
+    return (trace(RC) + this->scalar_xi(2)) / 3.;
+  }
+  T pressure_scale_factor() override { return compute_kappa(this->m_params[0], this->m_params[1]); }
+};
+
+// src/hypo_hill_plane_stress.cpp:138-408: xi = TC (2-D sym), alpha, lambda_z; single-field plane-stress
+// mechanics; material frame Q (params 9-12).  NB the unforced plastic branch alone divides R_TC by val(mu)
+// (:321); the elastic branch leaves it unscaled -- restated as written.
+template <class T>
+class HypoHillPlaneStress : public LocalResidual<T> {
+ public:
+  explicit HypoHillPlaneStress(int ndims) {
+    this->m_num_residuals = 3;
+    this->m_num_eqs = {get_num_eqs(SYM_TENSOR, ndims), 1, 1};
+    this->m_var_types = {SYM_TENSOR, SCALAR, SCALAR};
+    this->m_z_stretch_idx = 2;
+  }
+  void init_variables_impl() override {
+    this->set_sym_tensor_xi(0, zero<T>(this->m_num_dims));
+    this->set_scalar_xi(1, T(0.));
+    this->set_scalar_xi(2, T(1.));
+  }
+  Tensor<T> compute_Q() {   // :155-163
+    Tensor<T> Q = zero<T>(this->m_num_dims);
+    Q(0, 0) = this->m_params[9]; Q(0, 1) = this->m_params[10];
+    Q(1, 0) = this->m_params[11]; Q(1, 1) = this->m_params[12];
+    return Q;
+  }
+  Tensor<T> eval_d(GlobalResidual<T>& g, Tensor<T> const& Q) {   // :165-179
+    Tensor<T> const I = eye<T>(g.num_dims());
+    Tensor<T> const F = g.grad_vector_x(0) + I;
+    Tensor<T> const F_prev = g.grad_vector_x_prev(0) + I;
+    Tensor<T> const Finv = inverse(F);
+    Tensor<T> const R = polar_rotation(F);
+    Tensor<T> const L = (F - F_prev) * Finv;
+    Tensor<T> const D = 0.5 * (L + transpose(L));
+    return transpose(Q) * transpose(R) * D * R * Q;
+  }
+  int solve_nonlinear(GlobalResidual<T>& g) override {   // :186-250
+    double const E = val(this->m_params[0]), nu = val(this->m_params[1]);
+    double const lambda = compute_lambda(E, nu), mu = compute_mu(E, nu);
+    Tensor<T> const I = eye<T>(this->m_num_dims);
+    Tensor<T> const TC_old = this->sym_tensor_xi_prev(0);
+    T const alpha_old = this->scalar_xi_prev(1);
+    T const lambda_z_old = this->scalar_xi_prev(2);
+    Tensor<T> const Q = compute_Q();
+    Tensor<T> const d = eval_d(g, Q);
+    T const d_zz = -lambda * trace(d) / (lambda + 2. * mu);
+    Tensor<T> const TC = TC_old + (lambda * (trace(d) + d_zz)) * I + (2. * mu) * d;
+    T const lambda_z = lambda_z_old / (1. - d_zz);
+    this->set_sym_tensor_xi(0, TC);
+    this->set_scalar_xi(1, alpha_old);
+    this->set_scalar_xi(2, lambda_z);
+    return this->newton(g);
+  }
+  int evaluate(GlobalResidual<T>& g, bool force_path, int path_in) override {   // :257-364
+    int path = this->ELASTIC;
+    T const E = this->m_params[0], nu = this->m_params[1], Y = this->m_params[2];
+    T const S = this->m_params[3], D = this->m_params[4];
+    T const R00 = this->m_params[5], R11 = this->m_params[6], R22 = this->m_params[7], R01 = this->m_params[8];
+    T const lambda = compute_lambda(E, nu), mu = compute_mu(E, nu);
+    Tensor<T> const TC_old = this->sym_tensor_xi_prev(0);
+    T const alpha_old = this->scalar_xi_prev(1);
+    T const lambda_z_old = this->scalar_xi_prev(2);
+    Tensor<T> const TC = this->sym_tensor_xi(0);
+    T const alpha = this->scalar_xi(1);
+    T const lambda_z = this->scalar_xi(2);
+    Tensor<T> TC_3D = insert_2D_tensor_into_3D(TC);
+    T const R02 = T(1.), R12 = T(1.);
+    HillParams<T> const hp = compute_hill_params(R00, R11, R22, R01, R02, R12);
+    T const phi = compute_hill_value(TC_3D, hp);
+    T const sigma_yield = Y + S * (1. - exp(-D * alpha));
+    T const f = (phi - sigma_yield) / val(mu);
+    Tensor<T> const I = eye<T>(this->m_num_dims);
+    Tensor<T> const Q = compute_Q();
+    Tensor<T> const d = eval_d(g, Q);
+    T const d_zz = -lambda * trace(d) / (lambda + 2. * mu);
+    Tensor<T> R_TC = TC - TC_old - (lambda * (trace(d) + d_zz)) * I - (2. * mu) * d;
+    T R_alpha, R_lambda_z;
+    bool plastic;
+    if (!force_path) plastic = (f > this->m_abs_tol || std::abs(val(f)) < this->m_abs_tol);
+    else plastic = (path_in == this->PLASTIC);
+    if (plastic) {
+      Tensor<T> const n_3D = compute_hill_normal(TC_3D, hp, phi);
+      Tensor<T> const n_2D = extract_2D_tensor_from_3D(n_3D);
+      T const dgam = alpha - alpha_old;
+      Tensor<T> const dp_2D = dgam * n_2D;
+      T const dp_zz = -trace(dp_2D);
+      T const corr_dp_zz = 2. * mu * dp_zz / (2. * mu + lambda);
+      R_TC(0, 0) += 2. * mu * dp_2D(0, 0) - lambda * corr_dp_zz;
+      R_TC(1, 1) += 2. * mu * dp_2D(1, 1) - lambda * corr_dp_zz;
+      R_TC(0, 1) += 2. * mu * dp_2D(0, 1);
+      if (!force_path) R_TC = R_TC / val(mu);   // :321 (the forced branch, :336-347, has no such line)
+      R_alpha = f;
+      R_lambda_z = lambda_z - lambda_z_old / (1. - (d_zz + corr_dp_zz));
+      path = this->PLASTIC;
+    } else {
+      R_alpha = alpha - alpha_old;
+      R_lambda_z = lambda_z - lambda_z_old / (1. - d_zz);
+      path = this->ELASTIC;
+    }
+    this->set_sym_tensor_R(0, R_TC);
+    this->set_scalar_R(1, R_alpha);
+    this->set_scalar_R(2, R_lambda_z);
+    return path;
+  }
+  bool is_finite_deformation() override { return true; }
+  Tensor<T> rotated_cauchy(GlobalResidual<T>& g) {   // :366-377
+    Tensor<T> const Q = compute_Q();
+    Tensor<T> const I = eye<T>(this->m_num_dims);
+    Tensor<T> const F = g.grad_vector_x(0) + I;
+    Tensor<T> const TC = this->sym_tensor_xi(0);
+    Tensor<T> const R = polar_rotation(F);
+    return R * Q * TC * transpose(Q) * transpose(R);
+  }
+  Tensor<T> cauchy(GlobalResidual<T>& g) override { return rotated_cauchy(g); }   // :379-382
+  Tensor<T> dev_cauchy(GlobalResidual<T>& g) override {   // :384-389
+    Tensor<T> const I = eye<T>(this->m_num_dims);
+    return rotated_cauchy(g) - this->hydro_cauchy(g) * I;
+  }
+  T hydro_cauchy(GlobalResidual<T>& g) override { return trace(rotated_cauchy(g)) / 3.; }   // :391-394
+  T pressure_scale_factor() override { return T(0.); }
+};
+
 // ---- factories, src/local_residual.cpp:892-933, src/global_residual.cpp:619-630 ----
 enum LocalType {
   L_ELASTIC = 0, L_SMALL_J2 = 1, L_SMALL_HILL = 2, L_SMALL_HILL_PLANE_STRESS = 3,
   L_HYPER_J2 = 4, L_HYPER_J2_PLANE_STRESS = 5, L_SMALL_HILL_PLANE_STRAIN = 6,
-  L_HYPER_J2_PLANE_STRAIN = 7
+  L_HYPER_J2_PLANE_STRAIN = 7, L_HYPO_HILL = 8,
+  L_HYPO_HILL_PLANE_STRAIN = 9, L_HYPO_HILL_PLANE_STRESS = 10
 };
 enum GlobalType { G_MECHANICS = 0, G_MECHANICS_PLANE_STRESS = 1 };
 
@@ -855,6 +1190,9 @@ inline int local_num_params(int type) {
     case L_HYPER_J2: return 8;
     case L_HYPER_J2_PLANE_STRESS: return 8;
     case L_HYPER_J2_PLANE_STRAIN: return 6;
+    case L_HYPO_HILL: return 11;
+    case L_HYPO_HILL_PLANE_STRAIN: return 9;
+    case L_HYPO_HILL_PLANE_STRESS: return 13;
   }
   return -1;
 }
@@ -870,6 +1208,9 @@ std::unique_ptr<LocalResidual<T>> create_local_residual(int type, int ndims) {
     case L_HYPER_J2: return std::make_unique<HyperJ2<T>>(ndims);
     case L_HYPER_J2_PLANE_STRESS: return std::make_unique<HyperJ2PlaneStress<T>>(ndims);
     case L_HYPER_J2_PLANE_STRAIN: return std::make_unique<HyperJ2PlaneStrain<T>>(ndims);
+    case L_HYPO_HILL: return std::make_unique<HypoHill<T>>(ndims);
+    case L_HYPO_HILL_PLANE_STRAIN: return std::make_unique<HypoHillPlaneStrain<T>>(ndims);
+    case L_HYPO_HILL_PLANE_STRESS: return std::make_unique<HypoHillPlaneStress<T>>(ndims);
   }
   throw std::runtime_error("unknown local residual type");
 }

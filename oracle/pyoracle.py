@@ -18,7 +18,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LOCAL_TYPES = {
     "elastic": 0, "small_J2": 1, "small_hill": 2, "small_hill_plane_stress": 3,
     "hyper_J2": 4, "hyper_J2_plane_stress": 5, "small_hill_plane_strain": 6,
-    "hyper_J2_plane_strain": 7,
+    "hyper_J2_plane_strain": 7, "hypo_hill": 8, "hypo_hill_plane_strain": 9,
+    "hypo_hill_plane_stress": 10,
 }
 # parameter name order per model (init_params of each src/<model>.cpp)
 PARAM_NAMES = {
@@ -30,6 +31,9 @@ PARAM_NAMES = {
     "hyper_J2": ["E", "nu", "Y", "S", "D", "A", "n", "K"],
     "hyper_J2_plane_stress": ["E", "nu", "Y", "S", "D", "A", "n", "K"],
     "hyper_J2_plane_strain": ["E", "nu", "K", "Y", "Y_inf", "delta"],
+    "hypo_hill": ["E", "nu", "Y", "R00", "R11", "R22", "R01", "R02", "R12", "S", "D"],
+    "hypo_hill_plane_strain": ["E", "nu", "Y", "S", "D", "R00", "R11", "R22", "R01"],
+    "hypo_hill_plane_stress": ["E", "nu", "Y", "S", "D", "R00", "R11", "R22", "R01", "Q00", "Q01", "Q10", "Q11"],
 }
 GLOBAL_TYPES = {"mechanics": 0, "mechanics_plane_stress": 1}
 

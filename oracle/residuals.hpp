@@ -198,6 +198,10 @@ class GlobalResidual {
   double grad_weight(int, int n, int, int d) const { return m_geom.grad[n][d]; }
   Tensor<T> const& cof_F() const { return m_cof_F; }
   T const& det_F() const { return m_det_F; }
+  Tensor<T> const& F() const { return m_F; }
+  Tensor<T> const& F_prev() const { return m_F_prev; }
+  // src/global_residual.hpp:302-305 (cached there until the next interpolate / seed; same values)
+  Tensor<T> R() const { return polar_rotation(m_F); }
 
   // src/global_residual.cpp:373-414
   EVector eigen_residual() const {

@@ -142,6 +142,71 @@ template <class T> T norm(Tensor<T> const& A) {
   return sqrt(s);
 }
 
+// comparison on the value part (Sacado's max(a, b) returns the operand with the larger value, with its
+// derivatives)
+inline double fmax_val(double a, double b) { return a > b ? a : b; }
+template <class T> T tmax(T const& a, T const& b) { return val(a) >= val(b) ? a : b; }
+// MiniTensor norm_1 (max absolute column sum) and norm_infinity (max absolute row sum)
+template <class T> T norm_1(Tensor<T> const& A) {
+  T best = T(0.);
+  for (int j = 0; j < A.dim; ++j) {
+    T s = abs(A(0, j));
+    for (int i = 1; i < A.dim; ++i) s += abs(A(i, j));
+    best = (j == 0) ? s : tmax(best, s);
+  }
+  return best;
+}
+template <class T> T norm_infinity(Tensor<T> const& A) {
+  T best = T(0.);
+  for (int i = 0; i < A.dim; ++i) {
+    T s = abs(A(i, 0));
+    for (int j = 1; j < A.dim; ++j) s += abs(A(i, j));
+    best = (i == 0) ? s : tmax(best, s);
+  }
+  return best;
+}
+
+// minitensor::polar_rotation (Trilinos MiniTensor, MiniTensor_LinearAlgebra.t.h; pinned with Trilinos at
+// 33f21298..., pkg/trilinos/package.cmake:31-32; NOT vendored in the reference tree, restated from its
+// published algorithm): the rotation R of the polar decomposition A = R U by Higham's scaled Newton
+// iteration  X <- 1/2 (mu X + X^-T / mu),  mu = ((|Y|_1 |Y|_inf) / (|X|_1 |X|_inf))^(1/4), Y = X^-1,  with
+// the scaling switched off once the relative change falls below 0.01 and the loop left when
+// |Z - X|_F <= sqrt(sqrt(N) eps) or the change stops decreasing.  Evaluated in the AD scalar by the
+// reference (src/global_residual.hpp:302-305), so dR/dF is the derivative OF THIS ITERATION: it lags the
+// value by one step and is accurate to about |Z - X| of the last step (<= 2e-8), not to rounding.
+template <class T> Tensor<T> polar_rotation(Tensor<T> const& A) {
+  int const dimension = A.dim;
+  bool scale = true;
+  double const tol_scale = 0.01;
+  double const tol_conv = std::sqrt(double(dimension)) * std::numeric_limits<double>::epsilon();
+  Tensor<T> X = A;
+  double gamma = 2.0;
+  int const max_iter = 128;
+  int num_iter = 0;
+  while (num_iter < max_iter) {
+    Tensor<T> const Y = inverse(X);
+    T mu = T(1.0);
+    if (scale) {
+      mu = (norm_1(Y) * norm_infinity(Y)) / (norm_1(X) * norm_infinity(X));
+      mu = sqrt(sqrt(mu));
+    }
+    Tensor<T> Z(dimension);
+    Tensor<T> const YT = transpose(Y);
+    for (int i = 0; i < dimension; ++i)
+      for (int j = 0; j < dimension; ++j) Z(i, j) = 0.5 * (mu * X(i, j) + YT(i, j) / mu);
+    Tensor<T> const D = Z - X;
+    double const nD = val(norm(D));
+    double const delta = nD / val(norm(Z));
+    if (scale && delta < tol_scale) scale = false;
+    bool const end_iter = nD <= std::sqrt(tol_conv) || (delta > 0.5 * gamma && !scale);
+    X = Z;
+    gamma = delta;
+    if (end_iter) break;
+    num_iter++;
+  }
+  return X;
+}
+
 // ---------------------------------------------------------------------------
 // dense matrices (row-major) for the per-point solves
 struct EMatrix {

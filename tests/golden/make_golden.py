@@ -78,6 +78,24 @@ DECKS = {
         dbcs=B2 + [[0, 1, "ymax", "0.001 * t"]],
         num_steps=8, global_max_iters=15, global_tol=1e-8, local_max_iters=500, local_tol=1e-12,
         J=6.5626182813091150e-03, rel_tol=1e-4),
+    # finite-strain Hill through the unrotated rate of deformation (src/hypo_hill.cpp, minitensor::polar_rotation)
+    "notch_hypo_J2": dict(
+        src="test/primal/notch_hypo_J2.yaml.in:5-52", mesh="notch", global_type="mechanics", local_type="hypo_hill",
+        params=dict(E=1000., nu=.25, Y=2., S=10., D=2., R00=1., R11=1., R22=1., R01=1., R02=1., R12=1.),
+        dbcs=B3 + [[0, 1, "ymax", "0.005 * t"]],
+        num_steps=4, global_max_iters=15, global_tol=1e-8, local_max_iters=500, local_tol=1e-12,
+        J=7.5441386985803955e-04, rel_tol=1e-4),
+    "notch2D_hypo_J2_plane_strain": dict(
+        src="test/primal/notch2D_hypo_J2_plane_strain.yaml.in:5-48", mesh="notch2D", global_type="mechanics",
+        local_type="hypo_hill_plane_strain", params=HILL2D, dbcs=B2 + [[0, 1, "ymax", "0.005 * t"]],
+        num_steps=4, global_max_iters=30, global_tol=1e-8, local_max_iters=500, local_tol=1e-12,
+        J=7.10226176768509899e-03, rel_tol=1e-4),
+    "notch2D_hypo_J2_plane_stress": dict(
+        src="test/primal/notch2D_hypo_J2_plane_stress.yaml.in:5-52", mesh="notch2D",
+        global_type="mechanics_plane_stress", local_type="hypo_hill_plane_stress",
+        params=dict(HILL2D, Q00=1., Q01=0., Q10=0., Q11=1.), dbcs=B2 + [[0, 1, "ymax", "0.005 * t"]],
+        num_steps=4, global_max_iters=30, global_tol=1e-8, local_max_iters=500, local_tol=1e-12,
+        J=1.1852379652063684e-02, rel_tol=1e-4),
     # traction boundary condition (src/tbcs.cpp:17-98): [resid, side set, x-val, y-val, z-val]
     "cube_hyperelasticity_traction": dict(
         src="test/primal/cube_hyperelasticity_traction.yaml.in:5-51", mesh="cube", global_type="mechanics",

@@ -22,6 +22,13 @@ COMBOS = {
     "2d_small_hill_plane_stress": (2, "mechanics_plane_stress", "small_hill_plane_stress", HILL2D, 0.45e-3),
     "2d_hyper_J2_plane_stress": (2, "mechanics_plane_stress", "hyper_J2_plane_stress",
                                  dict(E=1000., nu=.25, Y=2., S=10., D=2., A=1., n=.5, K=20.), 0.45e-3),
+    # finite-strain Hill in the unrotated frame (AD through minitensor::polar_rotation); the plane-stress
+    # variant with a material frame Q rotated by 0.3 rad
+    "3d_hypo_hill": (3, "mechanics", "hypo_hill", HILL3D, 0.5e-3),
+    "2d_hypo_hill_plane_strain": (2, "mechanics", "hypo_hill_plane_strain", HILL2D, 0.5e-3),
+    "2d_hypo_hill_plane_stress": (2, "mechanics_plane_stress", "hypo_hill_plane_stress",
+                                  dict(HILL2D, Q00=0.9553364891256060, Q01=-0.2955202066613396,
+                                       Q10=0.2955202066613396, Q11=0.9553364891256060), 0.5e-3),
 }
 # Local Newton tolerance of the parity runs.  1e-14 rather than the decks' 1e-12: an iterate accepted at
 # |C| < 1e-12 carries a state error that the Jacobian amplifies (hyper-J2 with power-law hardening:

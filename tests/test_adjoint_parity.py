@@ -210,7 +210,10 @@ ADJ_CASES = [("3d_small_J2", "avg_disp"), ("3d_small_hill", "calibration"), ("3d
              # reaction / load / surface mismatch QoIs
              ("3d_small_hill", "reaction"), ("3d_hyper_J2", "reaction_torque"), ("3d_hyper_J2", "load"),
              ("3d_small_J2", "load"), ("2d_hyper_J2_plane_stress", "load"), ("2d_small_hill_plane_strain", "load"),
-             ("3d_small_J2", "surface"), ("2d_small_hill_plane_stress", "reaction")]
+             ("3d_small_J2", "surface"), ("2d_small_hill_plane_stress", "reaction"),
+             # finite-strain Hill (AD through the polar-rotation iteration)
+             ("3d_hypo_hill", "calibration"), ("2d_hypo_hill_plane_strain", "avg_disp"),
+             ("2d_hypo_hill_plane_stress", "load")]
 
 
 @pytest.mark.parametrize("name,qoi", ADJ_CASES)
@@ -272,7 +275,8 @@ def test_adjoint_entry_points(name, qoi):
     c.close()
 
 
-@pytest.mark.parametrize("name", ["2d_small_hill_plane_stress", "2d_hyper_J2_plane_stress"])
+@pytest.mark.parametrize("name", ["2d_small_hill_plane_stress", "2d_hyper_J2_plane_stress",
+                                  "2d_hypo_hill_plane_stress"])
 def test_vfm_entry_points(name):
     """K7 / K8 with the forward sensitivities carried over TWO steps (so dC/dxi_prev . dxi/dp_prev is
     exercised) and a random history h."""

@@ -96,7 +96,10 @@ def test_residual_factories_match_the_reference_metadata():
              ("elastic", "mechanics", 2): (["dummy"], [1]),
              ("small_hill_plane_stress", "mechanics_plane_stress", 2): (["pstrain", "alpha"], [3, 1]),
              ("hyper_J2_plane_stress", "mechanics_plane_stress", 2): (["zeta", "Ie", "lambda_z", "alpha"], [3, 1, 1, 1]),
-             ("hyper_J2_plane_strain", "mechanics", 2): (["zeta", "Ie", "alpha"], [3, 1, 1])}
+             ("hyper_J2_plane_strain", "mechanics", 2): (["zeta", "Ie", "alpha"], [3, 1, 1]),
+             ("hypo_hill", "mechanics", 3): (["TC", "alpha"], [6, 1]),
+             ("hypo_hill_plane_strain", "mechanics", 2): (["TC", "alpha", "TC_zz"], [3, 1, 1]),
+             ("hypo_hill_plane_stress", "mechanics_plane_stress", 2): (["TC", "alpha", "lambda_z"], [3, 1, 1])}
     for (lt, gt, nd), (names, neq) in cases.items():
         d = capi.describe_residuals(lt, gt, nd)
         assert d["local"]["resid_names"] == names and d["local"]["num_eqs"] == neq
@@ -105,7 +108,8 @@ def test_residual_factories_match_the_reference_metadata():
         assert d["global"]["resid_names"] == (["u", "p"] if gt == "mechanics" else ["u"])
         assert d["global"]["num_ip_sets"] == (2 if gt == "mechanics" else 1)
     assert capi.describe_residuals("hyper_J2_plane_stress", "mechanics_plane_stress", 2)["local"]["z_stretch_idx"] == 2
+    assert capi.describe_residuals("hypo_hill_plane_stress", "mechanics_plane_stress", 2)["local"]["z_stretch_idx"] == 2
     with pytest.raises(capi.C8Error):
-        capi.describe_residuals("hypo_hill", "mechanics", 3)          # out of the hot-path scope
+        capi.describe_residuals("hypo_barlat", "mechanics", 3)        # out of the hot-path scope
     with pytest.raises(capi.C8Error):
         capi.describe_residuals("small_hill_plane_stress", "mechanics_plane_stress", 3)

@@ -27,6 +27,9 @@ def _solve(d, mesh, params, act, nsteps, tol=1e-12):
 @pytest.mark.parametrize("name,active,nsteps", [
     ("notch2D_small_J2", ["E", "nu", "K", "Y"], 8),        # test/adjoint/notch2D_small_J2_adjoint_check
     ("cube_hyper_J2", ["E", "nu", "Y", "K"], 6),
+    # finite-strain Hill: the adjoint runs through d/dx and d/dx_prev of the AD'd polar-rotation iteration
+    ("notch2D_hypo_J2_plane_stress", ["E", "Y", "S", "R11"], 4),
+    ("notch2D_hypo_J2_plane_strain", ["nu", "Y", "D", "R01"], 4),
 ])
 def test_adjoint_gradient_matches_finite_differences(name, active, nsteps):
     d = G["decks"][name]

@@ -52,7 +52,8 @@ def oracle_problem(d, mesh, params=None, active=None):
 DECKS = ["cube_elastic", "cube_hyper_J2", "notch_small_J2", "notch_hyper_J2", "notch2D_small_J2",
          "notch2D_small_J2_plane_strain", "notch2D_small_J2_plane_stress",
          "notch2D_hyper_J2_plane_stress", "notch2D_hyper_J2_plane_strain",
-         "cube_hyperelasticity_traction"]       # traction bcs (src/tbcs.cpp:17-98)
+         "cube_hyperelasticity_traction",       # traction bcs (src/tbcs.cpp:17-98)
+         "notch_hypo_J2", "notch2D_hypo_J2_plane_strain", "notch2D_hypo_J2_plane_stress"]
 
 
 @pytest.mark.parametrize("name", DECKS)
@@ -79,6 +80,7 @@ def test_forward_regression_on_gpu(golden, name):
     ("notch2D_small_J2", ["E", "nu", "K", "Y"]),                 # test/adjoint/notch2D_small_J2_adjoint_check
     ("notch2D_small_J2_plane_stress", ["Y", "S", "D"]),          # the shipped example's parameters
     ("cube_hyper_J2", ["E", "nu", "Y", "K"]),
+    ("notch2D_hypo_J2_plane_stress", ["Y", "S", "D", "R11"]),
 ])
 def test_adjoint_gradient_vs_oracle(golden, name, active):
     """Avg-displacement objective: adjoint gradient on the GPU vs the oracle's adjoint gradient."""
