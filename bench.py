@@ -39,7 +39,8 @@ PARAMS = dict(E=1000., nu=.25, Y=10., S=0., D=0., A=0., n=0., K=100.)   # test/p
 LOCAL = dict(max_iters=500, abs_tol=1e-12, rel_tol=1e-12)             # same deck :20-24
 LINEAR_TOL = 1e-6   # Belos "Convergence Tolerance" of the same deck (:59); Newton tolerances 1e-8 (:16-18)
 # general-path rows: the iterated local Newton with exp / pow in the yield law, i.e. what a
-# Voce / power-law calibration runs, and the Hill model of BASELINE configs[2] (no closed-form predictor);
+# Voce / power-law calibration runs, and the Hill model of BASELINE configs[2] (anisotropic flow direction:
+# its return map reduces to one scalar equation, models.cuh hill_return_map);
 # name -> (local residual, parameters, displacement scale of the synthetic state)
 GENERAL_PATHS = {
     "hyper_J2_general": ("hyper_J2", dict(E=1000., nu=.25, Y=10., S=10., D=2., A=1., n=.5, K=100.), 1.0),
@@ -294,7 +295,7 @@ def kernel_rows(ctx, st, dfma_peak, hbm_peak):
 
 
 def general_path_rows(mesh, fields, dev_index, stream, dfma_peak):
-    """K1 on the states that take the GENERAL path of the local solve (no closed-form predictor, exp / pow
+    """K1 on the states that take the GENERAL path of the local solve (iterated return map, exp / pow
     in the yield law): hyper-J2 with Voce + power-law hardening, and the Hill model of BASELINE configs[2]."""
     import torch
     from calibr8_b200.capi import Context

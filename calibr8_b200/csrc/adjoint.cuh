@@ -9,6 +9,18 @@
 #include "forward.cuh"
 #include "qoi.cuh"
 
+// minimum resident CTAs per SM asked of ptxas for K3 / K4 / K6 (tuning: tools/build_variant.sh -DC8_K6_MINB=3).
+// K6 at 4 (128 registers, 300 B of spills): 0.520 -> 0.422 ms at 1 M hyper-J2 tets; K4 gains nothing from 3.
+#ifndef C8_K3_MINB
+#define C8_K3_MINB 1
+#endif
+#ifndef C8_K4_MINB
+#define C8_K4_MINB 1
+#endif
+#ifndef C8_K6_MINB
+#define C8_K6_MINB 4
+#endif
+
 namespace c8 {
 
 
@@ -54,7 +66,7 @@ C8_DI void load_measured(const QoiArgs& q, const Elem<C>& E, double (&um)[C::NN]
 //     xi-derivatives (needs the xi-seeded state) -> sensitivity solve -> (dxi/dx)^T g and the
 //     right-hand side -> element matrix rows last.
 template <class C>
-__global__ void __launch_bounds__(128) k_adjoint_jacobian(const AdjArgs a) {
+__global__ void __launch_bounds__(128, C8_K3_MINB) k_adjoint_jacobian(const AdjArgs a) {
   using Model = typename C::Model;
   constexpr int D = C::D, NN = C::NN, NB = C::NB, NX = C::NX, NXI = C::NXI, LX = C::LX,
                 LXI = C::LXI, G = C::G;
@@ -282,7 +294,7 @@ __global__ void __launch_bounds__(128) k_adjoint_jacobian(const AdjArgs a) {
 // ---------------------------------------------------------------------------------------
 // K4
 template <class C>
-__global__ void __launch_bounds__(128) k_adjoint_local(const AdjArgs a) {
+__global__ void __launch_bounds__(128, C8_K4_MINB) k_adjoint_local(const AdjArgs a) {
   using Model = typename C::Model;
   constexpr int D = C::D, NN = C::NN, NB = C::NB, NXI = C::NXI, LX = C::LX, LXI = C::LXI,
                 G = C::G;
@@ -427,7 +439,7 @@ __global__ void __launch_bounds__(128) k_adjoint_local(const AdjArgs a) {
 // active ones (LocalResidual::seed_wrt_params seeds only those, src/local_residual.cpp:811-819;
 // lanes are independent so the active lanes are identical).
 template <class C>
-__global__ void __launch_bounds__(128) k_qoi_gradient(const AdjArgs a) {
+__global__ void __launch_bounds__(128, C8_K6_MINB) k_qoi_gradient(const AdjArgs a) {
   using Model = typename C::Model;
   constexpr int D = C::D, NN = C::NN, NB = C::NB, NXI = C::NXI, NPAR = C::NPAR, G = C::G;
   constexpr int LP = (NPAR + G - 1) / G;

@@ -118,6 +118,137 @@ template <class T> C8_DI Mat<T, 2> extract2(const Mat<T, 3>& a) {
   return r;
 }
 
+// Closed-form structure of the Hill return map (plain doubles), used as the INITIAL GUESS of the local
+// Newton of the Hill models: with the associated flow n = M s / hill(s) (M the constant Hill matrix of
+// hill_normal) the flow rule  s = s_tr - 2 mu dgam n(s)  and the yield condition  hill(s) = sigma_y  give
+//   (I + c M) s = s_tr,   c = 2 mu dgam / sigma_y(alpha_old + dgam),
+// a 3 x 3 solve for the normal components and three divisions for the shears, which leaves ONE scalar
+// equation  g(dgam) = hill(s(dgam)) - sigma_y(alpha_old + dgam) = 0  (Newton, a few dozen flops per step)
+// instead of 4-5 iterations of the 7 x 7 AD Newton.  sigma_y = Y + S (1 - exp(-D alpha)).  Returns false
+// (and leaves the outputs untouched) when the scalar iteration does not converge: the caller then keeps
+// the reference's starting point.  Only a guess: the reference's Newton confirms |C| < tol at it.
+C8_DI bool hill_return_map(const Mat<double, 3>& s_tr, const Hill<double>& h, double mu, double Y,
+                           double S, double D, double alpha_old, Mat<double, 3>& s_out, double& dgam_out) {
+  auto sigma_y = [&](double a, double& dsy) {
+    double v = Y; dsy = 0.0;
+    if (S != 0.0) { const double ex = exp(-D * a); v += S * (1.0 - ex); dsy = S * D * ex; }
+    return v;
+  };
+  Mat<double, 3> Mn;   // normal block of M on (s00, s11, s22)
+  Mn(0, 0) = h.G + h.H; Mn(0, 1) = -h.H; Mn(0, 2) = -h.G;
+  Mn(1, 0) = -h.H; Mn(1, 1) = h.F + h.H; Mn(1, 2) = -h.F;
+  Mn(2, 0) = -h.G; Mn(2, 1) = -h.F; Mn(2, 2) = h.G + h.F;
+  const double hill_tr = hill_value(s_tr, h);
+  double dsy;
+  const double sy0 = sigma_y(alpha_old, dsy);
+  double dgam = (hill_tr - sy0) / (3.0 * mu + dsy);   // isotropic (J2) estimate
+  if (!(dgam > 0.0)) dgam = 0.0;
+  Mat<double, 3> s = s_tr;
+  bool ok = false, polish = false;
+#pragma unroll 1
+  for (int it = 0; it < 40; ++it) {
+    const double sy = sigma_y(alpha_old + dgam, dsy);
+    const double c = 2.0 * mu * dgam / sy;
+    Mat<double, 3> An = scale(c, Mn);
+    An(0, 0) += 1.0; An(1, 1) += 1.0; An(2, 2) += 1.0;
+    const Mat<double, 3> Ai = inverse(An);
+    const double i01 = 1.0 / (1.0 + c * h.N), i02 = 1.0 / (1.0 + c * h.M), i12 = 1.0 / (1.0 + c * h.L);
+    double sn[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) sn[i] = Ai(i, 0) * s_tr(0, 0) + Ai(i, 1) * s_tr(1, 1) + Ai(i, 2) * s_tr(2, 2);
+    s(0, 0) = sn[0]; s(1, 1) = sn[1]; s(2, 2) = sn[2];
+    s(0, 1) = s(1, 0) = s_tr(0, 1) * i01;
+    s(0, 2) = s(2, 0) = s_tr(0, 2) * i02;
+    s(1, 2) = s(2, 1) = s_tr(1, 2) * i12;
+    const double hv = hill_value(s, h);
+    const double g = hv - sy;
+    if (fabs(g) < 1e-13 * mu) {
+      if (polish) { ok = true; break; }
+      polish = true;   // one more quadratically convergent step: the state then sits at rounding level
+    }
+    // dg/ddgam = dhill/ds : ds/dc * dc/ddgam - sigma_y',  ds/dc = -(I + c M)^-1 M s
+    double ms[3], dsn[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) ms[i] = Mn(i, 0) * sn[0] + Mn(i, 1) * sn[1] + Mn(i, 2) * sn[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) dsn[i] = -(Ai(i, 0) * ms[0] + Ai(i, 1) * ms[1] + Ai(i, 2) * ms[2]);
+    const double ih = 1.0 / hv;
+    double dh = (ms[0] * dsn[0] + ms[1] * dsn[1] + ms[2] * dsn[2]) * ih;   // n_ii = ms_i / hill
+    dh += 2.0 * ih * (h.N * s(0, 1) * (-h.N * s(0, 1) * i01) + h.M * s(0, 2) * (-h.M * s(0, 2) * i02) +
+                      h.L * s(1, 2) * (-h.L * s(1, 2) * i12));
+    const double dc = 2.0 * mu * (sy - dgam * dsy) / (sy * sy);
+    const double dg = dh * dc - dsy;
+    if (!(dg < 0.0)) break;
+    double nd = dgam - g / dg;
+    if (!(nd > 0.0)) nd = 0.5 * dgam;   // stay on the loading side
+    dgam = nd;
+  }
+  if (!ok) return false;
+  s_out = s; dgam_out = dgam;
+  return true;
+}
+
+// Plane-stress counterpart (small_hill_plane_stress): the in-plane stress obeys sigma = Cps : (eps - pstrain)
+// with Cps = 2 mu I + lambda' 1 x 1, lambda' = 2 mu lambda / (lambda + 2 mu) (eps_zz eliminated), so
+//   (I + c Cps M2) sigma = sigma_tr,  c = dgam / sigma_y(alpha_old + dgam),
+// M2 the Hill matrix restricted to (00, 11, 01) at sigma_zz = 0: a 2 x 2 solve + one division per step.
+C8_DI bool hill_return_map_plane_stress(const Mat<double, 2>& s_tr, const Hill<double>& h, double mu,
+                                        double lambda, double Y, double S, double D, double alpha_old,
+                                        Mat<double, 2>& s_out, double& dgam_out) {
+  auto sigma_y = [&](double a, double& dsy) {
+    double v = Y; dsy = 0.0;
+    if (S != 0.0) { const double ex = exp(-D * a); v += S * (1.0 - ex); dsy = S * D * ex; }
+    return v;
+  };
+  auto hill2 = [&](double a, double b, double c) {
+    return sqrt(h.F * b * b + h.G * a * a + h.H * (a - b) * (a - b) + 2.0 * h.N * c * c);
+  };
+  const double lp = 2.0 * mu * lambda / (lambda + 2.0 * mu);
+  const double m00 = h.G + h.H, m01 = -h.H, m11 = h.F + h.H;
+  // CM = Cn Mn, Cn = [[2 mu + lp, lp], [lp, 2 mu + lp]]
+  const double c00 = (2.0 * mu + lp) * m00 + lp * m01, c01 = (2.0 * mu + lp) * m01 + lp * m11;
+  const double c10 = lp * m00 + (2.0 * mu + lp) * m01, c11 = lp * m01 + (2.0 * mu + lp) * m11;
+  const double a_tr = s_tr(0, 0), b_tr = s_tr(1, 1), t_tr = s_tr(0, 1);
+  double dsy;
+  const double sy0 = sigma_y(alpha_old, dsy);
+  double dgam = (hill2(a_tr, b_tr, t_tr) - sy0) / (3.0 * mu + dsy);
+  if (!(dgam > 0.0)) dgam = 0.0;
+  double sa = a_tr, sb = b_tr, st = t_tr;
+  bool ok = false, polish = false;
+#pragma unroll 1
+  for (int it = 0; it < 40; ++it) {
+    const double sy = sigma_y(alpha_old + dgam, dsy);
+    const double c = dgam / sy;
+    const double a00 = 1.0 + c * c00, a01 = c * c01, a10 = c * c10, a11 = 1.0 + c * c11;
+    const double idet = 1.0 / (a00 * a11 - a01 * a10);
+    const double i01 = 1.0 / (1.0 + c * 2.0 * mu * h.N);
+    sa = (a11 * a_tr - a01 * b_tr) * idet;
+    sb = (a00 * b_tr - a10 * a_tr) * idet;
+    st = t_tr * i01;
+    const double hv = hill2(sa, sb, st);
+    const double g = hv - sy;
+    if (fabs(g) < 1e-13 * mu) {
+      if (polish) { ok = true; break; }
+      polish = true;
+    }
+    const double ma = m00 * sa + m01 * sb, mb = m01 * sa + m11 * sb;     // M2 s (normal part)
+    const double ca = c00 * sa + c01 * sb, cb = c10 * sa + c11 * sb;     // Cn M2 s
+    const double da = -(a11 * ca - a01 * cb) * idet, db = -(a00 * cb - a10 * ca) * idet;   // ds/dc
+    const double ih = 1.0 / hv;
+    const double dh = (ma * da + mb * db) * ih + 2.0 * ih * h.N * st * (-2.0 * mu * h.N * st * i01);
+    const double dc = (sy - dgam * dsy) / (sy * sy);
+    const double dg = dh * dc - dsy;
+    if (!(dg < 0.0)) break;
+    double nd = dgam - g / dg;
+    if (!(nd > 0.0)) nd = 0.5 * dgam;
+    dgam = nd;
+  }
+  if (!ok) return false;
+  s_out(0, 0) = sa; s_out(1, 1) = sb; s_out(0, 1) = s_out(1, 0) = st;
+  dgam_out = dgam;
+  return true;
+}
+
 // small-strain deviatoric stress 2 mu (dev3(eps) - pstrain), shared by several models
 template <int DIM, class TK, class TX, class TP>
 C8_DI Mat<prom3_t<TK, TX, TP>, DIM> small_dev_stress(const Mat<TK, DIM>& gu, const TX* xi,
@@ -264,10 +395,37 @@ struct SmallHill {
 #pragma unroll
     for (int i = 0; i < NXI; ++i) xi[i] = 0.0;
   }
-  template <class K> static C8_DI void guess(const K&, const double* xip, const double* par, double abs_tol,
-                                                  double* xi) {
+  // The reference starts from xi_prev (src/small_hill.cpp:142-151).  A yielding point starts at the
+  // solution of hill_return_map() instead (same flow rule and yield condition as residual() below), so
+  // the AD Newton confirms |C| < tol in one evaluation; guess_r0 returns the residual norm at the
+  // REFERENCE's starting point for its relative test: there R_pstrain = 0 (dgam = 0), the zz row holds
+  // tr(pstrain_old) and R_alpha = f_trial.
+  static constexpr bool HAS_PREDICTOR = true;
+  template <class K> static C8_DI void guess(const K& k, const double* xip, const double* par, double abs_tol,
+                                             double* xi) {
+    (void)guess_r0(k, xip, par, abs_tol, xi);
+  }
+  template <class K> static C8_DI double guess_r0(const K& k, const double* xip, const double* par,
+                                                  double abs_tol, double* xi) {
 #pragma unroll
     for (int i = 0; i < NXI; ++i) xi[i] = xip[i];
+    const double mu = mu_of(par[0], par[1]);
+    const Hill<double> hp = hill_params(par[3], par[4], par[5], par[6], par[7], par[8]);
+    const Mat<double, 3> s_tr = small_dev_stress<3>(k.gu, xip, par[0], par[1]);
+    const double hill_tr = hill_value(s_tr, hp);
+    const double f = (hill_tr - (par[2] + par[9] * (1.0 - exp(-par[10] * xip[NS])))) / mu;
+    if (!(is_plastic(f, abs_tol) && hill_tr > 0.0)) return -1.0;
+    const double tr_old = xip[0] + xip[3] + xip[5];
+    const double r0 = sqrt(f * f + tr_old * tr_old);
+    Mat<double, 3> s; double dgam;
+    if (hill_return_map(s_tr, hp, mu, par[2], par[9], par[10], xip[NS], s, dgam)) {
+      const Mat<double, 3> n = hill_normal(s, hp, hill_value(s, hp));
+      xi[0] = xip[0] + dgam * n(0, 0); xi[1] = xip[1] + dgam * n(0, 1); xi[2] = xip[2] + dgam * n(0, 2);
+      xi[3] = xip[3] + dgam * n(1, 1); xi[4] = xip[4] + dgam * n(1, 2);
+      xi[5] = -(xi[0] + xi[3]);   // the zz row of the residual is tr(pstrain) = 0
+      xi[NS] = xip[NS] + dgam;
+    }
+    return r0;
   }
   template <class TK, class TKP, class TX, class TXP, class TP>
   static C8_DI int residual(const Kin<3, TK, TKP>& k, const TX* xi, const TXP* xip, const TP* par,
@@ -323,10 +481,32 @@ struct SmallHillPlaneStress {
 #pragma unroll
     for (int i = 0; i < NXI; ++i) xi[i] = 0.0;
   }
-  template <class K> static C8_DI void guess(const K&, const double* xip, const double* par, double abs_tol,
-                                                  double* xi) {
+  // Reference start = xi_prev (src/small_hill_plane_stress.cpp:140-149); a yielding point starts at the
+  // solution of hill_return_map_plane_stress() (see SmallHill); R_norm_0 = |f_trial| at the reference's start.
+  static constexpr bool HAS_PREDICTOR = true;
+  template <class K> static C8_DI void guess(const K& k, const double* xip, const double* par, double abs_tol,
+                                             double* xi) {
+    (void)guess_r0(k, xip, par, abs_tol, xi);
+  }
+  template <class K> static C8_DI double guess_r0(const K& k, const double* xip, const double* par,
+                                                  double abs_tol, double* xi) {
 #pragma unroll
     for (int i = 0; i < NXI; ++i) xi[i] = xip[i];
+    const double mu = mu_of(par[0], par[1]), lambda = lambda_of(par[0], par[1]);
+    const Hill<double> hp = hill_params(par[5], par[6], par[7], par[8], 1.0, 1.0);
+    const Mat<double, 2> s_tr = cauchy(k, xip, par);
+    const Mat<double, 3> s3 = embed3(s_tr);
+    const double hill_tr = hill_value(s3, hp);
+    const double f = (hill_tr - (par[2] + par[3] * (1.0 - exp(-par[4] * xip[NS])))) / mu;
+    if (!(is_plastic(f, abs_tol) && hill_tr > 0.0)) return -1.0;
+    Mat<double, 2> sg; double dgam;
+    if (hill_return_map_plane_stress(s_tr, hp, mu, lambda, par[2], par[3], par[4], xip[NS], sg, dgam)) {
+      const Mat<double, 3> g3 = embed3(sg);
+      const Mat<double, 3> n = hill_normal(g3, hp, hill_value(g3, hp));
+      xi[0] = xip[0] + dgam * n(0, 0); xi[1] = xip[1] + dgam * n(0, 1); xi[2] = xip[2] + dgam * n(1, 1);
+      xi[NS] = xip[NS] + dgam;
+    }
+    return fabs(f);
   }
   // full in-plane Cauchy stress with eps_zz eliminated, src/small_hill_plane_stress.cpp:278-327
   template <class TK, class TKP, class TX, class TP>
@@ -388,10 +568,32 @@ struct SmallHillPlaneStrain {
 #pragma unroll
     for (int i = 0; i < NXI; ++i) xi[i] = 0.0;
   }
-  template <class K> static C8_DI void guess(const K&, const double* xip, const double* par, double abs_tol,
-                                                  double* xi) {
+  // Reference start = xi_prev (src/small_hill_plane_strain.cpp:140-149).  The model is the 3-D one with
+  // eps_zz = 0, pstrain_zz = -(p00 + p11) and no out-of-plane shear, so a yielding point starts at the
+  // solution of the 3-D hill_return_map() (see SmallHill); R_norm_0 = |f_trial|.
+  static constexpr bool HAS_PREDICTOR = true;
+  template <class K> static C8_DI void guess(const K& k, const double* xip, const double* par, double abs_tol,
+                                             double* xi) {
+    (void)guess_r0(k, xip, par, abs_tol, xi);
+  }
+  template <class K> static C8_DI double guess_r0(const K& k, const double* xip, const double* par,
+                                                  double abs_tol, double* xi) {
 #pragma unroll
     for (int i = 0; i < NXI; ++i) xi[i] = xip[i];
+    const double mu = mu_of(par[0], par[1]);
+    const Hill<double> hp = hill_params(par[5], par[6], par[7], par[8], 1.0, 1.0);
+    Mat<double, 3> s_tr = embed3(small_dev_stress<2>(k.gu, xip, par[0], par[1]));
+    s_tr(2, 2) = 2.0 * mu * (-trace(sym_grad(k.gu)) / 3.0 + (xip[0] + xip[2]));
+    const double hill_tr = hill_value(s_tr, hp);
+    const double f = (hill_tr - (par[2] + par[3] * (1.0 - exp(-par[4] * xip[NS])))) / mu;
+    if (!(is_plastic(f, abs_tol) && hill_tr > 0.0)) return -1.0;
+    Mat<double, 3> sg; double dgam;
+    if (hill_return_map(s_tr, hp, mu, par[2], par[3], par[4], xip[NS], sg, dgam)) {
+      const Mat<double, 3> n = hill_normal(sg, hp, hill_value(sg, hp));
+      xi[0] = xip[0] + dgam * n(0, 0); xi[1] = xip[1] + dgam * n(0, 1); xi[2] = xip[2] + dgam * n(1, 1);
+      xi[NS] = xip[NS] + dgam;
+    }
+    return fabs(f);
   }
   template <class TK, class TKP, class TX, class TXP, class TP>
   static C8_DI int residual(const Kin<2, TK, TKP>& k, const TX* xi, const TXP* xip, const TP* par,
@@ -902,17 +1104,38 @@ struct HypoHill {
 #pragma unroll
     for (int i = 0; i < NXI; ++i) xi[i] = 0.0;
   }
-  // elastic predictor, src/hypo_hill.cpp:163-177
-  template <class K> static C8_DI void guess(const K& k, const double* xip, const double* par, double, double* xi) {
+  // elastic predictor, src/hypo_hill.cpp:163-177; a yielding point continues to the solution of
+  // hill_return_map() (TC = TC_tr - 2 mu dgam n(TC): the same structure as the small-strain model, the
+  // hydrostatic part of TC passes through M untouched).  R_norm_0 of the relative test is the norm at the
+  // reference's start, the elastic predictor: R_TC = 0 there and R_alpha = f_trial.
+  static constexpr bool HAS_PREDICTOR = true;
+  template <class K> static C8_DI void guess(const K& k, const double* xip, const double* par, double abs_tol,
+                                             double* xi) {
+    (void)guess_r0(k, xip, par, abs_tol, xi);
+  }
+  template <class K> static C8_DI double guess_r0(const K& k, const double* xip, const double* par,
+                                                  double abs_tol, double* xi) {
     const double lambda = lambda_of(par[0], par[1]), mu = mu_of(par[0], par[1]);
     const Mat<double, 3> d = unrotated_rate<3>(k);
     const double ltd = lambda * trace(d);
+    Mat<double, 3> T_tr;
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-      for (int j = i; j < 3; ++j)
-        xi[SymIdx<3>::idx(i, j)] = xip[SymIdx<3>::idx(i, j)] + (i == j ? ltd : 0.0) + 2.0 * mu * d.a[i][j];
+      for (int j = 0; j < 3; ++j)
+        T_tr(i, j) = xip[SymIdx<3>::idx(i, j)] + (i == j ? ltd : 0.0) + 2.0 * mu * d.a[i][j];
+    pack_sym<double, 3>(T_tr, xi);
     xi[NS] = xip[NS];
+    const Hill<double> hp = hill_params(par[3], par[4], par[5], par[6], par[7], par[8]);
+    const double hill_tr = hill_value(T_tr, hp);
+    const double f = (hill_tr - (par[2] + par[9] * (1.0 - exp(-par[10] * xip[NS])))) / mu;
+    if (!(is_plastic(f, abs_tol) && hill_tr > 0.0)) return -1.0;
+    Mat<double, 3> T; double dgam;
+    if (hill_return_map(T_tr, hp, mu, par[2], par[9], par[10], xip[NS], T, dgam)) {
+      pack_sym<double, 3>(T, xi);
+      xi[NS] = xip[NS] + dgam;
+    }
+    return fabs(f);
   }
   template <class TK, class TKP, class TX, class TXP, class TP>
   static C8_DI int residual(const Kin<3, TK, TKP>& k, const TX* xi, const TXP* xip, const TP* par,

@@ -88,6 +88,21 @@ def rel_err_blockwise(a, b, axis):
     return float((d / s).max())
 
 
+def rel_err_state(a, b, atol=None):
+    """Local-state fields: max over points of max(|a-b| - atol, 0) / max|b| of the point, atol = the absolute
+    tolerance of the local Newton.  Each side accepts an iterate with |C| < abs_tol, so two converged solves
+    that took different iteration paths (the reference's start vs a return-map predictor that lands at
+    rounding level) may differ by ~abs_tol in ABSOLUTE terms; relative to the tiny state of a point that has
+    only just yielded that is far more than 1e-10 (measured on the notch mesh with small_hill: element 1372,
+    |xi| = 6e-6 against a field maximum of 1.7e-3, |difference| = 2.1e-15 = 3.5e-10 of its own scale; every
+    other point agrees to < 7e-11)."""
+    atol = LOCAL_TOL["abs_tol"] if atol is None else atol
+    d = np.abs(a - b).reshape(a.shape[0], -1).max(axis=1)
+    s = np.abs(b).reshape(b.shape[0], -1).max(axis=1)
+    s = np.where(s > 0, s, 1.0)
+    return float((np.maximum(d - atol, 0.0) / s).max())
+
+
 def rel_err_rows(vals_a, vals_b, rowptr):
     """CSR values: max over rows of max|a-b| / max|b| in the row."""
     worst = 0.0

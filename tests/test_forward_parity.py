@@ -4,7 +4,7 @@ CSR pattern bit-exact).  North-star tolerance: 1e-10 relative on entries (BASELI
 import numpy as np
 import pytest
 
-from parity_common import (COMBOS, make_context, make_mesh, make_oracle, rel_err_blockwise,
+from parity_common import (COMBOS, make_context, make_mesh, make_oracle, rel_err_blockwise, rel_err_state,
                            rel_err_rows, synthetic_fields, xlist)
 
 TOL = 1e-10  # BASELINE.json north_star: residual/Jacobian entries within 1e-10 relative
@@ -53,7 +53,7 @@ def test_forward_jacobian_parity(name):
         assert 0 < path.sum() < path.size, "synthetic state should mix elastic and plastic points"
     # local state
     xi = ctx.unpack_xi(r["xi"])
-    assert rel_err_blockwise(xi, rB["xi"], 0) < TOL
+    assert rel_err_state(xi, rB["xi"]) < TOL
     # element Jacobians / residuals in the reference's dof order
     n, nx = ctx.n_elems, ctx.nx
     eJ = r["eJ"].cpu().numpy().reshape(n, nx, nx)
@@ -106,7 +106,7 @@ def test_forward_jacobian_reference_mesh(name):
     n, nx = ctx.n_elems, ctx.nx
     eJ = r["eJ"].cpu().numpy().reshape(n, nx, nx)
     assert rel_err_blockwise(eJ, rB["elem_dtotal"], 0) < TOL
-    assert rel_err_blockwise(ctx.unpack_xi(r["xi"]), rB["xi"], 0) < TOL
+    assert rel_err_state(ctx.unpack_xi(r["xi"]), rB["xi"]) < TOL
     ctx.close()
 
 
@@ -118,7 +118,7 @@ def test_host_buffer_entry_point():
     (u1, p1), (u2, p2) = r["fields"]
     nf, xi, bs = ctx.forward_jacobian_host(u2, p2, u1, p1, r["xi1"], r["xi1"])
     assert nf == 0
-    assert rel_err_blockwise(xi, rB["xi"], 0) < TOL
+    assert rel_err_state(xi, rB["xi"]) < TOL
     for i in range(2):
         assert np.abs(bs[i] - rB["b"][i]).max() < TOL * np.abs(rB["b"][i]).max()
     ctx.close()
@@ -157,7 +157,8 @@ def test_local_solve_failure_is_reported():
     """max_iters too small for a plastic step -> status -1 like the reference (evaluations.cpp:95-97)."""
     import torch
     from calibr8_b200.capi import Context
-    dim, gtype, ltype, params, amp = COMBOS["3d_small_hill"]   # no closed-form predictor: needs several Newton iterations
+    # a model whose local Newton starts at the reference's own point (no return-map predictor): several iterations
+    dim, gtype, ltype, params, amp = COMBOS["2d_hyper_J2_plane_strain"]
     mesh = make_mesh(dim)
     (u1, p1), (u2, p2) = synthetic_fields(mesh, amp, True)
     ctx = Context(0)
@@ -203,7 +204,7 @@ def test_two_element_sets_with_different_materials():
     assert (path.cpu().numpy().astype(np.int32) == rB["path"]).all()
     n, nx = ctx.n_elems, ctx.nx
     assert rel_err_blockwise(eJ.cpu().numpy().reshape(n, nx, nx), rB["elem_dtotal"], 0) < TOL
-    assert rel_err_blockwise(ctx.unpack_xi(xi), rB["xi"], 0) < TOL
+    assert rel_err_state(ctx.unpack_xi(xi), rB["xi"]) < TOL
     # the two sets really behave differently
     assert rB["path"][es == 0].mean() != rB["path"][es == 1].mean()
     ctx.close()
