@@ -646,7 +646,7 @@ def run_ours(args):
                          "flops_definition": "reference algorithm's count (16-wide AD on every op, 4-5 local Newton "
                                              "iterations per plastic point; op-counting oracle); the kernel executes fewer "
                                              "-- executed DFMA TFLOP/s: profiles/README.md",
-                         "kernels": "k_forward_jacobian<Cfg<3,0,HyperJ2<3>,4>,true> + k_bsr_gather<4,4,false>",
+                         "kernels": "k_forward_jacobian_persistent<Cfg<3,0,HyperJ2<3>,4>,true> + k_bsr_gather<4,4,false>",
                          "traffic": traffic["traffic"] if traffic else None,
                          "traffic_source": traffic["source"] if traffic else None},
             "roofline_hbm": {"bound": "hbm", "achieved": bytes_per_launch / (k_ms * 1e-3) * 1e-9,

@@ -57,7 +57,8 @@ struct FwdArgs {
   int elem_begin, elem_end;   // element range of this launch (0, n_elems unless chunked)
   double* b;              // residual (+=), may be nullptr
   signed char* path;      // per-element branch (0 elastic / 1 plastic), may be nullptr
-  int* n_failed;          // device counter of failed local solves
+  int* n_failed;          // device counter of failed local solves; n_failed[1]: tile counter of the persistent
+                          // element kernel (both zeroed by the caller before the launch)
   double* elem_J;         // optional [n_elems][NX][NX] element Jacobians (reference dof order)
   double* elem_R;         // optional [n_elems][NX]
   const int* cg_ptr_host;     // host side only: chunk -> first plan entry [n_chunks + 1], nullptr: one pass

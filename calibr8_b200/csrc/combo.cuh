@@ -7,6 +7,7 @@
 #define C8_G3D 4
 #endif
 #include <cstdio>
+#include <cstdlib>
 #include "vfm.cuh"
 #include "kernel_table.h"
 
@@ -20,6 +21,12 @@ __global__ void k_init_xi(double* xi, long long xi_ld, int n_elems) {
   C::Model::init(v);
 #pragma unroll
   for (int q = 0; q < C::NXI; ++q) xi[size_t(q) * xi_ld + e] = v[q];
+}
+
+// C8_K1_PERSISTENT=0 in the environment selects the one-tile-per-CTA element kernel (read once)
+inline bool k1_persistent_enabled() {
+  static const int on = [] { const char* v = getenv("C8_K1_PERSISTENT"); return (v && v[0] == '0') ? 0 : 1; }();
+  return on != 0;
 }
 
 template <class C>
@@ -64,7 +71,28 @@ struct Launch {
     a.elem_begin = 0; a.elem_end = a.mesh.n_elems;
     const long long threads = (long long)a.mesh.n_elems * C::G;
     const unsigned grid = (unsigned)((threads + block - 1) / block);
-    if (fast) k_forward_jacobian<C, true><<<grid, block, 0, s>>>(a);
+    if (fast && k1_persistent_enabled()) {
+      // production call: persistent CTAs (one per SM) that prefetch the next tile's element records
+      static int n_sm = 0;
+      static bool attr_set = false;
+      if (!n_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+      }
+      constexpr int smem = (int)sizeof(K1Smem<C>);
+      static int per_sm = 1;
+      if (!attr_set) {
+        cudaFuncSetAttribute(k_forward_jacobian_persistent<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_forward_jacobian_persistent<C, true>, block, smem) !=
+                cudaSuccess || per_sm < 1)
+          per_sm = 1;
+        attr_set = true;
+      }
+      const unsigned resident = (unsigned)(n_sm * per_sm);
+      const unsigned pgrid = grid < resident ? grid : resident;
+      k_forward_jacobian_persistent<C, true><<<pgrid, block, smem, s>>>(a);
+    } else if (fast) k_forward_jacobian<C, true><<<grid, block, 0, s>>>(a);
     else k_forward_jacobian<C, false><<<grid, block, 0, s>>>(a);
     if (a.elements_done) cudaEventRecord(a.elements_done, s);  // xi, b, path and the status are final here
     if (a.vals) gather<false>(a.mesh, a.emat, a.vals, s);

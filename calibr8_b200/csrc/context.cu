@@ -219,7 +219,7 @@ c8_ctx* c8_create(int device) {
     return nullptr;
   }
   ctx->own_stream = true;
-  if (cudaMalloc(&ctx->d_nfailed, sizeof(int)) != cudaSuccess) {
+  if (cudaMalloc(&ctx->d_nfailed, 2 * sizeof(int)) != cudaSuccess) {   // [0] failed local solves, [1] tile counter of the persistent K1
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return nullptr;
@@ -609,7 +609,7 @@ static int forward_impl(c8_ctx* ctx, const double* x, const double* xp, const do
     if (!a.emat) return C8_ERR_CUDA;
   }
   (void)transpose;
-  C8_CUDA(ctx, cudaMemsetAsync(ctx->d_nfailed, 0, sizeof(int), ctx->stream));
+  C8_CUDA(ctx, cudaMemsetAsync(ctx->d_nfailed, 0, 2 * sizeof(int), ctx->stream));
   ctx->kt->forward_jacobian(a, ctx->stream);
   C8_CUDA(ctx, cudaGetLastError());
   if (n_failed) {
@@ -637,7 +637,7 @@ int c8::forward_state_host(c8_ctx* ctx, const double* u, const double* p, double
   if (!ctx->side_stream) C8_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
   if (!ctx->ev_elements) C8_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_elements, cudaEventDisableTiming));
   C8_CUDA(ctx, cudaMemsetAsync(ctx->d_b, 0, size_t(n) * nb * sizeof(double), ctx->stream));
-  C8_CUDA(ctx, cudaMemsetAsync(ctx->d_nfailed, 0, sizeof(int), ctx->stream));
+  C8_CUDA(ctx, cudaMemsetAsync(ctx->d_nfailed, 0, 2 * sizeof(int), ctx->stream));
   FwdArgs a{};
   a.mesh = ctx->mesh_args();
   a.model = ctx->model;

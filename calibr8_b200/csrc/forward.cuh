@@ -425,34 +425,15 @@ static __device__ unsigned long long g_k1_phase_clocks[8];
 #define C8_K1_MINB 1
 #endif
 
+// Everything of K1 after the element record E and the gathered current-field xi are in registers:
+// kinematics, the three AD passes, the element rows and their stores.  Shared by the one-tile-per-CTA
+// kernel and the persistent, prefetching one below.
 template <class C, bool FAST>
-__global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian(const FwdArgs a) {
+C8_DI void k1_element(const FwdArgs& a, const Elem<C>& E, double (&xi)[C::NXI], int e, int t, bool in_range,
+                      unsigned mask) {
   using Model = typename C::Model;
   constexpr int D = C::D, NN = C::NN, NB = C::NB, NXI = C::NXI, LX = C::LX, G = C::G;
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int t = gid % G;
-  const bool in_range = a.elem_begin + (gid / G) < a.elem_end;
-  // out-of-range groups recompute the last element (no stores) so that every thread of the CTA
-  // reaches the phase barriers below
-  const int e = in_range ? a.elem_begin + gid / G : a.elem_end - 1;
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane / G * G));
-
   C8_PHASE_START();
-#ifdef C8_K1_SMEM_ELEM
-  // element record in shared memory, one copy per group (see load_elem_shared)
-  __shared__ Elem<C> sE[C8_K1_BLOCK / G];
-  load_elem_shared<C>(a.mesh, a.model, a.x, a.x_prev, a.xi_prev, a.xi_ld, e, t, sE[threadIdx.x / G]);
-  __syncwarp();
-  const Elem<C>& E = sE[threadIdx.x / G];
-#else
-  Elem<C> E;
-  load_elem<C>(a.mesh, a.model, a.x, a.x_prev, a.xi_prev, a.xi_ld, e, E);
-#endif
-  double xi[NXI];
-#pragma unroll
-  for (int q = 0; q < NXI; ++q) xi[q] = a.xi[size_t(q) * a.xi_ld + e];
-
   Kin<D, double, double> k0;
   k0.gu = grad_u_val<D, NB>(E.xn, E.g);
   k0.gup = grad_u_val<D, NB>(E.xpn, E.g);
@@ -588,6 +569,200 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian(co
   }
   sc.finish();
   C8_PHASE_MARK(4);
+}
+
+template <class C, bool FAST>
+__global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian(const FwdArgs a) {
+  constexpr int NXI = C::NXI, G = C::G;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = gid % G;
+  const bool in_range = a.elem_begin + (gid / G) < a.elem_end;
+  // out-of-range groups recompute the last element (no stores) so that every thread of the CTA
+  // reaches the phase barriers of k1_element
+  const int e = in_range ? a.elem_begin + gid / G : a.elem_end - 1;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane / G * G));
+#ifdef C8_K1_SMEM_ELEM
+  // element record in shared memory, one copy per group (see load_elem_shared)
+  __shared__ Elem<C> sE[C8_K1_BLOCK / G];
+  load_elem_shared<C>(a.mesh, a.model, a.x, a.x_prev, a.xi_prev, a.xi_ld, e, t, sE[threadIdx.x / G]);
+  __syncwarp();
+  const Elem<C>& E = sE[threadIdx.x / G];
+#else
+  Elem<C> E;
+  load_elem<C>(a.mesh, a.model, a.x, a.x_prev, a.xi_prev, a.xi_ld, e, E);
+#endif
+  double xi[NXI];
+#pragma unroll
+  for (int q = 0; q < NXI; ++q) xi[q] = a.xi[size_t(q) * a.xi_ld + e];
+  k1_element<C, FAST>(a, E, xi, e, t, in_range, mask);
+}
+
+// ---- persistent K1: one CTA per SM loops over tiles of C8_K1_BLOCK / G elements and PREFETCHES -------------
+// At 255 registers one CTA of 8 warps is resident per SM, all of them in the same phase (phase barriers),
+// so the dependent gathers at the start of a tile -- connectivity -> nodal coords / x / x_prev, plus the
+// xi_prev / xi rows -- are exposed latency (the "load" phase: 14 % of the warp cycles of the one-tile
+// kernel).  Here tile k+1's record is copied into shared memory with cp.async while tile k computes
+// (nodal rows gathered through the connectivity that was itself prefetched one tile earlier), and a tile
+// starts by reading its record from shared memory into registers.
+C8_DI void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+C8_DI void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+C8_DI void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+C8_DI void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+C8_DI void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// row stride (in doubles) >= n with stride % 4 == 2: the 32 / G groups of a warp then read the same entry of
+// their own rows from distinct bank pairs, and rows stay 16-byte aligned for the vector copies
+constexpr int k1_row_stride(int n) { return n + ((2 - n % 4) + 4) % 4; }
+
+template <class C>
+struct alignas(16) K1Stage {
+  static constexpr int EPB = C8_K1_BLOCK / C::G;
+  static constexpr int SX = k1_row_stride(C::NN * C::NB), SC = k1_row_stride(C::NN * C::D);
+  double xn[EPB][SX];      // [element][node * NB + eq]
+  double xpn[EPB][SX];
+  double xip[C::NXI][EPB];
+  double xi[C::NXI][EPB];
+  double X[EPB][SC];       // [element][node * D + k]
+  int nodes[EPB][C::NN];
+};
+template <class C>
+struct alignas(16) K1Smem {
+  K1Stage<C> stage[2];
+  int conn[2][K1Stage<C>::EPB][C::NN];
+};
+
+template <class C, bool FAST>
+__global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian_persistent(const FwdArgs a) {
+  constexpr int D = C::D, NN = C::NN, NB = C::NB, NXI = C::NXI, G = C::G;
+  constexpr int EPB = K1Stage<C>::EPB;
+  extern __shared__ __align__(16) unsigned char k1_smem_raw[];
+  K1Smem<C>& S = *reinterpret_cast<K1Smem<C>*>(k1_smem_raw);
+  const int tid = threadIdx.x;
+  const int t = tid % G, gl = tid / G;
+  const unsigned lane = tid & 31u;
+  const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane / G * G));
+  const int n_range = a.elem_end - a.elem_begin;
+  const int n_tiles = (n_range + EPB - 1) / EPB;
+  const int last = a.elem_end - 1;
+  const bool have_xp = a.x_prev != nullptr;
+
+  // element of slot j of tile `tile` (clamped: padding slots repeat the last element, no stores)
+  auto elem_of = [&](int tile, int j) { const int e = a.elem_begin + tile * EPB + j; return e < a.elem_end ? e : last; };
+  auto issue_conn = [&](int tile, int buf) {
+    for (int i = tid; i < EPB * NN; i += C8_K1_BLOCK) {
+      const int j = i / NN, n = i - j * NN;
+      cp_async4(&S.conn[buf][j][n], &a.mesh.conn[size_t(elem_of(tile, j)) * NN + n]);
+    }
+  };
+  auto issue_record = [&](int tile, int buf, int st) {
+    K1Stage<C>& T = S.stage[st];
+    for (int i = tid; i < EPB * NN; i += C8_K1_BLOCK) {
+      const int j = i / NN, n = i - j * NN;
+      const int nd = S.conn[buf][j][n];
+      T.nodes[j][n] = nd;
+#pragma unroll
+      for (int k = 0; k < D; ++k) cp_async8(&T.X[j][n * D + k], &a.mesh.coords[size_t(nd) * D + k]);
+      if constexpr (NB % 2 == 0) {
+#pragma unroll
+        for (int q = 0; q < NB; q += 2) {
+          cp_async16(&T.xn[j][n * NB + q], &a.x[size_t(nd) * NB + q]);
+          if (have_xp) cp_async16(&T.xpn[j][n * NB + q], &a.x_prev[size_t(nd) * NB + q]);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+          cp_async8(&T.xn[j][n * NB + q], &a.x[size_t(nd) * NB + q]);
+          if (have_xp) cp_async8(&T.xpn[j][n * NB + q], &a.x_prev[size_t(nd) * NB + q]);
+        }
+      }
+    }
+    // local state rows: EPB consecutive elements per component (a full tile is 16-byte aligned: elem_begin
+    // and xi_ld are multiples of 32); the ragged last tile goes element by element
+    const int e0 = a.elem_begin + tile * EPB;
+    if (e0 + EPB <= a.elem_end && (e0 % 2) == 0) {
+      for (int i = tid; i < NXI * (EPB / 2); i += C8_K1_BLOCK) {
+        const int q = i / (EPB / 2), j = (i - q * (EPB / 2)) * 2;
+        cp_async16(&T.xip[q][j], &a.xi_prev[size_t(q) * a.xi_ld + e0 + j]);
+        cp_async16(&T.xi[q][j], &a.xi[size_t(q) * a.xi_ld + e0 + j]);
+      }
+    } else {
+      for (int i = tid; i < NXI * EPB; i += C8_K1_BLOCK) {
+        const int q = i / EPB, j = i - q * EPB;
+        const int e = elem_of(tile, j);
+        cp_async8(&T.xip[q][j], &a.xi_prev[size_t(q) * a.xi_ld + e]);
+        cp_async8(&T.xi[q][j], &a.xi[size_t(q) * a.xi_ld + e]);
+      }
+    }
+  };
+
+  // Tiles are handed out dynamically (the cost of a tile depends on how many of its points yield): the
+  // first three of a CTA are static, every further one comes from the counter n_failed[1]; thread 0 fetches
+  // it one iteration ahead of its first use (the connectivity prefetch two tiles ahead).
+  __shared__ int s_fetch[2];
+  int tile = blockIdx.x, next = blockIdx.x + gridDim.x, next2 = blockIdx.x + 2 * gridDim.x;
+  if (tile >= n_tiles) return;
+  if (tid == 0) s_fetch[0] = 3 * (int)gridDim.x + atomicAdd(a.n_failed + 1, 1);
+  // prologue: connectivity of the first tile, then its record and the connectivity of the second
+  issue_conn(tile, 0);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+  issue_record(tile, 0, 0);
+  if (next < n_tiles) issue_conn(next, 1);
+  cp_async_commit();
+
+#pragma unroll 1
+  for (int k = 0; tile < n_tiles; ++k) {
+    const int st = k & 1;
+    cp_async_wait_all();
+    __syncthreads();   // record of this tile and connectivity of the next are in shared memory; every
+                       // thread is done with the other stage (previous tile)
+    const int fetched = s_fetch[st];
+    if (tid == 0)   // once a CTA has seen the end of the tile list it stops drawing (the list is handed out in order)
+      s_fetch[st ^ 1] = (next2 < n_tiles && fetched < n_tiles) ? 3 * (int)gridDim.x + atomicAdd(a.n_failed + 1, 1) : n_tiles;
+    if (next < n_tiles) {
+      issue_record(next, st ^ 1, st ^ 1);
+      // conn buffer `st` held THIS tile's connectivity, consumed when its record was issued
+      if (next2 < n_tiles) issue_conn(next2, st);
+    }
+    cp_async_commit();
+
+    const K1Stage<C>& T = S.stage[st];
+    const int slot = tile * EPB + gl;
+    const bool in_range = slot < n_range;
+    const int e = in_range ? a.elem_begin + slot : last;
+    Elem<C> E;
+    {
+      double X[NN][D];
+#pragma unroll
+      for (int n = 0; n < NN; ++n) {
+        E.nodes[n] = T.nodes[gl][n];
+#pragma unroll
+        for (int c = 0; c < D; ++c) X[n][c] = T.X[gl][n * D + c];
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+          E.xn[n][q] = T.xn[gl][n * NB + q];
+          E.xpn[n][q] = have_xp ? T.xpn[gl][n * NB + q] : 0.0;
+        }
+      }
+      geom_from_coords<D>(X, E.g);
+    }
+    const int es = a.mesh.elem_es ? __ldg(&a.mesh.elem_es[e]) : 0;
+#pragma unroll
+    for (int q = 0; q < C::NPAR; ++q) E.par[q] = __ldg(&a.model.params[es * a.model.npar + q]);
+    double xi[NXI];
+#pragma unroll
+    for (int q = 0; q < NXI; ++q) { E.xip[q] = T.xip[q][gl]; xi[q] = T.xi[q][gl]; }
+    k1_element<C, FAST>(a, E, xi, e, t, in_range, mask);
+    tile = next; next = next2; next2 = fetched;
+  }
 }
 
 // K2: residual only (eval_global_residual): no Newton, xi given, T = double

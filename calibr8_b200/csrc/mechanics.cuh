@@ -31,12 +31,20 @@ struct Geom {
 };
 
 template <int DIM>
+C8_DI void geom_from_coords(const double (&X)[DIM + 1][DIM], Geom<DIM>& g);
+
+template <int DIM>
 C8_DI void load_geom(const double* __restrict__ coords, const int* nodes, Geom<DIM>& g) {
   double X[DIM + 1][DIM];
 #pragma unroll
   for (int n = 0; n <= DIM; ++n)
 #pragma unroll
     for (int k = 0; k < DIM; ++k) X[n][k] = __ldg(&coords[size_t(nodes[n]) * DIM + k]);
+  geom_from_coords<DIM>(X, g);
+}
+
+template <int DIM>
+C8_DI void geom_from_coords(const double (&X)[DIM + 1][DIM], Geom<DIM>& g) {
   Mat<double, DIM> J;  // J(a,k) = dx_k/dxi_a
 #pragma unroll
   for (int a = 0; a < DIM; ++a)

@@ -23,10 +23,13 @@ from dataclasses import dataclass, field
 import numpy as np
 
 
-def rcb(centroids: np.ndarray, n_parts: int) -> np.ndarray:
+def rcb(centroids: np.ndarray, n_parts: int, weights: np.ndarray | None = None) -> np.ndarray:
     """Recursive coordinate bisection.  Returns part id per element; part sizes differ by <= 1
-    element per cut level (non-power-of-two counts are split proportionally)."""
+    element per cut level (non-power-of-two counts are split proportionally).  weights: per-element
+    cost estimate (the vertex weights a ParMETIS run would be given); the cuts then balance the summed
+    weight instead of the element count."""
     part = np.zeros(centroids.shape[0], dtype=np.int32)
+    w = None if weights is None else np.asarray(weights, dtype=np.float64)
 
     def split(idx, p0, np_):
         if np_ == 1:
@@ -35,9 +38,14 @@ def rcb(centroids: np.ndarray, n_parts: int) -> np.ndarray:
         c = centroids[idx]
         axis = int(np.argmax(c.max(axis=0) - c.min(axis=0)))
         left_parts = np_ // 2
-        n_left = int(round(len(idx) * left_parts / np_))
         # stable order on (coordinate, element id) makes the cut deterministic on structured grids
         order = np.lexsort((idx, c[:, axis]))
+        if w is None:
+            n_left = int(round(len(idx) * left_parts / np_))
+        else:
+            cw = np.cumsum(w[idx[order]])
+            n_left = int(np.searchsorted(cw, cw[-1] * left_parts / np_, side="left")) + 1
+            n_left = min(max(n_left, left_parts), len(idx) - (np_ - left_parts))
         split(idx[order[:n_left]], p0, left_parts)
         split(idx[order[n_left:]], p0 + left_parts, np_ - left_parts)
 
@@ -140,15 +148,16 @@ def build_part(mesh, elem_part: np.ndarray, rank: int, n_parts: int, owner=None)
                 recv_ptr=np.asarray(recv_ptr, dtype=np.int32), node_sets=node_sets)
 
 
-def partition_mesh(mesh, n_parts: int, rank: int | None = None, elem_part=None):
+def partition_mesh(mesh, n_parts: int, rank: int | None = None, elem_part=None, weights=None):
     """Element partition; returns (elem_part, [Part...]) or (elem_part, Part) for one rank.
     elem_part: the caller's own element -> part map (the hook for METIS / ParMETIS output or for the
     reference's offline SCOREC `split`, see meshio.reference_partition); None: recursive coordinate
-    bisection of the element centroids (works on unstructured meshes too, exact on structured boxes)."""
+    bisection of the element centroids (works on unstructured meshes too, exact on structured boxes),
+    balancing the element count or, with `weights`, a per-element cost estimate."""
     conn, coords = np.asarray(mesh.conn), np.asarray(mesh.coords)
     if elem_part is None:
         cent = coords[conn].mean(axis=1)[:, : mesh.dim]
-        elem_part = rcb(cent, n_parts)
+        elem_part = rcb(cent, n_parts, weights)
     else:
         elem_part = np.ascontiguousarray(elem_part, dtype=np.int32)
         if elem_part.shape != (conn.shape[0],) or elem_part.min() < 0 or elem_part.max() >= n_parts:
