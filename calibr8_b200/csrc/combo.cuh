@@ -80,7 +80,7 @@ struct Launch {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
       }
-      constexpr int smem = (int)sizeof(K1Smem<C>);
+      constexpr int smem = k1_smem_bytes<C>();
       static int per_sm = 1;
       if (!attr_set) {
         cudaFuncSetAttribute(k_forward_jacobian_persistent<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -255,13 +255,19 @@ struct SeededX {
 // The residual vector keeps reductions (16 per tet): each thread first collects the entries it
 // owns (values are replicated over the group), then adds them once in finish().
 // FAST: b is given and no element-level output is wanted (the production case, branch-free).
-template <class C, bool FAST = false>
+// STAGE (persistent K1, vector-store layouts only): the element matrix rows go to a shared-memory slot of
+// the CTA's output buffer instead (st.shared), and the whole 2 KB element matrix leaves with ONE bulk
+// asynchronous copy (cp.async.bulk) after the tile.  ncu on the direct path: the 32 STG.128 of a thread
+// funnel through the same 4 data registers, and the instruction that next overwrites them waits for the
+// store unit to have read them -- 15 % of all warp-stall samples of the kernel sat on that dependency.
+template <class C, bool FAST = false, bool STAGE = false>
 struct Scatter {
   const FwdArgs& a;
   const Elem<C>& E;
   const XLanes<C::D, C::NB, C::LX>& xl;
   int e, t;
   bool on;  // false: compute but store nothing (padding groups, failed local solves)
+  unsigned stage_addr = 0;  // STAGE: shared-memory address of this thread's columns in its element slot
   double* em = nullptr;    // this thread's columns of the element matrix: em[row*NX + s]
   static constexpr int NBACC = (C::NX + C::G - 1) / C::G;
   double bacc[NBACC];
@@ -293,7 +299,14 @@ struct Scatter {
     constexpr int NB = C::NB, NX = C::NX, LX = C::LX;
     const int row_dof = n * NB + eq;
     bacc[row_dof / C::G] = pick((row_dof % C::G) == t, r.v, bacc[row_dof / C::G]);
-    if (FAST || a.vals != nullptr) {
+    if constexpr (STAGE) {
+      static_assert(LX % 2 == 0 && C::G * LX == NX, "staged output needs the vector-store layout");
+      const unsigned dst = stage_addr + unsigned(row_dof * NX * sizeof(double));
+#pragma unroll
+      for (int s = 0; s < LX; s += 2)
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(dst + unsigned(s * sizeof(double))), "d"(r.d[s]),
+                     "d"(r.d[s + 1]) : "memory");
+    } else if (FAST || a.vals != nullptr) {
       double* dst = em + row_dof * NX;
       if constexpr (LX % 2 == 0 && C::G * LX == NX) {
 #pragma unroll
@@ -412,11 +425,16 @@ static __device__ unsigned long long g_k1_phase_clocks[8];
 #define C8_PHASE_START() do {} while (0)
 #endif
 
-// CTA-wide barriers between the phases keep the warps of a CTA close together in the long
-// straight-line program (instruction-cache locality).  Measured on B200: they pay for the
-// finite-strain models (hyper-J2 3.03 vs 3.57 ms / 1M tets) and cost ~6 % for the small-strain
-// ones (1.94 vs 1.82 ms), whose program is about half as long.
-#define C8_PHASE_SYNC() do { if constexpr (C::Model::FINITE) __syncthreads(); } while (0)
+// CTA-wide barriers between the phases kept the warps of a CTA close together in the long straight-line
+// program of the one-tile-per-CTA kernel (instruction-cache locality; measured then: hyper-J2 3.03 vs
+// 3.57 ms / 1M tets with / without).  The persistent kernel already meets twice per tile, and there the five
+// phase barriers cost more than they give (2.034 vs 2.011 ms), so they are OFF by default;
+// C8_K1_SYNC_MASK selects which stay (bit k = k-th barrier in program order, finite-strain models only).
+// They must be off when a team is a warp (C8_K1_TEAM=32): warps then run different numbers of tiles.
+#ifndef C8_K1_SYNC_MASK
+#define C8_K1_SYNC_MASK 0
+#endif
+#define C8_PHASE_SYNC_K(k) do { if constexpr (C::Model::FINITE && ((C8_K1_SYNC_MASK >> (k)) & 1)) __syncthreads(); } while (0)
 
 #ifndef C8_K1_BLOCK
 #define C8_K1_BLOCK 256
@@ -428,9 +446,11 @@ static __device__ unsigned long long g_k1_phase_clocks[8];
 // Everything of K1 after the element record E and the gathered current-field xi are in registers:
 // kinematics, the three AD passes, the element rows and their stores.  Shared by the one-tile-per-CTA
 // kernel and the persistent, prefetching one below.
-template <class C, bool FAST>
-C8_DI void k1_element(const FwdArgs& a, const Elem<C>& E, double (&xi)[C::NXI], int e, int t, bool in_range,
-                      unsigned mask) {
+// STAGE / stage_addr: see Scatter.  Returns true when the element's matrix was produced (in range, local
+// solve converged).
+template <class C, bool FAST, bool STAGE = false>
+C8_DI bool k1_element(const FwdArgs& a, const Elem<C>& E, double (&xi)[C::NXI], int e, int t, bool in_range,
+                      unsigned mask, unsigned stage_addr = 0) {
   using Model = typename C::Model;
   constexpr int D = C::D, NN = C::NN, NB = C::NB, NXI = C::NXI, LX = C::LX, G = C::G;
   C8_PHASE_START();
@@ -462,7 +482,7 @@ C8_DI void k1_element(const FwdArgs& a, const Elem<C>& E, double (&xi)[C::NXI], 
       if (q % G == t) a.xi[size_t(q) * a.xi_ld + e] = xi[q];
     if (a.path && t == 0) a.path[e] = (signed char)path;
   }
-  C8_PHASE_SYNC();
+  C8_PHASE_SYNC_K(0);
   C8_PHASE_MARK(1);
 
   // ---- P2: dC/dx, then dxi/dx ---------------------------------------------
@@ -490,7 +510,7 @@ C8_DI void k1_element(const FwdArgs& a, const Elem<C>& E, double (&xi)[C::NXI], 
       }
     Dual<L2> C2[NXI];
     Model::residual(k2n, xi, E.xip, E.par, a.model.abs_tol, C2);
-    C8_PHASE_SYNC();
+    C8_PHASE_SYNC_K(1);
     double Bc[NXI][L2];
 #pragma unroll
     for (int q = 0; q < NXI; ++q)
@@ -506,16 +526,17 @@ C8_DI void k1_element(const FwdArgs& a, const Elem<C>& E, double (&xi)[C::NXI], 
       for (int s = L2; s < LX; ++s) xid[q].d[s] = 0.0;
     }
   }
-  C8_PHASE_SYNC();
+  C8_PHASE_SYNC_K(2);
   C8_PHASE_MARK(2);
 
   // ---- P3: element residual and total Jacobian, scattered row by row ------
   const double wdv = quad1_weight<D>() * E.g.dv;
-  Scatter<C, FAST> sc{a, E, sx.xl, e, t, ok};
+  Scatter<C, FAST, STAGE> sc{a, E, sx.xl, e, t, ok};
+  sc.stage_addr = stage_addr;
   sc.init();
   {
     const Mat<Dual<LX>, D> P = first_pk<D, C::M, Model>(k2, sx.p, xid, E.par, a.model.thickness);
-    C8_PHASE_SYNC();
+    C8_PHASE_SYNC_K(3);
 #pragma unroll
     for (int n = 0; n < NN; ++n)
 #pragma unroll
@@ -528,7 +549,7 @@ C8_DI void k1_element(const FwdArgs& a, const Elem<C>& E, double (&xi)[C::NXI], 
   }
   C8_PHASE_MARK(3);
   if constexpr (C::M == MECH_MIXED) {
-    C8_PHASE_SYNC();
+    C8_PHASE_SYNC_K(4);
     Dual<LX> Rp[NN];
     {
       Dual<LX> hp, sv[D];
@@ -569,6 +590,7 @@ C8_DI void k1_element(const FwdArgs& a, const Elem<C>& E, double (&xi)[C::NXI], 
   }
   sc.finish();
   C8_PHASE_MARK(4);
+  return ok;
 }
 
 template <class C, bool FAST>
@@ -621,9 +643,13 @@ C8_DI void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memo
 // their own rows from distinct bank pairs, and rows stay 16-byte aligned for the vector copies
 constexpr int k1_row_stride(int n) { return n + ((2 - n % 4) + 4) % 4; }
 
-template <class C>
+#ifndef C8_K1_TEAM
+#define C8_K1_TEAM C8_K1_BLOCK   // threads that walk the tile list together: the CTA (256) or a warp (32)
+#endif
+
+template <class C, int TEAM>
 struct alignas(16) K1Stage {
-  static constexpr int EPB = C8_K1_BLOCK / C::G;
+  static constexpr int EPB = TEAM / C::G;   // elements per tile
   static constexpr int SX = k1_row_stride(C::NN * C::NB), SC = k1_row_stride(C::NN * C::D);
   double xn[EPB][SX];      // [element][node * NB + eq]
   double xpn[EPB][SX];
@@ -632,21 +658,45 @@ struct alignas(16) K1Stage {
   double X[EPB][SC];       // [element][node * D + k]
   int nodes[EPB][C::NN];
 };
-template <class C>
-struct alignas(16) K1Smem {
-  K1Stage<C> stage[2];
-  int conn[2][K1Stage<C>::EPB][C::NN];
+// element matrices of a tile staged for the bulk stores: one slot per element, 16 bytes of padding per slot
+// so that the 16-byte row stores of the two thread groups of a quarter warp fall into different banks
+template <class C, int TEAM>
+struct K1Out {
+  static constexpr bool STAGED = (C::LX % 2 == 0) && (C::G * C::LX == C::NX) && ((C::NX * C::NX * 8) % 16 == 0);
+  static constexpr int SLOT = C::NX * C::NX * 8 + 16;
+  static constexpr int BYTES = STAGED ? K1Stage<C, TEAM>::EPB * SLOT : 16;
 };
+template <class C, int TEAM>
+struct alignas(16) K1Smem {
+  K1Stage<C, TEAM> stage[2];
+  int conn[2][K1Stage<C, TEAM>::EPB][C::NN];
+  alignas(16) unsigned char out[K1Out<C, TEAM>::BYTES];
+  int out_ok[K1Stage<C, TEAM>::EPB];
+  int fetch[2];
+};
+template <class C>
+constexpr int k1_smem_bytes() { return int(sizeof(K1Smem<C, C8_K1_TEAM>)) * (C8_K1_BLOCK / C8_K1_TEAM); }
 
 template <class C, bool FAST>
 __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian_persistent(const FwdArgs a) {
   constexpr int D = C::D, NN = C::NN, NB = C::NB, NXI = C::NXI, G = C::G;
-  constexpr int EPB = K1Stage<C>::EPB;
+  constexpr int TEAM = C8_K1_TEAM;
+  static_assert(TEAM == C8_K1_BLOCK || TEAM == 32, "a team is the CTA or one warp");
+  static_assert(TEAM == C8_K1_BLOCK || C8_K1_SYNC_MASK == 0, "warp teams cannot meet at CTA-wide phase barriers");
+  constexpr int EPB = K1Stage<C, TEAM>::EPB;
+  constexpr bool STAGED = K1Out<C, TEAM>::STAGED && FAST;
   extern __shared__ __align__(16) unsigned char k1_smem_raw[];
-  K1Smem<C>& S = *reinterpret_cast<K1Smem<C>*>(k1_smem_raw);
-  const int tid = threadIdx.x;
+  const int team = threadIdx.x / TEAM;     // team of this thread inside the CTA
+  const int tid = threadIdx.x % TEAM;      // thread inside the team
+  K1Smem<C, TEAM>& S = reinterpret_cast<K1Smem<C, TEAM>*>(k1_smem_raw)[team];
+  auto team_sync = [] {
+    if constexpr (TEAM == C8_K1_BLOCK) __syncthreads();
+    else __syncwarp();
+  };
+  const int n_teams = gridDim.x * (C8_K1_BLOCK / TEAM);
+  const int team_id = blockIdx.x * (C8_K1_BLOCK / TEAM) + team;
   const int t = tid % G, gl = tid / G;
-  const unsigned lane = tid & 31u;
+  const unsigned lane = threadIdx.x & 31u;
   const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane / G * G));
   const int n_range = a.elem_end - a.elem_begin;
   const int n_tiles = (n_range + EPB - 1) / EPB;
@@ -656,14 +706,14 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian_pe
   // element of slot j of tile `tile` (clamped: padding slots repeat the last element, no stores)
   auto elem_of = [&](int tile, int j) { const int e = a.elem_begin + tile * EPB + j; return e < a.elem_end ? e : last; };
   auto issue_conn = [&](int tile, int buf) {
-    for (int i = tid; i < EPB * NN; i += C8_K1_BLOCK) {
+    for (int i = tid; i < EPB * NN; i += TEAM) {
       const int j = i / NN, n = i - j * NN;
       cp_async4(&S.conn[buf][j][n], &a.mesh.conn[size_t(elem_of(tile, j)) * NN + n]);
     }
   };
   auto issue_record = [&](int tile, int buf, int st) {
-    K1Stage<C>& T = S.stage[st];
-    for (int i = tid; i < EPB * NN; i += C8_K1_BLOCK) {
+    K1Stage<C, TEAM>& T = S.stage[st];
+    for (int i = tid; i < EPB * NN; i += TEAM) {
       const int j = i / NN, n = i - j * NN;
       const int nd = S.conn[buf][j][n];
       T.nodes[j][n] = nd;
@@ -687,13 +737,13 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian_pe
     // and xi_ld are multiples of 32); the ragged last tile goes element by element
     const int e0 = a.elem_begin + tile * EPB;
     if (e0 + EPB <= a.elem_end && (e0 % 2) == 0) {
-      for (int i = tid; i < NXI * (EPB / 2); i += C8_K1_BLOCK) {
+      for (int i = tid; i < NXI * (EPB / 2); i += TEAM) {
         const int q = i / (EPB / 2), j = (i - q * (EPB / 2)) * 2;
         cp_async16(&T.xip[q][j], &a.xi_prev[size_t(q) * a.xi_ld + e0 + j]);
         cp_async16(&T.xi[q][j], &a.xi[size_t(q) * a.xi_ld + e0 + j]);
       }
     } else {
-      for (int i = tid; i < NXI * EPB; i += C8_K1_BLOCK) {
+      for (int i = tid; i < NXI * EPB; i += TEAM) {
         const int q = i / EPB, j = i - q * EPB;
         const int e = elem_of(tile, j);
         cp_async8(&T.xip[q][j], &a.xi_prev[size_t(q) * a.xi_ld + e]);
@@ -703,17 +753,16 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian_pe
   };
 
   // Tiles are handed out dynamically (the cost of a tile depends on how many of its points yield): the
-  // first three of a CTA are static, every further one comes from the counter n_failed[1]; thread 0 fetches
-  // it one iteration ahead of its first use (the connectivity prefetch two tiles ahead).
-  __shared__ int s_fetch[2];
-  int tile = blockIdx.x, next = blockIdx.x + gridDim.x, next2 = blockIdx.x + 2 * gridDim.x;
-  if (tile >= n_tiles) return;
-  if (tid == 0) s_fetch[0] = 3 * (int)gridDim.x + atomicAdd(a.n_failed + 1, 1);
+  // first three of a team are static, every further one comes from the counter n_failed[1]; thread 0 of the
+  // team fetches it one iteration ahead of its first use (the connectivity prefetch two tiles ahead).
+  int tile = team_id, next = team_id + n_teams, next2 = team_id + 2 * n_teams;
+  if (tile >= n_tiles) return;   // team-uniform (a CTA-wide team leaves as a whole)
+  if (tid == 0) S.fetch[0] = 3 * n_teams + atomicAdd(a.n_failed + 1, 1);
   // prologue: connectivity of the first tile, then its record and the connectivity of the second
   issue_conn(tile, 0);
   cp_async_commit();
   cp_async_wait_all();
-  __syncthreads();
+  team_sync();
   issue_record(tile, 0, 0);
   if (next < n_tiles) issue_conn(next, 1);
   cp_async_commit();
@@ -722,11 +771,14 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian_pe
   for (int k = 0; tile < n_tiles; ++k) {
     const int st = k & 1;
     cp_async_wait_all();
-    __syncthreads();   // record of this tile and connectivity of the next are in shared memory; every
-                       // thread is done with the other stage (previous tile)
-    const int fetched = s_fetch[st];
-    if (tid == 0)   // once a CTA has seen the end of the tile list it stops drawing (the list is handed out in order)
-      s_fetch[st ^ 1] = (next2 < n_tiles && fetched < n_tiles) ? 3 * (int)gridDim.x + atomicAdd(a.n_failed + 1, 1) : n_tiles;
+    if constexpr (STAGED) {   // the bulk stores of the previous tile have read their shared-memory slots
+      if (tid < EPB) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    team_sync();   // record of this tile and connectivity of the next are in shared memory; every
+                   // thread is done with the other stage (previous tile)
+    const int fetched = S.fetch[st];
+    if (tid == 0)   // once a team has seen the end of the tile list it stops drawing (the list is handed out in order)
+      S.fetch[st ^ 1] = (next2 < n_tiles && fetched < n_tiles) ? 3 * n_teams + atomicAdd(a.n_failed + 1, 1) : n_tiles;
     if (next < n_tiles) {
       issue_record(next, st ^ 1, st ^ 1);
       // conn buffer `st` held THIS tile's connectivity, consumed when its record was issued
@@ -734,7 +786,7 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian_pe
     }
     cp_async_commit();
 
-    const K1Stage<C>& T = S.stage[st];
+    const K1Stage<C, TEAM>& T = S.stage[st];
     const int slot = tile * EPB + gl;
     const bool in_range = slot < n_range;
     const int e = in_range ? a.elem_begin + slot : last;
@@ -760,8 +812,29 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian_pe
     double xi[NXI];
 #pragma unroll
     for (int q = 0; q < NXI; ++q) { E.xip[q] = T.xip[q][gl]; xi[q] = T.xi[q][gl]; }
-    k1_element<C, FAST>(a, E, xi, e, t, in_range, mask);
+    if constexpr (STAGED) {
+      const unsigned slot_addr = (unsigned)__cvta_generic_to_shared(S.out) + unsigned(gl * K1Out<C, TEAM>::SLOT);
+      const bool ok = k1_element<C, FAST, true>(a, E, xi, e, t, in_range, mask,
+                                                slot_addr + unsigned(t * C::LX * sizeof(double)));
+      if (t == 0) S.out_ok[gl] = ok ? 1 : 0;
+      // generic-proxy writes of the slots -> visible to the async proxy, then one bulk store per element
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      team_sync();
+      if (tid < EPB && S.out_ok[tid]) {
+        const int ee = a.elem_begin + tile * EPB + tid;     // ok implies in range
+        double* dst = a.emat + size_t(ee - a.elem_begin) * C::NX * C::NX;
+        const unsigned src = (unsigned)__cvta_generic_to_shared(S.out) + unsigned(tid * K1Out<C, TEAM>::SLOT);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src),
+                     "n"(C::NX * C::NX * 8) : "memory");
+      }
+      if (tid < EPB) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    } else {
+      k1_element<C, FAST>(a, E, xi, e, t, in_range, mask);
+    }
     tile = next; next = next2; next2 = fetched;
+  }
+  if constexpr (STAGED) {
+    if (tid < EPB) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 }
 
