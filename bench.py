@@ -348,16 +348,19 @@ def general_path_rows(mesh, fields, dev_index, stream, dfma_peak):
 
 def measured_traffic():
     """DRAM bytes per launch of the K1 kernels from the committed ncu --set full summary of this round
-    (profiles/r02_ncu_summary.json, written by tools/ncu_extract.py); None when the file is absent."""
-    try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_summary.json")))
-        ks = d["kernels"]
-        el = next(v for k, v in ks.items() if k.startswith("k_forward_jacobian"))
-        ga = next(v for k, v in ks.items() if k.startswith("k_bsr_gather"))
-        return {"traffic": el["dram_bytes"] + ga["dram_bytes"], "element_kernel": el, "gather": ga,
-                "source": "profiles/r02_ncu_summary.json (" + d.get("command", "") + ")"}
-    except Exception:
-        return None
+    (profiles/r02b_ncu_summary.json -- the persistent element kernel --, written by tools/ncu_extract.py;
+    r02_ncu_summary.json as the fallback); None when neither file is there."""
+    for name in ("r02b_ncu_summary.json", "r02_ncu_summary.json"):
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", name)))
+            ks = d["kernels"]
+            el = next(v for k, v in ks.items() if k.startswith("k_forward_jacobian"))
+            ga = next(v for k, v in ks.items() if k.startswith("k_bsr_gather"))
+            return {"traffic": el["dram_bytes"] + ga["dram_bytes"], "element_kernel": el, "gather": ga,
+                    "source": "profiles/" + name + " (" + d.get("command", "") + ")"}
+        except Exception:
+            continue
+    return None
 
 
 def run_reference(args):

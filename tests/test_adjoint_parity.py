@@ -385,7 +385,17 @@ def test_bench_parameters_fast_path():
     xi.copy_(xip)
     assert c.forward_jacobian(x, xp, xip, xi, A2, b2, None) == 0
     torch.cuda.synchronize()
-    assert torch.equal(A, A2)
+    # (two instantiations of the same arithmetic -- one tile per CTA with direct stores vs the persistent kernel
+    # with staged bulk stores: the compiler contracts a few multiply-adds differently, so rounding level, not bits)
+    scale = A.abs().max().item()
+    assert (A - A2).abs().max().item() < 1e-14 * scale
+    # ... and the production path is bit-reproducible from call to call (deterministic gather order, dynamic
+    # tile scheduling notwithstanding)
+    A3, b3 = c.alloc("A"), c.alloc("b")
+    xi.copy_(xip)
+    assert c.forward_jacobian(x, xp, xip, xi, A3, b3, None) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(A2, A3)
     for i in range(2):
         for j in range(2):
             rp, _ = o.graph(i, j)

@@ -45,5 +45,7 @@ if "small_J2" in which:
     run("small_J2", dict(E=1000., nu=.25, K=100., Y=2., cte=0., delta_T=0.), 0.2, mesh)
 if "small_hill" in which:
     run("small_hill", dict(E=1000., nu=.25, Y=2., R00=1., R11=.9, R22=1.1, R01=1., R02=.95, R12=1.05, S=10., D=2.), 0.2, mesh)
+if "hypo_hill" in which:
+    run("hypo_hill", dict(E=1000., nu=.25, Y=2., R00=1., R11=.9, R22=1.1, R01=1., R02=.95, R12=1.05, S=10., D=2.), 0.2, mesh)
 if "elastic" in which:
     run("elastic", dict(E=1000., nu=.25, cte=0., delta_T=0.), 1.0, mesh)
