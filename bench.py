@@ -46,6 +46,9 @@ GENERAL_PATHS = {
     "hyper_J2_general": ("hyper_J2", dict(E=1000., nu=.25, Y=10., S=10., D=2., A=1., n=.5, K=100.), 1.0),
     "small_hill": ("small_hill", dict(E=1000., nu=.25, Y=2., R00=1., R11=.9, R22=1.1, R01=1., R02=.95, R12=1.05,
                                       S=10., D=2.), 0.2),
+    # finite-strain Hill in the unrotated frame (AD through the polar-rotation iteration), SURVEY 8(f) rank 4
+    "hypo_hill": ("hypo_hill", dict(E=1000., nu=.25, Y=2., R00=1., R11=.9, R22=1.1, R01=1., R02=.95, R12=1.05,
+                                    S=10., D=2.), 0.2),
 }
 AMP = 2.2e-3
 N_CELLS = 56

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(128, C8_K3_MINB) k_adjoint_jacobian(const AdjA
   Kin<D, double, double> k0;
   k0.gu = grad_u_val<D, NB>(E.xn, E.g);
   k0.gup = grad_u_val<D, NB>(E.xpn, E.g);
+  if constexpr (needs_rotation<Model>::value) cache_rotation(k0);
   const double wdv = quad1_weight<D>() * E.g.dv;
   const bool calib = a.qoi.type != QOI_AVG_DISP;
   const int nmask = a.qoi.has_node_load() ? load_node_mask<D>(a.qoi, a.mesh.coords, E.nodes) : 0;
@@ -159,6 +160,20 @@ __global__ void __launch_bounds__(128, C8_K3_MINB) k_adjoint_jacobian(const AdjA
 #pragma unroll
         for (int s = 0; s < L2; ++s) k2n.gu(i, j).d[s] = k2.gu(i, j).d[s];
       }
+    if constexpr (needs_rotation<Model>::value) {   // one rotation under AD for this pass and the next (see K1)
+      cache_rotation(k2n);
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          k2.rot(i, j).v = k2n.rot(i, j).v;
+#pragma unroll
+          for (int s = 0; s < L2; ++s) k2.rot(i, j).d[s] = k2n.rot(i, j).d[s];
+#pragma unroll
+          for (int s = L2; s < LX; ++s) k2.rot(i, j).d[s] = 0.0;
+        }
+      k2.has_rot = true;
+    }
     Dual<L2> C2[NXI];
     Model::residual(k2n, xi, E.xip, E.par, a.model.abs_tol, C2);
     double Bc[NXI][L2];
@@ -312,6 +327,7 @@ __global__ void __launch_bounds__(128, C8_K4_MINB) k_adjoint_local(const AdjArgs
   Kin<D, double, double> k0;
   k0.gu = grad_u_val<D, NB>(E.xn, E.g);
   k0.gup = grad_u_val<D, NB>(E.xpn, E.g);
+  if constexpr (needs_rotation<Model>::value) cache_rotation(k0);
   const double wdv = quad1_weight<D>() * E.g.dv;
   double z[NN][NB];
 #pragma unroll
@@ -465,6 +481,7 @@ __global__ void __launch_bounds__(128, C8_K6_MINB) k_qoi_gradient(const AdjArgs 
     Kin<D, double, double> k0;
     k0.gu = grad_u_val<D, NB>(E.xn, E.g);
     k0.gup = grad_u_val<D, NB>(E.xpn, E.g);
+    if constexpr (needs_rotation<Model>::value) cache_rotation(k0);
     const double wdv = quad1_weight<D>() * E.g.dv;
     double z[NN][NB];
 #pragma unroll
@@ -627,6 +644,7 @@ __global__ void __launch_bounds__(128) k_qoi_value(const AdjArgs a, int mode) {
         Kin<D, double, double> k0;
         k0.gu = grad_u_val<D, NB>(E.xn, E.g);
         k0.gup = grad_u_val<D, NB>(E.xpn, E.g);
+        if constexpr (needs_rotation<Model>::value) cache_rotation(k0);
         if (nmask) {
           double p0 = 0.0;
           if constexpr (C::M == MECH_MIXED) {

@@ -457,6 +457,7 @@ C8_DI bool k1_element(const FwdArgs& a, const Elem<C>& E, double (&xi)[C::NXI], 
   Kin<D, double, double> k0;
   k0.gu = grad_u_val<D, NB>(E.xn, E.g);
   k0.gup = grad_u_val<D, NB>(E.xpn, E.g);
+  if constexpr (needs_rotation<Model>::value) cache_rotation(k0);   // one polar rotation for the whole local Newton
   C8_PHASE_MARK(0);
 
   // ---- P1: local Newton (block-synchronous) ---------------------------------
@@ -508,6 +509,22 @@ C8_DI bool k1_element(const FwdArgs& a, const Elem<C>& E, double (&xi)[C::NXI], 
 #pragma unroll
         for (int s = 0; s < L2; ++s) k2n.gu(i, j).d[s] = k2.gu(i, j).d[s];
       }
+    if constexpr (needs_rotation<Model>::value) {
+      // ONE rotation under AD per point: R depends on the displacement dofs only, so the width-L2 result
+      // also serves P3 (its extra pressure lane carries a zero derivative)
+      cache_rotation(k2n);
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          k2.rot(i, j).v = k2n.rot(i, j).v;
+#pragma unroll
+          for (int s = 0; s < L2; ++s) k2.rot(i, j).d[s] = k2n.rot(i, j).d[s];
+#pragma unroll
+          for (int s = L2; s < LX; ++s) k2.rot(i, j).d[s] = 0.0;
+        }
+      k2.has_rot = true;
+    }
     Dual<L2> C2[NXI];
     Model::residual(k2n, xi, E.xip, E.par, a.model.abs_tol, C2);
     C8_PHASE_SYNC_K(1);
@@ -853,6 +870,7 @@ __global__ void __launch_bounds__(128) k_global_residual(const FwdArgs a) {
   Kin<D, double, double> k0;
   k0.gu = grad_u_val<D, NB>(E.xn, E.g);
   k0.gup = grad_u_val<D, NB>(E.xpn, E.g);
+  if constexpr (needs_rotation<Model>::value) cache_rotation(k0);
   const double wdv = quad1_weight<D>() * E.g.dv;
   double p = 0.0, gp[D];
   if constexpr (C::M == MECH_MIXED) {

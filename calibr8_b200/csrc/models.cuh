@@ -34,6 +34,16 @@ template <int DIM, class TK, class TKP>
 struct Kin {
   Mat<TK, DIM> gu;    // grad u at the point
   Mat<TKP, DIM> gup;  // grad u_prev at the point
+  // Optional cache of R = polar_rotation(I + grad u) for the hypoelastic models (the reference caches it per
+  // interpolation, src/global_residual.hpp:302-305).  has_rot is a compile-time constant at every use (local
+  // objects, everything inlined), so kernels that never set it carry no trace of the cache.
+  Mat<TK, DIM> rot;
+  bool has_rot = false;
+};
+// models that read the polar rotation declare NEEDS_ROTATION
+template <class M, class = void> struct needs_rotation { static constexpr bool value = false; };
+template <class M> struct needs_rotation<M, decltype(void(M::NEEDS_ROTATION))> {
+  static constexpr bool value = M::NEEDS_ROTATION;
 };
 
 template <class A, class B, class C, class D, class E>
@@ -1078,18 +1088,29 @@ struct HyperJ2PlaneStress {
 //   d = R^T sym((F - F_prev) F^-1) R,   R = polar_rotation(F)          src/hypo_kinematics.hpp:10-17
 // and the Cauchy stress handed to the mechanics residual is R TC R^T.
 template <int DIM, class TK, class TKP>
+C8_DI Mat<TK, DIM> kin_rotation(const Kin<DIM, TK, TKP>& k) {
+  if (k.has_rot) return k.rot;
+  return polar_rotation(add_diag(k.gu, 1.0));
+}
+// fill the cache (kernels call this once per AD pass for the models that need it)
+template <int DIM, class TK, class TKP>
+C8_DI void cache_rotation(Kin<DIM, TK, TKP>& k) {
+  k.rot = polar_rotation(add_diag(k.gu, 1.0));
+  k.has_rot = true;
+}
+template <int DIM, class TK, class TKP>
 C8_DI Mat<prom_t<TK, TKP>, DIM> unrotated_rate(const Kin<DIM, TK, TKP>& k) {
   const Mat<TK, DIM> F = add_diag(k.gu, 1.0);
   const Mat<TKP, DIM> Fp = add_diag(k.gup, 1.0);
   const Mat<TK, DIM> Fi = inverse(F);
-  const Mat<TK, DIM> R = polar_rotation(F);
+  const Mat<TK, DIM> R = kin_rotation(k);
   const auto Lv = (F - Fp) * Fi;
   const auto Dm = scale(0.5, Lv + transpose(Lv));
   return transpose(R) * Dm * R;
 }
-template <int DIM, class TK, class TX>
-C8_DI Mat<prom_t<TK, TX>, DIM> rotate_forward(const Mat<TK, DIM>& gu, const Mat<TX, DIM>& TC) {
-  const Mat<TK, DIM> R = polar_rotation(add_diag(gu, 1.0));
+template <int DIM, class TK, class TKP, class TX>
+C8_DI Mat<prom_t<TK, TX>, DIM> rotate_forward(const Kin<DIM, TK, TKP>& k, const Mat<TX, DIM>& TC) {
+  const Mat<TK, DIM> R = kin_rotation(k);
   return R * TC * transpose(R);
 }
 
@@ -1100,6 +1121,7 @@ struct HypoHill {
   static constexpr bool FINITE = true, HAS_NEWTON = true, PLANE_STRESS = false;
   static constexpr bool ELASTIC_J_IDENTITY = false;   // the TC rows are scaled by 1 / mu
   static constexpr int Z_STRETCH = -1;
+  static constexpr bool NEEDS_ROTATION = true;
   static C8_DI void init(double* xi) {
 #pragma unroll
     for (int i = 0; i < NXI; ++i) xi[i] = 0.0;
@@ -1178,11 +1200,11 @@ struct HypoHill {
   }
   template <class TK, class TKP, class TX, class TP>
   static C8_DI Mat<prom3_t<TK, TX, TP>, 3> dev_cauchy(const Kin<3, TK, TKP>& k, const TX* xi, const TP*) {
-    return mat_conv<prom3_t<TK, TX, TP>>(dev(rotate_forward<3>(k.gu, unpack_sym<TX, 3>(xi))));
+    return mat_conv<prom3_t<TK, TX, TP>>(dev(rotate_forward<3>(k, unpack_sym<TX, 3>(xi))));
   }
   template <class TK, class TKP, class TX, class TP>
   static C8_DI prom3_t<TK, TX, TP> hydro(const Kin<3, TK, TKP>& k, const TX* xi, const TP*) {
-    return conv<prom3_t<TK, TX, TP>>(trace(rotate_forward<3>(k.gu, unpack_sym<TX, 3>(xi))) / 3.0);
+    return conv<prom3_t<TK, TX, TP>>(trace(rotate_forward<3>(k, unpack_sym<TX, 3>(xi))) / 3.0);
   }
   template <class TP> static C8_DI TP pscale(const TP* par) { return kappa_of(par[0], par[1]); }
 };
@@ -1195,6 +1217,7 @@ struct HypoHillPlaneStrain {
   static constexpr bool FINITE = true, HAS_NEWTON = true, PLANE_STRESS = false;
   static constexpr bool ELASTIC_J_IDENTITY = true;    // no 1 / mu scaling in this variant
   static constexpr int Z_STRETCH = -1;
+  static constexpr bool NEEDS_ROTATION = true;
   static C8_DI void init(double* xi) {
 #pragma unroll
     for (int i = 0; i < NXI; ++i) xi[i] = 0.0;
@@ -1245,7 +1268,7 @@ struct HypoHillPlaneStrain {
   template <class TK, class TKP, class TX, class TP>
   static C8_DI Mat<prom3_t<TK, TX, TP>, 2> dev_cauchy(const Kin<2, TK, TKP>& k, const TX* xi, const TP*) {
     using R = prom3_t<TK, TX, TP>;
-    Mat<R, 2> rc = mat_conv<R>(rotate_forward<2>(k.gu, unpack_sym<TX, 2>(xi)));
+    Mat<R, 2> rc = mat_conv<R>(rotate_forward<2>(k, unpack_sym<TX, 2>(xi)));
     const R h = (trace(rc) + xi[4]) / 3.0;
     rc(0, 0) -= h; rc(1, 1) -= h;
     return rc;
@@ -1253,7 +1276,7 @@ struct HypoHillPlaneStrain {
   template <class TK, class TKP, class TX, class TP>
   static C8_DI prom3_t<TK, TX, TP> hydro(const Kin<2, TK, TKP>& k, const TX* xi, const TP*) {
     using R = prom3_t<TK, TX, TP>;
-    const Mat<R, 2> rc = mat_conv<R>(rotate_forward<2>(k.gu, unpack_sym<TX, 2>(xi)));
+    const Mat<R, 2> rc = mat_conv<R>(rotate_forward<2>(k, unpack_sym<TX, 2>(xi)));
     return (trace(rc) + xi[4]) / 3.0;
   }
   template <class TP> static C8_DI TP pscale(const TP* par) { return kappa_of(par[0], par[1]); }
@@ -1267,6 +1290,7 @@ struct HypoHillPlaneStress {
   static constexpr bool FINITE = true, HAS_NEWTON = true, PLANE_STRESS = true;
   static constexpr bool ELASTIC_J_IDENTITY = true;    // elastic branch: unscaled rows, C = xi - g(xi_prev, F)
   static constexpr int Z_STRETCH = 4;
+  static constexpr bool NEEDS_ROTATION = true;
   static C8_DI void init(double* xi) { xi[0] = xi[1] = xi[2] = xi[3] = 0.0; xi[4] = 1.0; }
   template <class TP> static C8_DI Mat<TP, 2> frame(const TP* par) {
     Mat<TP, 2> Q;
@@ -1331,7 +1355,7 @@ struct HypoHillPlaneStress {
     using R = prom3_t<TK, TX, TP>;
     const Mat<TP, 2> Q = frame(par);
     const auto core = Q * unpack_sym<TX, 2>(xi) * transpose(Q);
-    return mat_conv<R>(rotate_forward<2>(k.gu, core));
+    return mat_conv<R>(rotate_forward<2>(k, core));
   }
   template <class TP> static C8_DI TP pscale(const TP*) { return conv<TP>(0.0); }
 };

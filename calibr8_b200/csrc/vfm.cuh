@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(128) k_vfm_forward(const VfmArgs a) {
   Kin<D, double, double> k0;
   k0.gu = grad_u_val<D, NB>(E.xn, E.g);
   k0.gup = grad_u_val<D, NB>(E.xpn, E.g);
+  if constexpr (needs_rotation<Model>::value) cache_rotation(k0);
   Dual<LXI> Cd[NXI];
   const int path = local_newton<C>(k0, E, a.model, xi, Cd, mask, t, in_range);
   if (!in_range) return;
@@ -182,6 +183,7 @@ __global__ void __launch_bounds__(128) k_vfm_adjoint(const VfmArgs a) {
     Kin<D, double, double> k0;
     k0.gu = grad_u_val<D, NB>(E.xn, E.g);
     k0.gup = grad_u_val<D, NB>(E.xpn, E.g);
+    if constexpr (needs_rotation<Model>::value) cache_rotation(k0);
     const double wdv = quad1_weight<D>() * E.g.dv;
     double w[NN][NB];
 #pragma unroll

@@ -164,6 +164,7 @@ class GlobalResidual {
           }
         }
     compute_kinematics();
+    m_R_valid = false;   // src/global_residual.cpp:331
   }
 
   virtual void compute_kinematics() {}
@@ -200,8 +201,11 @@ class GlobalResidual {
   T const& det_F() const { return m_det_F; }
   Tensor<T> const& F() const { return m_F; }
   Tensor<T> const& F_prev() const { return m_F_prev; }
-  // src/global_residual.hpp:302-305 (cached there until the next interpolate / seed; same values)
-  Tensor<T> R() const { return polar_rotation(m_F); }
+  // src/global_residual.hpp:302-305: cached until the next interpolate (every re-seeding interpolates again)
+  Tensor<T> const& R() const {
+    if (!m_R_valid) { m_R = polar_rotation(m_F); m_R_valid = true; }
+    return m_R;
+  }
 
   // src/global_residual.cpp:373-414
   EVector eigen_residual() const {
@@ -249,6 +253,8 @@ class GlobalResidual {
   std::vector<std::vector<T>> m_x, m_x_prev;
   std::vector<std::vector<std::vector<T>>> m_grad_x, m_grad_x_prev;
   Tensor<T> m_F, m_F_prev, m_cof_F;
+  mutable Tensor<T> m_R;
+  mutable bool m_R_valid = false;
   T m_det_F;
   double m_time = 0., m_delta_t = 0.;
 };
