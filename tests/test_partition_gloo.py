@@ -71,6 +71,23 @@ def test_partition_invariants(kind, n_parts):
     assert partition.edge_cut(mesh, elem_part) > 0
 
 
+def test_weighted_rcb_balances_the_cost():
+    """rcb(weights=): the cuts balance the summed per-element cost (the role of ParMETIS vertex weights) and
+    the partition stays a valid one (owned nodes / elements disjoint and complete)."""
+    mesh = meshgen.box_tets(8, notch_radius=0.3)
+    cent = mesh.coords[mesh.conn].mean(axis=1)
+    w = 1.0 + 3.0 * (cent[:, 1] > 0.6)            # a "plastic zone" four times as expensive
+    for n_parts in (2, 3, 8):
+        ep, parts = partition.partition_mesh(mesh, n_parts, weights=w)
+        cost = np.array([w[ep == k].sum() for k in range(n_parts)])
+        assert cost.max() / cost.mean() < 1.03, cost
+        ep0, _ = partition.partition_mesh(mesh, n_parts)
+        cost0 = np.array([w[ep0 == k].sum() for k in range(n_parts)])
+        assert cost.max() < cost0.max()           # better balanced than the element-count cut
+        owned = np.concatenate([p.elem_gid[: p.n_owned_elems] for p in parts])
+        assert np.array_equal(np.sort(owned), np.arange(mesh.n_elems))
+
+
 def test_rcb_is_exact_on_structured_boxes():
     mesh = meshgen.box_tets(8)
     elem_part, _ = partition.partition_mesh(mesh, 2, rank=0)
