@@ -630,8 +630,8 @@ Context.comm_stats = _ctx_comm_stats
 SYMBOLS += ["c8_set_preconditioner", "c8_preconditioner_info", "c8_linalg_invalidate"]
 
 
-def _ctx_set_preconditioner(self, kind="amg", nu_pre=2, nu_post=2, omega=0.7, over_correction=1.6,
-                            coarsest_max_nodes=40, max_aggregate_size=8, coarse_aggregate_size=8, coarse_nu=0,
+def _ctx_set_preconditioner(self, kind="amg", nu_pre=2, nu_post=2, omega=0.8, over_correction=1.6,
+                            coarsest_max_nodes=40, max_aggregate_size=8, coarse_aggregate_size=12, coarse_nu=0,
                             distributed=True, replicate_max_nodes=30000):
     """right preconditioner of gmres(): 'amg' (aggregation multigrid, default) or 'block_jacobi'.
     distributed: on a partitioned run the hierarchy spans the parts (False: each part's owned block);
