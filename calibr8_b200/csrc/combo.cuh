@@ -72,23 +72,24 @@ struct Launch {
     const long long threads = (long long)a.mesh.n_elems * C::G;
     const unsigned grid = (unsigned)((threads + block - 1) / block);
     if (fast && k1_persistent_enabled()) {
-      // production call: persistent CTAs (one per SM) that prefetch the next tile's element records
-      static int n_sm = 0;
-      static bool attr_set = false;
-      if (!n_sm) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-      }
+      // production call: persistent CTAs (one per SM) that prefetch the next tile's element records.
+      // The shared-memory opt-in and the occupancy are per DEVICE (a process may hold contexts on several).
+      constexpr int MAXDEV = 64;
+      static int n_sm_dev[MAXDEV] = {0}, per_sm_dev[MAXDEV] = {0};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      const int di = dev < MAXDEV ? dev : MAXDEV - 1;
       constexpr int smem = k1_smem_bytes<C>();
-      static int per_sm = 1;
-      if (!attr_set) {
+      if (!n_sm_dev[di] || dev >= MAXDEV) {
+        int sm = 0, per = 1;
+        cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
         cudaFuncSetAttribute(k_forward_jacobian_persistent<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_forward_jacobian_persistent<C, true>, block, smem) !=
-                cudaSuccess || per_sm < 1)
-          per_sm = 1;
-        attr_set = true;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_forward_jacobian_persistent<C, true>, block, smem) !=
+                cudaSuccess || per < 1)
+          per = 1;
+        n_sm_dev[di] = sm; per_sm_dev[di] = per;
       }
+      const int n_sm = n_sm_dev[di], per_sm = per_sm_dev[di];
       const unsigned resident = (unsigned)(n_sm * per_sm);
       const unsigned pgrid = grid < resident ? grid : resident;
       k_forward_jacobian_persistent<C, true><<<pgrid, block, smem, s>>>(a);

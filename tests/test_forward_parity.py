@@ -213,6 +213,59 @@ def test_local_solve_failure_is_reported():
     ctx.close()
 
 
+def test_failed_local_solves_leave_no_stale_matrix_entries():
+    """Production path (persistent element kernel, staged bulk stores) with a matrix: points whose local
+    Newton fails contribute NOTHING -- their scratch slots are cleared, so the gather cannot sum an earlier
+    call's element matrices into A -- and the count is the same as on the element-output path."""
+    import torch
+    from calibr8_b200.capi import Context
+    dim, gtype, ltype, params, amp = COMBOS["3d_hyper_J2"]     # general hardening: the predictor is only a guess
+    mesh = make_mesh(dim)
+    (u1, p1), (u2, p2) = synthetic_fields(mesh, amp, True)
+    ctx = Context(0)
+    ctx.set_mesh(mesh.dim, mesh.conn, mesh.coords)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    x = ctx.alloc("x"); xp = ctx.alloc("x"); xi = ctx.alloc("xi"); xip = ctx.alloc("xi")
+    ctx.pack_x(u2, p2, x)
+    A, A0, b, path = ctx.alloc("A"), ctx.alloc("A"), ctx.alloc("b"), ctx.alloc("path")
+    # a converged assembly first fills every scratch slot with real element matrices
+    ctx.set_model(gtype, ltype, params, max_iters=60, abs_tol=1e-14, rel_tol=1e-14)
+    ctx.init_xi(xi); ctx.init_xi(xip)
+    assert ctx.forward_jacobian(x, xp, xip, xi, A0, b, path) == 0
+    # now a tolerance no iterate can meet: every yielding point fails, the elastic ones still converge
+    ctx.set_model(gtype, ltype, params, max_iters=2, abs_tol=1e-300, rel_tol=1e-300)
+    ctx.init_xi(xi); ctx.init_xi(xip); b.zero_()
+    nf = ctx.forward_jacobian(x, xp, xip, xi, A, b, path)
+    torch.cuda.synchronize()
+    failed = path.cpu().numpy() == -1
+    assert nf == int(failed.sum()) and 0 < nf
+    eJ = ctx.alloc("elem_J")
+    ctx.init_xi(xi)
+    nf2 = ctx.forward_jacobian(x, xp, xip, xi, None, None, path, eJ, None)
+    assert nf2 == nf
+    # the assembled matrix equals the sum of the converged elements' matrices only: rebuild it on the host
+    n, nx = ctx.n_elems, ctx.nx
+    eJh = eJ.cpu().numpy().reshape(n, nx, nx)
+    eJh[failed] = 0.0
+    ok = ~failed
+    assert np.abs(eJh[ok]).max() > 0
+    # compare through the action on a vector: A v == sum_e P_e^T J_e P_e v (reference dof order of elem_J)
+    v = np.random.RandomState(3).randn(mesh.n_nodes, ctx.nb)
+    vd = ctx.alloc("x"); vd.copy_(torch.from_numpy(v.reshape(-1)).cuda()); y = ctx.alloc("x")
+    ctx.spmv(A, vd, y); torch.cuda.synchronize()
+    yh = y.cpu().numpy().reshape(mesh.n_nodes, ctx.nb)
+    nn = mesh.conn.shape[1]
+    ref_dof = [(a, q) for a in range(nn) for q in range(dim)] + [(a, dim) for a in range(nn)]
+    yref = np.zeros_like(yh)
+    for e in np.nonzero(ok)[0]:
+        ve = np.array([v[mesh.conn[e, a], q] for a, q in ref_dof])
+        re = eJh[e] @ ve
+        for k, (a, q) in enumerate(ref_dof):
+            yref[mesh.conn[e, a], q] += re[k]
+    assert np.abs(yh - yref).max() < 1e-10 * np.abs(yref).max()
+    ctx.close()
+
+
 def test_two_element_sets_with_different_materials():
     """Two element sets with their own material parameters (`materials: {es: {...}}` of the reference
     decks, LocalResidual::init_params per element set): K1 parity against the oracle."""
