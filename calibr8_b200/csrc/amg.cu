@@ -41,7 +41,8 @@ __global__ void k_smooth(const int* __restrict__ rowptr, const int* __restrict__
                          const F* __restrict__ vals, const double* __restrict__ dinv,
                          const double* __restrict__ b, const double* __restrict__ xin,
                          double* __restrict__ xout, const int* __restrict__ agg,
-                         const double* __restrict__ xc, double pscale, double omega, int n, int npc) {
+                         const double* __restrict__ xc, double pscale, double omega, int n, int npc,
+                         const double* xprev = nullptr, double c1 = 0.0) {
   pdl_wait();
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   int node = gid >> 2;
@@ -81,6 +82,12 @@ __global__ void k_smooth(const int* __restrict__ rowptr, const int* __restrict__
   }
   double xo = xin[size_t(node) * NB + row];
   if (PROLONG) xo = fma(pscale, xc[size_t(agg[node]) * NB + row], xo);
+  // second step of a Chebyshev pair: x2 = x1 + c1 (x1 - x0) + c2 Dinv r1 (xprev = x0, may alias xout: a thread
+  // reads only its own entry of it, before it writes)
+  if (c1 != 0.0) {
+    const double xp = xprev ? xprev[size_t(node) * NB + row] : 0.0;
+    xo = fma(c1, xo - xp, xo);
+  }
   if (valid && active) xout[size_t(node) * NB + row] = xo + omega * upd;
 }
 
@@ -378,6 +385,10 @@ static bool env_flag(const char* name, bool dflt) {
 static bool cw_coarse() { static const bool v = env_flag("C8_CW_COARSE", true); return v; }   // coalesced warp kernel on levels >= 1
 static bool cw_fine() { static const bool v = env_flag("C8_CW_FINE", false); return v; }      // ... and on the fine level
 static bool fine_prolong_add() { static const bool v = env_flag("C8_FINE_PROLONG_ADD", true); return v; }
+// fine-level Chebyshev smoothing: upper bound of the spectrum of Dinv A (0: damped Jacobi) and hi / lo ratio
+static double env_num(const char* name, double dflt) { const char* e = getenv(name); return e ? atof(e) : dflt; }
+static double cheb_lmax() { static const double v = env_num("C8_CHEB_LMAX", 0.0); return v; }
+static double cheb_ratio() { static const double v = env_num("C8_CHEB_RATIO", 4.0); return v; }
 
 #define C8_NB_SWITCH(nb, CALL)  \
   switch (nb) {                 \
@@ -577,12 +588,13 @@ void Amg::smooth(int l, const double* b, double* x, int sweeps, bool zero_guess)
 
 // one out-of-place sweep on level l (fp32 matrix copy on the fine level when present); the ghost
 // entries of xin (and of xc) must be current
-void Amg::sweep(int l, const double* b, const double* xin, double* xout, const double* xc) {
+void Amg::sweep(int l, const double* b, const double* xin, double* xout, const double* xc, const double* xprev,
+                double c1, double c2) {
   AmgLevel& L = lv_[l];
   if (L.n == 0) return;
   cudaStream_t s = ctx_->stream;
   const int g = (L.n * 4 + 127) / 128;
-  const double oc = opt.over_correction, om = opt.omega;
+  const double oc = opt.over_correction, om = (c2 != 0.0) ? c2 : opt.omega;
   const int gw = (L.n * 32 + 127) / 128;
   if (nb_ == 4 && (l > 0 ? cw_coarse() : cw_fine())) {  // a warp per node, coalesced block reads
     if (l == 0 && L.vals32) {
@@ -600,11 +612,11 @@ void Amg::sweep(int l, const double* b, const double* xin, double* xout, const d
     return;
   }
   if (L.vals32) {
-    if (xc) { C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_smooth<NB, float, true>, L.rowptr, L.colind, L.vals32, L.dinv, b, xin, xout, L.agg, xc, oc, om, L.n, L.npc))); }
-    else { C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_smooth<NB, float, false>, L.rowptr, L.colind, L.vals32, L.dinv, b, xin, xout, nullptr, nullptr, 0.0, om, L.n, 0))); }
+    if (xc) { C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_smooth<NB, float, true>, L.rowptr, L.colind, L.vals32, L.dinv, b, xin, xout, L.agg, xc, oc, om, L.n, L.npc, xprev, c1))); }
+    else { C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_smooth<NB, float, false>, L.rowptr, L.colind, L.vals32, L.dinv, b, xin, xout, (const int*)nullptr, (const double*)nullptr, 0.0, om, L.n, 0, xprev, c1))); }
   } else {
-    if (xc) { C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_smooth<NB, double, true>, L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, L.agg, xc, oc, om, L.n, L.npc))); }
-    else { C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_smooth<NB, double, false>, L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, nullptr, nullptr, 0.0, om, L.n, 0))); }
+    if (xc) { C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_smooth<NB, double, true>, L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, L.agg, xc, oc, om, L.n, L.npc, xprev, c1))); }
+    else { C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_smooth<NB, double, false>, L.rowptr, L.colind, L.vals, L.dinv, b, xin, xout, (const int*)nullptr, (const double*)nullptr, 0.0, om, L.n, 0, xprev, c1))); }
   }
 }
 
@@ -634,9 +646,26 @@ void Amg::cycle(int l, const double* b, double* xout) {
   auto buf = [&](int w) { return bufs[(writes - 1 - w) & 1]; };  // the last write goes to xout
   const int g = (L.n * nb_ + 127) / 128;
   amg_dbg(s, "enter", l);
-  if (L.n > 0) { C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_jacobi_update<NB>, L.dinv, b, buf(0), opt.omega, 1, L.n))); }
+  // Fine level, V(2,2) only: the two sweeps of a side as ONE Chebyshev polynomial of degree 2 in Dinv A on
+  // [lmax / ratio, lmax] (same kernels and traffic as two damped Jacobi sweeps):
+  //   x1 = x0 + 1/theta Dinv r0,  x2 = x1 + rho1 rho0 (x1 - x0) + 2 rho1 / delta Dinv r1
+  const bool cheb = (l == 0) && cheb_lmax() > 0.0 && nu1 == 2 && nu2 == 2 && !(nb_ == 4 && cw_fine()) &&
+                    fine_prolong_add();
+  double ch_a0 = 0.0, ch_c1 = 0.0, ch_c2 = 0.0;
+  if (cheb) {
+    const double hi = cheb_lmax(), lo = hi / cheb_ratio();
+    const double theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo), sigma = theta / delta;
+    const double rho0 = 1.0 / sigma, rho1 = 1.0 / (2.0 * sigma - rho0);
+    ch_a0 = 1.0 / theta; ch_c1 = rho1 * rho0; ch_c2 = 2.0 * rho1 / delta;
+  }
+  if (L.n > 0) { C8_NB_SWITCH(nb_, (pdl_launch(g, 128, 0, s)(k_jacobi_update<NB>, L.dinv, b, buf(0), cheb ? ch_a0 : opt.omega, 1, L.n))); }
   amg_dbg(s, "jacobi zero-guess", l);
-  for (int w = 1; w < nu1; ++w) { halo(l, buf(w - 1)); sweep(l, b, buf(w - 1), buf(w), nullptr); amg_dbg(s, "pre sweep", l); }
+  for (int w = 1; w < nu1; ++w) {
+    halo(l, buf(w - 1));
+    if (cheb) sweep(l, b, buf(w - 1), buf(w), nullptr, nullptr, ch_c1, ch_c2);   // x0 = 0
+    else sweep(l, b, buf(w - 1), buf(w), nullptr);
+    amg_dbg(s, "pre sweep", l);
+  }
   const double* cur = buf(nu1 - 1);
   halo(l, cur);
   double* r = (l == 0) ? r0_ : L.r;
@@ -665,11 +694,17 @@ void Amg::cycle(int l, const double* b, double* xout) {
     // fine level: the correction as an elementwise pass (3 vectors) + a plain sweep, instead of two
     // more dependent gathers per block inside the sweep
     C8_NB_SWITCH(nb_, (pdl_launch((L.npc * nb_ + 255) / 256, 256, 0, s)(k_prolong_add<NB>, L.agg, C.x, const_cast<double*>(cur), opt.over_correction, L.npc)));
-    sweep(l, b, cur, buf(nu1), nullptr);
+    if (cheb) sweep(l, b, cur, buf(nu1), nullptr, nullptr, 0.0, ch_a0);
+    else sweep(l, b, cur, buf(nu1), nullptr);
   } else
   sweep(l, b, cur, buf(nu1), C.x);   // the ghost entries of cur are still current
   amg_dbg(s, "prolong sweep", l);
-  for (int w = nu1 + 1; w < writes; ++w) { halo(l, buf(w - 1)); sweep(l, b, buf(w - 1), buf(w), nullptr); amg_dbg(s, "post sweep", l); }
+  for (int w = nu1 + 1; w < writes; ++w) {
+    halo(l, buf(w - 1));
+    if (cheb) sweep(l, b, buf(w - 1), buf(w), nullptr, cur, ch_c1, ch_c2);   // x0 = cur (aliases the output buffer)
+    else sweep(l, b, buf(w - 1), buf(w), nullptr);
+    amg_dbg(s, "post sweep", l);
+  }
 }
 
 void Amg::apply(const double* r, double* z) {

@@ -82,7 +82,8 @@ class Amg {
  private:
   void cycle(int l, const double* b, double* x);
   void smooth(int l, const double* b, double* x, int sweeps, bool zero_guess);
-  void sweep(int l, const double* b, const double* xin, double* xout, const double* xc);
+  void sweep(int l, const double* b, const double* xin, double* xout, const double* xc,
+             const double* xprev = nullptr, double c1 = 0.0, double c2 = 0.0);
   void halo(int l, const double* v);
   c8_ctx* ctx_;
   int nb_ = 0;

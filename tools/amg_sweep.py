@@ -22,12 +22,12 @@ hp = HostProblem(ctx)
 hp.add_dbc(0, 0, ns["xmin"], "0.0"); hp.add_dbc(0, 1, ns["ymin"], "0.0"); hp.add_dbc(0, 2, ns["zmin"], "0.0")
 hp.add_dbc(0, 1, ns["ymax"], "%g * t" % (0.02 / STEPS))      # the same 2 % total stretch in STEPS steps
 hp.finalize_dbcs()
-hp.set_solver(15, 1e-8, 1e-8, gmres_restart=100, gmres_max_iters=20000, linear_tol=bench.LINEAR_TOL)
+hp.set_solver(15, 1e-8, 1e-8, gmres_restart=100, gmres_max_iters=int(os.environ.get("GMRES_MAX", "3000")), linear_tol=bench.LINEAR_TOL)
 hp.set_qoi_avg_disp()
 hp.set_time(STEPS, 1.0)
 
-BASE = dict(nu_pre=2, nu_post=2, omega=0.7, over_correction=1.6, coarsest_max_nodes=40, max_aggregate_size=8,
-            coarse_aggregate_size=8, coarse_nu=0)
+BASE = dict(nu_pre=2, nu_post=2, omega=0.8, over_correction=1.6, coarsest_max_nodes=40, max_aggregate_size=8,
+            coarse_aggregate_size=12, coarse_nu=0)
 sets = [("base", {})]
 for a, b in [(1, 1), (1, 2), (2, 1), (3, 3), (2, 3), (3, 2)]:
     sets.append((f"V({a},{b})", dict(nu_pre=a, nu_post=b)))
