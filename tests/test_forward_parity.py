@@ -225,11 +225,11 @@ def test_failed_local_solves_leave_no_stale_matrix_entries():
     ctx = Context(0)
     ctx.set_mesh(mesh.dim, mesh.conn, mesh.coords)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    # a converged assembly first fills every scratch slot with real element matrices
+    ctx.set_model(gtype, ltype, params, max_iters=60, abs_tol=1e-14, rel_tol=1e-14)
     x = ctx.alloc("x"); xp = ctx.alloc("x"); xi = ctx.alloc("xi"); xip = ctx.alloc("xi")
     ctx.pack_x(u2, p2, x)
     A, A0, b, path = ctx.alloc("A"), ctx.alloc("A"), ctx.alloc("b"), ctx.alloc("path")
-    # a converged assembly first fills every scratch slot with real element matrices
-    ctx.set_model(gtype, ltype, params, max_iters=60, abs_tol=1e-14, rel_tol=1e-14)
     ctx.init_xi(xi); ctx.init_xi(xip)
     assert ctx.forward_jacobian(x, xp, xip, xi, A0, b, path) == 0
     # now a tolerance no iterate can meet: every yielding point fails, the elastic ones still converge
