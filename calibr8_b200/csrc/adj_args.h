@@ -48,6 +48,7 @@ struct AdjArgs {
   double* phi;        // K4: out ; K6: in
   double* grad;       // K6: [n_es][NPAR] (+=), derivative w.r.t. EVERY parameter of the model
   double* scalars;    // K5: [0] += J, [1] += total load
+  int* tile_counter;  // K3 (persistent): device counter of the dynamic tile list, zeroed before the launch
 };
 
 struct VfmArgs {

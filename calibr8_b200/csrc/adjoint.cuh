@@ -65,26 +65,13 @@ C8_DI void load_measured(const QoiArgs& q, const Elem<C>& E, double (&um)[C::NN]
 //   * the passes are ordered so that each one's temporaries die before the next starts: QoI
 //     xi-derivatives (needs the xi-seeded state) -> sensitivity solve -> (dxi/dx)^T g and the
 //     right-hand side -> element matrix rows last.
+// everything of K3 after the element record E (in shared memory) and the stored xi are at hand
 template <class C>
-__global__ void __launch_bounds__(128, C8_K3_MINB) k_adjoint_jacobian(const AdjArgs a) {
+C8_DI void k3_element(const AdjArgs& a, const Elem<C>& E, const double (&xi)[C::NXI], int e, int t, bool in_range,
+                      unsigned mask) {
   using Model = typename C::Model;
   constexpr int D = C::D, NN = C::NN, NB = C::NB, NX = C::NX, NXI = C::NXI, LX = C::LX,
                 LXI = C::LXI, G = C::G;
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int t = gid % G;
-  // padding groups recompute the last element and store nothing, so that every lane of a warp
-  // reaches the in-group solves (full-mask shuffles, see groupsolve.cuh)
-  const bool in_range = (gid / G) < a.mesh.n_elems;
-  const int e = in_range ? gid / G : a.mesh.n_elems - 1;
-  const unsigned mask = group_mask<C>();
-
-  __shared__ Elem<C> sE[128 / G];
-  load_elem_shared<C>(a.mesh, a.model, a.x, a.x_prev, a.xi_prev, a.xi_ld, e, t, sE[threadIdx.x / G]);
-  __syncwarp();   // a group never spans two warps
-  const Elem<C>& E = sE[threadIdx.x / G];
-  double xi[NXI];
-#pragma unroll
-  for (int q = 0; q < NXI; ++q) xi[q] = __ldg(&a.xi[size_t(q) * a.xi_ld + e]);
   Kin<D, double, double> k0;
   k0.gu = grad_u_val<D, NB>(E.xn, E.g);
   k0.gup = grad_u_val<D, NB>(E.xpn, E.g);
@@ -304,6 +291,89 @@ __global__ void __launch_bounds__(128, C8_K3_MINB) k_adjoint_jacobian(const AdjA
 #pragma unroll
     for (int n = 0; n < NN; ++n) sc.row(n, D, Rp[n]);
   }
+}
+
+template <class C>
+__global__ void __launch_bounds__(128, C8_K3_MINB) k_adjoint_jacobian(const AdjArgs a) {
+  constexpr int NXI = C::NXI, G = C::G;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = gid % G;
+  // padding groups recompute the last element and store nothing, so that every lane of a warp
+  // reaches the in-group solves (full-mask shuffles, see groupsolve.cuh)
+  const bool in_range = (gid / G) < a.mesh.n_elems;
+  const int e = in_range ? gid / G : a.mesh.n_elems - 1;
+  const unsigned mask = group_mask<C>();
+  __shared__ Elem<C> sE[128 / G];
+  load_elem_shared<C>(a.mesh, a.model, a.x, a.x_prev, a.xi_prev, a.xi_ld, e, t, sE[threadIdx.x / G]);
+  __syncwarp();   // a group never spans two warps
+  const Elem<C>& E = sE[threadIdx.x / G];
+  double xi[NXI];
+#pragma unroll
+  for (int q = 0; q < NXI; ++q) xi[q] = __ldg(&a.xi[size_t(q) * a.xi_ld + e]);
+  k3_element<C>(a, E, xi, e, t, in_range, mask);
+}
+
+// Persistent K3, the K1 treatment (forward.cuh): one CTA per SM walks the tile list and prefetches the next
+// tile's element records with cp.async; a tile starts by building its Elem records in shared memory from the
+// prefetched stage (the threads of a group split the copy, the last one computes the geometry).  ncu on the
+// one-tile kernel: 30 % of the stall samples long-scoreboard on that load, 18 % no-instruction with two
+// 128-thread CTAs per SM drifting apart in the program.
+template <class C>
+struct alignas(16) K3Smem {
+  K1Smem<C, C8_K1_BLOCK, false> pf;
+  Elem<C> sE[C8_K1_BLOCK / C::G];
+};
+
+template <class C>
+__global__ void __launch_bounds__(C8_K1_BLOCK, 1) k_adjoint_jacobian_persistent(const AdjArgs a) {
+  constexpr int D = C::D, NN = C::NN, NB = C::NB, NXI = C::NXI, G = C::G;
+  constexpr int TEAM = C8_K1_BLOCK;
+  constexpr int EPB = K1Stage<C, TEAM>::EPB;
+  using SMEM = K1Smem<C, TEAM, false>;
+  extern __shared__ __align__(16) unsigned char k3_smem_raw[];
+  K3Smem<C>& S3 = *reinterpret_cast<K3Smem<C>*>(k3_smem_raw);
+  SMEM& S = S3.pf;
+  const int tid = threadIdx.x;
+  const int t = tid % G, gl = tid / G;
+  const unsigned mask = group_mask<C>();
+  const int n_range = a.mesh.n_elems;
+  const int n_tiles = (n_range + EPB - 1) / EPB;
+  const bool have_xp = a.x_prev != nullptr;
+  const TilePrefetch<C, TEAM, SMEM> pf{S, a.mesh.conn, a.mesh.coords, a.x, a.x_prev, a.xi_prev, a.xi, a.xi_ld,
+                                      0, a.mesh.n_elems, tid};
+  auto before = [](int) {};
+  auto body = [&](int tile, int st) __attribute__((always_inline)) {
+    const K1Stage<C, TEAM>& T = S.stage[st];
+    const int slot = tile * EPB + gl;
+    const bool in_range = slot < n_range;
+    const int e = in_range ? slot : n_range - 1;
+    Elem<C>& Ew = S3.sE[gl];
+    for (int n = t; n < NN; n += G) {
+      Ew.nodes[n] = T.nodes[gl][n];
+#pragma unroll
+      for (int q = 0; q < NB; ++q) {
+        Ew.xn[n][q] = T.xn[gl][n * NB + q];
+        Ew.xpn[n][q] = have_xp ? T.xpn[gl][n * NB + q] : 0.0;
+      }
+    }
+    const int es = a.mesh.elem_es ? __ldg(&a.mesh.elem_es[e]) : 0;
+    for (int q = t; q < C::NPAR; q += G) Ew.par[q] = __ldg(&a.model.params[es * a.model.npar + q]);
+    for (int q = t; q < NXI; q += G) Ew.xip[q] = T.xip[q][gl];
+    if (t == G - 1) {
+      double X[NN][D];
+#pragma unroll
+      for (int n = 0; n < NN; ++n)
+#pragma unroll
+        for (int c = 0; c < D; ++c) X[n][c] = T.X[gl][n * D + c];
+      geom_from_coords<D>(X, Ew.g);
+    }
+    double xi[NXI];
+#pragma unroll
+    for (int q = 0; q < NXI; ++q) xi[q] = T.xi[q][gl];
+    __syncwarp();   // a group never spans two warps
+    k3_element<C>(a, S3.sE[gl], xi, e, t, in_range, mask);
+  };
+  persistent_tile_loop<C, TEAM>(pf, S, a.tile_counter, n_tiles, (int)blockIdx.x, (int)gridDim.x, tid, before, body);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -55,6 +55,8 @@ int c8_adjoint_jacobian(c8_ctx* ctx, const c8_qoi* qoi, const double* x, const d
     a.emat = element_scratch(ctx);
     if (!a.emat) return C8_ERR_CUDA;
   }
+  a.tile_counter = ctx->d_nfailed + 1;
+  C8_CUDA(ctx, cudaMemsetAsync(a.tile_counter, 0, sizeof(int), ctx->stream));
   ctx->kt->adjoint_jacobian(a, ctx->stream);
   C8_CUDA(ctx, cudaGetLastError());
   return C8_OK;

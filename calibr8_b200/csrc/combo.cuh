@@ -29,6 +29,12 @@ inline bool k1_persistent_enabled() {
   return on != 0;
 }
 
+// C8_K3_PERSISTENT=0 selects the one-tile-per-CTA K3
+inline bool k3_persistent_enabled() {
+  static const int on = [] { const char* v = getenv("C8_K3_PERSISTENT"); return (v && v[0] == '0') ? 0 : 1; }();
+  return on != 0;
+}
+
 template <class C>
 struct Launch {
   // phase 2 of the assembly (forward.cuh): BSR values of the owned rows <- element matrices
@@ -123,7 +129,27 @@ struct Launch {
   static void adjoint_jacobian(const AdjArgs& a, cudaStream_t s) {
     if (a.mesh.n_elems == 0) return;
     const long long threads = (long long)a.mesh.n_elems * C::G;
-    k_adjoint_jacobian<C><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(a);
+    // 3-D combinations only: their one-tile K3 holds 8 warps per SM anyway (250+ registers); the 2-D ones run
+    // at 116-230 registers with more resident warps than one 256-thread CTA would give
+    if (C::D == 3 && k3_persistent_enabled() && a.tile_counter) {
+      constexpr int MAXDEV = 64;
+      static int n_sm_dev[MAXDEV] = {0};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      const int di = dev < MAXDEV ? dev : MAXDEV - 1;
+      constexpr int smem = (int)sizeof(K3Smem<C>);
+      if (!n_sm_dev[di] || dev >= MAXDEV) {
+        int sm = 0;
+        cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(k_adjoint_jacobian_persistent<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        n_sm_dev[di] = sm;
+      }
+      const unsigned tiles = (unsigned)((threads + C8_K1_BLOCK - 1) / C8_K1_BLOCK);
+      const unsigned pgrid = tiles < (unsigned)n_sm_dev[di] ? tiles : (unsigned)n_sm_dev[di];
+      k_adjoint_jacobian_persistent<C><<<pgrid, C8_K1_BLOCK, smem, s>>>(a);
+    } else {
+      k_adjoint_jacobian<C><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(a);
+    }
     if (a.vals) gather<true>(a.mesh, a.emat, a.vals, s);
   }
   static void adjoint_local(const AdjArgs& a, cudaStream_t s) {

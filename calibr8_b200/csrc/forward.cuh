@@ -683,16 +683,126 @@ struct K1Out {
   static constexpr int SLOT = C::NX * C::NX * 8 + 16;
   static constexpr int BYTES = STAGED ? K1Stage<C, TEAM>::EPB * SLOT : 16;
 };
-template <class C, int TEAM>
+template <class C, int TEAM, bool WITH_OUT = true>
 struct alignas(16) K1Smem {
   K1Stage<C, TEAM> stage[2];
   int conn[2][K1Stage<C, TEAM>::EPB][C::NN];
-  alignas(16) unsigned char out[K1Out<C, TEAM>::BYTES];
+  alignas(16) unsigned char out[WITH_OUT ? K1Out<C, TEAM>::BYTES : 16];
   int out_ok[K1Stage<C, TEAM>::EPB];
   int fetch[2];
 };
 template <class C>
 constexpr int k1_smem_bytes() { return int(sizeof(K1Smem<C, C8_K1_TEAM>)) * (C8_K1_BLOCK / C8_K1_TEAM); }
+
+// The asynchronous copies of a tile's element records (shared by the persistent K1 and K3): connectivity
+// of a tile into conn[buf], then -- once that has landed -- the nodal rows it names and the tile's local-state
+// rows into stage[st].
+template <class C, int TEAM, class SMEM>
+struct TilePrefetch {
+  static constexpr int D = C::D, NN = C::NN, NB = C::NB, NXI = C::NXI;
+  static constexpr int EPB = K1Stage<C, TEAM>::EPB;
+  SMEM& S;
+  const int* conn;
+  const double *coords, *x, *x_prev, *xi_prev, *xi;
+  long long xi_ld;
+  int elem_begin, elem_end, tid;
+  // element of slot j of tile `tile` (clamped: padding slots repeat the last element, no stores)
+  C8_DI int elem_of(int tile, int j) const {
+    const int e = elem_begin + tile * EPB + j;
+    return e < elem_end ? e : elem_end - 1;
+  }
+  C8_DI void issue_conn(int tile, int buf) const {
+    for (int i = tid; i < EPB * NN; i += TEAM) {
+      const int j = i / NN, n = i - j * NN;
+      cp_async4(&S.conn[buf][j][n], &conn[size_t(elem_of(tile, j)) * NN + n]);
+    }
+  }
+  C8_DI void issue_record(int tile, int buf, int st) const {
+    K1Stage<C, TEAM>& T = S.stage[st];
+    const bool have_xp = x_prev != nullptr;
+    for (int i = tid; i < EPB * NN; i += TEAM) {
+      const int j = i / NN, n = i - j * NN;
+      const int nd = S.conn[buf][j][n];
+      T.nodes[j][n] = nd;
+#pragma unroll
+      for (int k = 0; k < D; ++k) cp_async8(&T.X[j][n * D + k], &coords[size_t(nd) * D + k]);
+      if constexpr (NB % 2 == 0) {
+#pragma unroll
+        for (int q = 0; q < NB; q += 2) {
+          cp_async16(&T.xn[j][n * NB + q], &x[size_t(nd) * NB + q]);
+          if (have_xp) cp_async16(&T.xpn[j][n * NB + q], &x_prev[size_t(nd) * NB + q]);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+          cp_async8(&T.xn[j][n * NB + q], &x[size_t(nd) * NB + q]);
+          if (have_xp) cp_async8(&T.xpn[j][n * NB + q], &x_prev[size_t(nd) * NB + q]);
+        }
+      }
+    }
+    // local state rows: EPB consecutive elements per component (a full tile is 16-byte aligned: elem_begin
+    // and xi_ld are multiples of 32); the ragged last tile goes element by element
+    const int e0 = elem_begin + tile * EPB;
+    if (e0 + EPB <= elem_end && (e0 % 2) == 0) {
+      for (int i = tid; i < NXI * (EPB / 2); i += TEAM) {
+        const int q = i / (EPB / 2), j = (i - q * (EPB / 2)) * 2;
+        cp_async16(&T.xip[q][j], &xi_prev[size_t(q) * xi_ld + e0 + j]);
+        cp_async16(&T.xi[q][j], &xi[size_t(q) * xi_ld + e0 + j]);
+      }
+    } else {
+      for (int i = tid; i < NXI * EPB; i += TEAM) {
+        const int q = i / EPB, j = i - q * EPB;
+        const int e = elem_of(tile, j);
+        cp_async8(&T.xip[q][j], &xi_prev[size_t(q) * xi_ld + e]);
+        cp_async8(&T.xi[q][j], &xi[size_t(q) * xi_ld + e]);
+      }
+    }
+  }
+};
+
+// The tile loop of a persistent team: tiles are handed out dynamically (the cost of a tile depends on how
+// many of its points yield) -- the first three of a team are static, every further one comes from `counter`;
+// thread 0 of the team fetches it one iteration ahead of its first use (the connectivity prefetch runs two
+// tiles ahead).  before(k): runs ahead of the barrier that opens iteration k (e.g. wait for the bulk stores
+// of the previous tile); body(tile, st): the tile's record is in stage[st].
+template <class C, int TEAM, class PF, class SMEM, class BEFORE, class BODY>
+C8_DI void persistent_tile_loop(const PF& pf, SMEM& S, int* counter, int n_tiles, int team_id, int n_teams, int tid,
+                                BEFORE before, BODY body) {
+  auto team_sync = [] {
+    if constexpr (TEAM == C8_K1_BLOCK) __syncthreads();
+    else __syncwarp();
+  };
+  int tile = team_id, next = team_id + n_teams, next2 = team_id + 2 * n_teams;
+  if (tile >= n_tiles) return;   // team-uniform (a CTA-wide team leaves as a whole)
+  if (tid == 0) S.fetch[0] = 3 * n_teams + atomicAdd(counter, 1);
+  // prologue: connectivity of the first tile, then its record and the connectivity of the second
+  pf.issue_conn(tile, 0);
+  cp_async_commit();
+  cp_async_wait_all();
+  team_sync();
+  pf.issue_record(tile, 0, 0);
+  if (next < n_tiles) pf.issue_conn(next, 1);
+  cp_async_commit();
+#pragma unroll 1
+  for (int k = 0; tile < n_tiles; ++k) {
+    const int st = k & 1;
+    cp_async_wait_all();
+    before(k);
+    team_sync();   // record of this tile and connectivity of the next are in shared memory; every
+                   // thread is done with the other stage (previous tile)
+    const int fetched = S.fetch[st];
+    if (tid == 0)   // once a team has seen the end of the tile list it stops drawing (the list is handed out in order)
+      S.fetch[st ^ 1] = (next2 < n_tiles && fetched < n_tiles) ? 3 * n_teams + atomicAdd(counter, 1) : n_tiles;
+    if (next < n_tiles) {
+      pf.issue_record(next, st ^ 1, st ^ 1);
+      // conn buffer `st` held THIS tile's connectivity, consumed when its record was issued
+      if (next2 < n_tiles) pf.issue_conn(next2, st);
+    }
+    cp_async_commit();
+    body(tile, st);
+    tile = next; next = next2; next2 = fetched;
+  }
+}
 
 template <class C, bool FAST>
 __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian_persistent(const FwdArgs a) {
@@ -702,10 +812,11 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian_pe
   static_assert(TEAM == C8_K1_BLOCK || C8_K1_SYNC_MASK == 0, "warp teams cannot meet at CTA-wide phase barriers");
   constexpr int EPB = K1Stage<C, TEAM>::EPB;
   constexpr bool STAGED = K1Out<C, TEAM>::STAGED && FAST;
+  using SMEM = K1Smem<C, TEAM>;
   extern __shared__ __align__(16) unsigned char k1_smem_raw[];
   const int team = threadIdx.x / TEAM;     // team of this thread inside the CTA
   const int tid = threadIdx.x % TEAM;      // thread inside the team
-  K1Smem<C, TEAM>& S = reinterpret_cast<K1Smem<C, TEAM>*>(k1_smem_raw)[team];
+  SMEM& S = reinterpret_cast<SMEM*>(k1_smem_raw)[team];
   auto team_sync = [] {
     if constexpr (TEAM == C8_K1_BLOCK) __syncthreads();
     else __syncwarp();
@@ -719,90 +830,14 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian_pe
   const int n_tiles = (n_range + EPB - 1) / EPB;
   const int last = a.elem_end - 1;
   const bool have_xp = a.x_prev != nullptr;
-
-  // element of slot j of tile `tile` (clamped: padding slots repeat the last element, no stores)
-  auto elem_of = [&](int tile, int j) { const int e = a.elem_begin + tile * EPB + j; return e < a.elem_end ? e : last; };
-  auto issue_conn = [&](int tile, int buf) {
-    for (int i = tid; i < EPB * NN; i += TEAM) {
-      const int j = i / NN, n = i - j * NN;
-      cp_async4(&S.conn[buf][j][n], &a.mesh.conn[size_t(elem_of(tile, j)) * NN + n]);
-    }
-  };
-  auto issue_record = [&](int tile, int buf, int st) {
-    K1Stage<C, TEAM>& T = S.stage[st];
-    for (int i = tid; i < EPB * NN; i += TEAM) {
-      const int j = i / NN, n = i - j * NN;
-      const int nd = S.conn[buf][j][n];
-      T.nodes[j][n] = nd;
-#pragma unroll
-      for (int k = 0; k < D; ++k) cp_async8(&T.X[j][n * D + k], &a.mesh.coords[size_t(nd) * D + k]);
-      if constexpr (NB % 2 == 0) {
-#pragma unroll
-        for (int q = 0; q < NB; q += 2) {
-          cp_async16(&T.xn[j][n * NB + q], &a.x[size_t(nd) * NB + q]);
-          if (have_xp) cp_async16(&T.xpn[j][n * NB + q], &a.x_prev[size_t(nd) * NB + q]);
-        }
-      } else {
-#pragma unroll
-        for (int q = 0; q < NB; ++q) {
-          cp_async8(&T.xn[j][n * NB + q], &a.x[size_t(nd) * NB + q]);
-          if (have_xp) cp_async8(&T.xpn[j][n * NB + q], &a.x_prev[size_t(nd) * NB + q]);
-        }
-      }
-    }
-    // local state rows: EPB consecutive elements per component (a full tile is 16-byte aligned: elem_begin
-    // and xi_ld are multiples of 32); the ragged last tile goes element by element
-    const int e0 = a.elem_begin + tile * EPB;
-    if (e0 + EPB <= a.elem_end && (e0 % 2) == 0) {
-      for (int i = tid; i < NXI * (EPB / 2); i += TEAM) {
-        const int q = i / (EPB / 2), j = (i - q * (EPB / 2)) * 2;
-        cp_async16(&T.xip[q][j], &a.xi_prev[size_t(q) * a.xi_ld + e0 + j]);
-        cp_async16(&T.xi[q][j], &a.xi[size_t(q) * a.xi_ld + e0 + j]);
-      }
-    } else {
-      for (int i = tid; i < NXI * EPB; i += TEAM) {
-        const int q = i / EPB, j = i - q * EPB;
-        const int e = elem_of(tile, j);
-        cp_async8(&T.xip[q][j], &a.xi_prev[size_t(q) * a.xi_ld + e]);
-        cp_async8(&T.xi[q][j], &a.xi[size_t(q) * a.xi_ld + e]);
-      }
-    }
-  };
-
-  // Tiles are handed out dynamically (the cost of a tile depends on how many of its points yield): the
-  // first three of a team are static, every further one comes from the counter n_failed[1]; thread 0 of the
-  // team fetches it one iteration ahead of its first use (the connectivity prefetch two tiles ahead).
-  int tile = team_id, next = team_id + n_teams, next2 = team_id + 2 * n_teams;
-  if (tile >= n_tiles) return;   // team-uniform (a CTA-wide team leaves as a whole)
-  if (tid == 0) S.fetch[0] = 3 * n_teams + atomicAdd(a.n_failed + 1, 1);
-  // prologue: connectivity of the first tile, then its record and the connectivity of the second
-  issue_conn(tile, 0);
-  cp_async_commit();
-  cp_async_wait_all();
-  team_sync();
-  issue_record(tile, 0, 0);
-  if (next < n_tiles) issue_conn(next, 1);
-  cp_async_commit();
-
-#pragma unroll 1
-  for (int k = 0; tile < n_tiles; ++k) {
-    const int st = k & 1;
-    cp_async_wait_all();
+  const TilePrefetch<C, TEAM, SMEM> pf{S, a.mesh.conn, a.mesh.coords, a.x, a.x_prev, a.xi_prev, a.xi, a.xi_ld,
+                                      a.elem_begin, a.elem_end, tid};
+  auto before = [&](int) __attribute__((always_inline)) {
     if constexpr (STAGED) {   // the bulk stores of the previous tile have read their shared-memory slots
       if (tid < EPB) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
-    team_sync();   // record of this tile and connectivity of the next are in shared memory; every
-                   // thread is done with the other stage (previous tile)
-    const int fetched = S.fetch[st];
-    if (tid == 0)   // once a team has seen the end of the tile list it stops drawing (the list is handed out in order)
-      S.fetch[st ^ 1] = (next2 < n_tiles && fetched < n_tiles) ? 3 * n_teams + atomicAdd(a.n_failed + 1, 1) : n_tiles;
-    if (next < n_tiles) {
-      issue_record(next, st ^ 1, st ^ 1);
-      // conn buffer `st` held THIS tile's connectivity, consumed when its record was issued
-      if (next2 < n_tiles) issue_conn(next2, st);
-    }
-    cp_async_commit();
-
+  };
+  auto body = [&](int tile, int st) __attribute__((always_inline)) {
     const K1Stage<C, TEAM>& T = S.stage[st];
     const int slot = tile * EPB + gl;
     const bool in_range = slot < n_range;
@@ -848,8 +883,8 @@ __global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian_pe
     } else {
       k1_element<C, FAST>(a, E, xi, e, t, in_range, mask);
     }
-    tile = next; next = next2; next2 = fetched;
-  }
+  };
+  persistent_tile_loop<C, TEAM>(pf, S, a.n_failed + 1, n_tiles, team_id, n_teams, tid, before, body);
   if constexpr (STAGED) {
     if (tid < EPB) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
