@@ -86,19 +86,21 @@ struct Launch {
       cudaGetDevice(&dev);
       const int di = dev < MAXDEV ? dev : MAXDEV - 1;
       constexpr int smem = k1_smem_bytes<C>();
+      constexpr int pblock = K1PBlock<C>::value;
       if (!n_sm_dev[di] || dev >= MAXDEV) {
         int sm = 0, per = 1;
         cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
         cudaFuncSetAttribute(k_forward_jacobian_persistent<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_forward_jacobian_persistent<C, true>, block, smem) !=
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_forward_jacobian_persistent<C, true>, pblock, smem) !=
                 cudaSuccess || per < 1)
           per = 1;
         n_sm_dev[di] = sm; per_sm_dev[di] = per;
       }
       const int n_sm = n_sm_dev[di], per_sm = per_sm_dev[di];
       const unsigned resident = (unsigned)(n_sm * per_sm);
-      const unsigned pgrid = grid < resident ? grid : resident;
-      k_forward_jacobian_persistent<C, true><<<pgrid, block, smem, s>>>(a);
+      const unsigned tiles = (unsigned)((threads + pblock - 1) / pblock);
+      const unsigned pgrid = tiles < resident ? tiles : resident;
+      k_forward_jacobian_persistent<C, true><<<pgrid, pblock, smem, s>>>(a);
     } else if (fast) k_forward_jacobian<C, true><<<grid, block, 0, s>>>(a);
     else k_forward_jacobian<C, false><<<grid, block, 0, s>>>(a);
     if (a.elements_done) cudaEventRecord(a.elements_done, s);  // xi, b, path and the status are final here

@@ -430,7 +430,7 @@ static __device__ unsigned long long g_k1_phase_clocks[8];
 // 3.57 ms / 1M tets with / without).  The persistent kernel already meets twice per tile, and there the five
 // phase barriers cost more than they give (2.034 vs 2.011 ms), so they are OFF by default;
 // C8_K1_SYNC_MASK selects which stay (bit k = k-th barrier in program order, finite-strain models only).
-// They must be off when a team is a warp (C8_K1_TEAM=32): warps then run different numbers of tiles.
+// They must be off when an SM holds more than one persistent CTA (the 128-thread teams of the small-strain models).
 #ifndef C8_K1_SYNC_MASK
 #define C8_K1_SYNC_MASK 0
 #endif
@@ -660,9 +660,23 @@ C8_DI void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memo
 // their own rows from distinct bank pairs, and rows stay 16-byte aligned for the vector copies
 constexpr int k1_row_stride(int n) { return n + ((2 - n % 4) + 4) % 4; }
 
-#ifndef C8_K1_TEAM
-#define C8_K1_TEAM C8_K1_BLOCK   // threads that walk the tile list together: the CTA (256) or a warp (32)
+// Threads per CTA of the persistent K1 = the team that walks the tile list together.  Per model: the
+// finite-strain programs (~140 KB of straight-line code) want ONE 256-thread CTA per SM in lockstep (two
+// 128-thread CTAs drift apart and thrash the instruction caches: hyper-J2 2.37 against 2.01 ms), the
+// small-strain programs are about half as long and run faster as TWO independent 128-thread CTAs per SM,
+// each hiding the other's barrier and latency stalls (small-J2 1.35 against 1.47 ms, elastic 0.94 against 1.00).
+// A model overrides the default with K1_TEAM (3-D small-Hill with its return-map predictor: 1.88 at 256 against
+// 1.91 at 2 x 128).  C8_K1_PBLOCK forces one size for every model.
+template <class M, class = void> struct k1_team_of { static constexpr int value = M::FINITE ? 256 : 128; };
+template <class M> struct k1_team_of<M, decltype(void(M::K1_TEAM))> { static constexpr int value = M::K1_TEAM; };
+template <class C>
+struct K1PBlock {
+#ifdef C8_K1_PBLOCK
+  static constexpr int value = C8_K1_PBLOCK;
+#else
+  static constexpr int value = k1_team_of<typename C::Model>::value;
 #endif
+};
 
 template <class C, int TEAM>
 struct alignas(16) K1Stage {
@@ -692,7 +706,7 @@ struct alignas(16) K1Smem {
   int fetch[2];
 };
 template <class C>
-constexpr int k1_smem_bytes() { return int(sizeof(K1Smem<C, C8_K1_TEAM>)) * (C8_K1_BLOCK / C8_K1_TEAM); }
+constexpr int k1_smem_bytes() { return int(sizeof(K1Smem<C, K1PBlock<C>::value>)); }
 
 // The asynchronous copies of a tile's element records (shared by the persistent K1 and K3): connectivity
 // of a tile into conn[buf], then -- once that has landed -- the nodal rows it names and the tile's local-state
@@ -768,10 +782,7 @@ struct TilePrefetch {
 template <class C, int TEAM, class PF, class SMEM, class BEFORE, class BODY>
 C8_DI void persistent_tile_loop(const PF& pf, SMEM& S, int* counter, int n_tiles, int team_id, int n_teams, int tid,
                                 BEFORE before, BODY body) {
-  auto team_sync = [] {
-    if constexpr (TEAM == C8_K1_BLOCK) __syncthreads();
-    else __syncwarp();
-  };
+  auto team_sync = [] { __syncthreads(); };   // a team is a whole CTA
   int tile = team_id, next = team_id + n_teams, next2 = team_id + 2 * n_teams;
   if (tile >= n_tiles) return;   // team-uniform (a CTA-wide team leaves as a whole)
   if (tid == 0) S.fetch[0] = 3 * n_teams + atomicAdd(counter, 1);
@@ -805,24 +816,19 @@ C8_DI void persistent_tile_loop(const PF& pf, SMEM& S, int* counter, int n_tiles
 }
 
 template <class C, bool FAST>
-__global__ void __launch_bounds__(C8_K1_BLOCK, C8_K1_MINB) k_forward_jacobian_persistent(const FwdArgs a) {
+__global__ void __launch_bounds__(K1PBlock<C>::value, 256 / K1PBlock<C>::value) k_forward_jacobian_persistent(const FwdArgs a) {
   constexpr int D = C::D, NN = C::NN, NB = C::NB, NXI = C::NXI, G = C::G;
-  constexpr int TEAM = C8_K1_TEAM;
-  static_assert(TEAM == C8_K1_BLOCK || TEAM == 32, "a team is the CTA or one warp");
-  static_assert(TEAM == C8_K1_BLOCK || C8_K1_SYNC_MASK == 0, "warp teams cannot meet at CTA-wide phase barriers");
+  constexpr int TEAM = K1PBlock<C>::value;
+  static_assert(C8_K1_SYNC_MASK == 0 || TEAM == 256, "phase barriers: every CTA of an SM must be one team");
   constexpr int EPB = K1Stage<C, TEAM>::EPB;
   constexpr bool STAGED = K1Out<C, TEAM>::STAGED && FAST;
   using SMEM = K1Smem<C, TEAM>;
   extern __shared__ __align__(16) unsigned char k1_smem_raw[];
-  const int team = threadIdx.x / TEAM;     // team of this thread inside the CTA
-  const int tid = threadIdx.x % TEAM;      // thread inside the team
-  SMEM& S = reinterpret_cast<SMEM*>(k1_smem_raw)[team];
-  auto team_sync = [] {
-    if constexpr (TEAM == C8_K1_BLOCK) __syncthreads();
-    else __syncwarp();
-  };
-  const int n_teams = gridDim.x * (C8_K1_BLOCK / TEAM);
-  const int team_id = blockIdx.x * (C8_K1_BLOCK / TEAM) + team;
+  const int tid = threadIdx.x;
+  SMEM& S = *reinterpret_cast<SMEM*>(k1_smem_raw);
+  auto team_sync = [] { __syncthreads(); };
+  const int n_teams = gridDim.x;
+  const int team_id = blockIdx.x;
   const int t = tid % G, gl = tid / G;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane / G * G));

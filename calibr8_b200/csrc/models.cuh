@@ -397,6 +397,7 @@ template <int DIM>
 struct SmallHill {
   static_assert(DIM == 3, "small_hill is a 3-D model");
   static constexpr int NS = 6, NXI = 7, NPAR = 11, TYPE = L_SMALL_HILL;
+  static constexpr int K1_TEAM = 256;   // persistent K1: one 256-thread CTA per SM (forward.cuh, K1PBlock)
   static constexpr bool FINITE = false, HAS_NEWTON = true, PLANE_STRESS = false;
   // on the elastic branch C = xi - (a function of xi_prev and the kinematics): dC/dxi = I
   static constexpr bool ELASTIC_J_IDENTITY = true;
