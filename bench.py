@@ -351,9 +351,9 @@ def general_path_rows(mesh, fields, dev_index, stream, dfma_peak):
 
 def measured_traffic():
     """DRAM bytes per launch of the K1 kernels from the committed ncu --set full summary of this round
-    (profiles/r02b_ncu_summary.json -- the persistent element kernel --, written by tools/ncu_extract.py;
-    r02_ncu_summary.json as the fallback); None when neither file is there."""
-    for name in ("r02b_ncu_summary.json", "r02_ncu_summary.json"):
+    (profiles/r02d_ncu_summary.json -- the final persistent element kernel --, written by tools/ncu_extract.py;
+    earlier captures as the fallback); None when no file is there."""
+    for name in ("r02d_ncu_summary.json", "r02b_ncu_summary.json", "r02_ncu_summary.json"):
         try:
             d = json.load(open(os.path.join(ROOT, "profiles", name)))
             ks = d["kernels"]
