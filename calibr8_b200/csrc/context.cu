@@ -57,7 +57,8 @@ double* stage(c8_ctx* ctx, size_t bytes) {
 }
 double* pinned(c8_ctx* ctx, size_t bytes) {
   if (bytes > ctx->pinned_bytes) {
-    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->d_stage_out) cudaFree(ctx->d_stage_out);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     ctx->h_pinned = nullptr;
     if (cudaMallocHost(&ctx->h_pinned, bytes) != cudaSuccess) { ctx->pinned_bytes = 0; return nullptr; }
     ctx->pinned_bytes = bytes;
@@ -633,7 +634,19 @@ int c8::forward_state_host(c8_ctx* ctx, const double* u, const double* p, double
   const int nb = ctx->kt->nb, dim = ctx->dim, n = ctx->n_nodes;
   const size_t nu = size_t(n) * dim, np = (nb > dim) ? size_t(n) : 0;
   int rc;
-  if ((rc = c8_pack_x(ctx, u, p, ctx->d_x)) != C8_OK) return rc;
+  // inputs: H2D into the input staging buffer + interleave, NO host synchronisation before the element kernel is
+  // launched (the results leave through a second staging buffer on the side stream, and the call ends with both
+  // streams drained, so the next call's copies cannot overtake anything)
+  {
+    C8_REQUIRE(ctx, np == 0 || p != nullptr, "pressure field required for the mixed formulation");
+    double* din = stage(ctx, (nu + np) * sizeof(double));
+    C8_REQUIRE(ctx, din != nullptr, "staging allocation failed");
+    C8_CUDA(ctx, cudaMemcpyAsync(din, u, nu * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (np) C8_CUDA(ctx, cudaMemcpyAsync(din + nu, p, np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    k_interleave<<<(n * nb + 255) / 256, 256, 0, ctx->stream>>>(din, din + nu, ctx->d_x, n, dim, nb);
+    C8_CUDA(ctx, cudaGetLastError());
+  }
+  (void)rc;
   if (!ctx->side_stream) C8_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
   if (!ctx->ev_elements) C8_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_elements, cudaEventDisableTiming));
   C8_CUDA(ctx, cudaMemsetAsync(ctx->d_b, 0, size_t(n) * nb * sizeof(double), ctx->stream));
@@ -652,8 +665,13 @@ int c8::forward_state_host(c8_ctx* ctx, const double* u, const double* p, double
   C8_CUDA(ctx, cudaGetLastError());
   cudaStream_t side = ctx->side_stream;
   C8_CUDA(ctx, cudaStreamWaitEvent(side, ctx->ev_elements, 0));
-  double* d = stage(ctx, (nu + np) * sizeof(double));
-  C8_REQUIRE(ctx, d != nullptr, "staging allocation failed");
+  if ((nu + np) * sizeof(double) > ctx->stage_out_bytes) {
+    if (ctx->d_stage_out) cudaFree(ctx->d_stage_out);
+    ctx->d_stage_out = nullptr; ctx->stage_out_bytes = 0;
+    C8_CUDA(ctx, cudaMalloc(&ctx->d_stage_out, (nu + np) * sizeof(double)));
+    ctx->stage_out_bytes = (nu + np) * sizeof(double);
+  }
+  double* d = ctx->d_stage_out;
   k_deinterleave<<<(n * nb + 255) / 256, 256, 0, side>>>(ctx->d_b, d, d + nu, n, dim, nb);
   C8_CUDA(ctx, cudaMemcpyAsync(b_u, d, nu * sizeof(double), cudaMemcpyDeviceToHost, side));
   if (np && b_p) C8_CUDA(ctx, cudaMemcpyAsync(b_p, d + nu, np * sizeof(double), cudaMemcpyDeviceToHost, side));

@@ -69,6 +69,8 @@ struct c8_ctx {
   double* d_xi = nullptr, *d_xip = nullptr;
   double* d_stage = nullptr;   // staging for host<->device layout conversion
   size_t stage_bytes = 0;
+  double* d_stage_out = nullptr;   // second staging buffer: results on the side stream while d_stage holds the inputs
+  size_t stage_out_bytes = 0;
   double* h_pinned = nullptr;
   size_t pinned_bytes = 0;
 
