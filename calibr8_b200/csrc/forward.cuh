@@ -720,6 +720,11 @@ struct TilePrefetch {
   const double *coords, *x, *x_prev, *xi_prev, *xi;
   long long xi_ld;
   int elem_begin, elem_end, tid;
+  // 16-byte copies need 16-byte aligned arrays (any cudaMalloc'd array is; a caller's offset pointer may not be)
+  C8_DI bool aligned16() const {
+    return ((reinterpret_cast<size_t>(x) | reinterpret_cast<size_t>(x_prev) | reinterpret_cast<size_t>(xi_prev) |
+             reinterpret_cast<size_t>(xi)) & 15) == 0;
+  }
   // element of slot j of tile `tile` (clamped: padding slots repeat the last element, no stores)
   C8_DI int elem_of(int tile, int j) const {
     const int e = elem_begin + tile * EPB + j;
@@ -734,15 +739,16 @@ struct TilePrefetch {
   C8_DI void issue_record(int tile, int buf, int st) const {
     K1Stage<C, TEAM>& T = S.stage[st];
     const bool have_xp = x_prev != nullptr;
+    const bool a16 = aligned16();
     for (int i = tid; i < EPB * NN; i += TEAM) {
       const int j = i / NN, n = i - j * NN;
       const int nd = S.conn[buf][j][n];
       T.nodes[j][n] = nd;
 #pragma unroll
       for (int k = 0; k < D; ++k) cp_async8(&T.X[j][n * D + k], &coords[size_t(nd) * D + k]);
-      if constexpr (NB % 2 == 0) {
+      if (NB % 2 == 0 && a16) {
 #pragma unroll
-        for (int q = 0; q < NB; q += 2) {
+        for (int q = 0; q + 1 < NB; q += 2) {
           cp_async16(&T.xn[j][n * NB + q], &x[size_t(nd) * NB + q]);
           if (have_xp) cp_async16(&T.xpn[j][n * NB + q], &x_prev[size_t(nd) * NB + q]);
         }
@@ -757,7 +763,7 @@ struct TilePrefetch {
     // local state rows: EPB consecutive elements per component (a full tile is 16-byte aligned: elem_begin
     // and xi_ld are multiples of 32); the ragged last tile goes element by element
     const int e0 = elem_begin + tile * EPB;
-    if (e0 + EPB <= elem_end && (e0 % 2) == 0) {
+    if (e0 + EPB <= elem_end && (e0 % 2) == 0 && a16) {
       for (int i = tid; i < NXI * (EPB / 2); i += TEAM) {
         const int q = i / (EPB / 2), j = (i - q * (EPB / 2)) * 2;
         cp_async16(&T.xip[q][j], &xi_prev[size_t(q) * xi_ld + e0 + j]);

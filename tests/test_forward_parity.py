@@ -213,6 +213,32 @@ def test_local_solve_failure_is_reported():
     ctx.close()
 
 
+def test_unaligned_device_arrays_give_the_same_matrix():
+    """The persistent kernel prefetches with 16-byte asynchronous copies when the caller's arrays allow it; arrays
+    that are only 8-byte aligned (an offset pointer into a larger buffer) must take the 8-byte path and give
+    the same bits."""
+    import torch
+    r = run_pair("3d_hyper_J2")
+    ctx = r["ctx"]
+    def shifted(t):
+        big = torch.zeros(t.numel() + 1, dtype=t.dtype, device=t.device)
+        v = big[1:]
+        v.copy_(t)
+        assert v.data_ptr() % 16 == 8
+        return v
+    x, xp, xip = shifted(r["x"]), shifted(r["xp"]), shifted(r["xip"])
+    xi0 = r["xip"].clone()
+    A1, b1 = ctx.alloc("A"), ctx.alloc("b")
+    assert ctx.forward_jacobian(r["x"], r["xp"], r["xip"], xi0, A1, b1, None) == 0
+    xi2 = shifted(r["xip"])
+    A2, b2 = ctx.alloc("A"), ctx.alloc("b")
+    assert ctx.forward_jacobian(x, xp, xip, xi2, A2, b2, None) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(A1, A2) and torch.equal(xi0, xi2)
+    assert (b1 - b2).abs().max().item() <= 1e-13 * b1.abs().max().item()   # red.add order is not fixed
+    ctx.close()
+
+
 def test_failed_local_solves_leave_no_stale_matrix_entries():
     """Production path (persistent element kernel, staged bulk stores) with a matrix: points whose local
     Newton fails contribute NOTHING -- their scratch slots are cleared, so the gather cannot sum an earlier
