@@ -133,7 +133,9 @@ struct Launch {
     const long long threads = (long long)a.mesh.n_elems * C::G;
     // 3-D combinations only: their one-tile K3 holds 8 warps per SM anyway (250+ registers); the 2-D ones run
     // at 116-230 registers with more resident warps than one 256-thread CTA would give
-    if (C::D == 3 && k3_persistent_enabled() && a.tile_counter) {
+    // (measured at 1 M tets: hyper-J2 2.28 -> 2.04 ms, small-J2 1.78 -> 1.75, small-Hill 1.89 -> 1.86; the elastic model,
+    // with no local solve, is faster with many small CTAs: 1.43 against 1.52)
+    if (C::D == 3 && C::Model::HAS_NEWTON && k3_persistent_enabled() && a.tile_counter) {
       constexpr int MAXDEV = 64;
       static int n_sm_dev[MAXDEV] = {0};
       int dev = 0;
